@@ -1,0 +1,157 @@
+/* parvar_b200 - C ABI of the B200-native hot path of matthiaskoenig/parameter-variability.
+ *
+ * The reference has no FFI of its own for this path: its arithmetic sits behind two Python call
+ * shapes that drop into third-party native libraries:
+ *
+ *   B1  ODESampleSimulator.simulate_samples(parameters, settings)      -> libroadrunner (CVODE)
+ *       reference src/parvar/experiments/petab_factory.py:221-272  (hot loop :228-246)
+ *   B2  pypesto_problem.objective(x, sensi_orders)                     -> AMICI (CVODES + fwd sens)
+ *       reference src/parvar/optimization/petab_optimization.py:43-45 (built), :144-151, :168-173 (called)
+ *
+ * Each entry point below names the reference call it replaces.  Conventions:
+ *   - plain pointers and sizes, no torch / C++ types; the library is loaded with ctypes;
+ *   - every function returns int: 0 = ok, < 0 = argument / CUDA error (text via pv_last_error()),
+ *     > 0 (only the *_sync helpers) = number of trajectories whose integration failed;
+ *   - "device" pointers are CUDA device memory owned by the caller, fp64 unless stated, batch-minor:
+ *     consecutive trajectories are consecutive addresses;
+ *   - launches go to the given stream (a cudaStream_t passed as void*; NULL = legacy default stream),
+ *     nothing synchronises unless the name says so;
+ *   - a pv_problem may be used from one host thread at a time.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with PV_E_CUDA.
+ */
+#ifndef PARVAR_B200_H
+#define PARVAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PV_ABI_VERSION 1
+
+enum {
+    PV_E_ARG = -1,      /* bad argument */
+    PV_E_CUDA = -2,     /* CUDA runtime error */
+    PV_E_MODEL = -3,    /* unknown model / id */
+    PV_E_STATE = -4,    /* problem not fully configured */
+};
+
+/* per-trajectory status codes written to status[B] */
+enum { PV_TRAJ_OK = 0, PV_TRAJ_MAX_STEPS = 1, PV_TRAJ_STEP_TOO_SMALL = 2, PV_TRAJ_NONFINITE = 3 };
+
+enum { PV_METHOD_AUTO = 0, PV_METHOD_DOPRI5 = 1, PV_METHOD_RODAS4 = 2 };
+enum { PV_NOISE_NORMAL = 0, PV_NOISE_LOGNORMAL = 1 };
+
+typedef struct pv_problem pv_problem;
+
+/* ---- library / model registry (reference: parvar.MODELS, src/parvar/__init__.py:26-30) ---------------- */
+int pv_abi_version(void);
+const char* pv_last_error(void);
+int pv_device_count(void);
+int pv_model_count(void);
+const char* pv_model_name(int model_index);
+
+/* ---- problem = one loaded model + simulation settings ---------------------------------------------------
+ * pv_problem_create replaces `roadrunner.RoadRunner(str(model_path))` + integrator settings
+ * (petab_factory.py:183-190) and the AMICI model build behind `PetabImporter.create_problem()`
+ * (petab_optimization.py:43-45): the model's RHS / Jacobian / sensitivities are already compiled in. */
+pv_problem* pv_problem_create(const char* model_name, int device);
+void pv_problem_destroy(pv_problem* p);
+
+/* model description (roadrunner `getIds()`, petab_factory.py:190) */
+int pv_problem_dims(const pv_problem* p, int* n_states, int* n_theta, int* n_sens);
+const char* pv_problem_state_id(const pv_problem* p, int i);
+const char* pv_problem_theta_id(const pv_problem* p, int i);
+double pv_problem_theta_default(const pv_problem* p, int i);
+int pv_problem_sens_theta_index(const pv_problem* p, int k); /* theta index of sensitivity parameter k */
+/* algorithmic flop counts measured by the code generator: what[] = "rhs","rhs_sens","jac","lu","solve",
+ * "step_dopri5","step_dopri5_sens","step_rodas4","step_rodas4_sens","dense","dense_sens" */
+int pv_problem_flops(const pv_problem* p, const char* what);
+
+/* integrator settings (petab_factory.py:187-189: absolute_tolerance, relative_tolerance) */
+int pv_problem_set_solver(pv_problem* p, int method, double rtol, double atol, int max_steps);
+
+/* `r.resetAll(); r.setValue(key, value)` for values shared by the whole batch (dosage dict,
+ * petab_factory.py:229-233).  id = a theta id, or a state id / "[state id]" for an initial concentration. */
+int pv_problem_set_value(pv_problem* p, const char* id, double value);
+int pv_problem_reset_values(pv_problem* p);
+
+/* which ids the columns of the per-trajectory matrix P set (`r.setValue(pid, row[pid])`, :236-239) */
+int pv_problem_set_columns(pv_problem* p, int n_cols, const char* const* ids);
+
+/* output grid: `simulate(start, end, steps)` -> linspace(start, end, steps+1) (:242-246); any increasing grid */
+int pv_problem_set_timepoints(pv_problem* p, int n_t, const double* t_host);
+
+/* selected observables "[sid]" (:250-258); ids may carry the brackets */
+int pv_problem_set_observables(pv_problem* p, int n_obs, const char* const* ids);
+
+/* ---- B1: batched forward simulation --------------------------------------------------------------------
+ * Replaces the loop `for _, row in parameters.iterrows(): ... s = self.r.simulate(...)` (:228-246).
+ *   P_dev      [n_cols][B]   per-trajectory values of the configured columns
+ *   Y_dev      [n_t][n_obs][B] concentrations of the selected observables (may be NULL: integrate only)
+ *   status_dev [B] int32     PV_TRAJ_* (may be NULL)
+ *   steps_dev  [2][B] int32  accepted / rejected step counts (may be NULL)                               */
+int pv_simulate(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, int32_t* status_dev,
+                int32_t* steps_dev, void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): chunks the batch, overlaps H2D / kernel / D2H on
+ * internal streams and returns when Y_host is complete.  logp_host [B] may be NULL; when given (data must
+ * be set) the same pass also returns the log-likelihood.  Returns the number of failed trajectories. */
+int pv_simulate_host(pv_problem* p, int64_t B, const double* P_host, double* Y_host, double* logp_host,
+                     int32_t* status_host, int32_t* steps_host);
+
+/* ---- B2: log-likelihood (and gradient) ---------------------------------------------------------------------
+ * Measurements enter as sufficient statistics per (timepoint, observable, data set):
+ *   normal:     n, sum y, sum y^2            lognormal:  n, sum log y, sum (log y)^2  (+ const = -sum log y)
+ * so one trajectory can be compared with one individual (n = 1) or with a whole group (pooled fit:
+ * every measurement row of a group carries simulationConditionId = group, petab_factory.py:404-417).
+ *   stats_host [3][n_t][n_obs][n_data]; trajectory b uses data set  b % n_data.
+ *   sigma_host [n_obs]  noise sd per observable (`noiseFormula`, :394; the reference writes 1)
+ *   logp_b = sum_{t,k} -0.5*( n log(2 pi sigma^2) + (Syy - 2 f Sy + n f^2)/sigma^2 )          (normal)
+ * which is minus AMICI's  0.5*sum(log(2 pi sigma^2) + ((y-f)/sigma)^2).                                   */
+int pv_problem_set_data(pv_problem* p, int noise_model, int n_data, const double* stats_host,
+                        const double* sigma_host);
+
+/* logp only (`objective(x, sensi_orders=(0,))`, the sampler's call, petab_optimization.py:168-173).
+ *   logp_dev [B];  seg_len > 0 additionally sums consecutive runs of seg_len trajectories (one chain's
+ *   individuals / one x's groups) into logp_seg_dev [B/seg_len] in a fixed order (deterministic).        */
+int pv_logp(pv_problem* p, int64_t B, const double* P_dev, double* logp_dev, int64_t seg_len,
+            double* logp_seg_dev, int32_t* status_dev, int32_t* steps_dev, void* stream);
+
+/* logp and gradient by forward sensitivities (`objective(x, sensi_orders=(0,1))`, the optimiser's call,
+ * petab_optimization.py:144-151).  grad_dev [n_sens][B] = d logp_b / d theta_s of trajectory b.            */
+int pv_logp_grad(pv_problem* p, int64_t B, const double* P_dev, double* logp_dev, double* grad_dev,
+                 int64_t seg_len, double* logp_seg_dev, int32_t* status_dev, int32_t* steps_dev, void* stream);
+
+/* trajectories AND logp from one integration pass (BASELINE config 2: "trajectories + logp") */
+int pv_simulate_logp(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, double* logp_dev,
+                     int32_t* status_dev, int32_t* steps_dev, void* stream);
+
+/* trajectories and their sensitivities (AMICI `rdata.sy`): S_dev [n_sens][n_t][n_obs][B] (Y_dev may be NULL) */
+int pv_simulate_sens(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, double* S_dev,
+                     int32_t* status_dev, int32_t* steps_dev, void* stream);
+
+/* host-buffer versions of the two objective calls (sync; return number of failed trajectories) */
+int pv_logp_host(pv_problem* p, int64_t B, const double* P_host, double* logp_host, int64_t seg_len,
+                 double* logp_seg_host);
+int pv_logp_grad_host(pv_problem* p, int64_t B, const double* P_host, double* logp_host, double* grad_host,
+                      int64_t seg_len, double* logp_seg_host);
+
+/* page-locked host memory for the *_host calls (cudaHostAlloc / cudaFreeHost); NULL on failure */
+void* pv_host_alloc(size_t bytes);
+void pv_host_free(void* ptr);
+
+/* ---- measurement helpers ------------------------------------------------------------------------------ */
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t pv_launch_count(void);
+/* device time of the most recent hot kernel launched through the *_host calls, in ms (CUDA events) */
+double pv_last_kernel_ms(const pv_problem* p);
+/* fp64 / fp32 FMA-pipe peak microbenchmark: returns TFLOP/s achieved by a register-resident FMA chain kernel */
+double pv_fma_peak_tflops(int device, int use_fp64, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARVAR_B200_H */

@@ -1,0 +1,586 @@
+// C ABI of libparvar_b200.so (include/parvar_b200.h).  Host-side plumbing only: argument checks,
+// device-side copies of the small configuration arrays, kernel dispatch over
+// (model x integrator x mode), chunked host<->device pipelines.  No arithmetic of the path runs
+// on the host, and there is no CPU fallback: without a device every compute call returns PV_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/parvar_b200.h"
+#include "pv_kernels.cuh"
+#include "generated/simple_chain.cuh"
+#include "generated/simple_pk.cuh"
+#include "generated/icg_body_flat.cuh"
+#include "generated/model_tables.inc"
+
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_OK(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(PV_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));           \
+    } while (0)
+
+struct pv_problem {
+    int model = -1;
+    int device = 0;
+    const pv_model_table* tab = nullptr;
+    int method = PV_METHOD_AUTO;
+    double rtol = 1e-7, atol = 1e-10;
+    int max_steps = 1000000;
+    std::vector<double> theta_base, y0_base, tgrid, stats, sigma;
+    std::vector<int> col_target, obs_idx;
+    int noise_model = PV_NOISE_NORMAL;
+    int n_data = 0;
+    // device copies
+    double *d_theta = nullptr, *d_y0 = nullptr, *d_tgrid = nullptr, *d_stats = nullptr;
+    bool dirty_values = true;
+    // host pipeline
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double* stage_dev[3] = {nullptr, nullptr, nullptr};
+    size_t stage_bytes[3] = {0, 0, 0};
+    double* pin[3] = {nullptr, nullptr, nullptr};
+    size_t pin_bytes[3] = {0, 0, 0};
+    int* d_failed = nullptr;
+    double last_kernel_ms = 0.0;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int pv_abi_version(void) { return PV_ABI_VERSION; }
+extern "C" const char* pv_last_error(void) { return g_last_error.c_str(); }
+extern "C" int pv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+extern "C" int pv_model_count(void) { return PV_N_MODELS; }
+extern "C" const char* pv_model_name(int i) { return (i >= 0 && i < PV_N_MODELS) ? pv_model_tables[i].name : nullptr; }
+extern "C" int64_t pv_launch_count(void) { return g_launches.load(); }
+
+static int find_id(const char* const* ids, int n, const std::string& id) {
+    for (int i = 0; i < n; ++i)
+        if (id == ids[i]) return i;
+    return -1;
+}
+static std::string strip_brackets(const char* id) {
+    std::string s(id ? id : "");
+    if (s.size() >= 2 && s.front() == '[' && s.back() == ']') s = s.substr(1, s.size() - 2);
+    return s;
+}
+
+extern "C" pv_problem* pv_problem_create(const char* model_name, int device) {
+    if (!model_name) {
+        fail(PV_E_ARG, "model_name is NULL");
+        return nullptr;
+    }
+    int m = -1;
+    for (int i = 0; i < PV_N_MODELS; ++i)
+        if (!strcmp(pv_model_tables[i].name, model_name)) m = i;
+    if (m < 0) {
+        fail(PV_E_MODEL, std::string("unknown model '") + model_name + "' (not compiled into this library)");
+        return nullptr;
+    }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        fail(PV_E_CUDA, "no CUDA device: parvar_b200 has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0 || device >= n) {
+        fail(PV_E_ARG, "device index out of range");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fail(PV_E_CUDA, "cudaSetDevice failed");
+        return nullptr;
+    }
+    auto* p = new pv_problem();
+    p->model = m;
+    p->device = device;
+    p->tab = &pv_model_tables[m];
+    p->theta_base.assign(p->tab->theta_default, p->tab->theta_default + p->tab->n_theta);
+    p->y0_base.assign(p->tab->n_states, std::numeric_limits<double>::quiet_NaN());
+    bool ok = cudaMalloc(&p->d_theta, sizeof(double) * p->tab->n_theta) == cudaSuccess &&
+              cudaMalloc(&p->d_y0, sizeof(double) * p->tab->n_states) == cudaSuccess &&
+              cudaMalloc(&p->d_failed, sizeof(int)) == cudaSuccess;
+    for (int i = 0; i < 3 && ok; ++i) ok = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&p->ev0) == cudaSuccess && cudaEventCreate(&p->ev1) == cudaSuccess;
+    if (!ok) {
+        fail(PV_E_CUDA, std::string("problem setup: ") + cudaGetErrorString(cudaGetLastError()));
+        pv_problem_destroy(p);
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void pv_problem_destroy(pv_problem* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_theta);
+    cudaFree(p->d_y0);
+    cudaFree(p->d_tgrid);
+    cudaFree(p->d_stats);
+    cudaFree(p->d_failed);
+    for (int i = 0; i < 3; ++i) {
+        if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
+        cudaFree(p->stage_dev[i]);
+        if (p->pin[i]) cudaFreeHost(p->pin[i]);
+    }
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+}
+
+extern "C" int pv_problem_dims(const pv_problem* p, int* nx, int* nth, int* ns) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (nx) *nx = p->tab->n_states;
+    if (nth) *nth = p->tab->n_theta;
+    if (ns) *ns = p->tab->n_sens;
+    return 0;
+}
+extern "C" const char* pv_problem_state_id(const pv_problem* p, int i) {
+    return (p && i >= 0 && i < p->tab->n_states) ? p->tab->state_ids[i] : nullptr;
+}
+extern "C" const char* pv_problem_theta_id(const pv_problem* p, int i) {
+    return (p && i >= 0 && i < p->tab->n_theta) ? p->tab->theta_ids[i] : nullptr;
+}
+extern "C" double pv_problem_theta_default(const pv_problem* p, int i) {
+    return (p && i >= 0 && i < p->tab->n_theta) ? p->tab->theta_default[i] : std::numeric_limits<double>::quiet_NaN();
+}
+extern "C" int pv_problem_sens_theta_index(const pv_problem* p, int k) {
+    return (p && k >= 0 && k < p->tab->n_sens) ? p->tab->sens_index[k] : PV_E_ARG;
+}
+extern "C" int pv_problem_flops(const pv_problem* p, const char* what) {
+    if (!p || !what) return fail(PV_E_ARG, "NULL argument");
+    for (int i = 0; i < p->tab->n_flops; ++i)
+        if (!strcmp(p->tab->flop_names[i], what)) return p->tab->flop_values[i];
+    return fail(PV_E_ARG, std::string("unknown flop counter '") + what + "'");
+}
+
+extern "C" int pv_problem_set_solver(pv_problem* p, int method, double rtol, double atol, int max_steps) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (method < PV_METHOD_AUTO || method > PV_METHOD_RODAS4) return fail(PV_E_ARG, "unknown method");
+    if (!(rtol > 0) || !(atol >= 0) || max_steps <= 0) return fail(PV_E_ARG, "rtol > 0, atol >= 0, max_steps > 0 required");
+    p->method = method;
+    p->rtol = rtol;
+    p->atol = atol;
+    p->max_steps = max_steps;
+    return 0;
+}
+
+// returns theta index, or n_theta + state index, or -1
+static int resolve_id(const pv_problem* p, const char* id) {
+    const std::string s = strip_brackets(id);
+    int i = find_id(p->tab->theta_ids, p->tab->n_theta, s);
+    if (i >= 0) return i;
+    i = find_id(p->tab->state_ids, p->tab->n_states, s);
+    if (i >= 0) return p->tab->n_theta + i;
+    return -1;
+}
+
+extern "C" int pv_problem_set_value(pv_problem* p, const char* id, double value) {
+    if (!p || !id) return fail(PV_E_ARG, "NULL argument");
+    const int t = resolve_id(p, id);
+    if (t < 0) return fail(PV_E_MODEL, std::string("model '") + p->tab->name + "' has no settable id '" + id + "'");
+    if (t < p->tab->n_theta)
+        p->theta_base[t] = value;
+    else
+        p->y0_base[t - p->tab->n_theta] = value;
+    p->dirty_values = true;
+    return 0;
+}
+extern "C" int pv_problem_reset_values(pv_problem* p) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    p->theta_base.assign(p->tab->theta_default, p->tab->theta_default + p->tab->n_theta);
+    p->y0_base.assign(p->tab->n_states, std::numeric_limits<double>::quiet_NaN());
+    p->dirty_values = true;
+    return 0;
+}
+
+extern "C" int pv_problem_set_columns(pv_problem* p, int n_cols, const char* const* ids) {
+    if (!p || n_cols < 0 || (n_cols > 0 && !ids)) return fail(PV_E_ARG, "bad columns");
+    if (n_cols > PV_MAX_COLS) return fail(PV_E_ARG, "too many per-trajectory columns (max 8)");
+    std::vector<int> tgt;
+    for (int j = 0; j < n_cols; ++j) {
+        const int t = resolve_id(p, ids[j]);
+        if (t < 0) return fail(PV_E_MODEL, std::string("model '") + p->tab->name + "' has no settable id '" + ids[j] + "'");
+        tgt.push_back(t);
+    }
+    p->col_target = tgt;
+    return 0;
+}
+
+extern "C" int pv_problem_set_timepoints(pv_problem* p, int n_t, const double* t_host) {
+    if (!p || n_t <= 0 || !t_host) return fail(PV_E_ARG, "bad timepoints");
+    for (int i = 1; i < n_t; ++i)
+        if (!(t_host[i] > t_host[i - 1])) return fail(PV_E_ARG, "timepoints must be strictly increasing");
+    CUDA_OK(cudaSetDevice(p->device));
+    p->tgrid.assign(t_host, t_host + n_t);
+    cudaFree(p->d_tgrid);
+    p->d_tgrid = nullptr;
+    CUDA_OK(cudaMalloc(&p->d_tgrid, sizeof(double) * n_t));
+    CUDA_OK(cudaMemcpy(p->d_tgrid, t_host, sizeof(double) * n_t, cudaMemcpyHostToDevice));
+    p->stats.clear();   // data are tied to the grid
+    p->n_data = 0;
+    return 0;
+}
+
+extern "C" int pv_problem_set_observables(pv_problem* p, int n_obs, const char* const* ids) {
+    if (!p || n_obs <= 0 || !ids) return fail(PV_E_ARG, "bad observables");
+    if (n_obs > PV_MAX_OBS) return fail(PV_E_ARG, "too many observables (max 16)");
+    std::vector<int> idx;
+    for (int k = 0; k < n_obs; ++k) {
+        const int i = find_id(p->tab->state_ids, p->tab->n_states, strip_brackets(ids[k]));
+        if (i < 0) return fail(PV_E_MODEL, std::string("model '") + p->tab->name + "' has no state '" + ids[k] + "'");
+        idx.push_back(i);
+    }
+    p->obs_idx = idx;
+    p->stats.clear();
+    p->n_data = 0;
+    return 0;
+}
+
+extern "C" int pv_problem_set_data(pv_problem* p, int noise_model, int n_data, const double* stats_host,
+                                   const double* sigma_host) {
+    if (!p || !stats_host || !sigma_host || n_data <= 0) return fail(PV_E_ARG, "bad data");
+    if (noise_model != PV_NOISE_NORMAL && noise_model != PV_NOISE_LOGNORMAL) return fail(PV_E_ARG, "unknown noise model");
+    if (p->tgrid.empty() || p->obs_idx.empty()) return fail(PV_E_STATE, "set timepoints and observables before data");
+    const size_t n = (size_t)3 * p->tgrid.size() * p->obs_idx.size() * (size_t)n_data;
+    for (size_t k = 0; k < p->obs_idx.size(); ++k)
+        if (!(sigma_host[k] > 0)) return fail(PV_E_ARG, "sigma must be > 0");
+    CUDA_OK(cudaSetDevice(p->device));
+    p->stats.assign(stats_host, stats_host + n);
+    p->sigma.assign(sigma_host, sigma_host + p->obs_idx.size());
+    p->noise_model = noise_model;
+    p->n_data = n_data;
+    cudaFree(p->d_stats);
+    p->d_stats = nullptr;
+    CUDA_OK(cudaMalloc(&p->d_stats, sizeof(double) * n));
+    CUDA_OK(cudaMemcpy(p->d_stats, stats_host, sizeof(double) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------------------------------
+template <class M, int METHOD, int MODE>
+static cudaError_t launch_one(const pv_launch_params& lp, size_t shmem, cudaStream_t s) {
+    const int64_t blocks = (lp.B + PV_BLOCK - 1) / PV_BLOCK;
+    if (shmem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(pv_batch_kernel<M, METHOD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+        if (e != cudaSuccess) return e;
+    }
+    pv_batch_kernel<M, METHOD, MODE><<<(unsigned)blocks, PV_BLOCK, shmem, s>>>(lp);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+template <class M>
+static cudaError_t launch_model(int method, int mode, const pv_launch_params& lp, size_t shmem, cudaStream_t s) {
+#define PV_CASE(METH, MODE) \
+    if (method == METH && mode == MODE) return launch_one<M, METH, MODE>(lp, shmem, s);
+    PV_CASE(1, PV_MODE_TRAJ) PV_CASE(1, PV_MODE_LOGP) PV_CASE(1, PV_MODE_TRAJ_LOGP) PV_CASE(1, PV_MODE_LOGP_GRAD) PV_CASE(1, PV_MODE_TRAJ_SENS)
+    PV_CASE(2, PV_MODE_TRAJ) PV_CASE(2, PV_MODE_LOGP) PV_CASE(2, PV_MODE_TRAJ_LOGP) PV_CASE(2, PV_MODE_LOGP_GRAD) PV_CASE(2, PV_MODE_TRAJ_SENS)
+#undef PV_CASE
+    return cudaErrorInvalidValue;
+}
+
+static int sync_values(pv_problem* p, cudaStream_t s) {
+    if (!p->dirty_values) return 0;
+    // small synchronous copies: configuration time, not the hot loop
+    (void)s;
+    CUDA_OK(cudaMemcpy(p->d_theta, p->theta_base.data(), sizeof(double) * p->theta_base.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(p->d_y0, p->y0_base.data(), sizeof(double) * p->y0_base.size(), cudaMemcpyHostToDevice));
+    p->dirty_values = false;
+    return 0;
+}
+
+static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y, double* S, double* logp,
+                  double* grad, int32_t* status, int32_t* steps, cudaStream_t s) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (B < 0) return fail(PV_E_ARG, "B < 0");
+    if (B == 0) return 0;
+    if (B > ((int64_t)1 << 31) * PV_BLOCK / 2) return fail(PV_E_ARG, "B too large for one launch");
+    if (p->tgrid.empty()) return fail(PV_E_STATE, "timepoints not set");
+    const bool need_logp = (mode & PV_MODE_LOGP) != 0;
+    const bool sens = (mode & PV_MODE_SENS) != 0;
+    if (p->obs_idx.empty()) return fail(PV_E_STATE, "observables not set");
+    if (need_logp && p->stats.empty()) return fail(PV_E_STATE, "data not set");
+    if (!p->col_target.empty() && !P) return fail(PV_E_ARG, "P is NULL but columns are configured");
+    if (sens && p->tab->n_sens == 0) return fail(PV_E_MODEL, "model was generated without sensitivity parameters");
+    if (mode == PV_MODE_TRAJ_SENS && !S) return fail(PV_E_ARG, "S is NULL");
+    if (need_logp && !logp) return fail(PV_E_ARG, "logp is NULL");
+    if (mode == PV_MODE_LOGP_GRAD && !grad) return fail(PV_E_ARG, "grad is NULL");
+    CUDA_OK(cudaSetDevice(p->device));
+    if (int rc = sync_values(p, s)) return rc;
+
+    pv_launch_params lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.B = B;
+    lp.P = P;
+    lp.theta_base = p->d_theta;
+    lp.y0_base = p->d_y0;
+    lp.tgrid = p->d_tgrid;
+    lp.stats = p->d_stats;
+    lp.Y = Y;
+    lp.S = S;
+    lp.logp = logp;
+    lp.grad = grad;
+    lp.status = status;
+    lp.steps = steps;
+    lp.rtol = p->rtol;
+    lp.atol = p->atol;
+    lp.n_cols = (int)p->col_target.size();
+    for (int j = 0; j < lp.n_cols; ++j) lp.col_target[j] = p->col_target[j];
+    for (int j = lp.n_cols; j < PV_MAX_COLS; ++j) lp.col_target[j] = -1;
+    lp.T = (int)p->tgrid.size();
+    lp.n_obs = (int)p->obs_idx.size();
+    for (int k = 0; k < lp.n_obs; ++k) lp.obs_idx[k] = p->obs_idx[k];
+    lp.n_data = need_logp ? p->n_data : 1;
+    lp.noise_model = p->noise_model;
+    lp.max_steps = p->max_steps;
+    if (need_logp) {
+        const double LOG_2PI = 1.8378770664093454835606594728112;
+        for (int k = 0; k < lp.n_obs; ++k) {
+            const double sg = p->sigma[k];
+            lp.inv_sigma2[k] = 1.0 / (sg * sg);
+            lp.log_norm[k] = (p->noise_model == PV_NOISE_NORMAL) ? LOG_2PI + 2.0 * std::log(sg) : std::log(sg) + 0.5 * LOG_2PI;
+        }
+    }
+    int method = p->method;
+    if (method == PV_METHOD_AUTO) method = p->tab->stiff ? PV_METHOD_RODAS4 : PV_METHOD_DOPRI5;
+    size_t shmem = sizeof(double) * (lp.T + p->tab->n_theta + p->tab->n_states);
+    if (need_logp && lp.n_data == 1) shmem += sizeof(double) * 3 * lp.T * lp.n_obs;
+    if (shmem > 200 * 1024) return fail(PV_E_ARG, "time grid / data too large for shared memory");
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (p->model) {
+        PV_MODEL_DISPATCH(e = launch_model, (method, mode, lp, shmem, s))
+    }
+    if (e != cudaSuccess) return fail(PV_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+static int segment_sum(const double* x, int64_t B, int64_t seg_len, double* out, cudaStream_t s) {
+    if (seg_len <= 0 || !out) return 0;
+    if (B % seg_len) return fail(PV_E_ARG, "B must be a multiple of seg_len");
+    const int64_t n_seg = B / seg_len;
+    const int warps = 4;
+    pv_segment_sum_kernel<<<(unsigned)((n_seg + warps - 1) / warps), warps * 32, 0, s>>>(x, seg_len, n_seg, out);
+    g_launches.fetch_add(1);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pv_simulate(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, int32_t* status_dev,
+                           int32_t* steps_dev, void* stream) {
+    return launch(p, PV_MODE_TRAJ, B, P_dev, Y_dev, nullptr, nullptr, nullptr, status_dev, steps_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pv_simulate_logp(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, double* logp_dev,
+                                int32_t* status_dev, int32_t* steps_dev, void* stream) {
+    return launch(p, PV_MODE_TRAJ_LOGP, B, P_dev, Y_dev, nullptr, logp_dev, nullptr, status_dev, steps_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pv_simulate_sens(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, double* S_dev,
+                                int32_t* status_dev, int32_t* steps_dev, void* stream) {
+    return launch(p, PV_MODE_TRAJ_SENS, B, P_dev, Y_dev, S_dev, nullptr, nullptr, status_dev, steps_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pv_logp(pv_problem* p, int64_t B, const double* P_dev, double* logp_dev, int64_t seg_len,
+                       double* logp_seg_dev, int32_t* status_dev, int32_t* steps_dev, void* stream) {
+    if (int rc = launch(p, PV_MODE_LOGP, B, P_dev, nullptr, nullptr, logp_dev, nullptr, status_dev, steps_dev, (cudaStream_t)stream)) return rc;
+    return segment_sum(logp_dev, B, seg_len, logp_seg_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pv_logp_grad(pv_problem* p, int64_t B, const double* P_dev, double* logp_dev, double* grad_dev,
+                            int64_t seg_len, double* logp_seg_dev, int32_t* status_dev, int32_t* steps_dev, void* stream) {
+    if (int rc = launch(p, PV_MODE_LOGP_GRAD, B, P_dev, nullptr, nullptr, logp_dev, grad_dev, status_dev, steps_dev, (cudaStream_t)stream)) return rc;
+    return segment_sum(logp_dev, B, seg_len, logp_seg_dev, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-buffer pipelines
+// ---------------------------------------------------------------------------------------------------------
+static int ensure_dev(pv_problem* p, int slot, size_t bytes) {
+    if (p->stage_bytes[slot] >= bytes) return 0;
+    cudaFree(p->stage_dev[slot]);
+    p->stage_dev[slot] = nullptr;
+    p->stage_bytes[slot] = 0;
+    CUDA_OK(cudaMalloc(&p->stage_dev[slot], bytes));
+    p->stage_bytes[slot] = bytes;
+    return 0;
+}
+
+extern "C" int pv_simulate_host(pv_problem* p, int64_t B, const double* P_host, double* Y_host, double* logp_host,
+                                int32_t* status_host, int32_t* steps_host) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (B <= 0) return B == 0 ? 0 : fail(PV_E_ARG, "B < 0");
+    if (p->tgrid.empty() || p->obs_idx.empty()) return fail(PV_E_STATE, "timepoints / observables not set");
+    if (!Y_host) return fail(PV_E_ARG, "Y_host is NULL");
+    if (logp_host && p->stats.empty()) return fail(PV_E_STATE, "logp requested but data not set");
+    CUDA_OK(cudaSetDevice(p->device));
+    const int n_cols = (int)p->col_target.size();
+    const int64_t rows = (int64_t)p->tgrid.size() * (int64_t)p->obs_idx.size();
+    // chunks sized so that copy-out of chunk i overlaps the kernel of chunk i+1
+    const int64_t chunk = std::min<int64_t>(B, (int64_t)1 << 17);
+    // per slot: P [n_cols][chunk], Y [rows][chunk], logp [chunk], status [chunk] + steps [2][chunk] (int32)
+    const size_t bytesP = sizeof(double) * (size_t)std::max(n_cols, 1) * chunk;
+    const size_t bytesY = sizeof(double) * (size_t)rows * chunk;
+    const size_t bytesL = sizeof(double) * (size_t)chunk;
+    const size_t bytesI = sizeof(int32_t) * 3 * (size_t)chunk;
+    const size_t slot_bytes = bytesP + bytesY + bytesL + bytesI;
+    const int n_slots = (B > chunk) ? 3 : 1;
+    for (int s = 0; s < n_slots; ++s)
+        if (int rc = ensure_dev(p, s, slot_bytes)) return rc;
+    CUDA_OK(cudaMemsetAsync(p->d_failed, 0, sizeof(int), p->streams[0]));
+    CUDA_OK(cudaStreamSynchronize(p->streams[0]));
+    CUDA_OK(cudaEventRecord(p->ev0, p->streams[0]));
+    int k = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++k) {
+        const int slot = k % n_slots;
+        cudaStream_t s = p->streams[slot];
+        const int64_t nb = std::min(chunk, B - b0);
+        double* dP = p->stage_dev[slot];
+        double* dY = (double*)((char*)dP + bytesP);
+        double* dL = (double*)((char*)dY + bytesY);
+        int32_t* dStatus = (int32_t*)((char*)dL + bytesL);
+        int32_t* dSteps = dStatus + chunk;
+        if (n_cols > 0)
+            CUDA_OK(cudaMemcpy2DAsync(dP, sizeof(double) * nb, P_host + b0, sizeof(double) * B, sizeof(double) * nb, n_cols,
+                                      cudaMemcpyHostToDevice, s));
+        if (int rc = launch(p, logp_host ? PV_MODE_TRAJ_LOGP : PV_MODE_TRAJ, nb, n_cols ? dP : nullptr, dY, nullptr,
+                            logp_host ? dL : nullptr, nullptr, dStatus, dSteps, s))
+            return rc;
+        pv_count_failed_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(dStatus, nb, p->d_failed);
+        g_launches.fetch_add(1);
+        CUDA_OK(cudaMemcpy2DAsync(Y_host + b0, sizeof(double) * B, dY, sizeof(double) * nb, sizeof(double) * nb, rows,
+                                  cudaMemcpyDeviceToHost, s));
+        if (logp_host) CUDA_OK(cudaMemcpyAsync(logp_host + b0, dL, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
+        if (status_host) CUDA_OK(cudaMemcpyAsync(status_host + b0, dStatus, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+        if (steps_host)
+            CUDA_OK(cudaMemcpy2DAsync(steps_host + b0, sizeof(int32_t) * B, dSteps, sizeof(int32_t) * nb, sizeof(int32_t) * nb, 2,
+                                      cudaMemcpyDeviceToHost, s));
+    }
+    for (int s = 0; s < n_slots; ++s) CUDA_OK(cudaStreamSynchronize(p->streams[s]));
+    int failed = 0;
+    CUDA_OK(cudaMemcpy(&failed, p->d_failed, sizeof(int), cudaMemcpyDeviceToHost));
+    return failed;
+}
+
+static int logp_host_impl(pv_problem* p, bool with_grad, int64_t B, const double* P_host, double* logp_host,
+                          double* grad_host, int64_t seg_len, double* logp_seg_host) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (B <= 0) return B == 0 ? 0 : fail(PV_E_ARG, "B < 0");
+    if (seg_len > 0 && (B % seg_len)) return fail(PV_E_ARG, "B must be a multiple of seg_len");
+    CUDA_OK(cudaSetDevice(p->device));
+    const int n_cols = (int)p->col_target.size();
+    const int ns = p->tab->n_sens;
+    const int64_t n_seg = seg_len > 0 ? B / seg_len : 0;
+    const size_t bytesP = sizeof(double) * (size_t)std::max(n_cols, 1) * B;
+    const size_t bytesL = sizeof(double) * (size_t)B;
+    const size_t bytesG = with_grad ? sizeof(double) * (size_t)ns * B : 0;
+    const size_t bytesS = sizeof(double) * (size_t)std::max<int64_t>(n_seg, 1);
+    const size_t bytesI = sizeof(int32_t) * (size_t)B;
+    if (int rc = ensure_dev(p, 0, bytesP + bytesL + bytesG + bytesS + bytesI)) return rc;
+    cudaStream_t s = p->streams[0];
+    double* dP = p->stage_dev[0];
+    double* dL = (double*)((char*)dP + bytesP);
+    double* dG = (double*)((char*)dL + bytesL);
+    double* dS = (double*)((char*)dG + bytesG);
+    int32_t* dStatus = (int32_t*)((char*)dS + bytesS);
+    CUDA_OK(cudaMemsetAsync(p->d_failed, 0, sizeof(int), s));
+    if (n_cols > 0) CUDA_OK(cudaMemcpyAsync(dP, P_host, sizeof(double) * (size_t)n_cols * B, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaEventRecord(p->ev0, s));
+    int rc = with_grad ? pv_logp_grad(p, B, n_cols ? dP : nullptr, dL, dG, seg_len, n_seg ? dS : nullptr, dStatus, nullptr, s)
+                       : pv_logp(p, B, n_cols ? dP : nullptr, dL, seg_len, n_seg ? dS : nullptr, dStatus, nullptr, s);
+    if (rc) return rc;
+    CUDA_OK(cudaEventRecord(p->ev1, s));
+    pv_count_failed_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(dStatus, B, p->d_failed);
+    g_launches.fetch_add(1);
+    if (logp_host) CUDA_OK(cudaMemcpyAsync(logp_host, dL, bytesL, cudaMemcpyDeviceToHost, s));
+    if (with_grad && grad_host) CUDA_OK(cudaMemcpyAsync(grad_host, dG, bytesG, cudaMemcpyDeviceToHost, s));
+    if (n_seg && logp_seg_host) CUDA_OK(cudaMemcpyAsync(logp_seg_host, dS, sizeof(double) * n_seg, cudaMemcpyDeviceToHost, s));
+    int failed = 0;
+    CUDA_OK(cudaMemcpyAsync(&failed, p->d_failed, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) == cudaSuccess) p->last_kernel_ms = ms;
+    return failed;
+}
+
+extern "C" int pv_logp_host(pv_problem* p, int64_t B, const double* P_host, double* logp_host, int64_t seg_len,
+                            double* logp_seg_host) {
+    return logp_host_impl(p, false, B, P_host, logp_host, nullptr, seg_len, logp_seg_host);
+}
+extern "C" int pv_logp_grad_host(pv_problem* p, int64_t B, const double* P_host, double* logp_host, double* grad_host,
+                                 int64_t seg_len, double* logp_seg_host) {
+    return logp_host_impl(p, true, B, P_host, logp_host, grad_host, seg_len, logp_seg_host);
+}
+
+extern "C" void* pv_host_alloc(size_t bytes) {
+    void* ptr = nullptr;
+    if (cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        fail(PV_E_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return ptr;
+}
+extern "C" void pv_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+extern "C" double pv_last_kernel_ms(const pv_problem* p) { return p ? p->last_kernel_ms : -1.0; }
+
+extern "C" double pv_fma_peak_tflops(int device, int use_fp64, int iters) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        cudaGetLastError();
+        fail(PV_E_CUDA, "no CUDA device");
+        return -1.0;
+    }
+    cudaSetDevice(device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    void* out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * threads * 8) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        if (use_fp64)
+            pv_fma_peak_kernel<double><<<blocks, threads>>>((double*)out, iters, 0.999999, 1e-7);
+        else
+            pv_fma_peak_kernel<float><<<blocks, threads>>>((float*)out, iters, 0.999999f, 1e-7f);
+        g_launches.fetch_add(1);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return -1.0;
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+    return flops / (best * 1e-3) / 1e12;
+}

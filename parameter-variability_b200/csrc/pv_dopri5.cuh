@@ -1,0 +1,264 @@
+// Adaptive Dormand-Prince 5(4) with dense output, one trajectory per thread (north_star subsystem 2,
+// non-stiff path).  Replaces, for many parameter rows at once, the per-row
+// `RoadRunner.simulate(start, end, steps)` CVODE call of the reference
+// (src/parvar/experiments/petab_factory.py:242-246) and, with the augmented sensitivity system,
+// the CVODES forward-sensitivity solve behind pyPESTO's objective
+// (src/parvar/optimization/petab_optimization.py:144-151).
+//
+// Everything a lane needs lives in registers: state, 7 stage derivatives, hoisted model
+// coefficients.  The step-size controller (error norm, PI factor) runs in fp32 on the SFU
+// (`__powf`) - it only steers h; every quantity that enters the solution is fp64.
+#pragma once
+#include "pv_common.cuh"
+
+// ---- system adaptors: what the integrators see ---------------------------------------------
+template <class M, bool SENS>
+struct pv_system;
+
+template <class M>
+struct pv_system<M, false> {
+    static constexpr int NX = M::NX;
+    static constexpr int N = M::NX;
+    static constexpr int FLOPS_RHS = M::FLOPS_RHS;
+    struct Consts {
+        double c[M::NC];
+    };
+    PV_HD static void rhs(double t, const double (&z)[N], const Consts& k, double (&fz)[N]) {
+        M::rhs(t, z, k.c, fz);
+    }
+};
+
+template <class M>
+struct pv_system<M, true> {
+    static constexpr int NX = M::NX;
+    static constexpr int N = M::NX * (1 + M::NS);
+    static constexpr int FLOPS_RHS = M::FLOPS_RHS_SENS;
+    struct Consts {
+        double c[M::NC];
+        double dc[M::NDC];
+    };
+    PV_HD static void rhs(double t, const double (&z)[N], const Consts& k, double (&fz)[N]) {
+        double y[M::NX], s[M::NSD][M::NX], f[M::NX], fs[M::NSD][M::NX];
+#pragma unroll
+        for (int i = 0; i < M::NX; ++i) y[i] = z[i];
+#pragma unroll
+        for (int p = 0; p < M::NS; ++p)
+#pragma unroll
+            for (int i = 0; i < M::NX; ++i) s[p][i] = z[M::NX * (1 + p) + i];
+        M::rhs_sens(t, y, s, k.c, k.dc, f, fs);
+#pragma unroll
+        for (int i = 0; i < M::NX; ++i) fz[i] = f[i];
+#pragma unroll
+        for (int p = 0; p < M::NS; ++p)
+#pragma unroll
+            for (int i = 0; i < M::NX; ++i) fz[M::NX * (1 + p) + i] = fs[p][i];
+    }
+};
+
+// ---- controller helpers -------------------------------------------------------------------
+PV_HD float pv_powf_fast(float x, float a) {
+#if defined(__CUDA_ARCH__)
+    return __powf(x, a);
+#else
+    return powf(x, a);
+#endif
+}
+
+struct pv_step_stats {
+    int accepted;
+    int rejected;
+};
+
+enum pv_status_code : int {
+    PV_OK = 0,
+    PV_ERR_MAX_STEPS = 1,    // step budget exhausted before t_end
+    PV_ERR_STEP_TOO_SMALL = 2,
+    PV_ERR_NONFINITE = 3,
+};
+
+// Flops of one attempted step besides the RHS evaluations: 21 a_ij + 6 b/e FMAs for the stages
+// and the error vector (2 flop each) plus ~10 per component for the norm, per state.
+template <class Sys>
+struct pv_dopri5_cost {
+    static constexpr int STAGES = 6;   // FSAL: k7 of an accepted step is k1 of the next
+    static constexpr int FLOPS_STEP = Sys::N * (2 * (1 + 2 + 3 + 4 + 5 + 5 + 6) + 10) + STAGES * Sys::FLOPS_RHS + 12;
+    static constexpr int FLOPS_DENSE = Sys::N * (2 * 6 + 6 + 8);   // rcont5 + interpolant per output row
+};
+
+// Integrate z from tgrid[0] to tgrid[T-1]; `out(j, t_j, z_j)` is called once per grid point in
+// increasing j (j = 0 immediately).  Returns a pv_status_code.
+template <class Sys, class Out>
+PV_HD int pv_dopri5_integrate(const typename Sys::Consts& ks, double (&y)[Sys::N], const double* tgrid, int T,
+                              double rtol, double atol, int max_steps, Out& out, pv_step_stats& st) {
+    constexpr int N = Sys::N;
+    constexpr int NX = Sys::NX;   // error control on the states; sensitivities join with the same weights
+    st.accepted = 0;
+    st.rejected = 0;
+    double t = tgrid[0];
+    const double tend = tgrid[T - 1];
+    int jout = 0;
+    while (jout < T && tgrid[jout] <= t) {
+        out(jout, tgrid[jout], y);
+        ++jout;
+    }
+    if (jout >= T) return PV_OK;
+
+    double k1[N], k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], yn[N];
+    Sys::rhs(t, y, ks, k1);
+
+    // ---- initial step (Hairer, Norsett, Wanner I, II.4) --------------------------------------
+    double h;
+    {
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const float sc = (float)(atol + rtol * fabs(y[i]));
+            const float a = (float)y[i] / sc, b = (float)k1[i] / sc;
+            d0 += a * a;
+            d1 += b * b;
+        }
+        d0 = sqrtf(d0 / N);
+        d1 = sqrtf(d1 / N);
+        double h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6 : 0.01 * (double)(d0 / d1);
+        h0 = fmin(h0, tend - t);
+#pragma unroll
+        for (int i = 0; i < N; ++i) yn[i] = fma(h0, k1[i], y[i]);
+        Sys::rhs(t + h0, yn, ks, k2);
+        float d2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const float sc = (float)(atol + rtol * fabs(y[i]));
+            const float a = (float)(k2[i] - k1[i]) / sc;
+            d2 += a * a;
+        }
+        d2 = sqrtf(d2 / N) / (float)h0;
+        const float dm = fmaxf(d1, d2);
+        const double h1 = (dm <= 1e-15f) ? fmax(1e-6, h0 * 1e-3) : (double)pv_powf_fast(0.01f / dm, 0.2f);
+        h = fmin(fmin(100.0 * h0, h1), tend - t);
+    }
+
+    float facold = 1e-4f;
+    bool last_rejected = false;
+    int nstep = 0;
+    (void)NX;
+    while (true) {
+        if (nstep >= max_steps) return PV_ERR_MAX_STEPS;
+        ++nstep;
+        bool last = false;
+        if (t + 1.01 * h >= tend) {
+            h = tend - t;
+            last = true;
+        }
+        if (!(fabs(h) > 1e-14 * fmax(fabs(t), 1.0))) return PV_ERR_STEP_TOO_SMALL;
+
+        // ---- stages ----------------------------------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < N; ++i) yn[i] = fma(h * 0.2, k1[i], y[i]);
+        Sys::rhs(t + 0.2 * h, yn, ks, k2);
+#pragma unroll
+        for (int i = 0; i < N; ++i) yn[i] = fma(h, fma(3.0 / 40.0, k1[i], (9.0 / 40.0) * k2[i]), y[i]);
+        Sys::rhs(t + 0.3 * h, yn, ks, k3);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            yn[i] = fma(h, fma(44.0 / 45.0, k1[i], fma(-56.0 / 15.0, k2[i], (32.0 / 9.0) * k3[i])), y[i]);
+        Sys::rhs(t + 0.8 * h, yn, ks, k4);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            yn[i] = fma(h,
+                        fma(19372.0 / 6561.0, k1[i],
+                            fma(-25360.0 / 2187.0, k2[i], fma(64448.0 / 6561.0, k3[i], (-212.0 / 729.0) * k4[i]))),
+                        y[i]);
+        Sys::rhs(t + (8.0 / 9.0) * h, yn, ks, k5);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            yn[i] = fma(h,
+                        fma(9017.0 / 3168.0, k1[i],
+                            fma(-355.0 / 33.0, k2[i],
+                                fma(46732.0 / 5247.0, k3[i], fma(49.0 / 176.0, k4[i], (-5103.0 / 18656.0) * k5[i])))),
+                        y[i]);
+        Sys::rhs(t + h, yn, ks, k6);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            yn[i] = fma(h,
+                        fma(35.0 / 384.0, k1[i],
+                            fma(500.0 / 1113.0, k3[i],
+                                fma(125.0 / 192.0, k4[i], fma(-2187.0 / 6784.0, k5[i], (11.0 / 84.0) * k6[i])))),
+                        y[i]);
+        Sys::rhs(t + h, yn, ks, k7);
+
+        // ---- error estimate (fp32 norm of an fp64 difference) -----------------------------------
+        float err2 = 0.f;
+        bool finite = true;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double e = h * fma(71.0 / 57600.0, k1[i],
+                                     fma(-71.0 / 16695.0, k3[i],
+                                         fma(71.0 / 1920.0, k4[i],
+                                             fma(-17253.0 / 339200.0, k5[i], fma(22.0 / 525.0, k6[i], (-1.0 / 40.0) * k7[i])))));
+            const double sc = atol + rtol * fmax(fabs(y[i]), fabs(yn[i]));
+            const float r = (float)e / (float)sc;
+            err2 += r * r;
+            finite = finite && (fabs(yn[i]) < 1e300);
+        }
+        err2 *= (1.0f / N);
+        if (!finite || !(err2 == err2)) {
+            // treat as a failed step; give up if h is already tiny
+            err2 = 1e10f;
+            if (fabs(h) < 1e-12) return PV_ERR_NONFINITE;
+        }
+        // err^(0.2 - 0.75*beta), beta = 0.04, on err^2
+        const float fac11 = pv_powf_fast(fmaxf(err2, 1e-30f), 0.085f);
+        if (err2 <= 1.0f) {
+            // ---- accept: dense output for every grid point in (t, t+h] --------------------------
+            ++st.accepted;
+            const double tn = last ? tend : t + h;
+            if (jout < T && tgrid[jout] <= tn) {
+                double r5[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    r5[i] = h * fma(-12715105075.0 / 11282082432.0, k1[i],
+                                    fma(87487479700.0 / 32700410799.0, k3[i],
+                                        fma(-10690763975.0 / 1880347072.0, k4[i],
+                                            fma(701980252875.0 / 199316789632.0, k5[i],
+                                                fma(-1453857185.0 / 822651844.0, k6[i], (69997945.0 / 29380423.0) * k7[i])))));
+                do {
+                    const double tj = tgrid[jout];
+                    double yo[N];
+                    if (tj >= tn) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) yo[i] = yn[i];
+                    } else {
+                        const double th = (tj - t) / h, th1 = 1.0 - th;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            const double yd = yn[i] - y[i];
+                            const double bs = fma(h, k1[i], -yd);
+                            const double r4 = yd - fma(h, k7[i], bs);
+                            yo[i] = fma(th, fma(th1, fma(th, fma(th1, r5[i], r4), bs), yd), y[i]);
+                        }
+                    }
+                    out(jout, tj, yo);
+                    ++jout;
+                } while (jout < T && tgrid[jout] <= tn);
+            }
+            float fac = fac11 / pv_powf_fast(facold, 0.04f);
+            fac = fmaxf(0.1f, fminf(5.0f, fac * (1.0f / 0.9f)));
+            double hnew = h / (double)fac;
+            if (last_rejected) hnew = fmin(hnew, h);
+            facold = fmaxf(sqrtf(err2), 1e-4f);
+            last_rejected = false;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                y[i] = yn[i];
+                k1[i] = k7[i];
+            }
+            t = tn;
+            if (last || jout >= T) return PV_OK;
+            h = hnew;
+        } else {
+            ++st.rejected;
+            h = h / (double)fminf(5.0f, fac11 * (1.0f / 0.9f));
+            last_rejected = true;
+        }
+    }
+}

@@ -1,0 +1,235 @@
+// Batched trajectory / likelihood kernels: one trajectory per thread, everything per-lane in
+// registers, time grid + shared data in shared memory, batch-minor (coalescing) global layout.
+// Replaces the reference's per-row roadrunner loop (petab_factory.py:228-246) and the AMICI
+// objective (petab_optimization.py:144-151, 168-173).  See include/parvar_b200.h for the contract.
+#pragma once
+#include <cuda_runtime.h>
+#include "pv_common.cuh"
+#include "pv_dopri5.cuh"
+#include "pv_rosenbrock.cuh"
+
+#define PV_MAX_COLS 8
+#define PV_MAX_OBS 16
+#define PV_BLOCK 128
+
+// mode = bit set: what a launch produces
+enum pv_mode : int {
+    PV_MODE_TRAJ = 1,        // write Y (and S when SENS)
+    PV_MODE_LOGP = 2,        // accumulate the log-likelihood (and its gradient when SENS)
+    PV_MODE_SENS = 4,        // integrate the forward-sensitivity system as well
+    PV_MODE_TRAJ_LOGP = 3,
+    PV_MODE_LOGP_GRAD = 6,
+    PV_MODE_TRAJ_SENS = 5,
+};
+
+struct pv_launch_params {
+    int64_t B;
+    const double* P;           // [n_cols][B]
+    const double* theta_base;  // [NTH]
+    const double* y0_base;     // [NX], NaN = use the model's initial value
+    const double* tgrid;       // [T]
+    const double* stats;       // [3][T][n_obs][n_data]
+    double* Y;                 // [T][n_obs][B]
+    double* S;                 // [NS][T][n_obs][B]
+    double* logp;              // [B]
+    double* grad;              // [NS][B]
+    int32_t* status;           // [B]
+    int32_t* steps;            // [2][B]
+    double rtol, atol;
+    double inv_sigma2[PV_MAX_OBS];
+    double log_norm[PV_MAX_OBS];   // normal: log(2 pi sigma^2);  lognormal: log(sigma) + 0.5 log(2 pi)
+    int col_target[PV_MAX_COLS];   // < NTH: theta index; >= NTH: NTH + state index (initial value)
+    int obs_idx[PV_MAX_OBS];
+    int n_cols, T, n_obs, n_data, noise_model, max_steps;
+};
+
+template <int NX, int N>
+PV_D double pv_pick(const double (&a)[N], int block, int idx) {
+    double v = 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) v = (idx == i) ? a[block * NX + i] : v;
+    return v;
+}
+
+// ---- per-grid-point sink: stores the observables and / or folds them into the likelihood ---------------------
+template <class M, int MODE>
+struct pv_sink {
+    static constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
+    static constexpr bool TRAJ = (MODE & PV_MODE_TRAJ) != 0;
+    static constexpr bool LOGP = (MODE & PV_MODE_LOGP) != 0;
+    static constexpr int N = pv_system<M, SENS>::N;
+    const pv_launch_params& p;
+    const double* sh_stats;   // shared copy when n_data == 1, else nullptr
+    int64_t b;                // trajectory
+    int64_t d;                // data set of this trajectory
+    double obs[M::NX];
+    double lp;
+    double g[M::NSD];
+    PV_D void operator()(int j, double, const double (&z)[N]) {
+        for (int k = 0; k < p.n_obs; ++k) {
+            const int idx = p.obs_idx[k];
+            const double sc = pv_pick<M::NX>(obs, 0, idx);
+            const double f = pv_pick<M::NX>(z, 0, idx) * sc;
+            double df[M::NSD];
+            if constexpr (SENS) {
+#pragma unroll
+                for (int s = 0; s < M::NS; ++s) df[s] = pv_pick<M::NX>(z, 1 + s, idx) * sc;
+            }
+            (void)df;
+            if constexpr (TRAJ) {
+                if (p.Y) p.Y[((int64_t)j * p.n_obs + k) * p.B + b] = f;
+                if constexpr (SENS) {
+#pragma unroll
+                    for (int s = 0; s < M::NS; ++s) p.S[(((int64_t)s * p.T + j) * p.n_obs + k) * p.B + b] = df[s];
+                }
+            }
+            if constexpr (LOGP) {
+                const int64_t plane = (int64_t)p.T * p.n_obs * p.n_data;
+                const int64_t o = ((int64_t)j * p.n_obs + k) * p.n_data + d;
+                double n, s1, s2;
+                if (sh_stats) {
+                    n = sh_stats[o]; s1 = sh_stats[plane + o]; s2 = sh_stats[2 * plane + o];
+                } else {
+                    n = __ldg(p.stats + o); s1 = __ldg(p.stats + plane + o); s2 = __ldg(p.stats + 2 * plane + o);
+                }
+                if (n > 0.0) {
+                    double w;   // d lp / d f
+                    if (p.noise_model == 0) {
+                        lp -= 0.5 * fma(n, p.log_norm[k], fma(f, fma(n, f, -2.0 * s1), s2) * p.inv_sigma2[k]);
+                        w = fma(-n, f, s1) * p.inv_sigma2[k];
+                    } else {
+                        const double lf = log(f);
+                        lp -= s1 + fma(n, p.log_norm[k], 0.5 * fma(lf, fma(n, lf, -2.0 * s1), s2) * p.inv_sigma2[k]);
+                        w = fma(-n, lf, s1) * p.inv_sigma2[k] / f;
+                    }
+                    if constexpr (SENS) {
+#pragma unroll
+                        for (int s = 0; s < M::NS; ++s) g[s] = fma(w, df[s], g[s]);
+                    }
+                    (void)w;
+                }
+            }
+        }
+    }
+};
+
+// ---- the kernel ----------------------------------------------------------------------------------------
+template <class M, int METHOD, int MODE>
+__global__ void __launch_bounds__(PV_BLOCK)
+pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
+    constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
+    constexpr bool LOGP = (MODE & PV_MODE_LOGP) != 0;
+    using Sys = pv_system<M, SENS>;
+    extern __shared__ double sh[];
+    double* sh_t = sh;                    // [T]
+    double* sh_theta = sh_t + p.T;        // [NTH]
+    double* sh_y0 = sh_theta + M::NTH;    // [NX]
+    double* sh_stats = sh_y0 + M::NX;     // [3][T][n_obs] when LOGP && n_data == 1
+    for (int i = threadIdx.x; i < p.T; i += blockDim.x) sh_t[i] = p.tgrid[i];
+    for (int i = threadIdx.x; i < M::NTH; i += blockDim.x) sh_theta[i] = p.theta_base[i];
+    for (int i = threadIdx.x; i < M::NX; i += blockDim.x) sh_y0[i] = p.y0_base[i];
+    const bool stats_shared = LOGP && p.n_data == 1;
+    if (stats_shared)
+        for (int i = threadIdx.x; i < 3 * p.T * p.n_obs; i += blockDim.x) sh_stats[i] = p.stats[i];
+    __syncthreads();
+
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+
+    // ---- theta = batch-wide values, overridden by this trajectory's columns -------------------------------
+    double pc[PV_MAX_COLS];
+#pragma unroll
+    for (int j = 0; j < PV_MAX_COLS; ++j) pc[j] = (j < p.n_cols) ? __ldg(p.P + (int64_t)j * p.B + b) : 0.0;
+    typename Sys::Consts ks;
+    double z[Sys::N];
+    pv_sink<M, MODE> sink{p, stats_shared ? sh_stats : nullptr, b, (int64_t)(b % p.n_data), {}, 0.0, {}};
+    {
+        double th[M::NTH];
+#pragma unroll
+        for (int i = 0; i < M::NTH; ++i) {
+            double v = sh_theta[i];
+#pragma unroll
+            for (int j = 0; j < PV_MAX_COLS; ++j) v = (j < p.n_cols && p.col_target[j] == i) ? pc[j] : v;
+            th[i] = v;
+        }
+        double y0[M::NX];
+        M::hoist(th, ks.c, y0, sink.obs);
+        bool over[M::NX];
+#pragma unroll
+        for (int i = 0; i < M::NX; ++i) {
+            double v = sh_y0[i];
+            over[i] = (v == v);
+            v = over[i] ? v : y0[i];
+#pragma unroll
+            for (int j = 0; j < PV_MAX_COLS; ++j)
+                if (j < p.n_cols && p.col_target[j] == M::NTH + i) {
+                    v = pc[j];
+                    over[i] = true;
+                }
+            z[i] = v;
+        }
+        if constexpr (SENS) {
+            double dy0[M::NSD][M::NX];
+            M::hoist_sens(th, ks.dc, dy0);
+#pragma unroll
+            for (int s = 0; s < M::NS; ++s)
+#pragma unroll
+                for (int i = 0; i < M::NX; ++i) z[M::NX * (1 + s) + i] = over[i] ? 0.0 : dy0[s][i];
+        }
+    }
+
+    pv_step_stats st;
+    int rc;
+    if constexpr (METHOD == 1)
+        rc = pv_dopri5_integrate<Sys>(ks, z, sh_t, p.T, p.rtol, p.atol, p.max_steps, sink, st);
+    else
+        rc = pv_rosenbrock_integrate<M, SENS>(ks, z, sh_t, p.T, p.rtol, p.atol, p.max_steps, sink, st);
+    if constexpr (LOGP) {
+        p.logp[b] = (rc == 0) ? sink.lp : __longlong_as_double(0x7ff8000000000000LL);
+        if constexpr (SENS) {
+#pragma unroll
+            for (int s = 0; s < M::NS; ++s) p.grad[(int64_t)s * p.B + b] = sink.g[s];
+        }
+    }
+    if (p.status) p.status[b] = rc;
+    if (p.steps) {
+        p.steps[b] = st.accepted;
+        p.steps[p.B + b] = st.rejected;
+    }
+}
+
+// ---- deterministic segment sum: one warp per segment, fixed association order --------------------------------
+__global__ void pv_segment_sum_kernel(const double* __restrict__ x, int64_t seg_len, int64_t n_seg,
+                                      double* __restrict__ out) {
+    const int64_t seg = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (seg >= n_seg) return;
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int64_t i = lane; i < seg_len; i += 32) acc += x[seg * seg_len + i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[seg] = acc;
+}
+
+// count trajectories with status != 0 (for the *_host return value)
+__global__ void pv_count_failed_kernel(const int32_t* __restrict__ status, int64_t B, int* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = (i < B && status[i] != 0) ? 1 : 0;
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, bad);
+}
+
+// ---- FMA-pipe peak microbenchmark (roofline denominator) --------------------------------
+template <class Tp>
+__global__ void pv_fma_peak_kernel(Tp* out, int iters, Tp a, Tp bq) {
+    Tp x0 = threadIdx.x * (Tp)1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+       x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, bq); x1 = fma(x1, a, bq); x2 = fma(x2, a, bq); x3 = fma(x3, a, bq);
+            x4 = fma(x4, a, bq); x5 = fma(x5, a, bq); x6 = fma(x6, a, bq); x7 = fma(x7, a, bq);
+        }
+    }
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}

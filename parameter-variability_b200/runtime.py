@@ -1,0 +1,288 @@
+"""ctypes binding of libparvar_b200.so (include/parvar_b200.h) + a thin ``Problem`` object.
+
+PyTorch is used only for what it is good at here: device memory, streams and (in
+``distributed.py``) NCCL.  All arithmetic of the path runs in the CUDA library.  There is no
+CPU fallback: if the library or a CUDA device is missing, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "lib" / "libparvar_b200.so"
+
+METHOD_AUTO, METHOD_DOPRI5, METHOD_RODAS4 = 0, 1, 2
+NOISE_NORMAL, NOISE_LOGNORMAL = 0, 1
+STATUS_TEXT = {0: "ok", 1: "max_steps", 2: "step_too_small", 3: "nonfinite"}
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+# name -> (restype, argtypes); every symbol include/parvar_b200.h declares
+ABI = {
+    "pv_abi_version": (C.c_int, []),
+    "pv_last_error": (C.c_char_p, []),
+    "pv_device_count": (C.c_int, []),
+    "pv_model_count": (C.c_int, []),
+    "pv_model_name": (C.c_char_p, [C.c_int]),
+    "pv_problem_create": (C.c_void_p, [C.c_char_p, C.c_int]),
+    "pv_problem_destroy": (None, [C.c_void_p]),
+    "pv_problem_dims": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "pv_problem_state_id": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "pv_problem_theta_id": (C.c_char_p, [C.c_void_p, C.c_int]),
+    "pv_problem_theta_default": (C.c_double, [C.c_void_p, C.c_int]),
+    "pv_problem_sens_theta_index": (C.c_int, [C.c_void_p, C.c_int]),
+    "pv_problem_flops": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "pv_problem_set_solver": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int]),
+    "pv_problem_set_value": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+    "pv_problem_reset_values": (C.c_int, [C.c_void_p]),
+    "pv_problem_set_columns": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]),
+    "pv_problem_set_timepoints": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "pv_problem_set_observables": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]),
+    "pv_problem_set_data": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
+    "pv_simulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pv_simulate_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pv_simulate_logp": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "pv_simulate_sens": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "pv_logp": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                          C.c_void_p, C.c_void_p]),
+    "pv_logp_grad": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pv_logp_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pv_logp_grad_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pv_launch_count": (C.c_int64, []),
+    "pv_last_kernel_ms": (C.c_double, [C.c_void_p]),
+    "pv_fma_peak_tflops": (C.c_double, [C.c_int, C.c_int, C.c_int]),
+    "pv_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "pv_host_free": (None, [C.c_void_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class ParvarB200Error(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[Path] = None) -> C.CDLL:
+    """dlopen the in-tree library and type every exported symbol."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = Path(path or LIB_PATH)
+    if not path.exists():
+        raise ParvarB200Error(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(needs nvcc).  parvar_b200 has no CPU fallback.")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)     # AttributeError = header and library out of sync
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pv_abi_version() != 1:
+        raise ParvarB200Error("ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return (load_library().pv_last_error() or b"").decode()
+
+
+def _check(rc: int) -> int:
+    if rc < 0:
+        raise ParvarB200Error(f"parvar_b200 error {rc}: {last_error()}")
+    return rc
+
+
+def _ptr(t) -> Optional[int]:
+    """Device (or host) address of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+def _cstr_array(ids: Sequence[str]):
+    arr = (C.c_char_p * len(ids))()
+    arr[:] = [s.encode() for s in ids]
+    return arr
+
+
+def model_names() -> list[str]:
+    lib = load_library()
+    return [lib.pv_model_name(i).decode() for i in range(lib.pv_model_count())]
+
+
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block; numpy arrays made from it keep it alive as their base."""
+
+    def __init__(self, nbytes: int, shape, dtype: np.dtype):
+        lib = load_library()
+        self._free = lib.pv_host_free
+        self.addr = lib.pv_host_alloc(max(int(nbytes), 1))
+        if not self.addr:
+            raise ParvarB200Error(f"pinned allocation of {nbytes} bytes failed: {last_error()}")
+        self.__array_interface__ = {"data": (self.addr, False), "shape": tuple(shape), "typestr": dtype.str,
+                                    "version": 3}
+
+    def __del__(self):
+        if getattr(self, "addr", None):
+            self._free(self.addr)
+            self.addr = None
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array on page-locked host memory (cudaHostAlloc) so the *_host calls copy at PCIe speed."""
+    dtype = np.dtype(dtype)
+    shape = tuple(int(s) for s in (shape if hasattr(shape, "__len__") else (shape,)))
+    block = _PinnedBlock(int(np.prod(shape)) * dtype.itemsize, shape, dtype)
+    return np.asarray(block)
+
+
+class Problem:
+    """One loaded model + its simulation settings (a ``pv_problem``)."""
+
+    def __init__(self, model: str, device: int = 0):
+        self._lib = load_library()
+        self._h = self._lib.pv_problem_create(model.encode(), int(device))
+        if not self._h:
+            raise ParvarB200Error(f"cannot create problem for model {model!r}: {last_error()}")
+        self.model = model
+        self.device = int(device)
+        nx, nth, ns = C.c_int(), C.c_int(), C.c_int()
+        _check(self._lib.pv_problem_dims(self._h, C.byref(nx), C.byref(nth), C.byref(ns)))
+        self.n_states, self.n_theta, self.n_sens = nx.value, nth.value, ns.value
+        self.state_ids = [self._lib.pv_problem_state_id(self._h, i).decode() for i in range(self.n_states)]
+        self.theta_ids = [self._lib.pv_problem_theta_id(self._h, i).decode() for i in range(self.n_theta)]
+        self.theta_default = [self._lib.pv_problem_theta_default(self._h, i) for i in range(self.n_theta)]
+        self.sens_ids = [self.theta_ids[self._lib.pv_problem_sens_theta_index(self._h, k)] for k in range(self.n_sens)]
+        self.columns: list[str] = []
+        self.observables: list[str] = []
+        self.timepoints = np.zeros(0)
+        self.n_data = 0
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.pv_problem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration -------------------------------------------------------------------
+    def set_solver(self, method: int = METHOD_AUTO, rtol: float = 1e-7, atol: float = 1e-10,
+                   max_steps: int = 1_000_000) -> None:
+        _check(self._lib.pv_problem_set_solver(self._h, method, rtol, atol, max_steps))
+
+    def set_value(self, sid: str, value: float) -> None:
+        _check(self._lib.pv_problem_set_value(self._h, sid.encode(), float(value)))
+
+    def reset_values(self) -> None:
+        _check(self._lib.pv_problem_reset_values(self._h))
+
+    def set_columns(self, ids: Sequence[str]) -> None:
+        ids = list(ids)
+        _check(self._lib.pv_problem_set_columns(self._h, len(ids), _cstr_array(ids) if ids else None))
+        self.columns = ids
+
+    def set_timepoints(self, t: Sequence[float]) -> None:
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        _check(self._lib.pv_problem_set_timepoints(self._h, len(t), t.ctypes.data_as(_dp)))
+        self.timepoints = t.copy()
+        self.n_data = 0
+
+    def set_observables(self, ids: Sequence[str]) -> None:
+        ids = list(ids)
+        _check(self._lib.pv_problem_set_observables(self._h, len(ids), _cstr_array(ids)))
+        self.observables = [s.strip("[]") for s in ids]
+        self.n_data = 0
+
+    def set_data(self, stats: np.ndarray, sigma: Sequence[float], noise_model: int = NOISE_NORMAL) -> None:
+        """stats [3][T][n_obs][n_data] sufficient statistics (see include/parvar_b200.h)."""
+        stats = np.ascontiguousarray(stats, dtype=np.float64)
+        T, K = len(self.timepoints), len(self.observables)
+        if stats.ndim != 4 or stats.shape[:3] != (3, T, K):
+            raise ValueError(f"stats must have shape (3, {T}, {K}, n_data), got {stats.shape}")
+        sigma = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (K,)))
+        _check(self._lib.pv_problem_set_data(self._h, noise_model, stats.shape[3], stats.ctypes.data_as(_dp),
+                                             sigma.ctypes.data_as(_dp)))
+        self.n_data = stats.shape[3]
+
+    def flops(self, what: str) -> int:
+        return _check(self._lib.pv_problem_flops(self._h, what.encode()))
+
+    # ---- device-pointer calls (torch CUDA tensors) --------------------------------------------
+    def simulate(self, P, Y=None, status=None, steps=None, stream: int = 0, B: Optional[int] = None) -> None:
+        B = int(B if B is not None else (P.shape[-1] if P is not None else 0))
+        _check(self._lib.pv_simulate(self._h, B, _ptr(P), _ptr(Y), _ptr(status), _ptr(steps), stream))
+
+    def simulate_logp(self, P, Y, logp, status=None, steps=None, stream: int = 0, B: Optional[int] = None) -> None:
+        B = int(B if B is not None else P.shape[-1])
+        _check(self._lib.pv_simulate_logp(self._h, B, _ptr(P), _ptr(Y), _ptr(logp), _ptr(status), _ptr(steps), stream))
+
+    def simulate_sens(self, P, Y, S, status=None, steps=None, stream: int = 0, B: Optional[int] = None) -> None:
+        B = int(B if B is not None else P.shape[-1])
+        _check(self._lib.pv_simulate_sens(self._h, B, _ptr(P), _ptr(Y), _ptr(S), _ptr(status), _ptr(steps), stream))
+
+    def logp(self, P, logp, seg_len: int = 0, logp_seg=None, status=None, steps=None, stream: int = 0,
+             B: Optional[int] = None) -> None:
+        B = int(B if B is not None else P.shape[-1])
+        _check(self._lib.pv_logp(self._h, B, _ptr(P), _ptr(logp), seg_len, _ptr(logp_seg), _ptr(status),
+                                 _ptr(steps), stream))
+
+    def logp_grad(self, P, logp, grad, seg_len: int = 0, logp_seg=None, status=None, steps=None,
+                  stream: int = 0, B: Optional[int] = None) -> None:
+        B = int(B if B is not None else P.shape[-1])
+        _check(self._lib.pv_logp_grad(self._h, B, _ptr(P), _ptr(logp), _ptr(grad), seg_len, _ptr(logp_seg),
+                                      _ptr(status), _ptr(steps), stream))
+
+    # ---- host-buffer calls (numpy) -----------------------------------------------------------
+    def simulate_host(self, P: Optional[np.ndarray], B: int, Y: Optional[np.ndarray] = None,
+                      status: Optional[np.ndarray] = None, steps: Optional[np.ndarray] = None,
+                      logp: Optional[np.ndarray] = None):
+        """P [n_cols, B] float64 -> Y [T, n_obs, B] (and logp [B] when given).  Returns (Y, n_failed)."""
+        T, K = len(self.timepoints), len(self.observables)
+        if P is not None:
+            P = np.ascontiguousarray(P, dtype=np.float64)
+            if P.shape != (len(self.columns), B):
+                raise ValueError(f"P must have shape ({len(self.columns)}, {B}), got {P.shape}")
+        if Y is None:
+            Y = np.empty((T, K, B), dtype=np.float64)
+        n_failed = _check(self._lib.pv_simulate_host(self._h, B, _ptr(P), _ptr(Y), _ptr(logp), _ptr(status), _ptr(steps)))
+        return Y, n_failed
+
+    def logp_host(self, P: np.ndarray, seg_len: int = 0, grad: bool = False):
+        """-> (logp [B], grad [n_sens, B] or None, logp_seg [B/seg_len] or None, n_failed)."""
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        B = P.shape[-1]
+        lp = np.empty(B)
+        seg = np.empty(B // seg_len) if seg_len else None
+        if grad:
+            g = np.empty((self.n_sens, B))
+            nf = _check(self._lib.pv_logp_grad_host(self._h, B, _ptr(P), _ptr(lp), _ptr(g), seg_len, _ptr(seg)))
+            return lp, g, seg, nf
+        nf = _check(self._lib.pv_logp_host(self._h, B, _ptr(P), _ptr(lp), seg_len, _ptr(seg)))
+        return lp, None, seg, nf
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return self._lib.pv_last_kernel_ms(self._h)
+
+
+def launch_count() -> int:
+    return int(load_library().pv_launch_count())
+
+
+def fma_peak_tflops(device: int = 0, fp64: bool = True, iters: int = 4096) -> float:
+    return float(load_library().pv_fma_peak_tflops(device, 1 if fp64 else 0, iters))

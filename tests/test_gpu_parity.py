@@ -1,0 +1,280 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): trajectories rtol 1e-6 / atol 1e-9; logp and gradients 1e-6 relative.
+"""
+import numpy as np
+import pytest
+
+from conftest import lognormal_draws, parity_violation, pkg
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _problem(rt, model, columns, tgrid, observables, dosage=None, rtol=1e-7, atol=1e-10, method=0):
+    pb = rt.Problem(model)
+    pb.set_solver(method=method, rtol=rtol, atol=atol)
+    for k, v in (dosage or {}).items():
+        pb.set_value(k, v)
+    pb.set_columns(columns)
+    pb.set_timepoints(tgrid)
+    pb.set_observables(observables)
+    return pb
+
+
+def test_simple_chain_exact(cuda_lib, rt, oracle):
+    t = np.linspace(0, 10, 21)
+    k1 = lognormal_draws(1, 257)
+    pb = _problem(rt, "simple_chain", ["k1"], t, ["S1", "S2"])
+    Y, nf = pb.simulate_host(k1[None, :], len(k1))
+    assert nf == 0
+    ref = np.stack([oracle.simple_chain_exact(k, t) for k in k1], axis=-1)   # [T, 2, B]
+    assert parity_violation(Y, ref) <= 1.0
+
+
+def test_simple_pk_c1_single_set(cuda_lib, rt, oracle):
+    """BASELINE config C1: simple_pk, defaults, linspace(0,100,21) and (0,100,50)."""
+    for T in (21, 50):
+        t = np.linspace(0, 100, T)
+        pb = _problem(rt, "simple_pk", [], t, ["y_gut", "y_cent", "y_peri"])
+        Y, nf = pb.simulate_host(None, 1)
+        assert nf == 0
+        ref = oracle.simple_pk_exact({}, t)
+        assert parity_violation(Y[:, :, 0], ref) <= 1.0
+    # known-answer values
+    t = np.array([0.0, 5.0, 10.0])
+    pb = _problem(rt, "simple_pk", [], t, ["y_gut", "y_cent", "y_peri"])
+    Y, _ = pb.simulate_host(None, 1)
+    np.testing.assert_allclose(Y[1, :, 0], [0.00673795, 0.06623389, 0.10043281], rtol=1e-6)
+    np.testing.assert_allclose(Y[2, :, 0], [4.53999e-05, 9.80974e-03, 1.58271e-02], rtol=1e-5)
+
+
+def test_simple_pk_batched_draws(cuda_lib, rt, oracle):
+    """C2 at a size the oracle finishes in seconds: 2000 log-normal draws x 50 timepoints."""
+    B, T = 2000, 50
+    t = np.linspace(0, 100, T)
+    np.random.seed(1234)
+    k_abs = np.random.lognormal(-0.3465735902799726, 0.8325546111576977, B)
+    CL = np.random.lognormal(-0.3465735902799726, 0.8325546111576977, B)
+    pb = _problem(rt, "simple_pk", ["k_abs", "CL"], t, ["[y_gut]", "[y_cent]", "[y_peri]"])
+    status = np.empty(B, np.int32)
+    steps = np.empty((2, B), np.int32)
+    Y, nf = pb.simulate_host(np.stack([k_abs, CL]), B, status=status, steps=steps)
+    assert nf == 0 and not status.any()
+    assert steps[0].min() > 10
+    ref = np.stack([oracle.simple_pk_exact({"k_abs": a, "CL": c}, t) for a, c in zip(k_abs, CL)], axis=-1)
+    assert parity_violation(Y, ref) <= 1.0
+
+
+def test_device_pointer_call_matches_host_call(cuda_lib, rt):
+    torch = _torch()
+    B, T = 4096 + 17, 20
+    t = np.linspace(0, 100, T)
+    th = np.stack([lognormal_draws(5, B), lognormal_draws(6, B)])
+    pb = _problem(rt, "simple_pk", ["k_abs", "CL"], t, ["y_cent", "y_gut"])
+    Yh, nf = pb.simulate_host(th, B)
+    P = torch.from_numpy(th).cuda()
+    Y = torch.empty((T, 2, B), dtype=torch.float64, device="cuda")
+    status = torch.empty(B, dtype=torch.int32, device="cuda")
+    pb.simulate(P, Y, status=status, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert nf == 0 and int(status.abs().sum()) == 0
+    assert np.array_equal(Y.cpu().numpy(), Yh)       # same kernel, same inputs: bit identical
+
+
+def test_icg_rodas4_vs_oracle(cuda_lib, rt, oracle):
+    """Stiff PBPK model, dose 10 mg, BW and Vmax sampled (C4 inputs), 16 individuals."""
+    B = 16
+    t = np.linspace(0, 100, 21)
+    BW = lognormal_draws(11, B, 75.0, 10.0)
+    Vm = lognormal_draws(12, B, 0.0369598840327503, 0.01)
+    obs = ["Cre_plasma_icg", "Cgi_plasma_icg", "Cve_icg", "LI__icg", "Afeces_icg"]
+    pb = _problem(rt, "icg_body_flat", ["BW", "LI__ICGIM_Vmax"], t, obs, dosage={"IVDOSE_icg": 10.0})
+    Y, nf = pb.simulate_host(np.stack([BW, Vm]), B)
+    assert nf == 0
+    idx = [oracle.ICG_STATES.index(o) for o in obs]
+    ref = np.stack([oracle.simulate("icg_body_flat", {"IVDOSE_icg": 10.0, "BW": b, "LI__ICGIM_Vmax": v}, t)[:, idx]
+                    for b, v in zip(BW, Vm)], axis=-1)
+    assert parity_violation(Y, ref) <= 1.0
+    # known-answer values at defaults
+    pb2 = _problem(rt, "icg_body_flat", [], np.array([0.0, 5, 10, 15, 20]), ["Cre_plasma_icg"], dosage={"IVDOSE_icg": 10.0})
+    Y2, _ = pb2.simulate_host(None, 1)
+    np.testing.assert_allclose(Y2[1:, 0, 0], [1.25351163e-03, 3.13601386e-04, 7.80941642e-05, 1.94248499e-05], rtol=2e-6)
+
+
+def _noisy_data(oracle_Y, cv, seed):
+    rs = np.random.RandomState(seed)
+    return oracle_Y * (1.0 + cv * rs.normal(size=oracle_Y.shape))
+
+
+def test_simple_pk_logp_and_grad(cuda_lib, rt, oracle):
+    """logp (normal + lognormal) and forward-sensitivity gradient vs oracle, 1e-6 relative."""
+    T, B = 20, 64
+    t = np.linspace(0, 100, T)
+    obs = ["y_gut", "y_cent", "y_peri"]
+    truth = oracle.simple_pk_exact({}, t)
+    opt = pkg("optimization.petab_optimization")
+    k_abs, CL = lognormal_draws(21, B), lognormal_draws(22, B)
+    for noise_model, sigma in ((rt.NOISE_NORMAL, 0.05), (rt.NOISE_LOGNORMAL, 0.3)):
+        if noise_model == rt.NOISE_NORMAL:
+            data = _noisy_data(truth, 0.05, 3)[None]
+        else:
+            data = np.maximum(_noisy_data(truth[1:], 0.05, 3), 1e-300)[None]   # skip t=0 (zeros)
+        tt = t if noise_model == rt.NOISE_NORMAL else t[1:]
+        pb = _problem(rt, "simple_pk", ["k_abs", "CL"], tt, obs, rtol=1e-9, atol=1e-13)
+        pb.set_data(opt.sufficient_statistics(data, noise_model)[..., None], sigma, noise_model)
+        lp, g, _, nf = pb.logp_host(np.stack([k_abs, CL]), grad=True)
+        lp0, _, _, _ = pb.logp_host(np.stack([k_abs, CL]), grad=False)
+        assert nf == 0
+        ref_lp, ref_g = np.empty(B), np.empty((2, B))
+        for b in range(B):
+            over = {"k_abs": k_abs[b], "CL": CL[b]}
+            f = oracle.simple_pk_exact(over, tt)
+            s = oracle.simple_pk_exact_sens(over, tt)
+            if noise_model == rt.NOISE_NORMAL:
+                ref_lp[b] = oracle.loglik_normal(f, data[0], sigma)
+                ref_g[:, b] = oracle.loglik_normal_grad(f, s, data[0], sigma)
+            else:
+                ref_lp[b] = oracle.loglik_lognormal(f, data[0], sigma)
+                ref_g[:, b] = oracle.loglik_lognormal_grad(f, s, data[0], sigma)
+        np.testing.assert_allclose(lp, ref_lp, rtol=1e-6)
+        np.testing.assert_allclose(lp0, ref_lp, rtol=1e-6)
+        np.testing.assert_allclose(g, ref_g, rtol=1e-6, atol=1e-6 * np.abs(ref_g).max())
+
+
+def test_simple_pk_sensitivity_trajectories(cuda_lib, rt, oracle):
+    torch = _torch()
+    T, B = 21, 33
+    t = np.linspace(0, 100, T)
+    th = np.stack([lognormal_draws(31, B), lognormal_draws(32, B)])
+    pb = _problem(rt, "simple_pk", ["k_abs", "CL"], t, ["y_gut", "y_cent", "y_peri"], rtol=1e-9, atol=1e-12)
+    P = torch.from_numpy(th).cuda()
+    Y = torch.empty((T, 3, B), dtype=torch.float64, device="cuda")
+    S = torch.empty((2, T, 3, B), dtype=torch.float64, device="cuda")
+    pb.simulate_sens(P, Y, S)
+    torch.cuda.synchronize()
+    for b in range(0, B, 8):
+        over = {"k_abs": th[0, b], "CL": th[1, b]}
+        ref = oracle.simple_pk_exact_sens(over, t)                 # [T, 3, 2]
+        got = S[:, :, :, b].cpu().numpy().transpose(1, 2, 0)
+        assert parity_violation(got, ref, rtol=1e-6, atol=1e-9) <= 1.0
+
+
+def test_icg_logp_grad_vs_oracle(cuda_lib, rt, oracle):
+    """Rosenbrock forward sensitivities on the PBPK model: gradient of a Gaussian likelihood."""
+    B, T = 4, 11
+    t = np.linspace(0, 50, T)
+    obs = ["Cre_plasma_icg", "Cgi_plasma_icg"]
+    idx = [oracle.ICG_STATES.index(o) for o in obs]
+    sens = ["BW", "LI__ICGIM_Vmax"]
+    truth = oracle.simulate("icg_body_flat", {"IVDOSE_icg": 10.0}, t)[:, idx]
+    data = _noisy_data(truth, 0.05, 7)[None]
+    sigma = 1e-4
+    opt = pkg("optimization.petab_optimization")
+    BW = lognormal_draws(41, B, 75.0, 10.0)
+    Vm = lognormal_draws(42, B, 0.0369598840327503, 0.01)
+    pb = _problem(rt, "icg_body_flat", sens, t, obs, dosage={"IVDOSE_icg": 10.0}, rtol=1e-9, atol=1e-14)
+    pb.set_data(opt.sufficient_statistics(data, rt.NOISE_NORMAL)[..., None], sigma, rt.NOISE_NORMAL)
+    lp, g, _, nf = pb.logp_host(np.stack([BW, Vm]), grad=True)
+    assert nf == 0
+    for b in range(B):
+        over = {"IVDOSE_icg": 10.0, "BW": BW[b], "LI__ICGIM_Vmax": Vm[b]}
+        Yo, So = oracle.simulate_sens("icg_body_flat", over, t, sens)
+        ref_lp = oracle.loglik_normal(Yo[:, idx], data[0], sigma)
+        ref_g = oracle.loglik_normal_grad(Yo[:, idx], So[:, idx, :], data[0], sigma)
+        np.testing.assert_allclose(lp[b], ref_lp, rtol=1e-6)
+        np.testing.assert_allclose(g[:, b], ref_g, rtol=1e-5)
+
+
+def test_empty_and_ragged_batches(cuda_lib, rt):
+    t = np.linspace(0, 10, 5)
+    pb = _problem(rt, "simple_pk", ["k_abs"], t, ["y_cent"])
+    Y, nf = pb.simulate_host(np.zeros((1, 0)), 0)
+    assert Y.shape == (5, 1, 0) and nf == 0
+    for B in (1, 31, 32, 33, 127, 129):
+        Y, nf = pb.simulate_host(np.full((1, B), 0.7), B)
+        assert nf == 0 and np.all(Y == Y[:, :, :1])     # identical inputs -> identical lanes
+    # single time point = initial state only
+    pb.set_timepoints([0.0])
+    Y, nf = pb.simulate_host(np.full((1, 3), 0.7), 3)
+    assert nf == 0 and np.all(Y == 0.0)
+
+
+def test_failed_trajectories_are_reported(cuda_lib, rt):
+    t = np.linspace(0, 100, 5)
+    pb = _problem(rt, "simple_pk", ["k_abs"], t, ["y_cent"])
+    pb.set_solver(method=rt.METHOD_DOPRI5, rtol=1e-7, atol=1e-10, max_steps=10)
+    status = np.empty(4, np.int32)
+    Y, nf = pb.simulate_host(np.full((1, 4), 1.0), 4, status=status)
+    assert nf == 4 and np.all(status == 1)
+    pb.set_solver(method=rt.METHOD_DOPRI5, rtol=1e-7, atol=1e-10)
+    th = np.array([[1.0, np.nan, 1.0, 1.0]])
+    Y, nf = pb.simulate_host(th, 4, status=status)
+    assert nf == 1 and status[1] != 0 and status[0] == 0
+
+
+def test_full_size_properties_c2(cuda_lib, rt):
+    """BASELINE C2 at full size (1e6 draws x 50 timepoints): size-independent properties.
+    simple_pk is linear: mass only leaves through clearance, so 0 <= y_gut+y_cent+y_peri <= 1 and y_gut is
+    exp(-k_abs t) exactly; doubling the dose (y_gut(0)=2) doubles every trajectory (linearity)."""
+    torch = _torch()
+    B, T = 1_000_000, 50
+    t = np.linspace(0, 100, T)
+    np.random.seed(1234)
+    k_abs = np.random.lognormal(-0.3465735902799726, 0.8325546111576977, B)
+    CL = np.random.lognormal(-0.3465735902799726, 0.8325546111576977, B)
+    pb = _problem(rt, "simple_pk", ["k_abs", "CL"], t, ["y_gut", "y_cent", "y_peri"])
+    P = torch.from_numpy(np.stack([k_abs, CL])).cuda()
+    Y = torch.empty((T, 3, B), dtype=torch.float64, device="cuda")
+    status = torch.empty(B, dtype=torch.int32, device="cuda")
+    pb.simulate(P, Y, status=status)
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0
+    total = Y.sum(dim=1)
+    assert float(total.max()) <= 1.0 + 1e-9 and float(total.min()) >= -1e-9
+    gut = torch.exp(-P[0][None, :] * torch.from_numpy(t).cuda()[:, None])
+    assert float(((Y[:, 0, :] - gut).abs() / (1e-9 + 1e-6 * gut)).max()) <= 1.0
+    pb.set_value("y_gut", 2.0)
+    Y2 = torch.empty_like(Y)
+    pb.simulate(P, Y2)
+    torch.cuda.synchronize()
+    assert float(((Y2 - 2 * Y).abs() / (2e-9 + 2e-6 * Y.abs())).max()) <= 1.0
+
+
+def test_ode_sample_simulator_drop_in(cuda_lib, oracle):
+    """The reference-facing class: DataFrame in, (sim x time) dataset out, noise stream identical to the oracle's
+    restatement of petab_factory.py:192-219."""
+    import pandas as pd
+    pf = pkg("experiments.petab_factory")
+    ex = pkg("experiments.experiment")
+    P = pkg()
+    samples = pf.create_samples_parameters(
+        {pf.Category.MALE: {pf.PKPDParameters.CL: pf.LognormParameters(n=20, sigma=1.0, mu=1.0),
+                            pf.PKPDParameters.k_abs: pf.LognormParameters(n=20, sigma=1.0, mu=0.5)}})
+    df = pd.DataFrame({par.value: v for par, v in samples[pf.Category.MALE].items()})
+    np.testing.assert_allclose(df["CL"].values[:3], [1.04699267, 0.26233685, 2.33085045], rtol=1e-8)
+    np.testing.assert_allclose(df["k_abs"].values[:3], [0.81277741, 0.65610198, 0.97999947], rtol=1e-8)
+    sim = pf.ODESampleSimulator(P.MODELS["simple_pk"])
+    obs = [ex.Observable(id="y_cent"), ex.Observable(id="y_gut"), ex.Observable(id="y_peri")]
+    st = pf.SimulationSettings(start=0.0, end=100.0, steps=20, noise=ex.Noise(add_noise=False, cv=0.05), observables=obs)
+    ds = sim.simulate_samples(df, st)
+    assert list(ds.data_vars) == ["[y_cent]", "[y_gut]", "[y_peri]"] and obs[0].id == "[y_cent]"
+    t = np.linspace(0, 100, 21)
+    for i in (0, 7, 19):
+        ref = oracle.simple_pk_exact({"CL": df["CL"][i], "k_abs": df["k_abs"][i]}, t)
+        got = np.stack([ds["[y_gut]"].values[i], ds["[y_cent]"].values[i], ds["[y_peri]"].values[i]], axis=1)
+        assert parity_violation(got, ref) <= 1.0
+    # with noise: same global-RNG consumption as the reference loop
+    st.noise = ex.Noise(add_noise=True, cv=0.05)
+    np.random.seed(99)
+    dsn = sim.simulate_samples(df, st)
+    np.random.seed(99)
+    clean = np.stack([ds[v].values for v in ds.data_vars], axis=2)     # [sim, time, obs]
+    for i in range(20):
+        noisy = oracle.add_noise(clean[i], 0.05)
+        got = np.stack([dsn[v].values[i] for v in dsn.data_vars], axis=1)
+        np.testing.assert_array_equal(got, noisy)

@@ -73,6 +73,10 @@ int pv_problem_flops(const pv_problem* p, const char* what);
 /* integrator settings (petab_factory.py:187-189: absolute_tolerance, relative_tolerance) */
 int pv_problem_set_solver(pv_problem* p, int method, double rtol, double atol, int max_steps);
 
+/* warp scheduling of the batch kernels: a warp fetches new trajectories for its idle lanes once at least
+ * refill_min (1..32, default 8) of them are idle; 32 = classic one-trajectory-per-thread behaviour per warp */
+int pv_problem_set_schedule(pv_problem* p, int refill_min);
+
 /* `r.resetAll(); r.setValue(key, value)` for values shared by the whole batch (dosage dict,
  * petab_factory.py:229-233).  id = a theta id, or a state id / "[state id]" for an initial concentration. */
 int pv_problem_set_value(pv_problem* p, const char* id, double value);
@@ -81,8 +85,9 @@ int pv_problem_reset_values(pv_problem* p);
 /* which ids the columns of the per-trajectory matrix P set (`r.setValue(pid, row[pid])`, :236-239) */
 int pv_problem_set_columns(pv_problem* p, int n_cols, const char* const* ids);
 
-/* output grid: `simulate(start, end, steps)` -> linspace(start, end, steps+1) (:242-246); any increasing grid */
-int pv_problem_set_timepoints(pv_problem* p, int n_t, const double* t_host);
+/* output grid: `simulate(start, end, steps)` -> linspace(start, end, steps+1) (:242-246); any strictly increasing
+ * grid.  t0 <= t[0] is the time at which the initial values hold (roadrunner: `start`; PEtab/AMICI: 0). */
+int pv_problem_set_timepoints(pv_problem* p, double t0, int n_t, const double* t_host);
 
 /* selected observables "[sid]" (:250-258); ids may carry the brackets */
 int pv_problem_set_observables(pv_problem* p, int n_obs, const char* const* ids);

@@ -59,9 +59,9 @@ def _toposort(rules: dict[str, sp.Expr]) -> list[str]:
         if state.get(v) == 1:
             raise ValueError(f"algebraic loop through assignment rule {v!r}")
         state[v] = 1
-        for s in rules[v].free_symbols:
-            if s.name in rules:
-                visit(s.name)
+        for name in sorted(s.name for s in rules[v].free_symbols):
+            if name in rules:
+                visit(name)
         state[v] = 2
         order.append(v)
 

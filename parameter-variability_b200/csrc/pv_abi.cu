@@ -56,7 +56,15 @@ struct pv_problem {
     size_t pin_bytes[3] = {0, 0, 0};
     int* d_failed = nullptr;
     double last_kernel_ms = 0.0;
+    // lane-refill work counters: one per launch in flight (ring), zeroed in-stream before each launch
+    unsigned long long* d_counters = nullptr;
+    int counter_next = 0;
+    int num_sms = 0;
+    int refill_min = 8;
+    double t0 = 0.0;
+    bool t0_set = false;
 };
+#define PV_COUNTER_RING 1024
 
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int pv_abi_version(void) { return PV_ABI_VERSION; }
@@ -118,7 +126,9 @@ extern "C" pv_problem* pv_problem_create(const char* model_name, int device) {
     p->y0_base.assign(p->tab->n_states, std::numeric_limits<double>::quiet_NaN());
     bool ok = cudaMalloc(&p->d_theta, sizeof(double) * p->tab->n_theta) == cudaSuccess &&
               cudaMalloc(&p->d_y0, sizeof(double) * p->tab->n_states) == cudaSuccess &&
-              cudaMalloc(&p->d_failed, sizeof(int)) == cudaSuccess;
+              cudaMalloc(&p->d_failed, sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&p->d_counters, sizeof(unsigned long long) * PV_COUNTER_RING) == cudaSuccess &&
+              cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
     for (int i = 0; i < 3 && ok; ++i) ok = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&p->ev0) == cudaSuccess && cudaEventCreate(&p->ev1) == cudaSuccess;
     if (!ok) {
@@ -137,6 +147,7 @@ extern "C" void pv_problem_destroy(pv_problem* p) {
     cudaFree(p->d_tgrid);
     cudaFree(p->d_stats);
     cudaFree(p->d_failed);
+    cudaFree(p->d_counters);
     for (int i = 0; i < 3; ++i) {
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
         cudaFree(p->stage_dev[i]);
@@ -171,6 +182,13 @@ extern "C" int pv_problem_flops(const pv_problem* p, const char* what) {
     for (int i = 0; i < p->tab->n_flops; ++i)
         if (!strcmp(p->tab->flop_names[i], what)) return p->tab->flop_values[i];
     return fail(PV_E_ARG, std::string("unknown flop counter '") + what + "'");
+}
+
+extern "C" int pv_problem_set_schedule(pv_problem* p, int refill_min) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (refill_min < 1 || refill_min > 32) return fail(PV_E_ARG, "refill_min must be in [1, 32]");
+    p->refill_min = refill_min;
+    return 0;
 }
 
 extern "C" int pv_problem_set_solver(pv_problem* p, int method, double rtol, double atol, int max_steps) {
@@ -226,12 +244,14 @@ extern "C" int pv_problem_set_columns(pv_problem* p, int n_cols, const char* con
     return 0;
 }
 
-extern "C" int pv_problem_set_timepoints(pv_problem* p, int n_t, const double* t_host) {
+extern "C" int pv_problem_set_timepoints(pv_problem* p, double t0, int n_t, const double* t_host) {
     if (!p || n_t <= 0 || !t_host) return fail(PV_E_ARG, "bad timepoints");
+    if (!(t0 <= t_host[0])) return fail(PV_E_ARG, "t0 must be <= the first timepoint");
     for (int i = 1; i < n_t; ++i)
         if (!(t_host[i] > t_host[i - 1])) return fail(PV_E_ARG, "timepoints must be strictly increasing");
     CUDA_OK(cudaSetDevice(p->device));
     p->tgrid.assign(t_host, t_host + n_t);
+    p->t0 = t0;
     cudaFree(p->d_tgrid);
     p->d_tgrid = nullptr;
     CUDA_OK(cudaMalloc(&p->d_tgrid, sizeof(double) * n_t));
@@ -280,21 +300,27 @@ extern "C" int pv_problem_set_data(pv_problem* p, int noise_model, int n_data, c
 // dispatch
 // ---------------------------------------------------------------------------------------------------------
 template <class M, int METHOD, int MODE>
-static cudaError_t launch_one(const pv_launch_params& lp, size_t shmem, cudaStream_t s) {
-    const int64_t blocks = (lp.B + PV_BLOCK - 1) / PV_BLOCK;
+static cudaError_t launch_one(const pv_launch_params& lp, size_t shmem, int num_sms, cudaStream_t s) {
     if (shmem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(pv_batch_kernel<M, METHOD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
         if (e != cudaSuccess) return e;
     }
+    // persistent grid: as many CTAs as are resident at once (a multiple of the SM count), never more than the work
+    int per_sm = 0;
+    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pv_batch_kernel<M, METHOD, MODE>, PV_BLOCK, shmem);
+    if (eo != cudaSuccess) return eo;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t want = (lp.B + PV_BLOCK - 1) / PV_BLOCK;
+    const int64_t blocks = std::min<int64_t>(want, (int64_t)num_sms * per_sm);
     pv_batch_kernel<M, METHOD, MODE><<<(unsigned)blocks, PV_BLOCK, shmem, s>>>(lp);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
 
 template <class M>
-static cudaError_t launch_model(int method, int mode, const pv_launch_params& lp, size_t shmem, cudaStream_t s) {
+static cudaError_t launch_model(int method, int mode, const pv_launch_params& lp, size_t shmem, int num_sms, cudaStream_t s) {
 #define PV_CASE(METH, MODE) \
-    if (method == METH && mode == MODE) return launch_one<M, METH, MODE>(lp, shmem, s);
+    if (method == METH && mode == MODE) return launch_one<M, METH, MODE>(lp, shmem, num_sms, s);
     PV_CASE(1, PV_MODE_TRAJ) PV_CASE(1, PV_MODE_LOGP) PV_CASE(1, PV_MODE_TRAJ_LOGP) PV_CASE(1, PV_MODE_LOGP_GRAD) PV_CASE(1, PV_MODE_TRAJ_SENS)
     PV_CASE(2, PV_MODE_TRAJ) PV_CASE(2, PV_MODE_LOGP) PV_CASE(2, PV_MODE_TRAJ_LOGP) PV_CASE(2, PV_MODE_LOGP_GRAD) PV_CASE(2, PV_MODE_TRAJ_SENS)
 #undef PV_CASE
@@ -355,6 +381,11 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     lp.n_data = need_logp ? p->n_data : 1;
     lp.noise_model = p->noise_model;
     lp.max_steps = p->max_steps;
+    lp.t0 = p->t0;
+    lp.refill_min = p->refill_min;
+    lp.counter = p->d_counters + p->counter_next;
+    p->counter_next = (p->counter_next + 1) % PV_COUNTER_RING;
+    CUDA_OK(cudaMemsetAsync(lp.counter, 0, sizeof(unsigned long long), s));
     if (need_logp) {
         const double LOG_2PI = 1.8378770664093454835606594728112;
         for (int k = 0; k < lp.n_obs; ++k) {
@@ -370,7 +401,7 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     if (shmem > 200 * 1024) return fail(PV_E_ARG, "time grid / data too large for shared memory");
     cudaError_t e = cudaErrorInvalidValue;
     switch (p->model) {
-        PV_MODEL_DISPATCH(e = launch_model, (method, mode, lp, shmem, s))
+        PV_MODEL_DISPATCH(e = launch_model, (method, mode, lp, shmem, p->num_sms, s))
     }
     if (e != cudaSuccess) return fail(PV_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return 0;

@@ -85,30 +85,46 @@ struct pv_dopri5_cost {
     static constexpr int FLOPS_DENSE = Sys::N * (2 * 6 + 6 + 8);   // rcont5 + interpolant per output row
 };
 
-// Integrate z from tgrid[0] to tgrid[T-1]; `out(j, t_j, z_j)` is called once per grid point in
-// increasing j (j = 0 immediately).  Returns a pv_status_code.
-template <class Sys, class Out>
-PV_HD int pv_dopri5_integrate(const typename Sys::Consts& ks, double (&y)[Sys::N], const double* tgrid, int T,
-                              double rtol, double atol, int max_steps, Out& out, pv_step_stats& st) {
-    constexpr int N = Sys::N;
-    constexpr int NX = Sys::NX;   // error control on the states; sensitivities join with the same weights
-    st.accepted = 0;
-    st.rejected = 0;
-    double t = tgrid[0];
-    const double tend = tgrid[T - 1];
-    int jout = 0;
-    while (jout < T && tgrid[jout] <= t) {
-        out(jout, tgrid[jout], y);
-        ++jout;
-    }
-    if (jout >= T) return PV_OK;
+// status of a lane that still has work to do
+#define PV_RUNNING (-1)
 
-    double k1[N], k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], yn[N];
-    Sys::rhs(t, y, ks, k1);
+// Per-lane DOPRI5 state machine: start() once, then step() until it returns something other than
+// PV_RUNNING.  The batch kernels drive it either one trajectory per thread for the whole launch
+// (static schedule) or with lane refill (a lane that finishes picks the next trajectory while its
+// warp neighbours keep stepping).  `out(j, t_j, z_j)` is called once per grid point in increasing j.
+template <class Sys>
+struct pv_dopri5_lane {
+    static constexpr int N = Sys::N;
+    double t, h, tend;
+    double y[N], k1[N];
+    float facold;
+    bool last_rejected;
+    int jout, nstep;
+    pv_step_stats st;
 
-    // ---- initial step (Hairer, Norsett, Wanner I, II.4) --------------------------------------
-    double h;
-    {
+    // z0 -> y, outputs for grid points at t0, first derivative, initial step size
+    template <class Out>
+    PV_HD int start(const typename Sys::Consts& ks, const double (&z0)[N], double t0, const double* tgrid, int T,
+                    double rtol, double atol, Out& out) {
+        st.accepted = 0;
+        st.rejected = 0;
+        nstep = 0;
+        facold = 1e-4f;
+        last_rejected = false;
+        t = t0;
+        tend = tgrid[T - 1];
+        h = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] = z0[i];
+        jout = 0;
+        while (jout < T && tgrid[jout] <= t) {
+            out(jout, tgrid[jout], y);
+            ++jout;
+        }
+        if (jout >= T) return PV_OK;
+        Sys::rhs(t, y, ks, k1);
+        // ---- initial step (Hairer, Norsett, Wanner I, II.4) ----------------------------------
+        double yn[N], k2[N];
         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -135,13 +151,13 @@ PV_HD int pv_dopri5_integrate(const typename Sys::Consts& ks, double (&y)[Sys::N
         const float dm = fmaxf(d1, d2);
         const double h1 = (dm <= 1e-15f) ? fmax(1e-6, h0 * 1e-3) : (double)pv_powf_fast(0.01f / dm, 0.2f);
         h = fmin(fmin(100.0 * h0, h1), tend - t);
+        return PV_RUNNING;
     }
 
-    float facold = 1e-4f;
-    bool last_rejected = false;
-    int nstep = 0;
-    (void)NX;
-    while (true) {
+    // one attempted step
+    template <class Out>
+    PV_HD int step(const typename Sys::Consts& ks, const double* tgrid, int T, double rtol, double atol,
+                   int max_steps, Out& out) {
         if (nstep >= max_steps) return PV_ERR_MAX_STEPS;
         ++nstep;
         bool last = false;
@@ -151,6 +167,7 @@ PV_HD int pv_dopri5_integrate(const typename Sys::Consts& ks, double (&y)[Sys::N
         }
         if (!(fabs(h) > 1e-14 * fmax(fabs(t), 1.0))) return PV_ERR_STEP_TOO_SMALL;
 
+        double k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], yn[N];
         // ---- stages ----------------------------------------------------------------------------
 #pragma unroll
         for (int i = 0; i < N; ++i) yn[i] = fma(h * 0.2, k1[i], y[i]);
@@ -260,5 +277,19 @@ PV_HD int pv_dopri5_integrate(const typename Sys::Consts& ks, double (&y)[Sys::N
             h = h / (double)fminf(5.0f, fac11 * (1.0f / 0.9f));
             last_rejected = true;
         }
+        return PV_RUNNING;
     }
+};
+
+// Whole-trajectory driver (static schedule, host-side checks): integrate z from t0 over tgrid.
+template <class Sys, class Out>
+PV_HD int pv_dopri5_integrate(const typename Sys::Consts& ks, double (&z)[Sys::N], double t0, const double* tgrid, int T,
+                              double rtol, double atol, int max_steps, Out& out, pv_step_stats& st) {
+    pv_dopri5_lane<Sys> lane;
+    int rc = lane.start(ks, z, t0, tgrid, T, rtol, atol, out);
+    while (rc == PV_RUNNING) rc = lane.step(ks, tgrid, T, rtol, atol, max_steps, out);
+    st = lane.st;
+#pragma unroll
+    for (int i = 0; i < Sys::N; ++i) z[i] = lane.y[i];
+    return rc;
 }

@@ -40,7 +40,9 @@ struct pv_launch_params {
     double log_norm[PV_MAX_OBS];   // normal: log(2 pi sigma^2);  lognormal: log(sigma) + 0.5 log(2 pi)
     int col_target[PV_MAX_COLS];   // < NTH: theta index; >= NTH: NTH + state index (initial value)
     int obs_idx[PV_MAX_OBS];
-    int n_cols, T, n_obs, n_data, noise_model, max_steps;
+    unsigned long long* counter;   // next unprocessed trajectory (lane refill)
+    double t0;                     // integration start (initial values hold at t0 <= tgrid[0])
+    int n_cols, T, n_obs, n_data, noise_model, max_steps, refill_min;
 };
 
 template <int NX, int N>
@@ -113,13 +115,31 @@ struct pv_sink {
     }
 };
 
+// ---- integrator selection ---------------------------------------------------------------------------------
+template <class M, int METHOD, bool SENS>
+struct pv_lane_of {
+    using type = pv_dopri5_lane<pv_system<M, SENS>>;
+};
+template <class M, bool SENS>
+struct pv_lane_of<M, 2, SENS> {
+    using type = pv_rodas4_lane<M, SENS>;
+};
+
 // ---- the kernel ----------------------------------------------------------------------------------------
+// Persistent warps with LANE REFILL: a lane that finishes its trajectory takes the next unprocessed one
+// (one warp-aggregated atomicAdd on a global counter) while its 31 neighbours keep stepping, so a warp
+// never idles behind its slowest trajectory.  Step counts over a log-normal parameter cloud differ by
+// ~10x (SURVEY.md section 7 "Divergence"); with one fixed trajectory per lane the warp pays max-over-lanes.
+// Refills are batched (>= p.refill_min idle lanes, or nobody left working) so the start-up code
+// (parameter load, hoist, initial step size) runs with several lanes active.  Results do not depend on
+// the schedule: every trajectory is integrated by exactly one lane from its own inputs.
 template <class M, int METHOD, int MODE>
 __global__ void __launch_bounds__(PV_BLOCK)
 pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
     constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
     constexpr bool LOGP = (MODE & PV_MODE_LOGP) != 0;
     using Sys = pv_system<M, SENS>;
+    using Lane = typename pv_lane_of<M, METHOD, SENS>::type;
     extern __shared__ double sh[];
     double* sh_t = sh;                    // [T]
     double* sh_theta = sh_t + p.T;        // [NTH]
@@ -133,68 +153,101 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
         for (int i = threadIdx.x; i < 3 * p.T * p.n_obs; i += blockDim.x) sh_stats[i] = p.stats[i];
     __syncthreads();
 
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= p.B) return;
-
-    // ---- theta = batch-wide values, overridden by this trajectory's columns -------------------------------
-    double pc[PV_MAX_COLS];
-#pragma unroll
-    for (int j = 0; j < PV_MAX_COLS; ++j) pc[j] = (j < p.n_cols) ? __ldg(p.P + (int64_t)j * p.B + b) : 0.0;
+    const unsigned FULL = 0xffffffffu;
+    const int lane_id = threadIdx.x & 31;
     typename Sys::Consts ks;
-    double z[Sys::N];
-    pv_sink<M, MODE> sink{p, stats_shared ? sh_stats : nullptr, b, (int64_t)(b % p.n_data), {}, 0.0, {}};
-    {
-        double th[M::NTH];
-#pragma unroll
-        for (int i = 0; i < M::NTH; ++i) {
-            double v = sh_theta[i];
-#pragma unroll
-            for (int j = 0; j < PV_MAX_COLS; ++j) v = (j < p.n_cols && p.col_target[j] == i) ? pc[j] : v;
-            th[i] = v;
-        }
-        double y0[M::NX];
-        M::hoist(th, ks.c, y0, sink.obs);
-        bool over[M::NX];
-#pragma unroll
-        for (int i = 0; i < M::NX; ++i) {
-            double v = sh_y0[i];
-            over[i] = (v == v);
-            v = over[i] ? v : y0[i];
-#pragma unroll
-            for (int j = 0; j < PV_MAX_COLS; ++j)
-                if (j < p.n_cols && p.col_target[j] == M::NTH + i) {
-                    v = pc[j];
-                    over[i] = true;
-                }
-            z[i] = v;
-        }
-        if constexpr (SENS) {
-            double dy0[M::NSD][M::NX];
-            M::hoist_sens(th, ks.dc, dy0);
-#pragma unroll
-            for (int s = 0; s < M::NS; ++s)
-#pragma unroll
-                for (int i = 0; i < M::NX; ++i) z[M::NX * (1 + s) + i] = over[i] ? 0.0 : dy0[s][i];
-        }
-    }
+    Lane lane;
+    pv_sink<M, MODE> sink{p, stats_shared ? sh_stats : nullptr, 0, 0, {}, 0.0, {}};
+    bool have = false;        // this lane is integrating trajectory sink.b
+    bool exhausted = false;   // the work counter ran past B
 
-    pv_step_stats st;
-    int rc;
-    if constexpr (METHOD == 1)
-        rc = pv_dopri5_integrate<Sys>(ks, z, sh_t, p.T, p.rtol, p.atol, p.max_steps, sink, st);
-    else
-        rc = pv_rosenbrock_integrate<M, SENS>(ks, z, sh_t, p.T, p.rtol, p.atol, p.max_steps, sink, st);
-    if constexpr (LOGP) {
-        p.logp[b] = (rc == 0) ? sink.lp : __longlong_as_double(0x7ff8000000000000LL);
-        if constexpr (SENS) {
+    auto finish = [&](int rc) {
+        const int64_t b = sink.b;
+        if constexpr (LOGP) {
+            p.logp[b] = (rc == 0) ? sink.lp : __longlong_as_double(0x7ff8000000000000LL);
+            if constexpr (SENS) {
 #pragma unroll
-            for (int s = 0; s < M::NS; ++s) p.grad[(int64_t)s * p.B + b] = sink.g[s];
+                for (int s = 0; s < M::NS; ++s) p.grad[(int64_t)s * p.B + b] = sink.g[s];
+            }
         }
-    }
-    if (p.status) p.status[b] = rc;
-    if (p.steps) {
-        p.steps[b] = st.accepted;
-        p.steps[p.B + b] = st.rejected;
+        if (p.status) p.status[b] = rc;
+        if (p.steps) {
+            p.steps[b] = lane.st.accepted;
+            p.steps[p.B + b] = lane.st.rejected;
+        }
+        have = false;
+    };
+
+    while (true) {
+        __syncwarp();
+        const unsigned need = __ballot_sync(FULL, !have && !exhausted);
+        const unsigned busy = __ballot_sync(FULL, have);
+        if (need && (__popc(need) >= p.refill_min || busy == 0)) {
+            const int leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if (lane_id == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if ((need >> lane_id) & 1u) {
+                const int64_t b = (int64_t)base + __popc(need & ((1u << lane_id) - 1u));
+                if (b >= p.B) {
+                    exhausted = true;
+                } else {
+                    // ---- theta = batch-wide values, overridden by this trajectory's columns -----------------
+                    double pc[PV_MAX_COLS];
+#pragma unroll
+                    for (int j = 0; j < PV_MAX_COLS; ++j) pc[j] = (j < p.n_cols) ? __ldg(p.P + (int64_t)j * p.B + b) : 0.0;
+                    double z[Sys::N];
+                    double th[M::NTH];
+#pragma unroll
+                    for (int i = 0; i < M::NTH; ++i) {
+                        double v = sh_theta[i];
+#pragma unroll
+                        for (int j = 0; j < PV_MAX_COLS; ++j) v = (j < p.n_cols && p.col_target[j] == i) ? pc[j] : v;
+                        th[i] = v;
+                    }
+                    double y0[M::NX];
+                    M::hoist(th, ks.c, y0, sink.obs);
+                    bool over[M::NX];
+#pragma unroll
+                    for (int i = 0; i < M::NX; ++i) {
+                        double v = sh_y0[i];
+                        over[i] = (v == v);
+                        v = over[i] ? v : y0[i];
+#pragma unroll
+                        for (int j = 0; j < PV_MAX_COLS; ++j)
+                            if (j < p.n_cols && p.col_target[j] == M::NTH + i) {
+                                v = pc[j];
+                                over[i] = true;
+                            }
+                        z[i] = v;
+                    }
+                    if constexpr (SENS) {
+                        double dy0[M::NSD][M::NX];
+                        M::hoist_sens(th, ks.dc, dy0);
+#pragma unroll
+                        for (int s = 0; s < M::NS; ++s)
+#pragma unroll
+                            for (int i = 0; i < M::NX; ++i) z[M::NX * (1 + s) + i] = over[i] ? 0.0 : dy0[s][i];
+                    }
+                    sink.b = b;
+                    sink.d = b % p.n_data;
+                    sink.lp = 0.0;
+#pragma unroll
+                    for (int s = 0; s < M::NSD; ++s) sink.g[s] = 0.0;
+                    have = true;
+                    const int rc = lane.start(ks, z, p.t0, sh_t, p.T, p.rtol, p.atol, sink);
+                    if (rc != PV_RUNNING) finish(rc);
+                }
+            }
+        }
+        if (__all_sync(FULL, !have)) {
+            if (__all_sync(FULL, exhausted)) break;
+            continue;
+        }
+        if (have) {
+            const int rc = lane.step(ks, sh_t, p.T, p.rtol, p.atol, p.max_steps, sink);
+            if (rc != PV_RUNNING) finish(rc);
+        }
     }
 }
 

@@ -49,34 +49,23 @@ struct pv_rodas4_cost {
     static constexpr int FLOPS_DENSE = NB * M::NX * (2 * 10 + 8);
 };
 
-// Same contract as pv_dopri5_integrate.  z = (y, s_1 .. s_NS) when SENS.
-template <class M, bool SENS, class Out>
-PV_HD int pv_rosenbrock_integrate(const typename pv_system<M, SENS>::Consts& ks,
-                                  double (&z)[pv_system<M, SENS>::N], const double* tgrid, int T, double rtol,
-                                  double atol, int max_steps, Out& out, pv_step_stats& st) {
-    using namespace pv_rodas4;
-    constexpr int NX = M::NX;
-    constexpr int NB = SENS ? 1 + M::NS : 1;
-    constexpr int N = NX * NB;
-    st.accepted = 0;
-    st.rejected = 0;
-    double t = tgrid[0];
-    const double tend = tgrid[T - 1];
-    int jout = 0;
-    while (jout < T && tgrid[jout] <= t) {
-        out(jout, tgrid[jout], z);
-        ++jout;
-    }
-    if (jout >= T) return PV_OK;
+// Per-lane RODAS4 state machine; same contract as pv_dopri5_lane.  z = (y, s_1 .. s_NS) when SENS.
+template <class M, bool SENS>
+struct pv_rodas4_lane {
+    using Sys = pv_system<M, SENS>;
+    using Consts = typename Sys::Consts;
+    static constexpr int NX = M::NX;
+    static constexpr int NB = SENS ? 1 + M::NS : 1;
+    static constexpr int N = NX * NB;
+    double t, h, tend, h_acc;
+    double z[N];
+    float err_acc;
+    bool last_rejected;
+    int jout, nstep;
+    pv_step_stats st;
 
-    // K[stage][block][state]
-    double K1[NB][NX], K2[NB][NX], K3[NB][NX], K4[NB][NX], K5[NB][NX], K6[NB][NX];
-    double zs[N];        // stage value
-    double J[M::NNZ], W[M::NLU];
-
-    // evaluates F(zs) into r[block][state] (+ H_k v for the sensitivity blocks, v = y-block of the stage being solved
-    // is added later because it needs the freshly solved K^y)
-    auto eval_F = [&](double ts, double (&r)[NB][NX]) {
+    // F(zs) -> r[block][state]
+    PV_HD static void eval_F(double ts, const double (&zs)[N], const Consts& ks, double (&r)[NB][NX]) {
         if constexpr (SENS) {
             double y[NX], s[M::NSD][NX], f[NX], fs[M::NSD][NX];
 #pragma unroll
@@ -100,18 +89,19 @@ PV_HD int pv_rosenbrock_integrate(const typename pv_system<M, SENS>::Consts& ks,
 #pragma unroll
             for (int i = 0; i < NX; ++i) r[0][i] = f[i];
         }
-    };
+    }
 
-    // y_n, s_n at the step start are needed for H_k during all stages of the step
-    double yn0[NX];
-    double sn0[M::NSD][NX];
-    (void)sn0;
-
-    // solves all blocks of one stage in place: r[0] first, then r[k] += H_k r[0], solve
-    auto solve_stage = [&](double (&r)[NB][NX]) {
+    // solves all blocks of one stage in place: r[0] first, then r[k] += H_k r[0], solve (same LU)
+    PV_HD void solve_stage(const Consts& ks, const double (&W)[M::NLU], double (&r)[NB][NX]) const {
         M::lu_solve(W, r[0]);
         if constexpr (SENS) {
-            double hk[M::NSD][NX];
+            double yn0[NX], sn0[M::NSD][NX], hk[M::NSD][NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) yn0[i] = z[i];
+#pragma unroll
+            for (int p = 0; p < M::NS; ++p)
+#pragma unroll
+                for (int i = 0; i < NX; ++i) sn0[p][i] = z[NX * (1 + p) + i];
             M::sens_stage_term(t, yn0, sn0, r[0], ks.c, ks.dc, hk);
 #pragma unroll
             for (int p = 0; p < M::NS; ++p) {
@@ -120,21 +110,38 @@ PV_HD int pv_rosenbrock_integrate(const typename pv_system<M, SENS>::Consts& ks,
                 M::lu_solve(W, r[1 + p]);
             }
         }
-    };
+    }
 
-    // ---- initial step size -------------------------------------------------------------------------
-    double h;
-    {
+    template <class Out>
+    PV_HD int start(const Consts& ks, const double (&z0)[N], double t0, const double* tgrid, int T, double rtol,
+                    double atol, Out& out) {
+        st.accepted = 0;
+        st.rejected = 0;
+        nstep = 0;
+        last_rejected = false;
+        err_acc = 1e-2f;
+        t = t0;
+        tend = tgrid[T - 1];
+        h = 0.0;
+        h_acc = 0.0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) zs[i] = z[i];
-        eval_F(t, K1);
+        for (int i = 0; i < N; ++i) z[i] = z0[i];
+        jout = 0;
+        while (jout < T && tgrid[jout] <= t) {
+            out(jout, tgrid[jout], z);
+            ++jout;
+        }
+        if (jout >= T) return PV_OK;
+        // ---- initial step size ---------------------------------------------------------------------
+        double F0[NB][NX];
+        eval_F(t, z, ks, F0);
         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
                 const float sc = (float)(atol + rtol * fabs(z[b * NX + i]));
-                const float a = (float)z[b * NX + i] / sc, q = (float)K1[b][i] / sc;
+                const float a = (float)z[b * NX + i] / sc, q = (float)F0[b][i] / sc;
                 d0 += a * a;
                 d1 += q * q;
             }
@@ -142,13 +149,13 @@ PV_HD int pv_rosenbrock_integrate(const typename pv_system<M, SENS>::Consts& ks,
         d1 = sqrtf(d1 / N);
         h = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6 : 0.01 * (double)(d0 / d1);
         h = fmin(fmax(h, 1e-8), tend - t);
+        h_acc = h;
+        return PV_RUNNING;
     }
 
-    bool last_rejected = false;
-    float err_acc = 1e-2f;
-    double h_acc = h;
-    int nstep = 0;
-    while (true) {
+    template <class Out>
+    PV_HD int step(const Consts& ks, const double* tgrid, int T, double rtol, double atol, int max_steps, Out& out) {
+        using namespace pv_rodas4;
         if (nstep >= max_steps) return PV_ERR_MAX_STEPS;
         ++nstep;
         bool last = false;
@@ -159,59 +166,56 @@ PV_HD int pv_rosenbrock_integrate(const typename pv_system<M, SENS>::Consts& ks,
         if (!(fabs(h) > 1e-14 * fmax(fabs(t), 1.0))) return PV_ERR_STEP_TOO_SMALL;
         const double hi = 1.0 / h;
 
-        // ---- Jacobian, W = I/(gamma h) - J, LU ----------------------------------------------------------
+        double K1[NB][NX], K2[NB][NX], K3[NB][NX], K4[NB][NX], K5[NB][NX], K6[NB][NX];
+        double zs[N];
+        double W[M::NLU];
+        // ---- Jacobian, W = I/(gamma h) - J, LU ------------------------------------------------------------
+        {
+            double J[M::NNZ], yn0[NX];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) yn0[i] = z[i];
-        if constexpr (SENS) {
-#pragma unroll
-            for (int p = 0; p < M::NS; ++p)
-#pragma unroll
-                for (int i = 0; i < NX; ++i) sn0[p][i] = z[NX * (1 + p) + i];
+            for (int i = 0; i < NX; ++i) yn0[i] = z[i];
+            M::jac(t, yn0, ks.c, J);
+            M::lu_assemble(hi * (1.0 / GAMMA), J, W);
+            M::lu_factor(W);
         }
-        M::jac(t, yn0, ks.c, J);
-        M::lu_assemble(hi * (1.0 / GAMMA), J, W);
-        M::lu_factor(W);
-
         // ---- stage 1 ----------------------------------------------------------------------------------
-#pragma unroll
-        for (int i = 0; i < N; ++i) zs[i] = z[i];
-        eval_F(t, K1);
-        solve_stage(K1);
+        eval_F(t, z, ks, K1);
+        solve_stage(ks, W, K1);
         // ---- stage 2 ----------------------------------------------------------------------------------
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i) zs[b * NX + i] = fma(A21, K1[b][i], z[b * NX + i]);
-        eval_F(t + C2 * h, K2);
+        eval_F(t + C2 * h, zs, ks, K2);
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i) K2[b][i] = fma(hi * C21, K1[b][i], K2[b][i]);
-        solve_stage(K2);
+        solve_stage(ks, W, K2);
         // ---- stage 3 ----------------------------------------------------------------------------------
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i) zs[b * NX + i] = fma(A31, K1[b][i], fma(A32, K2[b][i], z[b * NX + i]));
-        eval_F(t + C3 * h, K3);
+        eval_F(t + C3 * h, zs, ks, K3);
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i) K3[b][i] = fma(hi, fma(C31, K1[b][i], C32 * K2[b][i]), K3[b][i]);
-        solve_stage(K3);
+        solve_stage(ks, W, K3);
         // ---- stage 4 ----------------------------------------------------------------------------------
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i)
                 zs[b * NX + i] = fma(A41, K1[b][i], fma(A42, K2[b][i], fma(A43, K3[b][i], z[b * NX + i])));
-        eval_F(t + C4 * h, K4);
+        eval_F(t + C4 * h, zs, ks, K4);
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i)
                 K4[b][i] = fma(hi, fma(C41, K1[b][i], fma(C42, K2[b][i], C43 * K3[b][i])), K4[b][i]);
-        solve_stage(K4);
+        solve_stage(ks, W, K4);
         // ---- stage 5 ----------------------------------------------------------------------------------
 #pragma unroll
         for (int b = 0; b < NB; ++b)
@@ -219,20 +223,20 @@ PV_HD int pv_rosenbrock_integrate(const typename pv_system<M, SENS>::Consts& ks,
             for (int i = 0; i < NX; ++i)
                 zs[b * NX + i] =
                     fma(A51, K1[b][i], fma(A52, K2[b][i], fma(A53, K3[b][i], fma(A54, K4[b][i], z[b * NX + i]))));
-        eval_F(t + h, K5);
+        eval_F(t + h, zs, ks, K5);
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i)
                 K5[b][i] =
                     fma(hi, fma(C51, K1[b][i], fma(C52, K2[b][i], fma(C53, K3[b][i], C54 * K4[b][i]))), K5[b][i]);
-        solve_stage(K5);
-        // ---- stage 6 (embedded solution zs + K5 is the evaluation point) -----------------------------------
+        solve_stage(ks, W, K5);
+        // ---- stage 6 (the embedded solution zs + K5 is the evaluation point) -------------------------------
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i) zs[b * NX + i] += K5[b][i];
-        eval_F(t + h, K6);
+        eval_F(t + h, zs, ks, K6);
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
@@ -241,7 +245,7 @@ PV_HD int pv_rosenbrock_integrate(const typename pv_system<M, SENS>::Consts& ks,
                                fma(C61, K1[b][i],
                                    fma(C62, K2[b][i], fma(C63, K3[b][i], fma(C64, K4[b][i], C65 * K5[b][i])))),
                                K6[b][i]);
-        solve_stage(K6);
+        solve_stage(ks, W, K6);
         // new solution = zs + K6, error estimate = K6
         float err2 = 0.f;
         bool finite = true;
@@ -310,5 +314,19 @@ PV_HD int pv_rosenbrock_integrate(const typename pv_system<M, SENS>::Consts& ks,
             h = (st.accepted == 0 && st.rejected >= 2) ? h * 0.1 : h / (double)fac;
             last_rejected = true;
         }
+        return PV_RUNNING;
     }
+};
+
+template <class M, bool SENS, class Out>
+PV_HD int pv_rosenbrock_integrate(const typename pv_system<M, SENS>::Consts& ks,
+                                  double (&z)[pv_system<M, SENS>::N], double t0, const double* tgrid, int T, double rtol,
+                                  double atol, int max_steps, Out& out, pv_step_stats& st) {
+    pv_rodas4_lane<M, SENS> lane;
+    int rc = lane.start(ks, z, t0, tgrid, T, rtol, atol, out);
+    while (rc == PV_RUNNING) rc = lane.step(ks, tgrid, T, rtol, atol, max_steps, out);
+    st = lane.st;
+#pragma unroll
+    for (int i = 0; i < pv_system<M, SENS>::N; ++i) z[i] = lane.z[i];
+    return rc;
 }

@@ -41,7 +41,8 @@ ABI = {
     "pv_problem_set_value": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "pv_problem_reset_values": (C.c_int, [C.c_void_p]),
     "pv_problem_set_columns": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]),
-    "pv_problem_set_timepoints": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "pv_problem_set_timepoints": (C.c_int, [C.c_void_p, C.c_double, C.c_int, _dp]),
+    "pv_problem_set_schedule": (C.c_int, [C.c_void_p, C.c_int]),
     "pv_problem_set_observables": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]),
     "pv_problem_set_data": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
     "pv_simulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -196,9 +197,14 @@ class Problem:
         _check(self._lib.pv_problem_set_columns(self._h, len(ids), _cstr_array(ids) if ids else None))
         self.columns = ids
 
-    def set_timepoints(self, t: Sequence[float]) -> None:
+    def set_schedule(self, refill_min: int = 8) -> None:
+        _check(self._lib.pv_problem_set_schedule(self._h, int(refill_min)))
+
+    def set_timepoints(self, t: Sequence[float], t0: Optional[float] = None) -> None:
+        """Output grid; ``t0`` (default: the first grid point) is where the initial values hold."""
         t = np.ascontiguousarray(t, dtype=np.float64)
-        _check(self._lib.pv_problem_set_timepoints(self._h, len(t), t.ctypes.data_as(_dp)))
+        t0 = float(t[0]) if t0 is None else float(t0)
+        _check(self._lib.pv_problem_set_timepoints(self._h, t0, len(t), t.ctypes.data_as(_dp)))
         self.timepoints = t.copy()
         self.n_data = 0
 

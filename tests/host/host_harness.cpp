@@ -3,6 +3,7 @@
 // Test infrastructure only: never linked into libparvar_b200.so, never used by the product.
 #include <cmath>
 #include <cstring>
+#include <vector>
 #include "../../parameter-variability_b200/csrc/pv_dopri5.cuh"
 #include "../../parameter-variability_b200/csrc/pv_rosenbrock.cuh"
 #include "../../parameter-variability_b200/csrc/generated/simple_chain.cuh"
@@ -38,9 +39,9 @@ static int run(int method, const double* theta, const double* y0_over, const dou
     pv_step_stats st;
     int rc;
     if (method == 1)
-        rc = pv_dopri5_integrate<Sys>(ks, z, tgrid, T, rtol, atol, max_steps, col, st);
+        rc = pv_dopri5_integrate<Sys>(ks, z, tgrid[0], tgrid, T, rtol, atol, max_steps, col, st);
     else
-        rc = pv_rosenbrock_integrate<M, SENS>(ks, z, tgrid, T, rtol, atol, max_steps, col, st);
+        rc = pv_rosenbrock_integrate<M, SENS>(ks, z, tgrid[0], tgrid, T, rtol, atol, max_steps, col, st);
     stats[0] = st.accepted;
     stats[1] = st.rejected;
     // apply observable scaling to the state block (and sensitivity blocks)
@@ -73,6 +74,35 @@ extern "C" int hh_simulate(const char* model, int method, int sens, const double
 #define C2(M) (sens ? run<M, true>(method, theta, y0_over, tgrid, T, rtol, atol, max_steps, out, stats) \
                     : run<M, false>(method, theta, y0_over, tgrid, T, rtol, atol, max_steps, out, stats))
     DISPATCH(C2)
+    return -1;
+}
+
+// n fixed RODAS4 steps of size h (step-size control bypassed) -> final state; for the order check
+template <class M>
+static int fixed_steps(const double* theta, const double* y0_over, double h, int n, double* out) {
+    using Sys = pv_system<M, false>;
+    double th[M::NTH];
+    for (int i = 0; i < M::NTH; ++i) th[i] = theta[i];
+    typename Sys::Consts ks;
+    double y0[M::NX], obs[M::NX], z[M::NX];
+    M::hoist(th, ks.c, y0, obs);
+    for (int i = 0; i < M::NX; ++i) z[i] = std::isnan(y0_over[i]) ? y0[i] : y0_over[i];
+    double tg[2] = {0.0, h * n};
+    std::vector<double> sink_buf(2 * M::NX);
+    Collect<M::NX> col{sink_buf.data()};
+    pv_rodas4_lane<M, false> lane;
+    int rc = lane.start(ks, z, 0.0, tg, 2, 1e30, 1e30, col);
+    for (int k = 0; k < n && rc == PV_RUNNING; ++k) {
+        lane.h = h;
+        rc = lane.step(ks, tg, 2, 1e30, 1e30, 1 << 30, col);
+    }
+    for (int i = 0; i < M::NX; ++i) out[i] = lane.z[i] * obs[i];
+    return rc;
+}
+
+extern "C" int hh_rodas4_fixed(const char* model, const double* theta, const double* y0_over, double h, int n, double* out) {
+#define C4(M) fixed_steps<M>(theta, y0_over, h, n, out)
+    DISPATCH(C4)
     return -1;
 }
 

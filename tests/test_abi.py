@@ -1,0 +1,64 @@
+"""The C-ABI library loads on a GPU-less host, exports every symbol include/parvar_b200.h declares, and refuses
+to compute without a device (no CPU fallback)."""
+import re
+from pathlib import Path
+
+import pytest
+
+from conftest import ROOT, has_cuda, pkg
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "parvar_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pv_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    rt = pkg("runtime")
+    lib = ctypes.CDLL(str(rt.LIB_PATH))
+    syms = _declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/parvar_b200.h but not exported"
+    assert sorted(rt.ABI) == syms, "runtime.ABI and the header disagree"
+
+
+def test_registry_and_versions():
+    rt = pkg("runtime")
+    lib = rt.load_library()
+    assert lib.pv_abi_version() == 1
+    assert rt.model_names() == ["simple_chain", "simple_pk", "icg_body_flat"]
+    P = pkg()
+    assert set(P.MODELS) == {"simple_chain", "simple_pk", "icg_body_flat"}
+    assert all(Path(p).exists() for p in P.MODELS.values())
+
+
+@pytest.mark.skipif(has_cuda(), reason="checks the behaviour WITHOUT a device")
+def test_no_cpu_fallback():
+    rt = pkg("runtime")
+    with pytest.raises(rt.ParvarB200Error, match="no CPU fallback"):
+        rt.Problem("simple_pk")
+    assert rt.fma_peak_tflops() < 0
+    pf = pkg("experiments.petab_factory")
+    with pytest.raises(rt.ParvarB200Error):
+        pf.ODESampleSimulator(pkg().MODELS["simple_pk"])
+
+
+def test_host_mirror_without_gpu():
+    """Sampling and model resolution are host logic and work anywhere."""
+    import numpy as np
+    pf = pkg("experiments.petab_factory")
+    P = pkg()
+    assert pf.resolve_model(P.MODELS["icg_body_flat"]) == "icg_body_flat"
+    s = pf.create_samples_parameters({"MALE": {"CL": pf.LognormParameters(n=20, sigma=1.0, mu=1.0),
+                                               "k_abs": pf.LognormParameters(n=20, sigma=1.0, mu=0.5)}})
+    np.testing.assert_allclose(s["MALE"]["k_abs"][:3], [0.81277741, 0.65610198, 0.97999947], rtol=1e-8)
+    s2 = pf.create_samples_parameters({"MALE": {"k_abs": pf.LognormParameters(n=4, sigma=1.0, mu=0.5)}}, literal=False)
+    assert abs(np.log(s2["MALE"]["k_abs"]).mean()) < 5      # intended parameterisation: just runs
+    assert pf.lognorm_par_transform(1, 1) == pytest.approx((-0.3465735902799726, 0.8325546111576977))
+    opt = pkg("optimization.petab_optimization")
+    y = np.array([[[1.0, np.nan], [2.0, 3.0]], [[3.0, 1.0], [4.0, 5.0]]])
+    st = opt.sufficient_statistics(y, 0)
+    assert st.shape == (3, 2, 2) and st[0, 0, 1] == 1 and st[1, 0, 0] == 4 and st[2, 1, 1] == 34

@@ -114,7 +114,7 @@ def _noisy_data(oracle_Y, cv, seed):
 def test_simple_pk_logp_and_grad(cuda_lib, rt, oracle):
     """logp (normal + lognormal) and forward-sensitivity gradient vs oracle, 1e-6 relative."""
     T, B = 20, 64
-    t = np.linspace(0, 100, T)
+    t = np.linspace(0, 15, T)         # positive signal everywhere after t = 0 (needed by the log-normal model)
     obs = ["y_gut", "y_cent", "y_peri"]
     truth = oracle.simple_pk_exact({}, t)
     opt = pkg("optimization.petab_optimization")
@@ -126,6 +126,7 @@ def test_simple_pk_logp_and_grad(cuda_lib, rt, oracle):
             data = np.maximum(_noisy_data(truth[1:], 0.05, 3), 1e-300)[None]   # skip t=0 (zeros)
         tt = t if noise_model == rt.NOISE_NORMAL else t[1:]
         pb = _problem(rt, "simple_pk", ["k_abs", "CL"], tt, obs, rtol=1e-9, atol=1e-13)
+        pb.set_timepoints(tt, t0=0.0)     # measurements start after t0: PEtab semantics, initial values hold at 0
         pb.set_data(opt.sufficient_statistics(data, noise_model)[..., None], sigma, noise_model)
         lp, g, _, nf = pb.logp_host(np.stack([k_abs, CL]), grad=True)
         lp0, _, _, _ = pb.logp_host(np.stack([k_abs, CL]), grad=False)
@@ -133,7 +134,7 @@ def test_simple_pk_logp_and_grad(cuda_lib, rt, oracle):
         ref_lp, ref_g = np.empty(B), np.empty((2, B))
         for b in range(B):
             over = {"k_abs": k_abs[b], "CL": CL[b]}
-            f = oracle.simple_pk_exact(over, tt)
+            f = oracle.simple_pk_exact(over, tt)            # exact solution from t = 0
             s = oracle.simple_pk_exact_sens(over, tt)
             if noise_model == rt.NOISE_NORMAL:
                 ref_lp[b] = oracle.loglik_normal(f, data[0], sigma)

@@ -1,0 +1,129 @@
+"""The oracle against everything that can pin it here (the reference's own tests hold no golden vectors for
+this path - SURVEY.md section 4 - so: exact solutions, independent integrators, the frozen numpy RNG stream,
+finite differences, and the committed golden fixtures)."""
+import numpy as np
+import pytest
+
+from conftest import parity_violation
+
+T21 = np.linspace(0, 100, 21)
+
+
+def test_simple_chain_closed_form_vs_integration(oracle):
+    Y = oracle.simulate("simple_chain", {"k1": 0.37}, T21)
+    ex = oracle.simple_chain_exact(0.37, T21)
+    assert parity_violation(Y, ex, rtol=1e-9, atol=1e-12) <= 1.0
+
+
+def test_simple_pk_known_answers(oracle):
+    """y(5), y(10) at default parameters (matrix exponential)."""
+    Y = oracle.simple_pk_exact({}, [0.0, 5.0, 10.0])
+    np.testing.assert_allclose(Y[0], [1, 0, 0], atol=0)
+    np.testing.assert_allclose(Y[1], [0.00673795, 0.06623389, 0.10043281], rtol=2e-7)
+    np.testing.assert_allclose(Y[2], [4.53999e-05, 9.80974e-03, 1.58271e-02], rtol=2e-6)
+    # eigenvalues of the default system
+    ev = np.sort(np.linalg.eigvals(oracle.simple_pk_matrix(oracle.SIMPLE_PK.defaults)).real)
+    np.testing.assert_allclose(ev, [-2.618034, -1.0, -0.381966], rtol=1e-6)
+
+
+def test_simple_pk_integration_matches_exact(oracle):
+    rs = np.random.RandomState(0)
+    for _ in range(5):
+        over = {"k_abs": rs.lognormal(-0.35, 0.83), "CL": rs.lognormal(-0.35, 0.83), "Q": rs.lognormal(0, 0.3)}
+        Y = oracle.simulate("simple_pk", over, T21)
+        assert parity_violation(Y, oracle.simple_pk_exact(over, T21), rtol=1e-9, atol=1e-12) <= 1.0
+
+
+def test_icg_three_integrators_agree(oracle):
+    """icg_body_flat has no closed form: LSODA, Radau and BDF at rtol 1e-12 must agree far inside the parity band."""
+    t = np.array([0.0, 5, 10, 15, 20, 50, 100])
+    over = {"IVDOSE_icg": 10.0}
+    Y = oracle.simulate("icg_body_flat", over, t)
+    for m in ("Radau", "BDF"):
+        Y2 = oracle.simulate("icg_body_flat", over, t, method=m)
+        assert parity_violation(Y2, Y, rtol=1e-7, atol=1e-10) <= 1.0
+    i = oracle.ICG_STATES.index
+    # SURVEY.md section 8c item 3
+    np.testing.assert_allclose(Y[1:5, i("Cre_plasma_icg")], [1.25351163e-03, 3.13601386e-04, 7.80941642e-05, 1.94248499e-05], rtol=1e-7)
+    np.testing.assert_allclose(Y[1:5, i("Cgi_plasma_icg")], [1.20801246e-03, 3.02147240e-04, 7.52373710e-05, 1.87139868e-05], rtol=1e-7)
+    np.testing.assert_allclose(Y[1:5, i("Cve_icg")], [1.17028395e-03, 2.92655014e-04, 7.28702583e-05, 1.81249942e-05], rtol=1e-7)
+    # mass balance: injected dose [mg] / Mr = total amount in all compartments + remaining dose
+    p = dict(oracle.ICG_DEFAULTS)
+    v = oracle._icg_volumes_flows(p)
+    vol = {"Afeces_icg": 1.0, "Car_icg": v["Var"], "Cgi_plasma_icg": v["Vgi_plasma"], "Chv_icg": v["Vhv"],
+           "Cli_plasma_icg": v["Vli_plasma"], "Clu_plasma_icg": v["Vlu_plasma"], "Cpo_icg": v["Vpo"],
+           "Cre_plasma_icg": v["Vre_plasma"], "Cve_icg": v["Vve"], "LI__icg": v["Vli_tissue"], "LI__icg_bi": v["Vbi"]}
+    amount = sum(Y[:, i(s)] * V for s, V in vol.items()) + Y[:, i("IVDOSE_icg")] / p["Mr_icg"]
+    np.testing.assert_allclose(amount, 10.0 / p["Mr_icg"], rtol=1e-9)
+
+
+def test_sampling_stream_known_answers(oracle):
+    """swapped (loc, scale), global legacy MT19937 stream, dict order."""
+    assert oracle.lognorm_par_transform(1.0, 1.0) == pytest.approx((-0.3465735902799726, 0.8325546111576977), abs=1e-15)
+    # k_abs_MALE: loc 0.5, scale 1 is drawn as mean 1 / sd 0.5 because of the swap
+    mu, sg = oracle.lognorm_par_transform(1.0, 0.5)
+    assert (mu, sg) == pytest.approx((-0.111572, 0.472381), abs=1e-6)
+    s = oracle.create_samples_parameters({"MALE": {"CL": (20, 1.0, 1.0), "k_abs": (20, 1.0, 0.5)}})
+    np.testing.assert_allclose(s["MALE"]["CL"][:3], [1.04699267, 0.26233685, 2.33085045], rtol=1e-8)
+    np.testing.assert_allclose(s["MALE"]["k_abs"][:3], [0.81277741, 0.65610198, 0.97999947], rtol=1e-8)
+
+
+def test_noise_restatement(oracle):
+    y = np.arange(12, dtype=float).reshape(4, 3)
+    np.random.seed(5)
+    a = oracle.add_noise(y, 0.1)
+    np.random.seed(5)
+    seed = np.random.randint(0, 2001)
+    rs = np.random.RandomState(seed)
+    np.testing.assert_array_equal(a, y + y * rs.normal(0, 1, y.shape) * 0.1)
+    assert np.all(a[0, :1] == 0.0)            # y = 0 stays 0 (quirk Q3)
+
+
+def test_sensitivities_vs_finite_differences(oracle):
+    t = np.linspace(0, 30, 7)
+    over = {"k_abs": 0.8, "CL": 1.3}
+    S = oracle.simple_pk_exact_sens(over, t)
+    Y, S2 = oracle.simulate_sens("simple_pk", over, t, ["k_abs", "CL"])
+    assert np.max(np.abs(S - S2)) < 1e-9
+    for si, name in enumerate(["k_abs", "CL"]):
+        e = 1e-5
+        up, dn = dict(over), dict(over)
+        up[name] += e
+        dn[name] -= e
+        fd = (oracle.simple_pk_exact(up, t) - oracle.simple_pk_exact(dn, t)) / (2 * e)
+        assert np.max(np.abs(fd - S[:, :, si])) < 1e-8
+    # icg: sympy forward sensitivities vs central differences
+    t = np.array([0.0, 5, 10, 20])
+    over = {"IVDOSE_icg": 10.0}
+    Y, S = oracle.simulate_sens("icg_body_flat", over, t, ["BW", "LI__ICGIM_Vmax"])
+    for si, (name, e) in enumerate([("BW", 75e-4), ("LI__ICGIM_Vmax", 0.037e-4)]):
+        up, dn = dict(over), dict(over)
+        up[name] = oracle.ICG_DEFAULTS[name] + e
+        dn[name] = oracle.ICG_DEFAULTS[name] - e
+        fd = (oracle.simulate("icg_body_flat", up, t) - oracle.simulate("icg_body_flat", dn, t)) / (2 * e)
+        scale = np.abs(S[:, :, si]).max(axis=0) + 1e-30
+        assert np.max(np.abs(fd - S[:, :, si]) / scale) < 1e-5
+
+
+def test_likelihood_forms(oracle):
+    rs = np.random.RandomState(1)
+    f = rs.rand(5, 3) + 0.1
+    y = f * (1 + 0.1 * rs.normal(size=(4, 5, 3)))       # 4 individuals pooled on one trajectory
+    lp = oracle.loglik_normal(f, y, 0.7)
+    ref = sum(-0.5 * np.log(2 * np.pi * 0.49) - 0.5 * ((yy - ff) / 0.7) ** 2 for yi in y for yy, ff in zip(yi.ravel(), f.ravel()))
+    assert lp == pytest.approx(ref, rel=1e-12)
+    ds = rs.normal(size=(5, 3, 2))
+    g = oracle.loglik_normal_grad(f, ds, y, 0.7)
+    e = 1e-6
+    for k in range(2):
+        fd = (oracle.loglik_normal(f + e * ds[..., k], y, 0.7) - oracle.loglik_normal(f - e * ds[..., k], y, 0.7)) / (2 * e)
+        assert g[k] == pytest.approx(fd, rel=1e-6)
+    y = np.abs(y) + 0.05
+    g = oracle.loglik_lognormal_grad(f, ds * 0.01, y, 0.4)
+    for k in range(2):
+        fd = (oracle.loglik_lognormal(f + e * 0.01 * ds[..., k], y, 0.4) - oracle.loglik_lognormal(f - e * 0.01 * ds[..., k], y, 0.4)) / (2 * e)
+        assert g[k] == pytest.approx(fd, rel=1e-5)
+    lp, dth, dmu, dsg = oracle.population_lognormal_logpdf(np.abs(rs.normal(size=(6, 2))) + 0.2, np.array([0.1, -0.2]), np.array([0.5, 0.8]))
+    from scipy.stats import lognorm
+    th = np.abs(np.random.RandomState(1).normal(size=(1,)))  # noqa: F841  (shape check only)
+    assert np.isfinite(lp) and dth.shape == (6, 2) and dmu.shape == (2,) and dsg.shape == (2,)

@@ -124,32 +124,33 @@ struct pv_dopri5_lane {
         if (jout >= T) return PV_OK;
         Sys::rhs(t, y, ks, k1);
         // ---- initial step (Hairer, Norsett, Wanner I, II.4) ----------------------------------
+        // (fp64 here: runs once per trajectory and must survive atol -> 0 without overflow)
         double yn[N], k2[N];
-        float d0 = 0.f, d1 = 0.f;
+        double d0 = 0.0, d1 = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const float sc = (float)(atol + rtol * fabs(y[i]));
-            const float a = (float)y[i] / sc, b = (float)k1[i] / sc;
+            const double sc = atol + rtol * fabs(y[i]);
+            const double a = y[i] / sc, b = k1[i] / sc;
             d0 += a * a;
             d1 += b * b;
         }
-        d0 = sqrtf(d0 / N);
-        d1 = sqrtf(d1 / N);
-        double h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6 : 0.01 * (double)(d0 / d1);
-        h0 = fmin(h0, tend - t);
+        d0 = sqrt(d0 / N);
+        d1 = sqrt(d1 / N);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+        h0 = fmin(fmax(h0, 1e-12), tend - t);
 #pragma unroll
         for (int i = 0; i < N; ++i) yn[i] = fma(h0, k1[i], y[i]);
         Sys::rhs(t + h0, yn, ks, k2);
-        float d2 = 0.f;
+        double d2 = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const float sc = (float)(atol + rtol * fabs(y[i]));
-            const float a = (float)(k2[i] - k1[i]) / sc;
+            const double sc = atol + rtol * fabs(y[i]);
+            const double a = (k2[i] - k1[i]) / sc;
             d2 += a * a;
         }
-        d2 = sqrtf(d2 / N) / (float)h0;
-        const float dm = fmaxf(d1, d2);
-        const double h1 = (dm <= 1e-15f) ? fmax(1e-6, h0 * 1e-3) : (double)pv_powf_fast(0.01f / dm, 0.2f);
+        d2 = sqrt(d2 / N) / h0;
+        const double dm = fmax(d1, d2);
+        const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
         h = fmin(fmin(100.0 * h0, h1), tend - t);
         return PV_RUNNING;
     }

@@ -54,7 +54,7 @@ def test_host_mirror_without_gpu():
     assert pf.resolve_model(P.MODELS["icg_body_flat"]) == "icg_body_flat"
     s = pf.create_samples_parameters({"MALE": {"CL": pf.LognormParameters(n=20, sigma=1.0, mu=1.0),
                                                "k_abs": pf.LognormParameters(n=20, sigma=1.0, mu=0.5)}})
-    np.testing.assert_allclose(s["MALE"]["k_abs"][:3], [0.81277741, 0.65610198, 0.97999947], rtol=1e-8)
+    np.testing.assert_allclose(s["MALE"]["k_abs"][:3], [0.81277741, 0.65610198, 0.97999947], rtol=1e-7)
     s2 = pf.create_samples_parameters({"MALE": {"k_abs": pf.LognormParameters(n=4, sigma=1.0, mu=0.5)}}, literal=False)
     assert abs(np.log(s2["MALE"]["k_abs"]).mean()) < 5      # intended parameterisation: just runs
     assert pf.lognorm_par_transform(1, 1) == pytest.approx((-0.3465735902799726, 0.8325546111576977))

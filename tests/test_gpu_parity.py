@@ -114,19 +114,20 @@ def _noisy_data(oracle_Y, cv, seed):
 def test_simple_pk_logp_and_grad(cuda_lib, rt, oracle):
     """logp (normal + lognormal) and forward-sensitivity gradient vs oracle, 1e-6 relative."""
     T, B = 20, 64
-    t = np.linspace(0, 15, T)         # positive signal everywhere after t = 0 (needed by the log-normal model)
-    obs = ["y_gut", "y_cent", "y_peri"]
-    truth = oracle.simple_pk_exact({}, t)
+    t = np.linspace(0, 15, T)
     opt = pkg("optimization.petab_optimization")
     k_abs, CL = lognormal_draws(21, B), lognormal_draws(22, B)
     for noise_model, sigma in ((rt.NOISE_NORMAL, 0.05), (rt.NOISE_LOGNORMAL, 0.3)):
         if noise_model == rt.NOISE_NORMAL:
-            data = _noisy_data(truth, 0.05, 3)[None]
+            obs, tt, atol = ["y_gut", "y_cent", "y_peri"], t, 1e-13
         else:
-            data = np.maximum(_noisy_data(truth[1:], 0.05, 3), 1e-300)[None]   # skip t=0 (zeros)
-        tt = t if noise_model == rt.NOISE_NORMAL else t[1:]
-        pb = _problem(rt, "simple_pk", ["k_abs", "CL"], tt, obs, rtol=1e-9, atol=1e-13)
-        pb.set_timepoints(tt, t0=0.0)     # measurements start after t0: PEtab semantics, initial values hold at 0
+            # the log-normal model needs a signal that stays far above atol: central/peripheral only, t > 0
+            obs, tt, atol = ["y_cent", "y_peri"], t[1:], 1e-16
+        cols = [oracle.SIMPLE_PK.states.index(o) for o in obs]
+        truth = oracle.simple_pk_exact({}, tt)[:, cols]
+        data = _noisy_data(truth, 0.05, 3)[None]
+        pb = _problem(rt, "simple_pk", ["k_abs", "CL"], tt, obs, rtol=1e-9, atol=atol)
+        pb.set_timepoints(tt, t0=0.0)     # measurements may start after t0 (PEtab: initial values hold at 0)
         pb.set_data(opt.sufficient_statistics(data, noise_model)[..., None], sigma, noise_model)
         lp, g, _, nf = pb.logp_host(np.stack([k_abs, CL]), grad=True)
         lp0, _, _, _ = pb.logp_host(np.stack([k_abs, CL]), grad=False)
@@ -134,8 +135,8 @@ def test_simple_pk_logp_and_grad(cuda_lib, rt, oracle):
         ref_lp, ref_g = np.empty(B), np.empty((2, B))
         for b in range(B):
             over = {"k_abs": k_abs[b], "CL": CL[b]}
-            f = oracle.simple_pk_exact(over, tt)            # exact solution from t = 0
-            s = oracle.simple_pk_exact_sens(over, tt)
+            f = oracle.simple_pk_exact(over, tt)[:, cols]            # exact solution from t = 0
+            s = oracle.simple_pk_exact_sens(over, tt)[:, cols, :]
             if noise_model == rt.NOISE_NORMAL:
                 ref_lp[b] = oracle.loglik_normal(f, data[0], sigma)
                 ref_g[:, b] = oracle.loglik_normal_grad(f, s, data[0], sigma)
@@ -257,8 +258,8 @@ def test_ode_sample_simulator_drop_in(cuda_lib, oracle):
         {pf.Category.MALE: {pf.PKPDParameters.CL: pf.LognormParameters(n=20, sigma=1.0, mu=1.0),
                             pf.PKPDParameters.k_abs: pf.LognormParameters(n=20, sigma=1.0, mu=0.5)}})
     df = pd.DataFrame({par.value: v for par, v in samples[pf.Category.MALE].items()})
-    np.testing.assert_allclose(df["CL"].values[:3], [1.04699267, 0.26233685, 2.33085045], rtol=1e-8)
-    np.testing.assert_allclose(df["k_abs"].values[:3], [0.81277741, 0.65610198, 0.97999947], rtol=1e-8)
+    np.testing.assert_allclose(df["CL"].values[:3], [1.04699267, 0.26233685, 2.33085045], rtol=1e-7)
+    np.testing.assert_allclose(df["k_abs"].values[:3], [0.81277741, 0.65610198, 0.97999947], rtol=1e-7)
     sim = pf.ODESampleSimulator(P.MODELS["simple_pk"])
     obs = [ex.Observable(id="y_cent"), ex.Observable(id="y_gut"), ex.Observable(id="y_peri")]
     st = pf.SimulationSettings(start=0.0, end=100.0, steps=20, noise=ex.Noise(add_noise=False, cv=0.05), observables=obs)

@@ -19,7 +19,7 @@ def test_simple_pk_known_answers(oracle):
     """y(5), y(10) at default parameters (matrix exponential)."""
     Y = oracle.simple_pk_exact({}, [0.0, 5.0, 10.0])
     np.testing.assert_allclose(Y[0], [1, 0, 0], atol=0)
-    np.testing.assert_allclose(Y[1], [0.00673795, 0.06623389, 0.10043281], rtol=2e-7)
+    np.testing.assert_allclose(Y[1], [0.00673795, 0.06623389, 0.10043281], rtol=1e-6)
     np.testing.assert_allclose(Y[2], [4.53999e-05, 9.80974e-03, 1.58271e-02], rtol=2e-6)
     # eigenvalues of the default system (SURVEY.md section 8a row a6)
     ev = np.sort(np.linalg.eigvals(oracle.simple_pk_matrix(oracle.SIMPLE_PK.defaults)).real)
@@ -31,7 +31,7 @@ def test_simple_pk_integration_matches_exact(oracle):
     for _ in range(5):
         over = {"k_abs": rs.lognormal(-0.35, 0.83), "CL": rs.lognormal(-0.35, 0.83), "Q": rs.lognormal(0, 0.3)}
         Y = oracle.simulate("simple_pk", over, T21)
-        assert parity_violation(Y, oracle.simple_pk_exact(over, T21), rtol=1e-9, atol=1e-12) <= 1.0
+        assert parity_violation(Y, oracle.simple_pk_exact(over, T21), rtol=1e-8, atol=1e-10) <= 1.0
 
 
 def test_icg_three_integrators_agree(oracle):
@@ -64,8 +64,8 @@ def test_sampling_stream_known_answers(oracle):
     mu, sg = oracle.lognorm_par_transform(1.0, 0.5)
     assert (mu, sg) == pytest.approx((-0.111572, 0.472381), abs=1e-6)
     s = oracle.create_samples_parameters({"MALE": {"CL": (20, 1.0, 1.0), "k_abs": (20, 1.0, 0.5)}})
-    np.testing.assert_allclose(s["MALE"]["CL"][:3], [1.04699267, 0.26233685, 2.33085045], rtol=1e-8)
-    np.testing.assert_allclose(s["MALE"]["k_abs"][:3], [0.81277741, 0.65610198, 0.97999947], rtol=1e-8)
+    np.testing.assert_allclose(s["MALE"]["CL"][:3], [1.04699267, 0.26233685, 2.33085045], rtol=1e-7)
+    np.testing.assert_allclose(s["MALE"]["k_abs"][:3], [0.81277741, 0.65610198, 0.97999947], rtol=1e-7)
 
 
 def test_noise_restatement(oracle):

@@ -60,7 +60,7 @@ struct pv_problem {
     unsigned long long* d_counters = nullptr;
     int counter_next = 0;
     int num_sms = 0;
-    int refill_min = 8;
+    int refill_min = 3;
     double t0 = 0.0;
     bool t0_set = false;
 };
@@ -299,28 +299,35 @@ extern "C" int pv_problem_set_data(pv_problem* p, int noise_model, int n_data, c
 // ---------------------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------------------
-template <class M, int METHOD, int MODE>
+template <class M, int METHOD, int MODE, bool OBSID>
 static cudaError_t launch_one(const pv_launch_params& lp, size_t shmem, int num_sms, cudaStream_t s) {
+    auto kern = pv_batch_kernel<M, METHOD, MODE, OBSID>;
     if (shmem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(pv_batch_kernel<M, METHOD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
         if (e != cudaSuccess) return e;
     }
     // persistent grid: as many CTAs as are resident at once (a multiple of the SM count), never more than the work
     int per_sm = 0;
-    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pv_batch_kernel<M, METHOD, MODE>, PV_BLOCK, shmem);
+    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PV_BLOCK, shmem);
     if (eo != cudaSuccess) return eo;
     if (per_sm < 1) per_sm = 1;
     const int64_t want = (lp.B + PV_BLOCK - 1) / PV_BLOCK;
     const int64_t blocks = std::min<int64_t>(want, (int64_t)num_sms * per_sm);
-    pv_batch_kernel<M, METHOD, MODE><<<(unsigned)blocks, PV_BLOCK, shmem, s>>>(lp);
+    kern<<<(unsigned)blocks, PV_BLOCK, shmem, s>>>(lp);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
 
 template <class M>
-static cudaError_t launch_model(int method, int mode, const pv_launch_params& lp, size_t shmem, int num_sms, cudaStream_t s) {
-#define PV_CASE(METH, MODE) \
-    if (method == METH && mode == MODE) return launch_one<M, METH, MODE>(lp, shmem, num_sms, s);
+static cudaError_t launch_model(int method, int mode, bool obsid, const pv_launch_params& lp, size_t shmem, int num_sms,
+                                cudaStream_t s) {
+    // the all-states-in-order specialisation is compiled for the explicit integrator only (cheap steps, where the
+    // per-output code matters); the Rosenbrock kernels always use the generic sink
+#define PV_CASE(METH, MODE)                                                                      \
+    if (method == METH && mode == MODE) {                                                        \
+        if (METH == 1 && obsid) return launch_one<M, METH, MODE, (METH == 1)>(lp, shmem, num_sms, s); \
+        return launch_one<M, METH, MODE, false>(lp, shmem, num_sms, s);                          \
+    }
     PV_CASE(1, PV_MODE_TRAJ) PV_CASE(1, PV_MODE_LOGP) PV_CASE(1, PV_MODE_TRAJ_LOGP) PV_CASE(1, PV_MODE_LOGP_GRAD) PV_CASE(1, PV_MODE_TRAJ_SENS)
     PV_CASE(2, PV_MODE_TRAJ) PV_CASE(2, PV_MODE_LOGP) PV_CASE(2, PV_MODE_TRAJ_LOGP) PV_CASE(2, PV_MODE_LOGP_GRAD) PV_CASE(2, PV_MODE_TRAJ_SENS)
 #undef PV_CASE
@@ -399,9 +406,11 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     size_t shmem = sizeof(double) * (lp.T + p->tab->n_theta + p->tab->n_states);
     if (need_logp && lp.n_data == 1) shmem += sizeof(double) * 3 * lp.T * lp.n_obs;
     if (shmem > 200 * 1024) return fail(PV_E_ARG, "time grid / data too large for shared memory");
+    bool obsid = lp.n_obs == p->tab->n_states;
+    for (int k = 0; k < lp.n_obs && obsid; ++k) obsid = (lp.obs_idx[k] == k);
     cudaError_t e = cudaErrorInvalidValue;
     switch (p->model) {
-        PV_MODEL_DISPATCH(e = launch_model, (method, mode, lp, shmem, p->num_sms, s))
+        PV_MODEL_DISPATCH(e = launch_model, (method, mode, obsid, lp, shmem, p->num_sms, s))
     }
     if (e != cudaSuccess) return fail(PV_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     return 0;

@@ -64,6 +64,43 @@ PV_HD float pv_powf_fast(float x, float a) {
 #endif
 }
 
+PV_HD float pv_fdiv_fast(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);     // MUFU.RCP + FMUL: the controller needs two digits, not IEEE division
+#else
+    return a / b;
+#endif
+}
+PV_HD double pv_drcp(double x) {
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(x);
+#else
+    return 1.0 / x;
+#endif
+}
+
+// Butcher tableau of DOPRI5 in __constant__ memory: fp64 literals cannot be instruction immediates, so the
+// compiler would otherwise rebuild every coefficient with two UMOVs per use; a c[bank][offset] operand is free.
+#if defined(__CUDACC__)
+#define PV_COEF_SPACE __constant__
+#else
+#define PV_COEF_SPACE static const
+#endif
+PV_COEF_SPACE double pv_dp5[32] = {
+    /* 0 a21 */ 1.0 / 5.0,
+    /* 1 a31 */ 3.0 / 40.0, /* 2 a32 */ 9.0 / 40.0,
+    /* 3 a41 */ 44.0 / 45.0, /* 4 a42 */ -56.0 / 15.0, /* 5 a43 */ 32.0 / 9.0,
+    /* 6 a51 */ 19372.0 / 6561.0, /* 7 a52 */ -25360.0 / 2187.0, /* 8 a53 */ 64448.0 / 6561.0, /* 9 a54 */ -212.0 / 729.0,
+    /* 10 a61 */ 9017.0 / 3168.0, /* 11 a62 */ -355.0 / 33.0, /* 12 a63 */ 46732.0 / 5247.0, /* 13 a64 */ 49.0 / 176.0,
+    /* 14 a65 */ -5103.0 / 18656.0,
+    /* 15 b1 */ 35.0 / 384.0, /* 16 b3 */ 500.0 / 1113.0, /* 17 b4 */ 125.0 / 192.0, /* 18 b5 */ -2187.0 / 6784.0,
+    /* 19 b6 */ 11.0 / 84.0,
+    /* 20 e1 */ 71.0 / 57600.0, /* 21 e3 */ -71.0 / 16695.0, /* 22 e4 */ 71.0 / 1920.0, /* 23 e5 */ -17253.0 / 339200.0,
+    /* 24 e6 */ 22.0 / 525.0, /* 25 e7 */ -1.0 / 40.0,
+    /* 26 d1 */ -12715105075.0 / 11282082432.0, /* 27 d3 */ 87487479700.0 / 32700410799.0,
+    /* 28 d4 */ -10690763975.0 / 1880347072.0, /* 29 d5 */ 701980252875.0 / 199316789632.0,
+    /* 30 d6 */ -1453857185.0 / 822651844.0, /* 31 d7 */ 69997945.0 / 29380423.0};
+
 struct pv_step_stats {
     int accepted;
     int rejected;
@@ -171,36 +208,33 @@ struct pv_dopri5_lane {
         double k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], yn[N];
         // ---- stages ----------------------------------------------------------------------------
 #pragma unroll
-        for (int i = 0; i < N; ++i) yn[i] = fma(h * 0.2, k1[i], y[i]);
+        for (int i = 0; i < N; ++i) yn[i] = fma(h * pv_dp5[0], k1[i], y[i]);
         Sys::rhs(t + 0.2 * h, yn, ks, k2);
 #pragma unroll
-        for (int i = 0; i < N; ++i) yn[i] = fma(h, fma(3.0 / 40.0, k1[i], (9.0 / 40.0) * k2[i]), y[i]);
+        for (int i = 0; i < N; ++i) yn[i] = fma(h, fma(pv_dp5[1], k1[i], pv_dp5[2] * k2[i]), y[i]);
         Sys::rhs(t + 0.3 * h, yn, ks, k3);
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            yn[i] = fma(h, fma(44.0 / 45.0, k1[i], fma(-56.0 / 15.0, k2[i], (32.0 / 9.0) * k3[i])), y[i]);
+            yn[i] = fma(h, fma(pv_dp5[3], k1[i], fma(pv_dp5[4], k2[i], pv_dp5[5] * k3[i])), y[i]);
         Sys::rhs(t + 0.8 * h, yn, ks, k4);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             yn[i] = fma(h,
-                        fma(19372.0 / 6561.0, k1[i],
-                            fma(-25360.0 / 2187.0, k2[i], fma(64448.0 / 6561.0, k3[i], (-212.0 / 729.0) * k4[i]))),
+                        fma(pv_dp5[6], k1[i], fma(pv_dp5[7], k2[i], fma(pv_dp5[8], k3[i], pv_dp5[9] * k4[i]))),
                         y[i]);
         Sys::rhs(t + (8.0 / 9.0) * h, yn, ks, k5);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             yn[i] = fma(h,
-                        fma(9017.0 / 3168.0, k1[i],
-                            fma(-355.0 / 33.0, k2[i],
-                                fma(46732.0 / 5247.0, k3[i], fma(49.0 / 176.0, k4[i], (-5103.0 / 18656.0) * k5[i])))),
+                        fma(pv_dp5[10], k1[i],
+                            fma(pv_dp5[11], k2[i], fma(pv_dp5[12], k3[i], fma(pv_dp5[13], k4[i], pv_dp5[14] * k5[i])))),
                         y[i]);
         Sys::rhs(t + h, yn, ks, k6);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             yn[i] = fma(h,
-                        fma(35.0 / 384.0, k1[i],
-                            fma(500.0 / 1113.0, k3[i],
-                                fma(125.0 / 192.0, k4[i], fma(-2187.0 / 6784.0, k5[i], (11.0 / 84.0) * k6[i])))),
+                        fma(pv_dp5[15], k1[i],
+                            fma(pv_dp5[16], k3[i], fma(pv_dp5[17], k4[i], fma(pv_dp5[18], k5[i], pv_dp5[19] * k6[i])))),
                         y[i]);
         Sys::rhs(t + h, yn, ks, k7);
 
@@ -209,12 +243,11 @@ struct pv_dopri5_lane {
         bool finite = true;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double e = h * fma(71.0 / 57600.0, k1[i],
-                                     fma(-71.0 / 16695.0, k3[i],
-                                         fma(71.0 / 1920.0, k4[i],
-                                             fma(-17253.0 / 339200.0, k5[i], fma(22.0 / 525.0, k6[i], (-1.0 / 40.0) * k7[i])))));
+            const double e = h * fma(pv_dp5[20], k1[i],
+                                     fma(pv_dp5[21], k3[i],
+                                         fma(pv_dp5[22], k4[i], fma(pv_dp5[23], k5[i], fma(pv_dp5[24], k6[i], pv_dp5[25] * k7[i])))));
             const double sc = atol + rtol * fmax(fabs(y[i]), fabs(yn[i]));
-            const float r = (float)e / (float)sc;
+            const float r = pv_fdiv_fast((float)e, (float)sc);
             err2 += r * r;
             finite = finite && (fabs(yn[i]) < 1e300);
         }
@@ -234,11 +267,10 @@ struct pv_dopri5_lane {
                 double r5[N];
 #pragma unroll
                 for (int i = 0; i < N; ++i)
-                    r5[i] = h * fma(-12715105075.0 / 11282082432.0, k1[i],
-                                    fma(87487479700.0 / 32700410799.0, k3[i],
-                                        fma(-10690763975.0 / 1880347072.0, k4[i],
-                                            fma(701980252875.0 / 199316789632.0, k5[i],
-                                                fma(-1453857185.0 / 822651844.0, k6[i], (69997945.0 / 29380423.0) * k7[i])))));
+                    r5[i] = h * fma(pv_dp5[26], k1[i],
+                                    fma(pv_dp5[27], k3[i],
+                                        fma(pv_dp5[28], k4[i], fma(pv_dp5[29], k5[i], fma(pv_dp5[30], k6[i], pv_dp5[31] * k7[i])))));
+                const double hinv = pv_drcp(h);
                 do {
                     const double tj = tgrid[jout];
                     double yo[N];
@@ -246,7 +278,7 @@ struct pv_dopri5_lane {
 #pragma unroll
                         for (int i = 0; i < N; ++i) yo[i] = yn[i];
                     } else {
-                        const double th = (tj - t) / h, th1 = 1.0 - th;
+                        const double th = (tj - t) * hinv, th1 = 1.0 - th;
 #pragma unroll
                         for (int i = 0; i < N; ++i) {
                             const double yd = yn[i] - y[i];
@@ -261,7 +293,7 @@ struct pv_dopri5_lane {
             }
             float fac = fac11 / pv_powf_fast(facold, 0.04f);
             fac = fmaxf(0.1f, fminf(5.0f, fac * (1.0f / 0.9f)));
-            double hnew = h / (double)fac;
+            double hnew = h * (double)pv_fdiv_fast(1.0f, fac);
             if (last_rejected) hnew = fmin(hnew, h);
             facold = fmaxf(sqrtf(err2), 1e-4f);
             last_rejected = false;
@@ -275,7 +307,7 @@ struct pv_dopri5_lane {
             h = hnew;
         } else {
             ++st.rejected;
-            h = h / (double)fminf(5.0f, fac11 * (1.0f / 0.9f));
+            h = h * (double)pv_fdiv_fast(1.0f, fminf(5.0f, fac11 * (1.0f / 0.9f)));
             last_rejected = true;
         }
         return PV_RUNNING;

@@ -54,7 +54,10 @@ PV_D double pv_pick(const double (&a)[N], int block, int idx) {
 }
 
 // ---- per-grid-point sink: stores the observables and / or folds them into the likelihood ---------------------
-template <class M, int MODE>
+// OBSID = true: the observables are exactly the model's states in order (n_obs == NX, obs_idx[k] == k), so the
+// selection chains, the indexed constant loads and the k-loop overhead disappear (the common case of the
+// cheap non-stiff models, where the per-output code is a sizeable share of a step).
+template <class M, int MODE, bool OBSID>
 struct pv_sink {
     static constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
     static constexpr bool TRAJ = (MODE & PV_MODE_TRAJ) != 0;
@@ -67,49 +70,66 @@ struct pv_sink {
     double obs[M::NX];
     double lp;
     double g[M::NSD];
-    PV_D void operator()(int j, double, const double (&z)[N]) {
-        for (int k = 0; k < p.n_obs; ++k) {
-            const int idx = p.obs_idx[k];
-            const double sc = pv_pick<M::NX>(obs, 0, idx);
-            const double f = pv_pick<M::NX>(z, 0, idx) * sc;
-            double df[M::NSD];
+
+    PV_D void one(int j, int k, double f, const double (&df)[M::NSD], double log_norm, double inv_sigma2) {
+        const int n_obs = OBSID ? M::NX : p.n_obs;
+        if constexpr (TRAJ) {
+            const int64_t row = (int64_t)j * n_obs + k;
+            if (p.Y) p.Y[row * p.B + b] = f;
             if constexpr (SENS) {
 #pragma unroll
-                for (int s = 0; s < M::NS; ++s) df[s] = pv_pick<M::NX>(z, 1 + s, idx) * sc;
+                for (int s = 0; s < M::NS; ++s) p.S[((int64_t)s * p.T * n_obs + row) * p.B + b] = df[s];
             }
-            (void)df;
-            if constexpr (TRAJ) {
-                if (p.Y) p.Y[((int64_t)j * p.n_obs + k) * p.B + b] = f;
+        }
+        if constexpr (LOGP) {
+            const int64_t plane = (int64_t)p.T * n_obs * p.n_data;
+            const int64_t o = ((int64_t)j * n_obs + k) * p.n_data + d;
+            double n, s1, s2;
+            if (sh_stats) {
+                n = sh_stats[o]; s1 = sh_stats[plane + o]; s2 = sh_stats[2 * plane + o];
+            } else {
+                n = __ldg(p.stats + o); s1 = __ldg(p.stats + plane + o); s2 = __ldg(p.stats + 2 * plane + o);
+            }
+            if (n > 0.0) {
+                double w;   // d lp / d f
+                if (p.noise_model == 0) {
+                    lp -= 0.5 * fma(n, log_norm, fma(f, fma(n, f, -2.0 * s1), s2) * inv_sigma2);
+                    w = fma(-n, f, s1) * inv_sigma2;
+                } else {
+                    const double lf = log(f);
+                    lp -= s1 + fma(n, log_norm, 0.5 * fma(lf, fma(n, lf, -2.0 * s1), s2) * inv_sigma2);
+                    w = fma(-n, lf, s1) * inv_sigma2 / f;
+                }
                 if constexpr (SENS) {
 #pragma unroll
-                    for (int s = 0; s < M::NS; ++s) p.S[(((int64_t)s * p.T + j) * p.n_obs + k) * p.B + b] = df[s];
+                    for (int s = 0; s < M::NS; ++s) g[s] = fma(w, df[s], g[s]);
                 }
+                (void)w;
             }
-            if constexpr (LOGP) {
-                const int64_t plane = (int64_t)p.T * p.n_obs * p.n_data;
-                const int64_t o = ((int64_t)j * p.n_obs + k) * p.n_data + d;
-                double n, s1, s2;
-                if (sh_stats) {
-                    n = sh_stats[o]; s1 = sh_stats[plane + o]; s2 = sh_stats[2 * plane + o];
-                } else {
-                    n = __ldg(p.stats + o); s1 = __ldg(p.stats + plane + o); s2 = __ldg(p.stats + 2 * plane + o);
-                }
-                if (n > 0.0) {
-                    double w;   // d lp / d f
-                    if (p.noise_model == 0) {
-                        lp -= 0.5 * fma(n, p.log_norm[k], fma(f, fma(n, f, -2.0 * s1), s2) * p.inv_sigma2[k]);
-                        w = fma(-n, f, s1) * p.inv_sigma2[k];
-                    } else {
-                        const double lf = log(f);
-                        lp -= s1 + fma(n, p.log_norm[k], 0.5 * fma(lf, fma(n, lf, -2.0 * s1), s2) * p.inv_sigma2[k]);
-                        w = fma(-n, lf, s1) * p.inv_sigma2[k] / f;
-                    }
-                    if constexpr (SENS) {
+        }
+    }
+
+    PV_D void operator()(int j, double, const double (&z)[N]) {
+        if constexpr (OBSID) {
 #pragma unroll
-                        for (int s = 0; s < M::NS; ++s) g[s] = fma(w, df[s], g[s]);
-                    }
-                    (void)w;
+            for (int k = 0; k < M::NX; ++k) {
+                double df[M::NSD];
+                if constexpr (SENS) {
+#pragma unroll
+                    for (int s = 0; s < M::NS; ++s) df[s] = z[M::NX * (1 + s) + k] * obs[k];
                 }
+                one(j, k, z[k] * obs[k], df, p.log_norm[k], p.inv_sigma2[k]);
+            }
+        } else {
+            for (int k = 0; k < p.n_obs; ++k) {
+                const int idx = p.obs_idx[k];
+                const double sc = pv_pick<M::NX>(obs, 0, idx);
+                double df[M::NSD];
+                if constexpr (SENS) {
+#pragma unroll
+                    for (int s = 0; s < M::NS; ++s) df[s] = pv_pick<M::NX>(z, 1 + s, idx) * sc;
+                }
+                one(j, k, pv_pick<M::NX>(z, 0, idx) * sc, df, p.log_norm[k], p.inv_sigma2[k]);
             }
         }
     }
@@ -133,7 +153,7 @@ struct pv_lane_of<M, 2, SENS> {
 // Refills are batched (>= p.refill_min idle lanes, or nobody left working) so the start-up code
 // (parameter load, hoist, initial step size) runs with several lanes active.  Results do not depend on
 // the schedule: every trajectory is integrated by exactly one lane from its own inputs.
-template <class M, int METHOD, int MODE>
+template <class M, int METHOD, int MODE, bool OBSID>
 __global__ void __launch_bounds__(PV_BLOCK)
 pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
     constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
@@ -157,7 +177,7 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
     const int lane_id = threadIdx.x & 31;
     typename Sys::Consts ks;
     Lane lane;
-    pv_sink<M, MODE> sink{p, stats_shared ? sh_stats : nullptr, 0, 0, {}, 0.0, {}};
+    pv_sink<M, MODE, OBSID> sink{p, stats_shared ? sh_stats : nullptr, 0, 0, {}, 0.0, {}};
     bool have = false;        // this lane is integrating trajectory sink.b
     bool exhausted = false;   // the work counter ran past B
 

@@ -112,36 +112,25 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------------------
 def cpu_baseline(sample: int, threads: int | None = None) -> dict:
-    """Oracle port timed on the host cores: the C restatement (oracle/_build/liboracle.so, OpenMP) when it is
-    built, else the numpy/scipy oracle loop on one core."""
+    """Oracle port timed on the host cores: the C restatement (oracle/parvar_oracle.c, variable-order BDF like
+    CVODE, the reference's tolerances rtol = atol = 1e-6, petab_factory.py:183-189) with OpenMP over all host
+    threads.  Same work per trajectory as one step of the GPU arm: 50 x 3 outputs + the Gaussian logp."""
     sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle_c
     tgrid = np.linspace(0.0, 100.0, T_POINTS)
     th = draws(0, sample)
-    try:
-        import oracle_c
-        lib = oracle_c.load()
-    except Exception:
-        lib = None
-    if lib is not None:
-        cores = threads or os.cpu_count() or 1
-        data = c1_data(tgrid)
-        t0 = time.perf_counter()
-        oracle_c.simulate_batch("simple_pk", {"k_abs": th[0], "CL": th[1]}, tgrid, OBS, rtol=1e-6, atol=1e-6,
-                                threads=cores, data=data, sigma=1.0)
-        dt = time.perf_counter() - t0
-        return {"value": sample / dt, "unit": "trajectories/s", "cores": cores, "kind": "port",
-                "sample": f"{sample} of the {B_PER_GPU} draws, C restatement (oracle/parvar_oracle.c: CVODE-style "
-                          f"variable-order BDF, rtol=atol=1e-6 as petab_factory.py:183-189), OpenMP {cores} threads",
-                "seconds": dt}
-    import parvar_oracle as oracle
-    n = min(sample, 300)
-    rows = [{"k_abs": th[0, i], "CL": th[1, i]} for i in range(n)]
+    cores = threads or os.cpu_count() or 1
+    data = c1_data(tgrid)
+    oracle_c.load()
     t0 = time.perf_counter()
-    oracle.simulate_reference_loop("simple_pk", rows, 0.0, 100.0, T_POINTS - 1, observables=OBS)
+    _, lp, nf, st = oracle_c.simulate_batch("simple_pk", {"k_abs": th[0], "CL": th[1]}, tgrid, OBS, rtol=1e-6, atol=1e-6,
+                                            threads=cores, data=data, sigma=1.0)
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "trajectories/s", "cores": 1, "kind": "port",
-            "sample": f"{n} of the {B_PER_GPU} draws, python loop + scipy LSODA rtol=atol=1e-6 "
-                      "(literal restatement of petab_factory.py:228-246)", "seconds": dt}
+    return {"value": sample / dt, "unit": "trajectories/s", "cores": cores, "kind": "port",
+            "sample": f"first {sample} of the {B_PER_GPU} draws; C restatement oracle/parvar_oracle.c (variable-order BDF + "
+                      f"Newton + dense LU as CVODE, rtol=atol=1e-6 as petab_factory.py:183-189), OpenMP {cores} threads; "
+                      f"{st[0] / sample:.0f} steps/trajectory",
+            "seconds": dt, "failed": nf}
 
 
 def run_reference(args) -> None:
@@ -182,7 +171,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--cpu-sample", type=int, default=400000)
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="trajectories per GPU (default = the named config)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -238,10 +238,15 @@ def main() -> None:
     bytes_per_launch = B * (8 * 2 + 8 * T * 3 + 8 + 4 + 8)
 
     # ---- timed region: value ------------------------------------------------------------------------------
-    n0 = rt.launch_count()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        # nvidia-smi needs ~0.3 s to start reporting: keep the GPU under the same load until it does
+        t_spin = time.perf_counter()
+        while time.perf_counter() - t_spin < 0.5:
+            pb.simulate_logp(P, Y, logp, status=status, steps=steps, stream=stream)
+            torch.cuda.synchronize()
+    n0 = rt.launch_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     barrier()

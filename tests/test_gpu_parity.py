@@ -280,3 +280,136 @@ def test_ode_sample_simulator_drop_in(cuda_lib, oracle):
         noisy = oracle.add_noise(clean[i], 0.05)
         got = np.stack([dsn[v].values[i] for v in dsn.data_vars], axis=1)
         np.testing.assert_array_equal(got, noisy)
+
+
+def test_c3_chains_times_individuals_logp_grad(cuda_lib, rt, oracle):
+    """BASELINE config C3 shape: n_chains x n_individuals trajectories, every individual has its own data and its own
+    (k_abs_i, CL_i); logp per chain = deterministic segment sum, gradient per individual.  Oracle-checked at
+    8 x 200 (exact solution + Van Loan sensitivities), shape/consistency-checked at the full 8 x 1000."""
+    torch = _torch()
+    opt = pkg("optimization.petab_optimization")
+    T = 20
+    t = np.linspace(0, 100, T)
+    obs = ["y_gut", "y_cent", "y_peri"]
+    for n_chains, n_ind, check in ((8, 200, True), (8, 1000, False)):
+        truth_th = np.stack([lognormal_draws(50, n_ind), lognormal_draws(51, n_ind)])
+        rs = np.random.RandomState(52)
+        y = np.stack([oracle.simple_pk_exact({"k_abs": a, "CL": c}, t) for a, c in zip(*truth_th)])     # [n_ind, T, 3]
+        y = y * (1.0 + 0.05 * rs.normal(size=y.shape))
+        stats = np.stack([opt.sufficient_statistics(y[i:i + 1], rt.NOISE_NORMAL) for i in range(n_ind)], axis=-1)
+        pb = _problem(rt, "simple_pk", ["k_abs", "CL"], t, obs, rtol=1e-9, atol=1e-13)
+        pb.set_data(stats, 0.05, rt.NOISE_NORMAL)
+        th = np.concatenate([np.stack([lognormal_draws(60 + c, n_ind), lognormal_draws(80 + c, n_ind)]) for c in range(n_chains)], axis=1)
+        B = n_chains * n_ind
+        P = torch.from_numpy(th).cuda()
+        lp = torch.empty(B, dtype=torch.float64, device="cuda")
+        g = torch.empty((2, B), dtype=torch.float64, device="cuda")
+        seg = torch.empty(n_chains, dtype=torch.float64, device="cuda")
+        status = torch.empty(B, dtype=torch.int32, device="cuda")
+        pb.logp_grad(P, lp, g, seg_len=n_ind, logp_seg=seg, status=status)
+        torch.cuda.synchronize()
+        assert int(status.abs().sum()) == 0
+        lp_h, g_h, seg_h = lp.cpu().numpy(), g.cpu().numpy(), seg.cpu().numpy()
+        np.testing.assert_allclose(seg_h, lp_h.reshape(n_chains, n_ind).sum(axis=1), rtol=1e-12)
+        # same call through the host-buffer entry point: bit identical
+        lp2, g2, seg2, nf = pb.logp_host(th, seg_len=n_ind, grad=True)
+        assert nf == 0 and np.array_equal(lp2, lp_h) and np.array_equal(g2, g_h) and np.array_equal(seg2, seg_h)
+        if check:
+            for c in (0, n_chains - 1):
+                ref = np.empty(n_ind)
+                for i in range(n_ind):
+                    over = {"k_abs": th[0, c * n_ind + i], "CL": th[1, c * n_ind + i]}
+                    f = oracle.simple_pk_exact(over, t)
+                    ref[i] = oracle.loglik_normal(f, y[i], 0.05)
+                    if i < 5:
+                        s = oracle.simple_pk_exact_sens(over, t)
+                        rg = oracle.loglik_normal_grad(f, s, y[i], 0.05)
+                        np.testing.assert_allclose(g_h[:, c * n_ind + i], rg, rtol=1e-6, atol=1e-6 * np.abs(rg).max())
+                np.testing.assert_allclose(lp_h[c * n_ind:(c + 1) * n_ind], ref, rtol=1e-6)
+                np.testing.assert_allclose(seg_h[c], ref.sum(), rtol=1e-6)
+
+
+def test_c5_sweep_problems_in_one_launch(cuda_lib, rt, oracle):
+    """BASELINE config C5: many independent PEtab problems of one model (different sample counts, noise levels)
+    evaluated in ONE launch - the problem index is just another data set.  Pooled statistics per (problem, group)."""
+    opt = pkg("optimization.petab_optimization")
+    T = 10
+    t = np.linspace(0, 100, T)
+    obs = ["y_gut", "y_cent", "y_peri"]
+    rs = np.random.RandomState(7)
+    problems = []
+    for n_samples in (1, 2, 5, 20, 80):            # factories/__init__.py:12-20 "samples"
+        for cv in (0.0, 0.05, 0.5):                 # "noise_cvs"
+            th = np.stack([lognormal_draws(int(rs.randint(1 << 30)), n_samples), lognormal_draws(int(rs.randint(1 << 30)), n_samples)])
+            y = np.stack([oracle.simple_pk_exact({"k_abs": a, "CL": c}, t) for a, c in zip(*th)])
+            problems.append(y * (1.0 + cv * rs.normal(size=y.shape)))
+    n_prob = len(problems)
+    stats = np.stack([opt.sufficient_statistics(y, rt.NOISE_NORMAL) for y in problems], axis=-1)          # [3,T,3,n_prob]
+    pb = _problem(rt, "simple_pk", ["k_abs", "CL"], t, obs, rtol=1e-9, atol=1e-13)
+    pb.set_data(stats, 1.0, rt.NOISE_NORMAL)       # sigma = 1 as the reference writes (quirk Q5)
+    n_x = 7                                        # 7 candidate parameter vectors per problem
+    X = np.stack([lognormal_draws(300, n_x), lognormal_draws(301, n_x)])                                   # [2, n_x]
+    P = np.repeat(X, n_prob, axis=1)               # trajectory x*n_prob + q  -> data set q
+    lp, g, _, nf = pb.logp_host(P, grad=True)
+    assert nf == 0
+    for x in (0, n_x - 1):
+        over = {"k_abs": X[0, x], "CL": X[1, x]}
+        f = oracle.simple_pk_exact(over, t)
+        s = oracle.simple_pk_exact_sens(over, t)
+        for q in (0, 4, n_prob - 1):
+            np.testing.assert_allclose(lp[x * n_prob + q], oracle.loglik_normal(f, problems[q], 1.0), rtol=1e-6)
+            rg = oracle.loglik_normal_grad(f, s, problems[q], 1.0)
+            np.testing.assert_allclose(g[:, x * n_prob + q], rg, rtol=1e-6, atol=1e-6 * np.abs(rg).max())
+
+
+def test_petab_objective_pypesto_conventions(cuda_lib, rt, oracle):
+    """The objective mirror: negative log posterior, x ordered par-major/group-minor, priors, literal mode (quirk Q4)."""
+    opt = pkg("optimization.petab_optimization")
+    t = np.linspace(0, 100, 21)
+    obs = ["y_cent", "y_gut", "y_peri"]                       # factories/simple_pk.py:4-17 order
+    cols = [oracle.SIMPLE_PK.states.index(o) for o in obs]
+    rs = np.random.RandomState(3)
+    groups, ys = [], {}
+    for gid, (ka, cl) in (("MALE", (0.8, 1.1)), ("FEMALE", (1.3, 0.6))):
+        y = np.stack([oracle.simple_pk_exact({"k_abs": ka, "CL": cl}, t)[:, cols]] * 4)
+        y = y * (1 + 0.05 * rs.normal(size=y.shape))
+        groups.append(opt.GroupData(gid, y))
+        ys[gid] = y
+    priors = {"k_abs_MALE": (0.5, 1.0), "k_abs_FEMALE": (1.0, 1.0), "CL_MALE": (1.0, 1.0), "CL_FEMALE": (0.5, 1.0)}
+    obj = opt.PetabObjective("simple_pk", ["k_abs", "CL"], groups, t, obs, sigma=1.0, priors=priors, rtol=1e-9, atol=1e-13)
+    assert obj.x_names == ["k_abs_MALE", "k_abs_FEMALE", "CL_MALE", "CL_FEMALE"]
+    x = np.array([0.9, 1.2, 1.0, 0.7])
+    fval, grad = obj(x, sensi_orders=(0, 1))
+    ref, ref_g = 0.0, np.zeros(4)
+    for gi, gid in enumerate(("MALE", "FEMALE")):
+        over = {"k_abs": x[gi], "CL": x[2 + gi]}
+        f = oracle.simple_pk_exact(over, t)[:, cols]
+        s = oracle.simple_pk_exact_sens(over, t)[:, cols, :]
+        ref -= oracle.loglik_normal(f, ys[gid], 1.0)
+        gg = oracle.loglik_normal_grad(f, s, ys[gid], 1.0)
+        ref_g[gi] -= gg[0]
+        ref_g[2 + gi] -= gg[1]
+    lp, glp = oracle.log_prior_normal(x, [0.5, 1.0, 1.0, 0.5], [1.0, 1.0, 1.0, 1.0])
+    ref -= lp
+    ref_g -= glp
+    assert fval == pytest.approx(ref, rel=1e-6)
+    np.testing.assert_allclose(grad, ref_g, rtol=1e-6, atol=1e-6 * np.abs(ref_g).max())
+    assert obj.fun(x) == pytest.approx(fval, rel=1e-12)
+    assert obj(x, (0,), return_dict=True)["fval"] == pytest.approx(fval, rel=1e-12)
+    # batched entry = the single-point calls
+    X = np.stack([x, x * 1.1, x * 0.7])
+    L, G = obj.logp_and_grad(X)
+    assert L[0] == pytest.approx(-fval, rel=1e-12) and np.allclose(G[0], -grad, rtol=1e-12)
+    # literal mode (quirk Q4): observed species start at 0, no dose -> the model output is identically 0, the
+    # likelihood is constant in x and the gradient comes from the prior alone
+    lit = opt.PetabObjective("simple_pk", ["k_abs", "CL"], groups, t, obs, sigma=1.0, priors=priors, mode="literal")
+    f1, g1 = lit(x, (0, 1))
+    f2, g2 = lit(x * 2.0, (0, 1))
+    const = sum(-oracle.loglik_normal(np.zeros_like(ys[g][0]), ys[g], 1.0) for g in ys)
+    assert f1 == pytest.approx(const - oracle.log_prior_normal(x, [0.5, 1.0, 1.0, 0.5], [1.0] * 4)[0], rel=1e-9)
+    np.testing.assert_allclose(g1, -oracle.log_prior_normal(x, [0.5, 1.0, 1.0, 0.5], [1.0] * 4)[1], rtol=1e-9, atol=1e-12)
+    assert f2 != f1
+    # failed integration -> inf / nan, not an exception
+    obj.problem.set_solver(method=rt.METHOD_DOPRI5, rtol=1e-9, atol=1e-13, max_steps=3)
+    fbad, gbad = obj(x, (0, 1))
+    assert np.isinf(fbad) and np.all(np.isnan(gbad))

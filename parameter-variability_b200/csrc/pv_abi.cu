@@ -299,9 +299,8 @@ extern "C" int pv_problem_set_data(pv_problem* p, int noise_model, int n_data, c
 // ---------------------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------------------
-template <class M, int METHOD, int MODE, bool OBSID>
-static cudaError_t launch_one(const pv_launch_params& lp, size_t shmem, int num_sms, cudaStream_t s) {
-    auto kern = pv_batch_kernel<M, METHOD, MODE, OBSID>;
+template <class KernelT>
+static cudaError_t launch_persistent(KernelT kern, const pv_launch_params& lp, size_t shmem, int num_sms, cudaStream_t s) {
     if (shmem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
         if (e != cudaSuccess) return e;
@@ -310,12 +309,17 @@ static cudaError_t launch_one(const pv_launch_params& lp, size_t shmem, int num_
     int per_sm = 0;
     cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PV_BLOCK, shmem);
     if (eo != cudaSuccess) return eo;
-    if (per_sm < 1) per_sm = 1;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     const int64_t want = (lp.B + PV_BLOCK - 1) / PV_BLOCK;
     const int64_t blocks = std::min<int64_t>(want, (int64_t)num_sms * per_sm);
     kern<<<(unsigned)blocks, PV_BLOCK, shmem, s>>>(lp);
     g_launches.fetch_add(1);
     return cudaGetLastError();
+}
+
+template <class M, int METHOD, int MODE, bool OBSID>
+static cudaError_t launch_one(const pv_launch_params& lp, size_t shmem, int num_sms, cudaStream_t s) {
+    return launch_persistent(pv_batch_kernel<M, METHOD, MODE, OBSID>, lp, shmem, num_sms, s);
 }
 
 template <class M>
@@ -349,12 +353,14 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     if (!p) return fail(PV_E_ARG, "problem is NULL");
     if (B < 0) return fail(PV_E_ARG, "B < 0");
     if (B == 0) return 0;
-    if (B > ((int64_t)1 << 31) * PV_BLOCK / 2) return fail(PV_E_ARG, "B too large for one launch");
+    if (B >= ((int64_t)1 << 31)) return fail(PV_E_ARG, "B too large for one launch (< 2^31)");
     if (p->tgrid.empty()) return fail(PV_E_STATE, "timepoints not set");
     const bool need_logp = (mode & PV_MODE_LOGP) != 0;
     const bool sens = (mode & PV_MODE_SENS) != 0;
     if (p->obs_idx.empty()) return fail(PV_E_STATE, "observables not set");
     if (need_logp && p->stats.empty()) return fail(PV_E_STATE, "data not set");
+    if ((int64_t)p->tgrid.size() * (int64_t)p->obs_idx.size() * (int64_t)std::max(p->n_data, 1) >= ((int64_t)1 << 29))
+        return fail(PV_E_ARG, "T * n_obs * n_data too large (< 2^29)");
     if (!p->col_target.empty() && !P) return fail(PV_E_ARG, "P is NULL but columns are configured");
     if (sens && p->tab->n_sens == 0) return fail(PV_E_MODEL, "model was generated without sensitivity parameters");
     if (mode == PV_MODE_TRAJ_SENS && !S) return fail(PV_E_ARG, "S is NULL");

@@ -125,6 +125,44 @@ struct pv_dopri5_cost {
 // status of a lane that still has work to do
 #define PV_RUNNING (-1)
 
+// Dense-output record of one accepted DOPRI5 step: everything needed to evaluate the 4th-order interpolant at
+// the grid points j0 <= j < j1 that fall into (t, tn].  The batch kernel queues these records in shared memory
+// and evaluates them 32 at a time with full warps instead of inside the (divergent) accept branch.
+template <int N>
+struct pv_dense_rec {
+    double t, h, tn;
+    int j0, j1;
+    double y[N], yn[N], bs[N], r4[N], r5[N];
+    PV_HD void eval(double tj, double hinv, double (&yo)[N]) const {
+        if (tj >= tn) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) yo[i] = yn[i];
+        } else {
+            const double th = (tj - t) * hinv, th1 = 1.0 - th;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double yd = yn[i] - y[i];
+                yo[i] = fma(th, fma(th1, fma(th, fma(th1, r5[i], r4[i]), bs[i]), yd), y[i]);
+            }
+        }
+    }
+};
+
+// evaluate a record right away, on the lane that produced it (host checks, Rosenbrock-free static schedule)
+template <int N, class Out>
+struct pv_emit_now {
+    const double* tgrid;
+    Out& out;
+    PV_HD void operator()(const pv_dense_rec<N>& rec, bool /*final*/) {
+        const double hinv = pv_drcp(rec.h);
+        for (int j = rec.j0; j < rec.j1; ++j) {
+            double yo[N];
+            rec.eval(tgrid[j], hinv, yo);
+            out(j, tgrid[j], yo);
+        }
+    }
+};
+
 // Per-lane DOPRI5 state machine: start() once, then step() until it returns something other than
 // PV_RUNNING.  The batch kernels drive it either one trajectory per thread for the whole launch
 // (static schedule) or with lane refill (a lane that finishes picks the next trajectory while its
@@ -192,10 +230,18 @@ struct pv_dopri5_lane {
         return PV_RUNNING;
     }
 
-    // one attempted step
+    // one attempted step, dense output evaluated immediately through `out`
     template <class Out>
     PV_HD int step(const typename Sys::Consts& ks, const double* tgrid, int T, double rtol, double atol,
                    int max_steps, Out& out) {
+        pv_emit_now<N, Out> emit{tgrid, out};
+        return step_emit(ks, tgrid, T, rtol, atol, max_steps, emit);
+    }
+
+    // one attempted step; an accepted step that covers grid points hands a pv_dense_rec to `emit`
+    template <class Emit>
+    PV_HD int step_emit(const typename Sys::Consts& ks, const double* tgrid, int T, double rtol, double atol,
+                        int max_steps, Emit& emit) {
         if (nstep >= max_steps) return PV_ERR_MAX_STEPS;
         ++nstep;
         bool last = false;
@@ -264,32 +310,27 @@ struct pv_dopri5_lane {
             ++st.accepted;
             const double tn = last ? tend : t + h;
             if (jout < T && tgrid[jout] <= tn) {
-                double r5[N];
+                pv_dense_rec<N> rec;
+                rec.t = t;
+                rec.h = h;
+                rec.tn = tn;
 #pragma unroll
-                for (int i = 0; i < N; ++i)
-                    r5[i] = h * fma(pv_dp5[26], k1[i],
-                                    fma(pv_dp5[27], k3[i],
-                                        fma(pv_dp5[28], k4[i], fma(pv_dp5[29], k5[i], fma(pv_dp5[30], k6[i], pv_dp5[31] * k7[i])))));
-                const double hinv = pv_drcp(h);
+                for (int i = 0; i < N; ++i) {
+                    const double yd = yn[i] - y[i];
+                    rec.y[i] = y[i];
+                    rec.yn[i] = yn[i];
+                    rec.bs[i] = fma(h, k1[i], -yd);
+                    rec.r4[i] = yd - fma(h, k7[i], rec.bs[i]);
+                    rec.r5[i] = h * fma(pv_dp5[26], k1[i],
+                                        fma(pv_dp5[27], k3[i],
+                                            fma(pv_dp5[28], k4[i], fma(pv_dp5[29], k5[i], fma(pv_dp5[30], k6[i], pv_dp5[31] * k7[i])))));
+                }
+                rec.j0 = jout;
                 do {
-                    const double tj = tgrid[jout];
-                    double yo[N];
-                    if (tj >= tn) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) yo[i] = yn[i];
-                    } else {
-                        const double th = (tj - t) * hinv, th1 = 1.0 - th;
-#pragma unroll
-                        for (int i = 0; i < N; ++i) {
-                            const double yd = yn[i] - y[i];
-                            const double bs = fma(h, k1[i], -yd);
-                            const double r4 = yd - fma(h, k7[i], bs);
-                            yo[i] = fma(th, fma(th1, fma(th, fma(th1, r5[i], r4), bs), yd), y[i]);
-                        }
-                    }
-                    out(jout, tj, yo);
                     ++jout;
                 } while (jout < T && tgrid[jout] <= tn);
+                rec.j1 = jout;
+                emit(rec, last || jout >= T);
             }
             float fac = fac11 / pv_powf_fast(facold, 0.04f);
             fac = fmaxf(0.1f, fminf(5.0f, fac * (1.0f / 0.9f)));

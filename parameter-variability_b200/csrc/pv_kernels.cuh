@@ -11,6 +11,9 @@
 #define PV_MAX_COLS 8
 #define PV_MAX_OBS 16
 #define PV_BLOCK 128
+#ifndef PV_MINB_SMALL
+#define PV_MINB_SMALL 4
+#endif
 
 // mode = bit set: what a launch produces
 enum pv_mode : int {
@@ -57,6 +60,8 @@ PV_D double pv_pick(const double (&a)[N], int block, int idx) {
 // OBSID = true: the observables are exactly the model's states in order (n_obs == NX, obs_idx[k] == k), so the
 // selection chains, the indexed constant loads and the k-loop overhead disappear (the common case of the
 // cheap non-stiff models, where the per-output code is a sizeable share of a step).
+// Index arithmetic is kept in 32 bits wherever the host has checked the ranges (T * n_obs * n_data < 2^31,
+// B < 2^31); only the final row offset into Y / S is 64-bit, one IMAD.WIDE per grid point.
 template <class M, int MODE, bool OBSID>
 struct pv_sink {
     static constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
@@ -66,24 +71,24 @@ struct pv_sink {
     const pv_launch_params& p;
     const double* sh_stats;   // shared copy when n_data == 1, else nullptr
     int64_t b;                // trajectory
-    int64_t d;                // data set of this trajectory
+    int d;                    // data set of this trajectory (b % n_data, computed once per trajectory)
     double obs[M::NX];
     double lp;
     double g[M::NSD];
 
-    PV_D void one(int j, int k, double f, const double (&df)[M::NSD], double log_norm, double inv_sigma2) {
+    // yrow = &Y[j][0][b] (or nullptr), srow = &S[0][j][0][b]; so = index of (j, 0, d) in one statistics plane
+    PV_D void one(int k, double f, const double (&df)[M::NSD], double* yrow, double* srow, int so, int plane,
+                  double log_norm, double inv_sigma2) {
         const int n_obs = OBSID ? M::NX : p.n_obs;
         if constexpr (TRAJ) {
-            const int64_t row = (int64_t)j * n_obs + k;
-            if (p.Y) p.Y[row * p.B + b] = f;
+            if (yrow) yrow[(int64_t)k * p.B] = f;
             if constexpr (SENS) {
 #pragma unroll
-                for (int s = 0; s < M::NS; ++s) p.S[((int64_t)s * p.T * n_obs + row) * p.B + b] = df[s];
+                for (int s = 0; s < M::NS; ++s) srow[((int64_t)s * p.T * n_obs + k) * p.B] = df[s];
             }
         }
         if constexpr (LOGP) {
-            const int64_t plane = (int64_t)p.T * n_obs * p.n_data;
-            const int64_t o = ((int64_t)j * n_obs + k) * p.n_data + d;
+            const int o = so + k * p.n_data;
             double n, s1, s2;
             if (sh_stats) {
                 n = sh_stats[o]; s1 = sh_stats[plane + o]; s2 = sh_stats[2 * plane + o];
@@ -110,6 +115,16 @@ struct pv_sink {
     }
 
     PV_D void operator()(int j, double, const double (&z)[N]) {
+        const int n_obs = OBSID ? M::NX : p.n_obs;
+        double* yrow = nullptr;
+        double* srow = nullptr;
+        if constexpr (TRAJ) {
+            const int64_t off = (int64_t)(j * n_obs) * p.B + b;
+            yrow = p.Y ? p.Y + off : nullptr;
+            if constexpr (SENS) srow = p.S + off;
+        }
+        const int plane = p.T * n_obs * p.n_data;
+        const int so = j * n_obs * p.n_data + d;
         if constexpr (OBSID) {
 #pragma unroll
             for (int k = 0; k < M::NX; ++k) {
@@ -118,10 +133,10 @@ struct pv_sink {
 #pragma unroll
                     for (int s = 0; s < M::NS; ++s) df[s] = z[M::NX * (1 + s) + k] * obs[k];
                 }
-                one(j, k, z[k] * obs[k], df, p.log_norm[k], p.inv_sigma2[k]);
+                one(k, z[k] * obs[k], df, yrow, srow, so, plane, p.log_norm[k], p.inv_sigma2[k]);
             }
         } else {
-            for (int k = 0; k < p.n_obs; ++k) {
+            for (int k = 0; k < n_obs; ++k) {
                 const int idx = p.obs_idx[k];
                 const double sc = pv_pick<M::NX>(obs, 0, idx);
                 double df[M::NSD];
@@ -129,7 +144,7 @@ struct pv_sink {
 #pragma unroll
                     for (int s = 0; s < M::NS; ++s) df[s] = pv_pick<M::NX>(z, 1 + s, idx) * sc;
                 }
-                one(j, k, pv_pick<M::NX>(z, 0, idx) * sc, df, p.log_norm[k], p.inv_sigma2[k]);
+                one(k, pv_pick<M::NX>(z, 0, idx) * sc, df, yrow, srow, so, plane, p.log_norm[k], p.inv_sigma2[k]);
             }
         }
     }
@@ -153,8 +168,16 @@ struct pv_lane_of<M, 2, SENS> {
 // Refills are batched (>= p.refill_min idle lanes, or nobody left working) so the start-up code
 // (parameter load, hoist, initial step size) runs with several lanes active.  Results do not depend on
 // the schedule: every trajectory is integrated by exactly one lane from its own inputs.
+// resident CTAs per SM the register allocation must allow: 4 (128 registers) for the small explicit systems, where
+// occupancy hides the fp64 dependency latency; the augmented / Rosenbrock kernels take what they need
+template <class M, int METHOD, int MODE>
+struct pv_kernel_traits {
+    static constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
+    static constexpr int MIN_BLOCKS = (METHOD == 1 && pv_system<M, SENS>::N <= 4) ? PV_MINB_SMALL : 1;
+};
+
 template <class M, int METHOD, int MODE, bool OBSID>
-__global__ void __launch_bounds__(PV_BLOCK)
+__global__ void __launch_bounds__(PV_BLOCK, pv_kernel_traits<M, METHOD, MODE>::MIN_BLOCKS)
 pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
     constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
     constexpr bool LOGP = (MODE & PV_MODE_LOGP) != 0;
@@ -250,7 +273,7 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
                             for (int i = 0; i < M::NX; ++i) z[M::NX * (1 + s) + i] = over[i] ? 0.0 : dy0[s][i];
                     }
                     sink.b = b;
-                    sink.d = b % p.n_data;
+                    sink.d = (int)(b % p.n_data);
                     sink.lp = 0.0;
 #pragma unroll
                     for (int s = 0; s < M::NSD; ++s) sink.g[s] = 0.0;

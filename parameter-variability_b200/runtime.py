@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "lib" / "libparvar_b200.so"
+LIB_PATH = Path(__import__("os").environ.get("PARVAR_B200_LIB", PKG_DIR / "lib" / "libparvar_b200.so"))
 
 METHOD_AUTO, METHOD_DOPRI5, METHOD_RODAS4 = 0, 1, 2
 NOISE_NORMAL, NOISE_LOGNORMAL = 0, 1

@@ -130,6 +130,12 @@ int pv_logp(pv_problem* p, int64_t B, const double* P_dev, double* logp_dev, int
 int pv_logp_grad(pv_problem* p, int64_t B, const double* P_dev, double* logp_dev, double* grad_dev,
                  int64_t seg_len, double* logp_seg_dev, int32_t* status_dev, int32_t* steps_dev, void* stream);
 
+/* logp, gradient and the Fisher information matrix FIM = sum_obs (df/dtheta)(df/dtheta)^T / sigma^2 that AMICI hands
+ * to fides as Hessian approximation (`FidesOptimizer`, petab_optimization.py:113-116).
+ * fim_dev [n_sens (n_sens + 1) / 2][B]: upper triangle, row-major ((0,0),(0,1),..,(1,1),..).                        */
+int pv_logp_grad_fim(pv_problem* p, int64_t B, const double* P_dev, double* logp_dev, double* grad_dev,
+                     double* fim_dev, int32_t* status_dev, int32_t* steps_dev, void* stream);
+
 /* trajectories AND logp from one integration pass (BASELINE config 2: "trajectories + logp") */
 int pv_simulate_logp(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, double* logp_dev,
                      int32_t* status_dev, int32_t* steps_dev, void* stream);
@@ -143,6 +149,8 @@ int pv_logp_host(pv_problem* p, int64_t B, const double* P_host, double* logp_ho
                  double* logp_seg_host);
 int pv_logp_grad_host(pv_problem* p, int64_t B, const double* P_host, double* logp_host, double* grad_host,
                       int64_t seg_len, double* logp_seg_host);
+int pv_logp_grad_fim_host(pv_problem* p, int64_t B, const double* P_host, double* logp_host, double* grad_host,
+                          double* fim_host, int64_t seg_len, double* logp_seg_host);
 
 /* page-locked host memory for the *_host calls (cudaHostAlloc / cudaFreeHost); NULL on failure */
 void* pv_host_alloc(size_t bytes);

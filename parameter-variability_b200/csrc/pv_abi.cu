@@ -333,7 +333,9 @@ static cudaError_t launch_model(int method, int mode, bool obsid, const pv_launc
         return launch_one<M, METH, MODE, false>(lp, shmem, num_sms, s);                          \
     }
     PV_CASE(1, PV_MODE_TRAJ) PV_CASE(1, PV_MODE_LOGP) PV_CASE(1, PV_MODE_TRAJ_LOGP) PV_CASE(1, PV_MODE_LOGP_GRAD) PV_CASE(1, PV_MODE_TRAJ_SENS)
+    PV_CASE(1, PV_MODE_LOGP_GRAD_FIM)
     PV_CASE(2, PV_MODE_TRAJ) PV_CASE(2, PV_MODE_LOGP) PV_CASE(2, PV_MODE_TRAJ_LOGP) PV_CASE(2, PV_MODE_LOGP_GRAD) PV_CASE(2, PV_MODE_TRAJ_SENS)
+    PV_CASE(2, PV_MODE_LOGP_GRAD_FIM)
 #undef PV_CASE
     return cudaErrorInvalidValue;
 }
@@ -349,7 +351,7 @@ static int sync_values(pv_problem* p, cudaStream_t s) {
 }
 
 static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y, double* S, double* logp,
-                  double* grad, int32_t* status, int32_t* steps, cudaStream_t s) {
+                  double* grad, int32_t* status, int32_t* steps, cudaStream_t s, double* fim = nullptr) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
     if (B < 0) return fail(PV_E_ARG, "B < 0");
     if (B == 0) return 0;
@@ -365,7 +367,8 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     if (sens && p->tab->n_sens == 0) return fail(PV_E_MODEL, "model was generated without sensitivity parameters");
     if (mode == PV_MODE_TRAJ_SENS && !S) return fail(PV_E_ARG, "S is NULL");
     if (need_logp && !logp) return fail(PV_E_ARG, "logp is NULL");
-    if (mode == PV_MODE_LOGP_GRAD && !grad) return fail(PV_E_ARG, "grad is NULL");
+    if ((mode & PV_MODE_LOGP) && (mode & PV_MODE_SENS) && !grad) return fail(PV_E_ARG, "grad is NULL");
+    if ((mode & PV_MODE_FIM) && !fim) return fail(PV_E_ARG, "fim is NULL");
     CUDA_OK(cudaSetDevice(p->device));
     if (int rc = sync_values(p, s)) return rc;
 
@@ -381,6 +384,7 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     lp.S = S;
     lp.logp = logp;
     lp.grad = grad;
+    lp.fim = fim;
     lp.status = status;
     lp.steps = steps;
     lp.rtol = p->rtol;
@@ -460,6 +464,12 @@ extern "C" int pv_logp_grad(pv_problem* p, int64_t B, const double* P_dev, doubl
     return segment_sum(logp_dev, B, seg_len, logp_seg_dev, (cudaStream_t)stream);
 }
 
+extern "C" int pv_logp_grad_fim(pv_problem* p, int64_t B, const double* P_dev, double* logp_dev, double* grad_dev,
+                                double* fim_dev, int32_t* status_dev, int32_t* steps_dev, void* stream) {
+    return launch(p, PV_MODE_LOGP_GRAD_FIM, B, P_dev, nullptr, nullptr, logp_dev, grad_dev, status_dev, steps_dev,
+                  (cudaStream_t)stream, fim_dev);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host-buffer pipelines
 // ---------------------------------------------------------------------------------------------------------
@@ -530,7 +540,7 @@ extern "C" int pv_simulate_host(pv_problem* p, int64_t B, const double* P_host, 
 }
 
 static int logp_host_impl(pv_problem* p, bool with_grad, int64_t B, const double* P_host, double* logp_host,
-                          double* grad_host, int64_t seg_len, double* logp_seg_host) {
+                          double* grad_host, int64_t seg_len, double* logp_seg_host, double* fim_host = nullptr) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
     if (B <= 0) return B == 0 ? 0 : fail(PV_E_ARG, "B < 0");
     if (seg_len > 0 && (B % seg_len)) return fail(PV_E_ARG, "B must be a multiple of seg_len");
@@ -541,26 +551,35 @@ static int logp_host_impl(pv_problem* p, bool with_grad, int64_t B, const double
     const size_t bytesP = sizeof(double) * (size_t)std::max(n_cols, 1) * B;
     const size_t bytesL = sizeof(double) * (size_t)B;
     const size_t bytesG = with_grad ? sizeof(double) * (size_t)ns * B : 0;
+    const size_t bytesF = fim_host ? sizeof(double) * (size_t)(ns * (ns + 1) / 2) * B : 0;
     const size_t bytesS = sizeof(double) * (size_t)std::max<int64_t>(n_seg, 1);
     const size_t bytesI = sizeof(int32_t) * (size_t)B;
-    if (int rc = ensure_dev(p, 0, bytesP + bytesL + bytesG + bytesS + bytesI)) return rc;
+    if (int rc = ensure_dev(p, 0, bytesP + bytesL + bytesG + bytesF + bytesS + bytesI)) return rc;
     cudaStream_t s = p->streams[0];
     double* dP = p->stage_dev[0];
     double* dL = (double*)((char*)dP + bytesP);
     double* dG = (double*)((char*)dL + bytesL);
-    double* dS = (double*)((char*)dG + bytesG);
+    double* dF = (double*)((char*)dG + bytesG);
+    double* dS = (double*)((char*)dF + bytesF);
     int32_t* dStatus = (int32_t*)((char*)dS + bytesS);
     CUDA_OK(cudaMemsetAsync(p->d_failed, 0, sizeof(int), s));
     if (n_cols > 0) CUDA_OK(cudaMemcpyAsync(dP, P_host, sizeof(double) * (size_t)n_cols * B, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaEventRecord(p->ev0, s));
-    int rc = with_grad ? pv_logp_grad(p, B, n_cols ? dP : nullptr, dL, dG, seg_len, n_seg ? dS : nullptr, dStatus, nullptr, s)
+    int rc;
+    if (fim_host) {
+        rc = pv_logp_grad_fim(p, B, n_cols ? dP : nullptr, dL, dG, dF, dStatus, nullptr, s);
+        if (!rc) rc = segment_sum(dL, B, seg_len, n_seg ? dS : nullptr, s);
+    } else {
+        rc = with_grad ? pv_logp_grad(p, B, n_cols ? dP : nullptr, dL, dG, seg_len, n_seg ? dS : nullptr, dStatus, nullptr, s)
                        : pv_logp(p, B, n_cols ? dP : nullptr, dL, seg_len, n_seg ? dS : nullptr, dStatus, nullptr, s);
+    }
     if (rc) return rc;
     CUDA_OK(cudaEventRecord(p->ev1, s));
     pv_count_failed_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(dStatus, B, p->d_failed);
     g_launches.fetch_add(1);
     if (logp_host) CUDA_OK(cudaMemcpyAsync(logp_host, dL, bytesL, cudaMemcpyDeviceToHost, s));
     if (with_grad && grad_host) CUDA_OK(cudaMemcpyAsync(grad_host, dG, bytesG, cudaMemcpyDeviceToHost, s));
+    if (fim_host) CUDA_OK(cudaMemcpyAsync(fim_host, dF, bytesF, cudaMemcpyDeviceToHost, s));
     if (n_seg && logp_seg_host) CUDA_OK(cudaMemcpyAsync(logp_seg_host, dS, sizeof(double) * n_seg, cudaMemcpyDeviceToHost, s));
     int failed = 0;
     CUDA_OK(cudaMemcpyAsync(&failed, p->d_failed, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -589,6 +608,12 @@ extern "C" void* pv_host_alloc(size_t bytes) {
 }
 extern "C" void pv_host_free(void* ptr) {
     if (ptr) cudaFreeHost(ptr);
+}
+
+extern "C" int pv_logp_grad_fim_host(pv_problem* p, int64_t B, const double* P_host, double* logp_host, double* grad_host,
+                                     double* fim_host, int64_t seg_len, double* logp_seg_host) {
+    if (!fim_host) return fail(PV_E_ARG, "fim_host is NULL");
+    return logp_host_impl(p, true, B, P_host, logp_host, grad_host, seg_len, logp_seg_host, fim_host);
 }
 
 extern "C" double pv_last_kernel_ms(const pv_problem* p) { return p ? p->last_kernel_ms : -1.0; }

@@ -23,6 +23,8 @@ enum pv_mode : int {
     PV_MODE_TRAJ_LOGP = 3,
     PV_MODE_LOGP_GRAD = 6,
     PV_MODE_TRAJ_SENS = 5,
+    PV_MODE_FIM = 8,         // also accumulate the Fisher information (needs LOGP | SENS)
+    PV_MODE_LOGP_GRAD_FIM = 14,
 };
 
 struct pv_launch_params {
@@ -36,6 +38,7 @@ struct pv_launch_params {
     double* S;                 // [NS][T][n_obs][B]
     double* logp;              // [B]
     double* grad;              // [NS][B]
+    double* fim;               // [NS(NS+1)/2][B]  upper triangle, row-major
     int32_t* status;           // [B]
     int32_t* steps;            // [2][B]
     double rtol, atol;
@@ -67,7 +70,9 @@ struct pv_sink {
     static constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
     static constexpr bool TRAJ = (MODE & PV_MODE_TRAJ) != 0;
     static constexpr bool LOGP = (MODE & PV_MODE_LOGP) != 0;
+    static constexpr bool FIM = (MODE & PV_MODE_FIM) != 0;
     static constexpr int N = pv_system<M, SENS>::N;
+    static constexpr int NFIM = FIM ? M::NSD * (M::NSD + 1) / 2 : 1;
     const pv_launch_params& p;
     const double* sh_stats;   // shared copy when n_data == 1, else nullptr
     int64_t b;                // trajectory
@@ -75,6 +80,7 @@ struct pv_sink {
     double obs[M::NX];
     double lp;
     double g[M::NSD];
+    double fim[NFIM];         // sum over measurements of (df/dtheta)(df/dtheta)^T / sigma^2  (AMICI's FIM)
 
     // yrow = &Y[j][0][b] (or nullptr), srow = &S[0][j][0][b]; so = index of (j, 0, d) in one statistics plane
     PV_D void one(int k, double f, const double (&df)[M::NSD], double* yrow, double* srow, int so, int plane,
@@ -108,6 +114,18 @@ struct pv_sink {
                 if constexpr (SENS) {
 #pragma unroll
                     for (int s = 0; s < M::NS; ++s) g[s] = fma(w, df[s], g[s]);
+                    if constexpr (FIM) {
+                        // expected information of n measurements at this point: n/sigma^2 (normal), n/(sigma f)^2 (log-normal)
+                        const double wi = (p.noise_model == 0) ? n * inv_sigma2 : n * inv_sigma2 / (f * f);
+                        int q = 0;
+#pragma unroll
+                        for (int s = 0; s < M::NS; ++s)
+#pragma unroll
+                            for (int r = s; r < M::NS; ++r) {
+                                fim[q] = fma(wi * df[s], df[r], fim[q]);
+                                ++q;
+                            }
+                    }
                 }
                 (void)w;
             }
@@ -200,7 +218,7 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
     const int lane_id = threadIdx.x & 31;
     typename Sys::Consts ks;
     Lane lane;
-    pv_sink<M, MODE, OBSID> sink{p, stats_shared ? sh_stats : nullptr, 0, 0, {}, 0.0, {}};
+    pv_sink<M, MODE, OBSID> sink{p, stats_shared ? sh_stats : nullptr, 0, 0, {}, 0.0, {}, {}};
     bool have = false;        // this lane is integrating trajectory sink.b
     bool exhausted = false;   // the work counter ran past B
 
@@ -211,6 +229,10 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
             if constexpr (SENS) {
 #pragma unroll
                 for (int s = 0; s < M::NS; ++s) p.grad[(int64_t)s * p.B + b] = sink.g[s];
+                if constexpr ((MODE & PV_MODE_FIM) != 0) {
+#pragma unroll
+                    for (int q = 0; q < M::NS * (M::NS + 1) / 2; ++q) p.fim[(int64_t)q * p.B + b] = sink.fim[q];
+                }
             }
         }
         if (p.status) p.status[b] = rc;
@@ -277,6 +299,8 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
                     sink.lp = 0.0;
 #pragma unroll
                     for (int s = 0; s < M::NSD; ++s) sink.g[s] = 0.0;
+#pragma unroll
+                    for (int q = 0; q < pv_sink<M, MODE, OBSID>::NFIM; ++q) sink.fim[q] = 0.0;
                     have = true;
                     const int rc = lane.start(ks, z, p.t0, sh_t, p.T, p.rtol, p.atol, sink);
                     if (rc != PV_RUNNING) finish(rc);

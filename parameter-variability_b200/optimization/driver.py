@@ -1,0 +1,175 @@
+"""GPU mirror of the reference's estimation driver.
+
+Reference: ``PyPestoSampler`` (load_problem / run_optimization / bayesian_sampler / results_dict / results_df,
+src/parvar/optimization/petab_optimization.py:29-269) and ``optimize_experiment`` / ``optimize_experiments``
+(:272-368).  Same stages, same settings dictionary, same ``<uid>_results.tsv`` columns, so the reference's analysis
+(``src/parvar/analysis/utils.py:28-98``) reads the output unchanged - but all experiments that share a model and a
+measurement grid are advanced TOGETHER (one launch per optimiser iteration / sampler iteration for all of them),
+instead of one process per experiment (``optimize_experiments_multicore``, :370-391).
+"""
+from __future__ import annotations
+
+import json
+import time
+import traceback
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+from . import optimizer as opt_mod
+from . import sampler as smp_mod
+from .petab_io import load_petab_problem, read_petab_tables
+from .petab_optimization import GroupData, PetabObjectiveBatch
+
+DEFAULT_SETTINGS = dict(          # petab_optimization.py:294-306
+    maxiter=1e4, fatol=1e-12, frtol=1e-12, optim="fides", startpoint_method="uniform", n_starts=100, seed=1234,
+    create_optimization_plots=False, engine="gpu-batched", n_samples=5000, n_chains=4,
+)
+
+
+def get_group_from_pid(pid: str) -> Optional[str]:
+    """``k_abs_MALE`` -> ``MALE`` (reference src/parvar/experiments/utils.py:48-62)."""
+    last = pid.rsplit("_", 1)[-1]
+    return last if last and last.isascii() else None
+
+
+def get_parameter_from_pid(pid: str) -> str:
+    """``k_abs_MALE`` -> ``k_abs`` (reference src/parvar/experiments/utils.py:65-87)."""
+    idx = pid.rfind("_")
+    if idx == -1:
+        return pid
+    last = pid[idx + 1:]
+    return pid[:idx] if last and last.isascii() else pid
+
+
+class GpuPetabSampler:
+    """Optimise + sample Q PEtab problems of one model together.  Mirrors ``PyPestoSampler`` (:29-269)."""
+
+    def __init__(self, objective: PetabObjectiveBatch, uids: Optional[Sequence[str]] = None,
+                 start_box: Optional[tuple[np.ndarray, np.ndarray]] = None):
+        self.objective = objective
+        self.uids = list(uids) if uids is not None else [f"problem{q}" for q in range(objective.Q)]
+        self.start_box = start_box
+        self.optimize_result: Optional[opt_mod.OptimizeResult] = None
+        self.sample_result: Optional[smp_mod.SampleResult] = None
+        self.optim_duration: Optional[float] = None
+        self.sampler_duration: Optional[float] = None
+
+    # ---- objective adapters ------------------------------------------------------------------------------------------
+    def _eval_opt(self, X):
+        o = self.objective.evaluate(X, order=2)
+        fval = -(o["llh"] + o["lprior"])
+        grad = -(o["dllh"] + o["dlprior"])
+        dim = X.shape[-1]
+        hess = o["fim"] + o["prior_precision"][..., None] * np.eye(dim)
+        bad = ~np.isfinite(fval)
+        fval = np.where(bad, np.inf, fval)
+        return {"fval": fval, "grad": grad, "hess": hess}
+
+    def _eval_sample(self, X):
+        o = self.objective.evaluate(X, order=0)
+        return o["llh"], o["lprior"]
+
+    # ---- stages ------------------------------------------------------------------------------------------------------------
+    def run_optimization(self, maxiter: float = 1e4, fatol: float = 1e-12, frtol: float = 1e-12, n_starts: int = 100,
+                         seed: int = 1234, **_):
+        """Multistart optimisation (:99-156).  Start points are uniform in the bounds like the reference
+        (``pypesto.startpoint.uniform`` on [0, 1e8], :120-121) unless a ``start_box`` was given."""
+        lb, ub = self.objective.lb, self.objective.ub
+        slb, sub = self.start_box if self.start_box is not None else (lb, ub)
+        x0 = opt_mod.uniform_startpoints(n_starts, np.asarray(slb, float), np.asarray(sub, float), Q=self.objective.Q, seed=seed)
+        t0 = time.perf_counter()
+        self.optimize_result = opt_mod.minimize(self._eval_opt, x0, lb, ub, maxiter=int(min(maxiter, 1e4)), fatol=fatol, frtol=frtol)
+        self.optim_duration = time.perf_counter() - t0
+        return self.optimize_result
+
+    def bayesian_sampler(self, n_samples: int = 5000, n_chains: int = 4, seed: int = 1234):
+        """Adaptive Metropolis inside adaptive parallel tempering, started at the best optimisation result (:158-194)."""
+        if self.optimize_result is None:
+            raise RuntimeError("run_optimization first (pyPESTO starts the chains at the best optimisation result)")
+        x0 = self.optimize_result.x[:, 0, :]
+        t0 = time.perf_counter()
+        self.sample_result = smp_mod.sample(self._eval_sample, x0, self.objective.lb, self.objective.ub,
+                                            n_samples=n_samples, n_chains=n_chains, seed=seed)
+        smp_mod.effective_sample_size(self.sample_result)
+        self.sampler_duration = time.perf_counter() - t0
+        return self.sample_result
+
+    # ---- results (columns of results_df, :254-269) ---------------------------------------------------------------------------
+    def results_dict(self, q: int, settings: dict, pool_tempered_chains: bool = True) -> dict:
+        """Posterior statistics of problem q.  The reference feeds ``trace_x`` of ALL tempered chains to arviz
+        (``az.convert_to_inference_data(trace_)``, :204-211), so its mean / std / median / HDI pool the hot chains as
+        well; ``pool_tempered_chains=True`` reproduces that, ``False`` uses the beta = 1 chain only."""
+        tr = self.sample_result.trace_x[q]                    # [C, n+1, dim]
+        vals = tr if pool_tempered_chains else tr[:1]
+        res = {}
+        for i, pid in enumerate(self.objective.x_names):
+            v = vals[:, :, i]
+            lo, hi = smp_mod.hdi(v)
+            res[pid] = {"mean": float(np.mean(v)), "std": float(np.std(v)), "median": float(np.median(v)),
+                        "ess": float(self.sample_result.effective_sample_size[q]), "n_samples": settings["n_samples"],
+                        "optim_duration": self.optim_duration, "sampler_duration": self.sampler_duration,
+                        "values": v, "hdi_low": lo, "hdi_high": hi}
+        return res
+
+    def results_df(self, q: int, settings: dict, pool_tempered_chains: bool = True) -> pd.DataFrame:
+        rows = []
+        for pid, stats in self.results_dict(q, settings, pool_tempered_chains).items():
+            rows.append({"id": self.uids[q], "group": get_group_from_pid(pid), "parameter": get_parameter_from_pid(pid),
+                         "pid": pid, **stats})
+        return pd.DataFrame(rows)
+
+
+def _batch_from_yaml(yaml_paths: Sequence[Path], mode: str, dosage, device: int) -> PetabObjectiveBatch:
+    objs = [load_petab_problem(p, mode=mode, dosage=dosage, device=device) for p in yaml_paths[:1]]
+    first = objs[0]
+    problems, priors = [], []
+    for p in yaml_paths:
+        o = first if p == yaml_paths[0] else load_petab_problem(p, mode=mode, dosage=dosage, device=device)
+        if (o.model, o.parameters, o.observables) != (first.model, first.parameters, first.observables) or \
+                not np.array_equal(o.timepoints, first.timepoints):
+            raise ValueError("experiments batched together must share model, parameters, observables and time grid")
+        problems.append(o.groups)
+        priors.append({n: (l, s) for n, l, s in zip(o.x_names, o.prior_loc, o.prior_scale) if np.isfinite(l)})
+    batch = PetabObjectiveBatch(first.model, first.parameters, problems, first.timepoints, first.observables,
+                                sigma=1.0, priors=priors, mode=mode, dosage=dosage, device=device)
+    batch.lb, batch.ub = first.lb, first.ub
+    return batch
+
+
+def optimize_experiments(results_dir: Path, yaml_paths: Sequence[Path], caching: bool = True, settings: Optional[dict] = None,
+                         mode: str = "literal", dosage: Optional[dict] = None, device: int = 0,
+                         start_box: Optional[tuple[np.ndarray, np.ndarray]] = None) -> list[bool]:
+    """Reference ``optimize_experiments`` (:351-368) for experiments that share model and time grid: optimise and
+    sample them together, write one ``<uid>_results.tsv`` per experiment (errors -> ``<uid>_errors.tsv``, :340-348)."""
+    results_dir = Path(results_dir)
+    results_dir.mkdir(parents=True, exist_ok=True)
+    settings = {**DEFAULT_SETTINGS, **(settings or {})}
+    todo = [Path(p) for p in yaml_paths if not (caching and (results_dir / f"{Path(p).parent.name}_results.tsv").exists())]
+    ok = {Path(p): True for p in yaml_paths}
+    if not todo:
+        return [True] * len(yaml_paths)
+    uids = [p.parent.name for p in todo]
+    try:
+        batch = _batch_from_yaml(todo, mode, dosage, device)
+        drv = GpuPetabSampler(batch, uids=uids, start_box=start_box)
+        drv.run_optimization(maxiter=settings["maxiter"], fatol=settings["fatol"], frtol=settings["frtol"],
+                             n_starts=settings["n_starts"], seed=settings["seed"])
+        drv.bayesian_sampler(n_samples=settings["n_samples"], n_chains=settings["n_chains"], seed=settings["seed"])
+        for q, uid in enumerate(uids):
+            df = drv.results_df(q, settings)
+            df["values"] = df["values"].apply(lambda x: json.dumps(np.asarray(x).tolist()))
+            df.to_csv(results_dir / f"{uid}_results.tsv", sep="\t", index=False)
+    except Exception:
+        err = traceback.format_exc()
+        for p, uid in zip(todo, uids):
+            (results_dir / f"{uid}_errors.tsv").write_text(err)
+            ok[p] = False
+    return [ok[Path(p)] for p in yaml_paths]
+
+
+def optimize_experiment(yaml_path: Path, results_dir: Path, caching: bool = True, **kwargs) -> bool:
+    """Reference ``optimize_experiment`` (:272-348) for a single PEtab problem."""
+    return optimize_experiments(results_dir, [Path(yaml_path)], caching=caching, **kwargs)[0]

@@ -178,3 +178,171 @@ def make_problem(*args, **kwargs):
     """-> (fun, grad, lb, ub, x_names): the plain callables pyPESTO's ``Objective(fun=, grad=)`` takes."""
     obj = PetabObjective(*args, **kwargs)
     return obj.fun, obj.grad, obj.lb, obj.ub, obj.x_names
+
+
+class PetabObjectiveBatch:
+    """Q independent PEtab problems of one model (same parameters, time grid, observables; different measurements
+    and priors) evaluated together: ``X [Q, B, dim] -> loglik [Q, B], logprior [Q, B], grad [Q, B, dim], fim [Q, B, dim, dim]``.
+
+    This is the reference's hyper-parameter sweep (3 x 2160 problems, ``factories/__init__.py:12-20``) turned from a
+    process pool over problems (``petab_optimization.py:381-391``) into ONE launch per evaluation: the problem index
+    is just another data set (trajectory ((b * Q + q) * G + g) reads data set q * G + g).
+    ``PetabObjective`` is the Q = 1 view with pyPESTO's calling conventions.
+    """
+
+    def __init__(self, model: str, parameters: Sequence[str], problems: Sequence[Sequence[GroupData]],
+                 timepoints: Sequence[float], observables: Sequence[str], sigma=1.0,
+                 priors: Optional[Sequence[dict[str, tuple[float, float]]]] = None,
+                 noise_model: int = runtime.NOISE_NORMAL, mode: str = "intended",
+                 dosage: Optional[dict[str, float]] = None, device: int = 0, rtol: float = 1e-8, atol: float = 1e-11,
+                 method: int = runtime.METHOD_AUTO, t0: float = 0.0):
+        self.model = model
+        self.parameters = list(parameters)
+        self.Q = len(problems)
+        self.group_ids = [g.id for g in problems[0]]
+        self.G = len(self.group_ids)
+        for pr in problems:
+            if [g.id for g in pr] != self.group_ids:
+                raise ValueError("all problems must have the same groups")
+        self.observables = [o.strip("[]") for o in observables]
+        self.timepoints = np.asarray(timepoints, dtype=np.float64)
+        self.x_names = [f"{par}_{g}" for par in self.parameters for g in self.group_ids]
+        self.dim = len(self.x_names)
+        self.lb = np.zeros(self.dim)
+        self.ub = np.full(self.dim, 1e8)
+        self.prior_loc = np.full((self.Q, self.dim), np.nan)
+        self.prior_scale = np.full((self.Q, self.dim), np.nan)
+        for q, pri in enumerate(priors or []):
+            for name, (loc, scale) in pri.items():
+                i = self.x_names.index(name)
+                self.prior_loc[q, i], self.prior_scale[q, i] = loc, scale
+        self.has_prior = np.isfinite(self.prior_loc)
+
+        pb = runtime.Problem(model, device=device)
+        pb.set_solver(method=method, rtol=rtol, atol=atol)
+        if mode == "literal":
+            for o in self.observables:
+                pb.set_value(o, 0.0)
+        elif mode == "intended":
+            for k, v in (dosage or {}).items():
+                pb.set_value(k, v)
+        else:
+            raise ValueError("mode must be 'intended' or 'literal'")
+        pb.set_columns(self.parameters)
+        pb.set_timepoints(self.timepoints, t0=min(t0, float(self.timepoints[0])))
+        pb.set_observables(self.observables)
+        stats = np.stack([sufficient_statistics(g.y, noise_model) for pr in problems for g in pr], axis=-1)  # [3,T,K,Q*G]
+        pb.set_data(stats, sigma, noise_model)
+        self.problem = pb
+        self._sens_row = [pb.sens_ids.index(p) if p in pb.sens_ids else -1 for p in self.parameters]
+        self.n_evals = 0
+
+    def log_prior(self, X: np.ndarray, grad: bool = False):
+        """parameterScaleNormal priors on the lin scale (petab_factory.py:443-449), constant included."""
+        z = np.where(self.has_prior[:, None, :], (X - self.prior_loc[:, None, :]) / self.prior_scale[:, None, :], 0.0)
+        const = np.where(self.has_prior, LOG_2PI + 2.0 * np.log(np.where(self.has_prior, self.prior_scale, 1.0)), 0.0)
+        lp = -0.5 * np.sum(z * z, axis=2) - 0.5 * np.sum(const, axis=1)[:, None]
+        if not grad:
+            return lp, None, None
+        inv = np.where(self.has_prior, 1.0 / np.where(self.has_prior, self.prior_scale, 1.0), 0.0)
+        return lp, -z * inv[:, None, :], (inv * inv)[:, None, :] * np.ones_like(X)
+
+    def evaluate(self, X: np.ndarray, order: int = 0):
+        """X [Q, B, dim].  order 0: (llh, lprior); 1: + (dllh, dlprior); 2: + (fim [Q,B,dim,dim], prior precision diag)."""
+        X = np.asarray(X, dtype=np.float64)
+        Q, B, dim = X.shape
+        if Q != self.Q or dim != self.dim:
+            raise ValueError(f"X must be [{self.Q}, B, {self.dim}]")
+        G, NP = self.G, len(self.parameters)
+        if order > 0 and min(self._sens_row) < 0:
+            raise runtime.ParvarB200Error(f"{self.parameters} are not all compiled sensitivity parameters of {self.model}")
+        # trajectory ((b*Q + q)*G + g): theta_g of X[q, b]  ->  P[p, (b*Q+q)*G + g] = X[q, b, p*G + g]
+        P = np.ascontiguousarray(X.reshape(Q, B, NP, G).transpose(2, 1, 0, 3).reshape(NP, B * Q * G))
+        self.n_evals += Q * B
+        out = {}
+        if order == 0:
+            lp_t, _, seg, nf = self.problem.logp_host(P, seg_len=G, grad=False)
+        elif order == 1:
+            lp_t, g_t, seg, nf = self.problem.logp_host(P, seg_len=G, grad=True)
+        else:
+            lp_t, g_t, f_t, seg, nf = self.problem.logp_fim_host(P, seg_len=G)
+        llh = seg.reshape(B, Q).T.copy()
+        bad = ~np.isfinite(llh)
+        llh[bad] = -np.inf
+        lprior, dprior, hprior = self.log_prior(X, grad=order > 0)
+        out["llh"], out["lprior"] = llh, lprior
+        if order > 0:
+            g_t = g_t[self._sens_row].reshape(NP, B, Q, G)                       # [p, b, q, g]
+            dllh = np.ascontiguousarray(g_t.transpose(2, 1, 0, 3).reshape(Q, B, dim))
+            dllh[bad] = np.nan
+            out["dllh"], out["dlprior"] = dllh, dprior
+        if order > 1:
+            ns = self.problem.n_sens
+            tri = [(s, r) for s in range(ns) for r in range(s, ns)]
+            F = np.zeros((Q, B, dim, dim))
+            f_t = f_t.reshape(len(tri), B, Q, G)
+            for k, (s, r) in enumerate(tri):
+                # sens index -> position among self.parameters
+                if s not in self._sens_row or r not in self._sens_row:
+                    continue
+                ps, pr_ = self._sens_row.index(s), self._sens_row.index(r)
+                for g in range(G):
+                    v = f_t[k, :, :, g].T                                          # [Q, B]
+                    F[:, :, ps * G + g, pr_ * G + g] = v
+                    F[:, :, pr_ * G + g, ps * G + g] = v
+            out["fim"], out["prior_precision"] = F, hprior
+        return out
+
+
+class HierarchicalObjective:
+    """Population (hierarchical) form of BASELINE.json configs 3-4: every individual i has its own
+    theta_i = (theta_i1 .. theta_iP) and its own measurements; theta_ip ~ LogNormal(mu_p, omega_p); hyper-priors
+    mu_p ~ Normal(m_p, s_p), omega_p ~ HalfNormal(h_p).  (Build-defined: the reference has no hierarchy)
+
+        log p(theta, mu, omega | y) = sum_i loglik_i(theta_i) + sum_i,p log LogNormal(theta_ip; mu_p, omega_p)
+                                      + sum_p [log N(mu_p; m_p, s_p) + log HalfNormal(omega_p; h_p)]
+
+    The per-individual likelihoods and their gradients come from ONE kernel launch over n_chains x n_individuals
+    trajectories (``Problem.logp_grad`` with ``seg_len = n_individuals``); the population terms are O(n) host algebra.
+    With several ranks the individuals are sharded and ``distributed.ShardedLikelihood`` all-reduces
+    ``[n_chains, 1 + 2P]`` (logp and the hyper-parameter gradient).
+    """
+
+    def __init__(self, problem: "runtime.Problem", n_individuals: int, mu_prior: Sequence[tuple[float, float]],
+                 omega_prior: Sequence[float], first_individual: int = 0, n_local: Optional[int] = None):
+        self.problem = problem
+        self.n_ind = n_individuals
+        self.first = first_individual
+        self.n_local = n_individuals if n_local is None else n_local
+        self.P = len(problem.columns)
+        self.mu_prior = np.asarray(mu_prior, dtype=np.float64)       # [P, 2]
+        self.omega_prior = np.asarray(omega_prior, dtype=np.float64)  # [P]
+        self._sens_row = [problem.sens_ids.index(c) for c in problem.columns]
+
+    def local_terms(self, theta: np.ndarray, mu: np.ndarray, omega: np.ndarray):
+        """theta [C, n_local, P], mu / omega [C, P] -> (logp_local [C], dtheta [C, n_local, P], dmu [C, P], domega [C, P])
+        for this rank's individuals (likelihood + population density); hyper-priors are added once by ``finish``."""
+        C, L, P = theta.shape
+        Pm = np.ascontiguousarray(theta.transpose(2, 0, 1).reshape(P, C * L))
+        lp, g, seg, nf = self.problem.logp_host(Pm, seg_len=L, grad=True)
+        dth = g[self._sens_row].reshape(P, C, L).transpose(1, 2, 0).copy()
+        z = (np.log(theta) - mu[:, None, :]) / omega[:, None, :]
+        pop = np.sum(-np.log(theta) - np.log(omega)[:, None, :] - 0.5 * LOG_2PI - 0.5 * z * z, axis=(1, 2))
+        dth += (-1.0 - z / omega[:, None, :]) / theta
+        dmu = np.sum(z / omega[:, None, :], axis=1)
+        domega = np.sum((z * z - 1.0) / omega[:, None, :], axis=1)
+        return seg + pop, dth, dmu, domega
+
+    def finish(self, logp: np.ndarray, dmu: np.ndarray, domega: np.ndarray, mu: np.ndarray, omega: np.ndarray):
+        """Add the hyper-priors (after the cross-rank reduction)."""
+        m, s = self.mu_prior[:, 0], self.mu_prior[:, 1]
+        h = self.omega_prior
+        zm = (mu - m) / s
+        logp = logp + np.sum(-0.5 * (LOG_2PI + 2 * np.log(s)) - 0.5 * zm * zm, axis=1)
+        logp = logp + np.sum(0.5 * np.log(2.0 / np.pi) - np.log(h) - 0.5 * (omega / h) ** 2, axis=1)
+        return logp, dmu - zm / s, domega - omega / (h * h)
+
+    def __call__(self, theta: np.ndarray, mu: np.ndarray, omega: np.ndarray):
+        lp, dth, dmu, dom = self.local_terms(theta, mu, omega)
+        lp, dmu, dom = self.finish(lp, dmu, dom, mu, omega)
+        return lp, dth, dmu, dom

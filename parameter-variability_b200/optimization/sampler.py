@@ -1,0 +1,204 @@
+"""Batched adaptive-Metropolis + adaptive parallel tempering.
+
+The reference samples each PEtab problem with
+``pypesto.sample.AdaptiveParallelTemperingSampler(internal_sampler=AdaptiveMetropolisSampler(), n_chains=4)`` for
+5000 samples (src/parvar/optimization/petab_optimization.py:158-173, settings :294-306): 4 x 5000 sequential Python ->
+AMICI objective calls per problem, problems spread over a process pool.  Here every iteration evaluates the proposals
+of ALL chains of ALL problems in one kernel launch (``PetabObjectiveBatch.evaluate``); the bookkeeping around it is
+vectorised numpy over [problems, chains].
+
+Algorithms (restated from the publications pyPESTO implements; pyPESTO 0.6.0 is not in /root/reference):
+  * adaptive Metropolis: Haario, Saksman, Tamminen (2001) with the decaying update of the running mean / covariance
+    and of the proposal scale towards the 0.234 acceptance rate (pyPESTO ``AdaptiveMetropolisSampler``:
+    decay_constant 0.51, reg_factor 1e-6, target_acceptance_rate 0.234, threshold_sample 1);
+  * parallel tempering with swaps between neighbouring temperatures, likelihood tempered (posterior_beta
+    ~ L^beta * prior), initial ladder beta_k = 1 / T_k with near-exponentially spaced temperatures (exponent 4,
+    max_temp 5e4), ladder adapted as in Vousden, Farr, Mandel (2016) (nu = 1e3, eta = 100).
+Proposals outside the bounds are rejected (pyPESTO: objective = inf outside [lb, ub]).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import numpy as np
+
+
+def near_exponential_decay_betas(n_chains: int, exponent: float = 4.0, max_temp: float = 5e4) -> np.ndarray:
+    if n_chains == 1:
+        return np.array([1.0])
+    temps = 1.0 + np.linspace(0.0, 1.0, n_chains) ** exponent * (max_temp - 1.0) if np.isfinite(max_temp) else None
+    if temps is None:
+        temps = np.linspace(1.0, np.inf, n_chains)
+    return 1.0 / temps
+
+
+def _regularize(cov: np.ndarray, reg: float) -> np.ndarray:
+    cov = 0.5 * (cov + np.swapaxes(cov, -1, -2))
+    w = np.linalg.eigvalsh(cov)
+    bad = w[..., 0] <= 0
+    if np.any(bad):
+        dim = cov.shape[-1]
+        while np.any(bad):
+            cov = cov + np.where(bad[..., None, None], reg * np.eye(dim), 0.0)
+            w = np.linalg.eigvalsh(cov)
+            bad = w[..., 0] <= 0
+            reg *= 10.0
+    return cov
+
+
+@dataclass
+class SampleResult:
+    trace_x: np.ndarray            # [Q, n_chains, n_samples + 1, dim]
+    trace_neglogpost: np.ndarray   # [Q, n_chains, n_samples + 1]
+    trace_neglogprior: np.ndarray  # [Q, n_chains, n_samples + 1]
+    betas: np.ndarray              # [Q, n_chains] final temperature ladder
+    acceptance_rate: np.ndarray    # [Q, n_chains]
+    swap_rate: np.ndarray          # [Q, n_chains - 1]
+    n_evals: int
+    burn_in: Optional[np.ndarray] = None
+    effective_sample_size: Optional[np.ndarray] = None
+
+
+def sample(evaluate: Callable[[np.ndarray], tuple[np.ndarray, np.ndarray]], x0: np.ndarray, lb: np.ndarray, ub: np.ndarray,
+           n_samples: int = 5000, n_chains: int = 4, seed: int = 1234, cov0: Optional[np.ndarray] = None,
+           decay_constant: float = 0.51, target_acceptance_rate: float = 0.234, reg_factor: float = 1e-6,
+           threshold_sample: int = 1, nu: float = 1e3, eta: float = 100.0, adapt_betas: bool = True) -> SampleResult:
+    """``evaluate(X [Q, C, dim]) -> (llh [Q, C], lprior [Q, C])``; ``x0`` [Q, dim] (start of every chain, as pyPESTO
+    starts all tempered chains at the best optimisation result)."""
+    rs = np.random.RandomState(seed)
+    x0 = np.atleast_2d(np.asarray(x0, dtype=np.float64))
+    Q, dim = x0.shape
+    C = n_chains
+    x = np.repeat(x0[:, None, :], C, axis=1)
+    llh, lpr = evaluate(x)
+    n_evals = Q * C
+    betas = np.repeat(near_exponential_decay_betas(C)[None, :], Q, axis=0)
+    cov = np.broadcast_to(np.eye(dim) if cov0 is None else np.asarray(cov0, dtype=np.float64), (Q, C, dim, dim)).copy()
+    cov = _regularize(cov, reg_factor)
+    mean_hist = x.copy()
+    cov_hist = cov.copy()
+    cov_scale = np.ones((Q, C))
+    trace_x = np.empty((Q, C, n_samples + 1, dim))
+    trace_lp = np.empty((Q, C, n_samples + 1))
+    trace_pr = np.empty((Q, C, n_samples + 1))
+    trace_x[:, :, 0], trace_lp[:, :, 0], trace_pr[:, :, 0] = x, -(llh + lpr), -lpr
+    n_acc = np.zeros((Q, C))
+    n_swap = np.zeros((Q, max(C - 1, 1)))
+    n_swap_try = np.zeros((Q, max(C - 1, 1)))
+
+    for it in range(1, n_samples + 1):
+        # ---- Metropolis step for every chain of every problem -------------------------------------------------------
+        Lc = np.linalg.cholesky(cov)
+        x_new = x + np.einsum("qcij,qcj->qci", Lc, rs.normal(size=(Q, C, dim)))
+        inside = np.all((x_new >= lb) & (x_new <= ub), axis=2)
+        llh_new, lpr_new = evaluate(np.where(inside[..., None], x_new, x))
+        n_evals += Q * C
+        llh_new = np.where(inside, llh_new, -np.inf)
+        with np.errstate(invalid="ignore"):
+            log_acc = betas * (llh_new - llh) + (lpr_new - lpr)
+        log_acc = np.where(np.isnan(log_acc), -np.inf, np.minimum(log_acc, 0.0))
+        accept = np.log(rs.uniform(size=(Q, C))) < log_acc
+        x = np.where(accept[..., None], x_new, x)
+        llh = np.where(accept, llh_new, llh)
+        lpr = np.where(accept, lpr_new, lpr)
+        n_acc += accept
+        # ---- adapt proposal (Haario et al.) ---------------------------------------------------------------------------
+        if it > threshold_sample:
+            rate = it ** (-decay_constant)
+            mean_hist = (1 - rate) * mean_hist + rate * x
+            dx = x - mean_hist
+            cov_hist = (1 - rate) * cov_hist + rate * np.einsum("qci,qcj->qcij", dx, dx)
+            cov_scale = cov_scale * np.exp((np.exp(log_acc) - target_acceptance_rate) / (it + 1) ** decay_constant)
+            cov = _regularize(cov_scale[..., None, None] * cov_hist, reg_factor)
+        # ---- swaps between neighbouring temperatures, hottest pair first ---------------------------------------------
+        swapped = np.zeros((Q, max(C - 1, 1)), dtype=bool)
+        for k in range(C - 1, 0, -1):
+            dbeta = betas[:, k - 1] - betas[:, k]
+            with np.errstate(invalid="ignore"):
+                p_swap = dbeta * (llh[:, k] - llh[:, k - 1])
+            p_swap = np.where(np.isnan(p_swap), -np.inf, p_swap)
+            do = np.log(rs.uniform(size=Q)) < p_swap
+            n_swap_try[:, k - 1] += 1
+            n_swap[:, k - 1] += do
+            swapped[:, k - 1] = do
+            for arr in (x, llh, lpr):
+                a, b = arr[:, k - 1].copy(), arr[:, k].copy()
+                sel = do[:, None] if arr.ndim == 3 else do
+                arr[:, k - 1] = np.where(sel, b, a)
+                arr[:, k] = np.where(sel, a, b)
+        # ---- adapt the ladder (Vousden et al. 2016) ---------------------------------------------------------------------
+        if adapt_betas and C > 2:
+            kappa = nu / (it + 1 + nu) / eta
+            ds = kappa * (swapped[:, :-1].astype(float) - swapped[:, 1:].astype(float))
+            with np.errstate(divide="ignore"):
+                temps = 1.0 / betas
+            dtemps = np.diff(temps[:, :-1], axis=1) * np.exp(ds[:, :C - 2])
+            temps[:, 1:-1] = temps[:, :1] + np.cumsum(dtemps, axis=1)
+            betas = 1.0 / temps
+        trace_x[:, :, it], trace_lp[:, :, it], trace_pr[:, :, it] = x, -(llh + lpr), -lpr
+
+    return SampleResult(trace_x=trace_x, trace_neglogpost=trace_lp, trace_neglogprior=trace_pr, betas=betas,
+                        acceptance_rate=n_acc / n_samples, swap_rate=n_swap / np.maximum(n_swap_try, 1), n_evals=n_evals)
+
+
+# ---- diagnostics (pyPESTO ``effective_sample_size``: Geweke burn-in + Sokal autocorrelation time) ----------------------
+def autocorrelation_time_sokal(chain: np.ndarray) -> float:
+    """Integrated autocorrelation time of a 1-D chain with Sokal's adaptive window (as pyPESTO's ``autocorrelation_sokal``)."""
+    n = len(chain)
+    xc = chain - chain.mean()
+    if np.allclose(xc, 0):
+        return float(n)
+    nfft = 1 << int(np.ceil(np.log2(2 * n)))
+    f = np.fft.rfft(xc, nfft)
+    ac = np.fft.irfft(f * np.conjugate(f))[:n].real
+    ac /= ac[0]
+    tau = 1.0
+    for m in range(1, n):
+        tau = 1.0 + 2.0 * np.sum(ac[1:m + 1])
+        if m >= 6.0 * tau:           # Sokal window
+            break
+    return float(max(tau, 1.0))
+
+
+def geweke_burn_in(chain: np.ndarray, zscore: float = 2.0) -> int:
+    """First index (in 5 % steps of the chain) from which first 10 % and last 50 % of the rest agree (Geweke 1992)."""
+    n = chain.shape[0]
+    for frac in np.linspace(0.0, 0.95, 20):
+        s = int(frac * n)
+        rest = chain[s:]
+        if len(rest) < 20:
+            break
+        a, b = rest[: max(len(rest) // 10, 2)], rest[len(rest) // 2:]
+        z = (a.mean(axis=0) - b.mean(axis=0)) / np.sqrt(a.var(axis=0) / len(a) + b.var(axis=0) / len(b) + 1e-300)
+        if np.all(np.abs(z) < zscore):
+            return s
+    return int(0.5 * n)
+
+
+def effective_sample_size(result: SampleResult) -> np.ndarray:
+    """ESS of the cold chain of every problem: (n - burn_in) / (1 + max_p tau_p)  (pyPESTO's definition)."""
+    Q = result.trace_x.shape[0]
+    ess = np.zeros(Q)
+    burn = np.zeros(Q, dtype=int)
+    for q in range(Q):
+        chain = result.trace_x[q, 0]
+        b = geweke_burn_in(chain)
+        burn[q] = b
+        rest = chain[b:]
+        tau = max(autocorrelation_time_sokal(rest[:, p]) for p in range(rest.shape[1]))
+        ess[q] = len(rest) / (1.0 + tau)
+    result.burn_in, result.effective_sample_size = burn, ess
+    return ess
+
+
+def hdi(samples: np.ndarray, prob: float = 0.94) -> tuple[float, float]:
+    """Highest-density interval of a 1-D sample (arviz ``az.hdi`` default hdi_prob = 0.94, petab_optimization.py:217-226)."""
+    s = np.sort(np.asarray(samples).ravel())
+    n = len(s)
+    k = int(np.floor(prob * n))
+    if k < 1 or k >= n:
+        return float(s[0]), float(s[-1])
+    widths = s[k:] - s[: n - k]
+    i = int(np.argmin(widths))
+    return float(s[i]), float(s[i + k])

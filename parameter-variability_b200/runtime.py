@@ -55,6 +55,10 @@ ABI = {
                           C.c_void_p, C.c_void_p]),
     "pv_logp_grad": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pv_logp_grad_fim": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "pv_logp_grad_fim_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_void_p]),
     "pv_logp_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pv_logp_grad_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pv_launch_count": (C.c_int64, []),
@@ -267,6 +271,16 @@ class Problem:
             Y = np.empty((T, K, B), dtype=np.float64)
         n_failed = _check(self._lib.pv_simulate_host(self._h, B, _ptr(P), _ptr(Y), _ptr(logp), _ptr(status), _ptr(steps)))
         return Y, n_failed
+
+    def logp_fim_host(self, P: np.ndarray, seg_len: int = 0):
+        """-> (logp [B], grad [n_sens, B], fim [n_sens(n_sens+1)/2, B], logp_seg or None, n_failed)."""
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        B = P.shape[-1]
+        lp, g = np.empty(B), np.empty((self.n_sens, B))
+        f = np.empty((self.n_sens * (self.n_sens + 1) // 2, B))
+        seg = np.empty(B // seg_len) if seg_len else None
+        nf = _check(self._lib.pv_logp_grad_fim_host(self._h, B, _ptr(P), _ptr(lp), _ptr(g), _ptr(f), seg_len, _ptr(seg)))
+        return lp, g, f, seg, nf
 
     def logp_host(self, P: np.ndarray, seg_len: int = 0, grad: bool = False):
         """-> (logp [B], grad [n_sens, B] or None, logp_seg [B/seg_len] or None, n_failed)."""

@@ -1,0 +1,112 @@
+"""Host logic of the SURVEY 8(f) "next" rows (sampler, optimiser, PEtab tables, result helpers) - no GPU needed:
+the objective is replaced by analytic functions."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import pkg
+
+
+def test_adaptive_metropolis_parallel_tempering_on_gaussian():
+    smp = pkg("optimization.sampler")
+    mean = np.array([[1.0, -2.0], [0.5, 3.0]])                 # two problems
+    sd = np.array([[0.5, 2.0], [1.5, 0.2]])
+
+    def evaluate(X):                                           # X [Q, C, dim]
+        z = (X - mean[:, None, :]) / sd[:, None, :]
+        return -0.5 * np.sum(z * z, axis=2), np.zeros(X.shape[:2])
+
+    lb, ub = np.full(2, -50.0), np.full(2, 50.0)
+    res = smp.sample(evaluate, x0=mean + 0.1, lb=lb, ub=ub, n_samples=6000, n_chains=4, seed=1)
+    assert res.trace_x.shape == (2, 4, 6001, 2) and res.n_evals == 2 * 4 * 6001
+    cold = res.trace_x[:, 0, 1000:, :]
+    np.testing.assert_allclose(cold.mean(axis=1), mean, atol=0.25 * sd.max())
+    np.testing.assert_allclose(cold.std(axis=1), sd, rtol=0.25)
+    assert np.all(res.acceptance_rate[:, 0] > 0.1) and np.all(res.acceptance_rate[:, 0] < 0.5)
+    assert np.all(res.betas[:, 0] == 1.0) and np.all(np.diff(res.betas, axis=1) < 0)
+    hot = res.trace_x[:, -1, 1000:, :]
+    assert np.all(hot.std(axis=1) > 2 * sd)                   # the hottest chain explores far more widely
+    ess = smp.effective_sample_size(res)
+    assert np.all(ess > 50) and np.all(ess < 6001)
+    res2 = smp.sample(evaluate, x0=mean + 0.1, lb=lb, ub=ub, n_samples=200, n_chains=4, seed=1)
+    res3 = smp.sample(evaluate, x0=mean + 0.1, lb=lb, ub=ub, n_samples=200, n_chains=4, seed=1)
+    assert np.array_equal(res2.trace_x, res3.trace_x)         # seeded -> reproducible
+
+
+def test_sampler_respects_bounds_and_failed_evaluations():
+    smp = pkg("optimization.sampler")
+
+    def evaluate(X):
+        llh = -0.5 * np.sum(X * X, axis=2)
+        llh[X[..., 0] > 0.8] = -np.inf                        # "integration failed" region
+        return llh, np.zeros(X.shape[:2])
+
+    res = smp.sample(evaluate, x0=np.array([[0.1, 0.1]]), lb=np.array([-1.0, 0.0]), ub=np.array([1.0, 1.0]), n_samples=1500, seed=3)
+    x = res.trace_x[0, 0]
+    assert x[:, 0].min() >= -1.0 and x[:, 1].min() >= 0.0 and x[:, 1].max() <= 1.0 and x[:, 0].max() <= 0.8
+
+
+def test_ladder_hdi_and_autocorrelation():
+    smp = pkg("optimization.sampler")
+    b = smp.near_exponential_decay_betas(4)
+    assert b[0] == 1.0 and b[-1] == pytest.approx(1 / 5e4) and np.all(np.diff(b) < 0)
+    assert np.array_equal(smp.near_exponential_decay_betas(1), [1.0])
+    rs = np.random.RandomState(0)
+    lo, hi = smp.hdi(rs.normal(size=200000))
+    assert lo == pytest.approx(-1.88, abs=0.05) and hi == pytest.approx(1.88, abs=0.05)
+    assert smp.autocorrelation_time_sokal(rs.normal(size=20000)) == pytest.approx(1.0, abs=0.2)
+    ar = np.zeros(50000)
+    for i in range(1, len(ar)):
+        ar[i] = 0.9 * ar[i - 1] + rs.normal()
+    assert smp.autocorrelation_time_sokal(ar) == pytest.approx((1 + 0.9) / (1 - 0.9), rel=0.2)
+
+
+def test_batched_trust_region_optimizer():
+    om = pkg("optimization.optimizer")
+    t = np.linspace(0, 4, 30)
+    truth = np.array([[2.0, 0.7], [1.0, 1.5]])                # two problems: y = a * exp(-k t)
+
+    def evaluate(X):                                           # X [Q, S, 2]
+        a, k = X[..., 0:1], X[..., 1:2]
+        y = truth[:, None, 0:1] * np.exp(-truth[:, None, 1:2] * t)
+        m = a * np.exp(-k * t)
+        r = m - y
+        J = np.stack([np.exp(-k * t), -a * t * np.exp(-k * t)], axis=-1)        # [Q, S, T, 2]
+        return {"fval": 0.5 * np.sum(r * r, axis=-1), "grad": np.einsum("qst,qstd->qsd", r, J),
+                "hess": np.einsum("qstd,qste->qsde", J, J)}
+
+    lb, ub = np.array([0.0, 0.0]), np.array([10.0, 10.0])
+    x0 = om.uniform_startpoints(16, lb, ub, Q=2, seed=5)
+    res = om.minimize(evaluate, x0, lb, ub, maxiter=200)
+    np.testing.assert_allclose(res.x[:, 0, :], truth, rtol=1e-6)
+    assert np.all(res.fval[:, 0] < 1e-12) and np.all(np.diff(res.fval, axis=1) >= 0)      # sorted, best first
+    assert res.converged[:, 0].all()
+    # a bound-constrained optimum: true k above the upper bound
+    res = om.minimize(evaluate, x0, lb, np.array([10.0, 0.5]), maxiter=200)
+    assert np.allclose(res.x[0, 0, 1], 0.5)
+
+
+def test_petab_tables_roundtrip(tmp_path):
+    io = pkg("optimization.petab_io")
+    po = pkg("optimization.petab_optimization")
+    P = pkg()
+    rs = np.random.RandomState(0)
+    t = np.linspace(0, 100, 5)
+    groups = [po.GroupData("MALE", rs.rand(3, 5, 2)), po.GroupData("FEMALE", rs.rand(3, 5, 2))]
+    yaml_path = io.write_petab_like_reference(tmp_path / "abc123", P.MODELS["simple_pk"], groups, t, ["y_cent", "y_gut"],
+                                              ["k_abs", "CL"], {"k_abs_MALE": (0.5, 1.0), "CL_FEMALE": (0.5, 1.0)})
+    tb = io.read_petab_tables(yaml_path)
+    assert len(tb.measurements) == 2 * 3 * 5 * 2
+    assert list(tb.conditions["conditionId"]) == ["MALE", "FEMALE"] and list(tb.conditions["k_abs"]) == ["k_abs_MALE", "k_abs_FEMALE"]
+    assert set(tb.conditions.columns) >= {"y_cent", "y_gut"} and (tb.conditions["y_cent"] == 0.0).all()      # quirk Q4
+    assert list(tb.parameters["parameterId"]) == ["k_abs_MALE", "k_abs_FEMALE", "CL_MALE", "CL_FEMALE"]
+    assert tb.parameters.set_index("parameterId").loc["k_abs_MALE", "objectivePriorParameters"] == "0.5;1.0"
+    assert tb.model_path.exists()
+
+
+def test_result_helpers():
+    d = pkg("optimization.driver")
+    assert d.get_group_from_pid("k_abs_MALE") == "MALE" and d.get_parameter_from_pid("k_abs_MALE") == "k_abs"
+    assert d.get_parameter_from_pid("LI__ICGIM_Vmax_FEMALE") == "LI__ICGIM_Vmax"
+    assert d.get_parameter_from_pid("k1") == "k1"
+    assert d.DEFAULT_SETTINGS["n_starts"] == 100 and d.DEFAULT_SETTINGS["n_samples"] == 5000 and d.DEFAULT_SETTINGS["n_chains"] == 4

@@ -1,0 +1,179 @@
+"""GPU tests of the estimation stack built on the objective op: FIM, multi-problem batches, hierarchical form,
+PEtab directories, multistart optimisation, adaptive-Metropolis/parallel-tempering sampling, results TSV."""
+import json
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import lognormal_draws, pkg
+
+pytestmark = pytest.mark.gpu
+OBS = ["y_cent", "y_gut", "y_peri"]
+
+
+def _pk_groups(oracle, t, truths, n_ind, cv, seed):
+    po = pkg("optimization.petab_optimization")
+    cols = [oracle.SIMPLE_PK.states.index(o) for o in OBS]
+    rs = np.random.RandomState(seed)
+    groups = []
+    for gid, (ka, cl) in truths.items():
+        f = oracle.simple_pk_exact({"k_abs": ka, "CL": cl}, t)[:, cols]
+        groups.append(po.GroupData(gid, f[None] * (1 + cv * rs.normal(size=(n_ind,) + f.shape))))
+    return groups
+
+
+def test_fim_and_problem_batch_vs_oracle(cuda_lib, rt, oracle):
+    po = pkg("optimization.petab_optimization")
+    t = np.linspace(0, 30, 12)
+    cols = [oracle.SIMPLE_PK.states.index(o) for o in OBS]
+    truths = {"MALE": (0.8, 1.1), "FEMALE": (1.3, 0.6)}
+    problems = [_pk_groups(oracle, t, truths, n, cv, s) for n, cv, s in ((3, 0.05, 1), (10, 0.2, 2), (1, 0.0, 3))]
+    priors = [{"k_abs_MALE": (0.5, 1.0), "CL_FEMALE": (0.5, 2.0)}, {}, {"CL_MALE": (1.0, 0.3)}]
+    sigma = 0.1
+    batch = po.PetabObjectiveBatch("simple_pk", ["k_abs", "CL"], problems, t, OBS, sigma=sigma, priors=priors, rtol=1e-9, atol=1e-13)
+    X = np.stack([np.stack([lognormal_draws(10 + q, 4), lognormal_draws(20 + q, 4), lognormal_draws(30 + q, 4),
+                            lognormal_draws(40 + q, 4)], axis=1) for q in range(3)])           # [Q, B, 4]
+    o = batch.evaluate(X, order=2)
+    for q in range(3):
+        single = po.PetabObjective("simple_pk", ["k_abs", "CL"], problems[q], t, OBS, sigma=sigma, priors=priors[q], rtol=1e-9, atol=1e-13)
+        lp, dlp = single.logp_and_grad(X[q])
+        np.testing.assert_allclose(o["llh"][q] + o["lprior"][q], lp, rtol=1e-10)
+        np.testing.assert_allclose(o["dllh"][q] + o["dlprior"][q], dlp, rtol=1e-8, atol=1e-8 * np.abs(dlp).max())
+    # FIM against the oracle for one point: sum over groups of n_ind * s^T s / sigma^2, block diagonal per group
+    q, b = 1, 2
+    F = np.zeros((4, 4))
+    for gi in range(2):
+        over = {"k_abs": X[q, b, gi], "CL": X[q, b, 2 + gi]}
+        s = oracle.simple_pk_exact_sens(over, t)[:, cols, :].reshape(-1, 2)
+        Fg = 10 * s.T @ s / sigma**2
+        for a, ia in ((0, gi), (1, 2 + gi)):
+            for c, ic in ((0, gi), (1, 2 + gi)):
+                F[ia, ic] = Fg[a, c]
+    np.testing.assert_allclose(o["fim"][q, b], F, rtol=1e-6, atol=1e-8 * np.abs(F).max())
+
+
+def test_hierarchical_objective_vs_oracle(cuda_lib, rt, oracle):
+    po = pkg("optimization.petab_optimization")
+    t = np.linspace(0, 40, 10)
+    n_ind, C = 37, 3
+    th_true = np.stack([lognormal_draws(1, n_ind), lognormal_draws(2, n_ind)], axis=1)
+    rs = np.random.RandomState(5)
+    y = np.stack([oracle.simple_pk_exact({"k_abs": a, "CL": c}, t) for a, c in th_true])
+    y = y * (1 + 0.05 * rs.normal(size=y.shape))
+    pb = rt.Problem("simple_pk")
+    pb.set_solver(rtol=1e-9, atol=1e-13)
+    pb.set_columns(["k_abs", "CL"])
+    pb.set_timepoints(t)
+    pb.set_observables(["y_gut", "y_cent", "y_peri"])
+    pb.set_data(np.stack([po.sufficient_statistics(y[i:i + 1], 0) for i in range(n_ind)], axis=-1), 0.05)
+    H = po.HierarchicalObjective(pb, n_ind, mu_prior=[(0.0, 1.0), (-0.3, 0.5)], omega_prior=[1.0, 0.7])
+    theta = np.stack([np.stack([lognormal_draws(10 + c, n_ind), lognormal_draws(20 + c, n_ind)], axis=1) for c in range(C)])
+    mu = rs.normal(size=(C, 2)) * 0.3
+    omega = 0.5 + rs.rand(C, 2)
+    lp, dth, dmu, dom = H(theta, mu, omega)
+    for c in range(C):
+        ref = 0.0
+        for i in range(n_ind):
+            ref += oracle.loglik_normal(oracle.simple_pk_exact({"k_abs": theta[c, i, 0], "CL": theta[c, i, 1]}, t), y[i], 0.05)
+        pop, d_theta, d_mu, d_sigma = oracle.population_lognormal_logpdf(theta[c], mu[c], omega[c])
+        ref += pop
+        ref += oracle.log_prior_normal(mu[c], [0.0, -0.3], [1.0, 0.5])[0]
+        ref += np.sum(0.5 * np.log(2 / np.pi) - np.log([1.0, 0.7]) - 0.5 * (omega[c] / np.array([1.0, 0.7])) ** 2)
+        assert lp[c] == pytest.approx(ref, rel=1e-7)
+        np.testing.assert_allclose(dmu[c], d_mu + oracle.log_prior_normal(mu[c], [0.0, -0.3], [1.0, 0.5])[1], rtol=1e-9)
+        np.testing.assert_allclose(dom[c], d_sigma - omega[c] / np.array([1.0, 0.7]) ** 2, rtol=1e-9)
+        i = 4
+        s = oracle.simple_pk_exact_sens({"k_abs": theta[c, i, 0], "CL": theta[c, i, 1]}, t)
+        g = oracle.loglik_normal_grad(oracle.simple_pk_exact({"k_abs": theta[c, i, 0], "CL": theta[c, i, 1]}, t), s, y[i], 0.05)
+        np.testing.assert_allclose(dth[c, i], g + d_theta[i], rtol=1e-6)
+
+
+def test_petab_directory_literal_and_intended(cuda_lib, rt, oracle, tmp_path):
+    io = pkg("optimization.petab_io")
+    po = pkg("optimization.petab_optimization")
+    P = pkg()
+    t = np.linspace(0, 100, 6)
+    groups = _pk_groups(oracle, t, {"MALE": (0.8, 1.1), "FEMALE": (1.3, 0.6)}, 4, 0.05, 9)
+    priors = {"k_abs_MALE": (0.5, 1.0), "k_abs_FEMALE": (1.0, 1.0), "CL_MALE": (1.0, 1.0), "CL_FEMALE": (0.5, 1.0)}
+    y = io.write_petab_like_reference(tmp_path / "uid1", P.MODELS["simple_pk"], groups, t, OBS, ["k_abs", "CL"], priors)
+    lit = io.load_petab_problem(y, mode="literal")
+    assert lit.x_names == ["k_abs_MALE", "k_abs_FEMALE", "CL_MALE", "CL_FEMALE"] and np.all(lit.ub == 1e8)
+    x = np.array([0.9, 1.2, 1.0, 0.7])
+    # literal: all observed species start at 0 -> model output 0 -> likelihood constant in x (quirk Q4)
+    const = sum(-oracle.loglik_normal(np.zeros_like(g.y[0]), g.y, 1.0) for g in groups)
+    lp0 = oracle.log_prior_normal(x, [0.5, 1.0, 1.0, 0.5], [1.0] * 4)[0]
+    assert lit.fun(x) == pytest.approx(const - lp0, rel=1e-9)
+    it = io.load_petab_problem(y, mode="intended")
+    direct = po.PetabObjective("simple_pk", ["k_abs", "CL"], groups, t, OBS, sigma=1.0, priors=priors)
+    assert it.fun(x) == pytest.approx(direct.fun(x), rel=1e-12)
+
+
+def test_multistart_optimizer_recovers_parameters(cuda_lib, rt, oracle):
+    po = pkg("optimization.petab_optimization")
+    drv = pkg("optimization.driver")
+    t = np.linspace(0, 30, 16)
+    truths = [{"MALE": (0.8, 1.1), "FEMALE": (1.3, 0.6)}, {"MALE": (2.0, 0.4), "FEMALE": (0.5, 1.8)}]
+    problems = [_pk_groups(oracle, t, tr, 2, 0.0, 1) for tr in truths]
+    batch = po.PetabObjectiveBatch("simple_pk", ["k_abs", "CL"], problems, t, OBS, sigma=0.01, rtol=1e-9, atol=1e-13)
+    d = drv.GpuPetabSampler(batch, start_box=(np.full(4, 0.05), np.full(4, 5.0)))
+    res = d.run_optimization(n_starts=24, maxiter=100, seed=7)
+    for q, tr in enumerate(truths):
+        want = np.array([tr["MALE"][0], tr["FEMALE"][0], tr["MALE"][1], tr["FEMALE"][1]])
+        np.testing.assert_allclose(res.x[q, 0], want, rtol=1e-5)
+    assert (res.converged[:, 0]).all()
+
+
+def test_sampler_posterior_matches_laplace(cuda_lib, rt, oracle):
+    """simple_chain, one well-identified parameter per group: the sampled posterior must agree with the Laplace
+    approximation (mean = optimum, sd = FIM^-1/2) that the optimiser's own quantities give."""
+    po = pkg("optimization.petab_optimization")
+    drv = pkg("optimization.driver")
+    t = np.linspace(0, 10, 21)
+    rs = np.random.RandomState(2)
+    groups = []
+    for gid, k1 in (("MALE", 0.6), ("FEMALE", 1.4)):
+        f = oracle.simple_chain_exact(k1, t)
+        groups.append(po.GroupData(gid, f[None] * (1 + 0.05 * rs.normal(size=(5,) + f.shape))))
+    batch = po.PetabObjectiveBatch("simple_chain", ["k1"], [groups], t, ["S1", "S2"], sigma=0.05, rtol=1e-9, atol=1e-13)
+    d = drv.GpuPetabSampler(batch, start_box=(np.full(2, 0.1), np.full(2, 3.0)))
+    res = d.run_optimization(n_starts=8, maxiter=100)
+    xopt = res.x[0, 0]
+    np.testing.assert_allclose(xopt, [0.6, 1.4], rtol=0.05)
+    F = batch.evaluate(xopt[None, None, :], order=2)["fim"][0, 0]
+    sd_laplace = np.sqrt(np.diag(np.linalg.inv(F)))
+    sr = d.bayesian_sampler(n_samples=4000, n_chains=4, seed=11)
+    cold = sr.trace_x[0, 0, 500:]
+    np.testing.assert_allclose(cold.mean(axis=0), xopt, atol=3 * sd_laplace.max() / np.sqrt(50))
+    np.testing.assert_allclose(cold.std(axis=0), sd_laplace, rtol=0.3)
+    assert sr.effective_sample_size[0] > 50
+
+
+def test_optimize_experiments_writes_reference_results_tsv(cuda_lib, rt, oracle, tmp_path):
+    io = pkg("optimization.petab_io")
+    drv = pkg("optimization.driver")
+    P = pkg()
+    t = np.linspace(0, 30, 8)
+    yamls = []
+    for k, cv in enumerate((0.01, 0.1)):
+        groups = _pk_groups(oracle, t, {"MALE": (0.8, 1.1), "FEMALE": (1.3, 0.6)}, 3, cv, 20 + k)
+        priors = {"k_abs_MALE": (0.5, 1.0), "k_abs_FEMALE": (1.0, 1.0), "CL_MALE": (1.0, 1.0), "CL_FEMALE": (0.5, 1.0)}
+        yamls.append(io.write_petab_like_reference(tmp_path / "xps" / f"uid{k}", P.MODELS["simple_pk"], groups, t, OBS, ["k_abs", "CL"], priors))
+    ok = drv.optimize_experiments(tmp_path / "results", yamls, mode="intended", start_box=(np.full(4, 0.05), np.full(4, 5.0)),
+                                  settings={"n_starts": 8, "n_samples": 300, "n_chains": 4, "maxiter": 50})
+    assert ok == [True, True]
+    df = pd.read_csv(tmp_path / "results" / "uid0_results.tsv", sep="\t")
+    # the reference's result columns (petab_optimization.py:228-269)
+    assert list(df.columns) == ["id", "group", "parameter", "pid", "mean", "std", "median", "ess", "n_samples", "optim_duration",
+                                "sampler_duration", "values", "hdi_low", "hdi_high"]
+    assert list(df["pid"]) == ["k_abs_MALE", "k_abs_FEMALE", "CL_MALE", "CL_FEMALE"] and list(df["group"]) == ["MALE", "FEMALE"] * 2
+    vals = np.array(json.loads(df["values"][0]))
+    assert vals.shape == (4, 301) and (df["hdi_low"] <= df["median"]).all() and (df["median"] <= df["hdi_high"]).all()
+    # caching: a second call does nothing (petab_optimization.py:287-292)
+    assert drv.optimize_experiments(tmp_path / "results", yamls) == [True, True]
+    # errors are written to <uid>_errors.tsv, not raised (:340-348)
+    bad = tmp_path / "xps" / "uidbad" / "petab.yaml"
+    bad.parent.mkdir(parents=True)
+    bad.write_text("format_version: 2\n")
+    assert drv.optimize_experiment(bad, tmp_path / "results") is False
+    assert (tmp_path / "results" / "uidbad_errors.tsv").exists()

@@ -77,6 +77,12 @@ int pv_problem_set_solver(pv_problem* p, int method, double rtol, double atol, i
  * refill_min (1..32, default 3) of them are idle; 32 = classic one-trajectory-per-thread behaviour per warp */
 int pv_problem_set_schedule(pv_problem* p, int refill_min);
 
+/* PV_METHOD_AUTO on a model classified non-stiff integrates with DOPRI5 first; trajectories that use up
+ * switch_steps (default 4000) explicit steps - stiff parameter values, e.g. rate constants near the PEtab upper bound
+ * 1e8 that a tempered chain or a uniform start point visits - are re-run with RODAS4 in a second launch on the
+ * same stream (the reference's CVODE is implicit throughout).  switch_steps >= max_steps disables the second pass. */
+int pv_problem_set_stiff_switch(pv_problem* p, int switch_steps);
+
 /* `r.resetAll(); r.setValue(key, value)` for values shared by the whole batch (dosage dict,
  * petab_factory.py:229-233).  id = a theta id, or a state id / "[state id]" for an initial concentration. */
 int pv_problem_set_value(pv_problem* p, const char* id, double value);

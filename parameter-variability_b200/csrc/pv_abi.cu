@@ -63,6 +63,13 @@ struct pv_problem {
     int refill_min = 3;
     double t0 = 0.0;
     bool t0_set = false;
+    // METHOD_AUTO on a non-stiff model: trajectories that exhaust switch_steps explicit steps (stiff parameter
+    // values) are re-run with RODAS4.  Scratch per launch slot: 0 = caller's stream, 1..3 = internal pipeline streams.
+    int switch_steps = 4000;
+    int32_t* d_scratch_status[4] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t* d_scratch_index[4] = {nullptr, nullptr, nullptr, nullptr};
+    int* d_scratch_count[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t scratch_cap[4] = {0, 0, 0, 0};
 };
 #define PV_COUNTER_RING 1024
 
@@ -148,6 +155,11 @@ extern "C" void pv_problem_destroy(pv_problem* p) {
     cudaFree(p->d_stats);
     cudaFree(p->d_failed);
     cudaFree(p->d_counters);
+    for (int i = 0; i < 4; ++i) {
+        cudaFree(p->d_scratch_status[i]);
+        cudaFree(p->d_scratch_index[i]);
+        cudaFree(p->d_scratch_count[i]);
+    }
     for (int i = 0; i < 3; ++i) {
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
         cudaFree(p->stage_dev[i]);
@@ -188,6 +200,13 @@ extern "C" int pv_problem_set_schedule(pv_problem* p, int refill_min) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
     if (refill_min < 1 || refill_min > 32) return fail(PV_E_ARG, "refill_min must be in [1, 32]");
     p->refill_min = refill_min;
+    return 0;
+}
+
+extern "C" int pv_problem_set_stiff_switch(pv_problem* p, int switch_steps) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (switch_steps < 1) return fail(PV_E_ARG, "switch_steps must be >= 1");
+    p->switch_steps = switch_steps;
     return 0;
 }
 
@@ -350,8 +369,21 @@ static int sync_values(pv_problem* p, cudaStream_t s) {
     return 0;
 }
 
+static int ensure_scratch(pv_problem* p, int slot, int64_t B) {
+    if (p->scratch_cap[slot] >= B) return 0;
+    cudaFree(p->d_scratch_status[slot]);
+    cudaFree(p->d_scratch_index[slot]);
+    p->d_scratch_status[slot] = p->d_scratch_index[slot] = nullptr;
+    p->scratch_cap[slot] = 0;
+    CUDA_OK(cudaMalloc(&p->d_scratch_status[slot], sizeof(int32_t) * B));
+    CUDA_OK(cudaMalloc(&p->d_scratch_index[slot], sizeof(int32_t) * B));
+    if (!p->d_scratch_count[slot]) CUDA_OK(cudaMalloc(&p->d_scratch_count[slot], sizeof(int)));
+    p->scratch_cap[slot] = B;
+    return 0;
+}
+
 static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y, double* S, double* logp,
-                  double* grad, int32_t* status, int32_t* steps, cudaStream_t s, double* fim = nullptr) {
+                  double* grad, int32_t* status, int32_t* steps, cudaStream_t s, double* fim = nullptr, int slot = 0) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
     if (B < 0) return fail(PV_E_ARG, "B < 0");
     if (B == 0) return 0;
@@ -413,6 +445,13 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     }
     int method = p->method;
     if (method == PV_METHOD_AUTO) method = p->tab->stiff ? PV_METHOD_RODAS4 : PV_METHOD_DOPRI5;
+    // explicit first pass with a step budget, implicit second pass for what did not finish (stiff parameter values)
+    const bool two_pass = p->method == PV_METHOD_AUTO && !p->tab->stiff && p->switch_steps < p->max_steps;
+    if (two_pass) {
+        if (int rc = ensure_scratch(p, slot, B)) return rc;
+        lp.max_steps = p->switch_steps;
+        if (!lp.status) lp.status = p->d_scratch_status[slot];
+    }
     size_t shmem = sizeof(double) * (lp.T + p->tab->n_theta + p->tab->n_states);
     if (need_logp && lp.n_data == 1) shmem += sizeof(double) * 3 * lp.T * lp.n_obs;
     if (shmem > 200 * 1024) return fail(PV_E_ARG, "time grid / data too large for shared memory");
@@ -423,6 +462,25 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
         PV_MODEL_DISPATCH(e = launch_model, (method, mode, obsid, lp, shmem, p->num_sms, s))
     }
     if (e != cudaSuccess) return fail(PV_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+    if (two_pass) {
+        int* cnt = p->d_scratch_count[slot];
+        CUDA_OK(cudaMemsetAsync(cnt, 0, sizeof(int), s));
+        pv_compact_status_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(lp.status, B, PV_ERR_MAX_STEPS,
+                                                                           p->d_scratch_index[slot], cnt);
+        g_launches.fetch_add(1);
+        CUDA_OK(cudaGetLastError());
+        lp.max_steps = p->max_steps;
+        lp.index_map = p->d_scratch_index[slot];
+        lp.n_items_dev = cnt;
+        lp.counter = p->d_counters + p->counter_next;
+        p->counter_next = (p->counter_next + 1) % PV_COUNTER_RING;
+        CUDA_OK(cudaMemsetAsync(lp.counter, 0, sizeof(unsigned long long), s));
+        e = cudaErrorInvalidValue;
+        switch (p->model) {
+            PV_MODEL_DISPATCH(e = launch_model, (PV_METHOD_RODAS4, mode, false, lp, shmem, p->num_sms, s))
+        }
+        if (e != cudaSuccess) return fail(PV_E_CUDA, std::string("kernel launch (stiff re-run): ") + cudaGetErrorString(e));
+    }
     return 0;
 }
 
@@ -521,7 +579,7 @@ extern "C" int pv_simulate_host(pv_problem* p, int64_t B, const double* P_host, 
             CUDA_OK(cudaMemcpy2DAsync(dP, sizeof(double) * nb, P_host + b0, sizeof(double) * B, sizeof(double) * nb, n_cols,
                                       cudaMemcpyHostToDevice, s));
         if (int rc = launch(p, logp_host ? PV_MODE_TRAJ_LOGP : PV_MODE_TRAJ, nb, n_cols ? dP : nullptr, dY, nullptr,
-                            logp_host ? dL : nullptr, nullptr, dStatus, dSteps, s))
+                            logp_host ? dL : nullptr, nullptr, dStatus, dSteps, s, nullptr, 1 + slot))
             return rc;
         pv_count_failed_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(dStatus, nb, p->d_failed);
         g_launches.fetch_add(1);

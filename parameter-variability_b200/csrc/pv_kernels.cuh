@@ -46,7 +46,9 @@ struct pv_launch_params {
     double log_norm[PV_MAX_OBS];   // normal: log(2 pi sigma^2);  lognormal: log(sigma) + 0.5 log(2 pi)
     int col_target[PV_MAX_COLS];   // < NTH: theta index; >= NTH: NTH + state index (initial value)
     int obs_idx[PV_MAX_OBS];
-    unsigned long long* counter;   // next unprocessed trajectory (lane refill)
+    unsigned long long* counter;   // next unprocessed work item (lane refill)
+    const int32_t* index_map;      // work item -> trajectory (nullptr: identity); used by the stiff re-run pass
+    const int* n_items_dev;        // number of work items if it lives on the device (nullptr: B)
     double t0;                     // integration start (initial values hold at t0 <= tgrid[0])
     int n_cols, T, n_obs, n_data, noise_model, max_steps, refill_min;
 };
@@ -216,6 +218,7 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
 
     const unsigned FULL = 0xffffffffu;
     const int lane_id = threadIdx.x & 31;
+    const int64_t n_items = p.n_items_dev ? (int64_t)*p.n_items_dev : p.B;
     typename Sys::Consts ks;
     Lane lane;
     pv_sink<M, MODE, OBSID> sink{p, stats_shared ? sh_stats : nullptr, 0, 0, {}, 0.0, {}, {}};
@@ -253,10 +256,11 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
             if (lane_id == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(need));
             base = __shfl_sync(FULL, base, leader);
             if ((need >> lane_id) & 1u) {
-                const int64_t b = (int64_t)base + __popc(need & ((1u << lane_id) - 1u));
-                if (b >= p.B) {
+                const int64_t item = (int64_t)base + __popc(need & ((1u << lane_id) - 1u));
+                if (item >= n_items) {
                     exhausted = true;
                 } else {
+                    const int64_t b = p.index_map ? (int64_t)p.index_map[item] : item;
                     // ---- theta = batch-wide values, overridden by this trajectory's columns -----------------
                     double pc[PV_MAX_COLS];
 #pragma unroll
@@ -329,6 +333,20 @@ __global__ void pv_segment_sum_kernel(const double* __restrict__ x, int64_t seg_
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) out[seg] = acc;
+}
+
+// work list of the trajectories whose status == code (order irrelevant: results go to their own slots)
+__global__ void pv_compact_status_kernel(const int32_t* __restrict__ status, int64_t B, int code, int32_t* __restrict__ index,
+                                         int* __restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool hit = i < B && status[i] == code;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (hit) index[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
 }
 
 // count trajectories with status != 0 (for the *_host return value)

@@ -43,6 +43,7 @@ ABI = {
     "pv_problem_set_columns": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]),
     "pv_problem_set_timepoints": (C.c_int, [C.c_void_p, C.c_double, C.c_int, _dp]),
     "pv_problem_set_schedule": (C.c_int, [C.c_void_p, C.c_int]),
+    "pv_problem_set_stiff_switch": (C.c_int, [C.c_void_p, C.c_int]),
     "pv_problem_set_observables": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]),
     "pv_problem_set_data": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
     "pv_simulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -203,6 +204,9 @@ class Problem:
 
     def set_schedule(self, refill_min: int = 8) -> None:
         _check(self._lib.pv_problem_set_schedule(self._h, int(refill_min)))
+
+    def set_stiff_switch(self, switch_steps: int = 4000) -> None:
+        _check(self._lib.pv_problem_set_stiff_switch(self._h, int(switch_steps)))
 
     def set_timepoints(self, t: Sequence[float], t0: Optional[float] = None) -> None:
         """Output grid; ``t0`` (default: the first grid point) is where the initial values hold."""

@@ -413,3 +413,32 @@ def test_petab_objective_pypesto_conventions(cuda_lib, rt, oracle):
     obj.problem.set_solver(method=rt.METHOD_DOPRI5, rtol=1e-9, atol=1e-13, max_steps=3)
     fbad, gbad = obj(x, (0, 1))
     assert np.isinf(fbad) and np.all(np.isnan(gbad))
+
+
+def test_stiff_parameter_values_switch_to_rodas4(cuda_lib, rt, oracle):
+    """METHOD_AUTO on the (non-stiff) simple_pk model: rows with huge rate constants - what a tempered chain or a
+    uniform start point in the PEtab bounds [0, 1e8] produces - exhaust the explicit step budget and are re-run with
+    RODAS4 in the same call; the other rows keep their DOPRI5 result bit for bit."""
+    t = np.linspace(0, 100, 21)
+    k_abs = np.array([1.0, 3e4, 0.5, 1e8, 2.0, 7e5])
+    CL = np.array([1.0, 0.5, 2e6, 1.0, 0.3, 5e7])
+    pb = _problem(rt, "simple_pk", ["k_abs", "CL"], t, ["y_gut", "y_cent", "y_peri"])
+    status = np.empty(6, np.int32)
+    steps = np.empty((2, 6), np.int32)
+    Y, nf = pb.simulate_host(np.stack([k_abs, CL]), 6, status=status, steps=steps)
+    assert nf == 0 and not status.any()
+    assert steps.sum(axis=0).max() < 4000                      # nobody ground through millions of explicit steps
+    ref = np.stack([oracle.simple_pk_exact({"k_abs": a, "CL": c}, t) for a, c in zip(k_abs, CL)], axis=-1)
+    assert parity_violation(Y, ref) <= 1.0
+    pb.set_solver(method=rt.METHOD_DOPRI5, rtol=1e-7, atol=1e-10)
+    Y2, _ = pb.simulate_host(np.stack([k_abs[[0, 2 - 2, 4]], CL[[0, 0, 4]]]), 3)
+    assert np.array_equal(Y2[:, :, 0], Y[:, :, 0]) and np.array_equal(Y2[:, :, 2], Y[:, :, 4])
+    # gradient mode goes through the same switch
+    pb.set_solver(method=rt.METHOD_AUTO, rtol=1e-8, atol=1e-12)
+    truth = oracle.simple_pk_exact({}, t)
+    pb.set_data(np.stack([np.ones_like(truth), truth, truth * truth])[..., None], 0.1)
+    lp, g, _, nf = pb.logp_host(np.stack([k_abs, CL]), grad=True)
+    assert nf == 0 and np.all(np.isfinite(lp)) and np.all(np.isfinite(g))
+    for b in (1, 3):
+        f = oracle.simple_pk_exact({"k_abs": k_abs[b], "CL": CL[b]}, t)
+        assert lp[b] == pytest.approx(oracle.loglik_normal(f, truth, 0.1), rel=1e-6)

@@ -34,17 +34,16 @@ def near_exponential_decay_betas(n_chains: int, exponent: float = 4.0, max_temp:
 
 
 def _regularize(cov: np.ndarray, reg: float) -> np.ndarray:
+    """Symmetrise and make positive definite.  pyPESTO adds reg_factor * I until the matrix is PD; the hot chains of a
+    problem with bounds [0, 1e8] reach variances of 1e15, where an absolute 1e-6 no longer cures round-off, so the
+    eigenvalues are floored relative to the largest one as well."""
     cov = 0.5 * (cov + np.swapaxes(cov, -1, -2))
-    w = np.linalg.eigvalsh(cov)
-    bad = w[..., 0] <= 0
-    if np.any(bad):
-        dim = cov.shape[-1]
-        while np.any(bad):
-            cov = cov + np.where(bad[..., None, None], reg * np.eye(dim), 0.0)
-            w = np.linalg.eigvalsh(cov)
-            bad = w[..., 0] <= 0
-            reg *= 10.0
-    return cov
+    w, V = np.linalg.eigh(cov)
+    floor = np.maximum(reg, 1e-12 * np.abs(w[..., -1:]))
+    if np.all(w > floor):
+        return cov
+    w = np.maximum(w, floor)
+    return np.einsum("...ik,...k,...jk->...ij", V, w, V)
 
 
 @dataclass

@@ -135,12 +135,16 @@ def test_sampler_posterior_matches_laplace(cuda_lib, rt, oracle):
     for gid, k1 in (("MALE", 0.6), ("FEMALE", 1.4)):
         f = oracle.simple_chain_exact(k1, t)
         groups.append(po.GroupData(gid, f[None] * (1 + 0.05 * rs.normal(size=(5,) + f.shape))))
-    batch = po.PetabObjectiveBatch("simple_chain", ["k1"], [groups], t, ["S1", "S2"], sigma=0.05, rtol=1e-9, atol=1e-13)
+    # priors as in the reference's exact_prior experiments (factories/simple_chain.py): Normal(loc, scale) on the lin
+    # scale; they are what keeps the tempered chains (likelihood ^ beta, prior untempered) inside a proper region
+    priors = [{"k1_MALE": (0.6, 1.0), "k1_FEMALE": (1.4, 1.0)}]
+    batch = po.PetabObjectiveBatch("simple_chain", ["k1"], [groups], t, ["S1", "S2"], sigma=0.05, priors=priors, rtol=1e-9, atol=1e-13)
     d = drv.GpuPetabSampler(batch, start_box=(np.full(2, 0.1), np.full(2, 3.0)))
     res = d.run_optimization(n_starts=8, maxiter=100)
     xopt = res.x[0, 0]
     np.testing.assert_allclose(xopt, [0.6, 1.4], rtol=0.05)
-    F = batch.evaluate(xopt[None, None, :], order=2)["fim"][0, 0]
+    o2 = batch.evaluate(xopt[None, None, :], order=2)
+    F = o2["fim"][0, 0] + np.diag(o2["prior_precision"][0, 0])
     sd_laplace = np.sqrt(np.diag(np.linalg.inv(F)))
     sr = d.bayesian_sampler(n_samples=4000, n_chains=4, seed=11)
     cold = sr.trace_x[0, 0, 500:]

@@ -12,8 +12,10 @@
  *   - plain pointers and sizes, no torch / C++ types; the library is loaded with ctypes;
  *   - every function returns int: 0 = ok, < 0 = argument / CUDA error (text via pv_last_error()),
  *     > 0 (only the *_sync helpers) = number of trajectories whose integration failed;
- *   - "device" pointers are CUDA device memory owned by the caller, fp64 unless stated, batch-minor:
- *     consecutive trajectories are consecutive addresses;
+ *   - "device" pointers are CUDA device memory owned by the caller, fp64 unless stated.  Inputs and the
+ *     per-trajectory scalars are batch-minor (P[n_cols][B], logp[B], grad[n_sens][B]: consecutive trajectories are
+ *     consecutive addresses); trajectories are trajectory-major (Y[B][n_t][n_obs]: one contiguous block per
+ *     parameter row, the reference's own sim x time layout, petab_factory.py:269-271);
  *   - launches go to the given stream (a cudaStream_t passed as void*; NULL = legacy default stream),
  *     nothing synchronises unless the name says so;
  *   - a pv_problem may be used from one host thread at a time.
@@ -101,7 +103,7 @@ int pv_problem_set_observables(pv_problem* p, int n_obs, const char* const* ids)
 /* ---- B1: batched forward simulation --------------------------------------------------------------------
  * Replaces the loop `for _, row in parameters.iterrows(): ... s = self.r.simulate(...)` (:228-246).
  *   P_dev      [n_cols][B]   per-trajectory values of the configured columns
- *   Y_dev      [n_t][n_obs][B] concentrations of the selected observables (may be NULL: integrate only)
+ *   Y_dev      [B][n_t][n_obs] concentrations of the selected observables (may be NULL: integrate only)
  *   status_dev [B] int32     PV_TRAJ_* (may be NULL)
  *   steps_dev  [2][B] int32  accepted / rejected step counts (may be NULL)                               */
 int pv_simulate(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, int32_t* status_dev,
@@ -146,7 +148,7 @@ int pv_logp_grad_fim(pv_problem* p, int64_t B, const double* P_dev, double* logp
 int pv_simulate_logp(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, double* logp_dev,
                      int32_t* status_dev, int32_t* steps_dev, void* stream);
 
-/* trajectories and their sensitivities (AMICI `rdata.sy`): S_dev [n_sens][n_t][n_obs][B] (Y_dev may be NULL) */
+/* trajectories and their sensitivities (AMICI `rdata.sy`): S_dev [B][n_t][n_obs][n_sens] (Y_dev may be NULL) */
 int pv_simulate_sens(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, double* S_dev,
                      int32_t* status_dev, int32_t* steps_dev, void* stream);
 

@@ -553,7 +553,7 @@ extern "C" int pv_simulate_host(pv_problem* p, int64_t B, const double* P_host, 
     const int64_t rows = (int64_t)p->tgrid.size() * (int64_t)p->obs_idx.size();
     // chunks sized so that copy-out of chunk i overlaps the kernel of chunk i+1
     const int64_t chunk = std::min<int64_t>(B, (int64_t)1 << 17);
-    // per slot: P [n_cols][chunk], Y [rows][chunk], logp [chunk], status [chunk] + steps [2][chunk] (int32)
+    // per slot: P [n_cols][chunk], Y [chunk][rows], logp [chunk], status [chunk] + steps [2][chunk] (int32)
     const size_t bytesP = sizeof(double) * (size_t)std::max(n_cols, 1) * chunk;
     const size_t bytesY = sizeof(double) * (size_t)rows * chunk;
     const size_t bytesL = sizeof(double) * (size_t)chunk;
@@ -583,8 +583,7 @@ extern "C" int pv_simulate_host(pv_problem* p, int64_t B, const double* P_host, 
             return rc;
         pv_count_failed_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(dStatus, nb, p->d_failed);
         g_launches.fetch_add(1);
-        CUDA_OK(cudaMemcpy2DAsync(Y_host + b0, sizeof(double) * B, dY, sizeof(double) * nb, sizeof(double) * nb, rows,
-                                  cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaMemcpyAsync(Y_host + b0 * rows, dY, sizeof(double) * rows * nb, cudaMemcpyDeviceToHost, s));
         if (logp_host) CUDA_OK(cudaMemcpyAsync(logp_host + b0, dL, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
         if (status_host) CUDA_OK(cudaMemcpyAsync(status_host + b0, dStatus, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
         if (steps_host)

@@ -34,8 +34,8 @@ struct pv_launch_params {
     const double* y0_base;     // [NX], NaN = use the model's initial value
     const double* tgrid;       // [T]
     const double* stats;       // [3][T][n_obs][n_data]
-    double* Y;                 // [T][n_obs][B]
-    double* S;                 // [NS][T][n_obs][B]
+    double* Y;                 // [B][T][n_obs]
+    double* S;                 // [B][T][n_obs][NS]
     double* logp;              // [B]
     double* grad;              // [NS][B]
     double* fim;               // [NS(NS+1)/2][B]  upper triangle, row-major
@@ -84,15 +84,15 @@ struct pv_sink {
     double g[M::NSD];
     double fim[NFIM];         // sum over measurements of (df/dtheta)(df/dtheta)^T / sigma^2  (AMICI's FIM)
 
-    // yrow = &Y[j][0][b] (or nullptr), srow = &S[0][j][0][b]; so = index of (j, 0, d) in one statistics plane
+    // yrow = &Y[b][j][0] (or nullptr), srow = &S[b][j][0][0]; so = index of (j, 0, d) in one statistics plane
     PV_D void one(int k, double f, const double (&df)[M::NSD], double* yrow, double* srow, int so, int plane,
                   double log_norm, double inv_sigma2) {
         const int n_obs = OBSID ? M::NX : p.n_obs;
         if constexpr (TRAJ) {
-            if (yrow) yrow[(int64_t)k * p.B] = f;
+            if (yrow) yrow[k] = f;
             if constexpr (SENS) {
 #pragma unroll
-                for (int s = 0; s < M::NS; ++s) srow[((int64_t)s * p.T * n_obs + k) * p.B] = df[s];
+                for (int s = 0; s < M::NS; ++s) srow[k * M::NS + s] = df[s];
             }
         }
         if constexpr (LOGP) {
@@ -139,9 +139,13 @@ struct pv_sink {
         double* yrow = nullptr;
         double* srow = nullptr;
         if constexpr (TRAJ) {
-            const int64_t off = (int64_t)(j * n_obs) * p.B + b;
+            // trajectory-major: a lane writes its own contiguous [T][n_obs] block, so consecutive grid points of one
+            // trajectory fill whole 32-byte sectors and 128-byte lines no matter which lane integrates it (lane refill
+            // scatters neighbouring trajectories over warps and time; batch-minor output made every store a partial
+            // sector that was evicted half filled: 2.7x the algorithmic DRAM traffic in ncu)
+            const int64_t off = (b * p.T + j) * n_obs;
             yrow = p.Y ? p.Y + off : nullptr;
-            if constexpr (SENS) srow = p.S + off;
+            if constexpr (SENS) srow = p.S + off * M::NS;
         }
         const int plane = p.T * n_obs * p.n_data;
         const int so = j * n_obs * p.n_data + d;

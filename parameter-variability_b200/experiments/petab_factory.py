@@ -201,7 +201,7 @@ class ODESampleSimulator:
         P = np.ascontiguousarray(parameters.to_numpy(dtype=np.float64).T) if pids else None
         status = np.empty(n, dtype=np.int32)
         steps = np.empty((2, n), dtype=np.int32)
-        Y, n_failed = pb.simulate_host(P, n, status=status, steps=steps)   # [T, n_obs, n]
+        Y, n_failed = pb.simulate_host(P, n, status=status, steps=steps)   # [sim, time, obs]
         self.last_status, self.last_steps = status, steps
         if n_failed:
             bad = np.nonzero(status)[0]
@@ -209,7 +209,7 @@ class ODESampleSimulator:
                 f"integration failed for {n_failed} of {n} parameter rows (first: row {bad[0]}, "
                 f"{runtime.STATUS_TEXT.get(int(status[bad[0]]), status[bad[0]])})")
 
-        data = np.ascontiguousarray(np.transpose(Y, (2, 0, 1)))              # [sim, time, obs]
+        data = Y                                                              # [sim, time, obs], as written by the kernel
         noise = st.noise
         if noise is not None and getattr(noise, "add_noise", False):
             # host side, row by row, in the reference's order: every row reseeds the global stream (:260-265)

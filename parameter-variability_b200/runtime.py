@@ -265,14 +265,16 @@ class Problem:
     def simulate_host(self, P: Optional[np.ndarray], B: int, Y: Optional[np.ndarray] = None,
                       status: Optional[np.ndarray] = None, steps: Optional[np.ndarray] = None,
                       logp: Optional[np.ndarray] = None):
-        """P [n_cols, B] float64 -> Y [T, n_obs, B] (and logp [B] when given).  Returns (Y, n_failed)."""
+        """P [n_cols, B] float64 -> Y [B, T, n_obs] (and logp [B] when given).  Returns (Y, n_failed)."""
         T, K = len(self.timepoints), len(self.observables)
         if P is not None:
             P = np.ascontiguousarray(P, dtype=np.float64)
             if P.shape != (len(self.columns), B):
                 raise ValueError(f"P must have shape ({len(self.columns)}, {B}), got {P.shape}")
         if Y is None:
-            Y = np.empty((T, K, B), dtype=np.float64)
+            Y = np.empty((B, T, K), dtype=np.float64)
+        elif Y.shape != (B, T, K) or not Y.flags.c_contiguous:
+            raise ValueError(f"Y must be a C-contiguous array of shape ({B}, {T}, {K})")
         n_failed = _check(self._lib.pv_simulate_host(self._h, B, _ptr(P), _ptr(Y), _ptr(logp), _ptr(status), _ptr(steps)))
         return Y, n_failed
 

@@ -32,7 +32,7 @@ def test_simple_chain_exact(cuda_lib, rt, oracle):
     pb = _problem(rt, "simple_chain", ["k1"], t, ["S1", "S2"])
     Y, nf = pb.simulate_host(k1[None, :], len(k1))
     assert nf == 0
-    ref = np.stack([oracle.simple_chain_exact(k, t) for k in k1], axis=-1)   # [T, 2, B]
+    ref = np.stack([oracle.simple_chain_exact(k, t) for k in k1])   # [B, T, 2]
     assert parity_violation(Y, ref) <= 1.0
 
 
@@ -44,13 +44,13 @@ def test_simple_pk_c1_single_set(cuda_lib, rt, oracle):
         Y, nf = pb.simulate_host(None, 1)
         assert nf == 0
         ref = oracle.simple_pk_exact({}, t)
-        assert parity_violation(Y[:, :, 0], ref) <= 1.0
+        assert parity_violation(Y[0], ref) <= 1.0
     # known-answer values
     t = np.array([0.0, 5.0, 10.0])
     pb = _problem(rt, "simple_pk", [], t, ["y_gut", "y_cent", "y_peri"])
     Y, _ = pb.simulate_host(None, 1)
-    np.testing.assert_allclose(Y[1, :, 0], [0.00673795, 0.06623389, 0.10043281], rtol=1e-6)
-    np.testing.assert_allclose(Y[2, :, 0], [4.53999e-05, 9.80974e-03, 1.58271e-02], rtol=1e-5)
+    np.testing.assert_allclose(Y[0, 1, :], [0.00673795, 0.06623389, 0.10043281], rtol=1e-6)
+    np.testing.assert_allclose(Y[0, 2, :], [4.53999e-05, 9.80974e-03, 1.58271e-02], rtol=1e-5)
 
 
 def test_simple_pk_batched_draws(cuda_lib, rt, oracle):
@@ -66,7 +66,7 @@ def test_simple_pk_batched_draws(cuda_lib, rt, oracle):
     Y, nf = pb.simulate_host(np.stack([k_abs, CL]), B, status=status, steps=steps)
     assert nf == 0 and not status.any()
     assert steps[0].min() > 10
-    ref = np.stack([oracle.simple_pk_exact({"k_abs": a, "CL": c}, t) for a, c in zip(k_abs, CL)], axis=-1)
+    ref = np.stack([oracle.simple_pk_exact({"k_abs": a, "CL": c}, t) for a, c in zip(k_abs, CL)])
     assert parity_violation(Y, ref) <= 1.0
 
 
@@ -78,7 +78,7 @@ def test_device_pointer_call_matches_host_call(cuda_lib, rt):
     pb = _problem(rt, "simple_pk", ["k_abs", "CL"], t, ["y_cent", "y_gut"])
     Yh, nf = pb.simulate_host(th, B)
     P = torch.from_numpy(th).cuda()
-    Y = torch.empty((T, 2, B), dtype=torch.float64, device="cuda")
+    Y = torch.empty((B, T, 2), dtype=torch.float64, device="cuda")
     status = torch.empty(B, dtype=torch.int32, device="cuda")
     pb.simulate(P, Y, status=status, stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
@@ -98,12 +98,12 @@ def test_icg_rodas4_vs_oracle(cuda_lib, rt, oracle):
     assert nf == 0
     idx = [oracle.ICG_STATES.index(o) for o in obs]
     ref = np.stack([oracle.simulate("icg_body_flat", {"IVDOSE_icg": 10.0, "BW": b, "LI__ICGIM_Vmax": v}, t)[:, idx]
-                    for b, v in zip(BW, Vm)], axis=-1)
+                    for b, v in zip(BW, Vm)])
     assert parity_violation(Y, ref) <= 1.0
     # known-answer values at defaults
     pb2 = _problem(rt, "icg_body_flat", [], np.array([0.0, 5, 10, 15, 20]), ["Cre_plasma_icg"], dosage={"IVDOSE_icg": 10.0})
     Y2, _ = pb2.simulate_host(None, 1)
-    np.testing.assert_allclose(Y2[1:, 0, 0], [1.25351163e-03, 3.13601386e-04, 7.80941642e-05, 1.94248499e-05], rtol=2e-6)
+    np.testing.assert_allclose(Y2[0, 1:, 0], [1.25351163e-03, 3.13601386e-04, 7.80941642e-05, 1.94248499e-05], rtol=2e-6)
 
 
 def _noisy_data(oracle_Y, cv, seed):
@@ -155,14 +155,14 @@ def test_simple_pk_sensitivity_trajectories(cuda_lib, rt, oracle):
     th = np.stack([lognormal_draws(31, B), lognormal_draws(32, B)])
     pb = _problem(rt, "simple_pk", ["k_abs", "CL"], t, ["y_gut", "y_cent", "y_peri"], rtol=1e-9, atol=1e-12)
     P = torch.from_numpy(th).cuda()
-    Y = torch.empty((T, 3, B), dtype=torch.float64, device="cuda")
-    S = torch.empty((2, T, 3, B), dtype=torch.float64, device="cuda")
+    Y = torch.empty((B, T, 3), dtype=torch.float64, device="cuda")
+    S = torch.empty((B, T, 3, 2), dtype=torch.float64, device="cuda")
     pb.simulate_sens(P, Y, S)
     torch.cuda.synchronize()
     for b in range(0, B, 8):
         over = {"k_abs": th[0, b], "CL": th[1, b]}
         ref = oracle.simple_pk_exact_sens(over, t)                 # [T, 3, 2]
-        got = S[:, :, :, b].cpu().numpy().transpose(1, 2, 0)
+        got = S[b].cpu().numpy()
         assert parity_violation(got, ref, rtol=1e-6, atol=1e-9) <= 1.0
 
 
@@ -196,10 +196,10 @@ def test_empty_and_ragged_batches(cuda_lib, rt):
     t = np.linspace(0, 10, 5)
     pb = _problem(rt, "simple_pk", ["k_abs"], t, ["y_cent"])
     Y, nf = pb.simulate_host(np.zeros((1, 0)), 0)
-    assert Y.shape == (5, 1, 0) and nf == 0
+    assert Y.shape == (0, 5, 1) and nf == 0
     for B in (1, 31, 32, 33, 127, 129):
         Y, nf = pb.simulate_host(np.full((1, B), 0.7), B)
-        assert nf == 0 and np.all(Y == Y[:, :, :1])     # identical inputs -> identical lanes
+        assert nf == 0 and np.all(Y == Y[:1])     # identical inputs -> identical lanes
     # single time point = initial state only
     pb.set_timepoints([0.0])
     Y, nf = pb.simulate_host(np.full((1, 3), 0.7), 3)
@@ -231,15 +231,15 @@ def test_full_size_properties_c2(cuda_lib, rt):
     CL = np.random.lognormal(-0.3465735902799726, 0.8325546111576977, B)
     pb = _problem(rt, "simple_pk", ["k_abs", "CL"], t, ["y_gut", "y_cent", "y_peri"])
     P = torch.from_numpy(np.stack([k_abs, CL])).cuda()
-    Y = torch.empty((T, 3, B), dtype=torch.float64, device="cuda")
+    Y = torch.empty((B, T, 3), dtype=torch.float64, device="cuda")
     status = torch.empty(B, dtype=torch.int32, device="cuda")
     pb.simulate(P, Y, status=status)
     torch.cuda.synchronize()
     assert int(status.abs().sum()) == 0
-    total = Y.sum(dim=1)
+    total = Y.sum(dim=2)
     assert float(total.max()) <= 1.0 + 1e-9 and float(total.min()) >= -1e-9
-    gut = torch.exp(-P[0][None, :] * torch.from_numpy(t).cuda()[:, None])
-    assert float(((Y[:, 0, :] - gut).abs() / (1e-9 + 1e-6 * gut)).max()) <= 1.0
+    gut = torch.exp(-P[0][:, None] * torch.from_numpy(t).cuda()[None, :])
+    assert float(((Y[:, :, 0] - gut).abs() / (1e-9 + 1e-6 * gut)).max()) <= 1.0
     pb.set_value("y_gut", 2.0)
     Y2 = torch.empty_like(Y)
     pb.simulate(P, Y2)
@@ -428,11 +428,11 @@ def test_stiff_parameter_values_switch_to_rodas4(cuda_lib, rt, oracle):
     Y, nf = pb.simulate_host(np.stack([k_abs, CL]), 6, status=status, steps=steps)
     assert nf == 0 and not status.any()
     assert steps.sum(axis=0).max() < 4000                      # nobody ground through millions of explicit steps
-    ref = np.stack([oracle.simple_pk_exact({"k_abs": a, "CL": c}, t) for a, c in zip(k_abs, CL)], axis=-1)
+    ref = np.stack([oracle.simple_pk_exact({"k_abs": a, "CL": c}, t) for a, c in zip(k_abs, CL)])
     assert parity_violation(Y, ref) <= 1.0
     pb.set_solver(method=rt.METHOD_DOPRI5, rtol=1e-7, atol=1e-10)
     Y2, _ = pb.simulate_host(np.stack([k_abs[[0, 2 - 2, 4]], CL[[0, 0, 4]]]), 3)
-    assert np.array_equal(Y2[:, :, 0], Y[:, :, 0]) and np.array_equal(Y2[:, :, 2], Y[:, :, 4])
+    assert np.array_equal(Y2[0], Y[0]) and np.array_equal(Y2[2], Y[4])
     # gradient mode goes through the same switch
     pb.set_solver(method=rt.METHOD_AUTO, rtol=1e-8, atol=1e-12)
     truth = oracle.simple_pk_exact({}, t)

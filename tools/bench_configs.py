@@ -113,7 +113,7 @@ def main():
             pb.set_observables(obs)
             pb.set_data(stats, 1e-4)
             P = torch.from_numpy(th).cuda()
-            Y = torch.empty((T, 2, B), dtype=torch.float64, device="cuda")
+            Y = torch.empty((B, T, 2), dtype=torch.float64, device="cuda")
             lp = torch.empty(B, dtype=torch.float64, device="cuda")
             g = torch.empty((2, B), dtype=torch.float64, device="cuda")
             seg = torch.empty(n_chains, dtype=torch.float64, device="cuda")

@@ -293,6 +293,10 @@ def main() -> None:
         if peaks_file.exists():
             hbm_peak = float(json.loads(peaks_file.read_text())["hbm_gbs"])
             hbm_src = "measured (MEASURED_PEAKS.json)"
+        traffic = None
+        tf = ROOT / "profiles" / "r01_dominant_kernel_traffic.json"
+        if tf.exists() and B == B_PER_GPU:
+            traffic = json.loads(tf.read_text())["traffic_bytes_per_launch"]     # from the committed ncu --set full capture
         kernel_ms = ms / args.steps
         ach_tf = flops_per_launch / (kernel_ms * 1e-3) / 1e12
         ach_gbs = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
@@ -309,7 +313,9 @@ def main() -> None:
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "fp64_fma", "achieved": ach_tf, "peak": peak64, "unit": "TFLOP/s",
-                         "frac": ach_tf / peak64 if peak64 > 0 else None, "traffic": None,
+                         "frac": ach_tf / peak64 if peak64 > 0 else None, "traffic": traffic,
+                         "traffic_note": "dram read+write bytes per launch of the dominant kernel (ncu --set full, profiles/); algorithmic "
+                                         f"bytes per launch = {bytes_per_launch}",
                          "peak_source": "measured in this run: pv_fma_peak_tflops (register-resident DFMA chains)",
                          "fp32_fma_peak_tflops": peak32,
                          "kernel": "pv_batch_kernel<pv_model_simple_pk, DOPRI5, TRAJ|LOGP>",

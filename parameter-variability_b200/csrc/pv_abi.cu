@@ -60,7 +60,7 @@ struct pv_problem {
     unsigned long long* d_counters = nullptr;
     int counter_next = 0;
     int num_sms = 0;
-    int refill_min = 3;
+    int refill_min = 6;
     double t0 = 0.0;
     bool t0_set = false;
     // METHOD_AUTO on a non-stiff model: trajectories that exhaust switch_steps explicit steps (stiff parameter

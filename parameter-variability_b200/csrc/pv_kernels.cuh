@@ -14,6 +14,9 @@
 #ifndef PV_MINB_SMALL
 #define PV_MINB_SMALL 4
 #endif
+#ifndef PV_MINB_STIFF
+#define PV_MINB_STIFF 1
+#endif
 
 // mode = bit set: what a launch produces
 enum pv_mode : int {
@@ -197,7 +200,7 @@ struct pv_lane_of<M, 2, SENS> {
 template <class M, int METHOD, int MODE>
 struct pv_kernel_traits {
     static constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
-    static constexpr int MIN_BLOCKS = (METHOD == 1 && pv_system<M, SENS>::N <= 4) ? PV_MINB_SMALL : 1;
+    static constexpr int MIN_BLOCKS = (METHOD == 1 && pv_system<M, SENS>::N <= 4) ? PV_MINB_SMALL : (METHOD == 2 ? PV_MINB_STIFF : 1);
 };
 
 template <class M, int METHOD, int MODE, bool OBSID>

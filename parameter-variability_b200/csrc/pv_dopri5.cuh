@@ -56,6 +56,20 @@ struct pv_system<M, true> {
 };
 
 // ---- controller helpers -------------------------------------------------------------------
+PV_HD float pv_log2f_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    return __log2f(x);           // MUFU.LG2
+#else
+    return log2f(x);
+#endif
+}
+PV_HD float pv_exp2f_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    return exp2f(x);             // MUFU.EX2 under -use_fast_math semantics is not needed: exp2f maps to EX2 + scaling
+#else
+    return exp2f(x);
+#endif
+}
 PV_HD float pv_powf_fast(float x, float a) {
 #if defined(__CUDA_ARCH__)
     return __powf(x, a);
@@ -69,6 +83,16 @@ PV_HD float pv_fdiv_fast(float a, float b) {
     return __fdividef(a, b);     // MUFU.RCP + FMUL: the controller needs two digits, not IEEE division
 #else
     return a / b;
+#endif
+}
+// ~20-bit reciprocal (one MUFU.RCP64H): enough for the error *norm*, which only steers the step size
+PV_HD double pv_rcp_approx(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+#else
+    return 1.0 / x;
 #endif
 }
 PV_HD double pv_drcp(double x) {
@@ -171,8 +195,9 @@ template <class Sys>
 struct pv_dopri5_lane {
     static constexpr int N = Sys::N;
     double t, h, tend;
+    double t_next;     // tgrid[jout]: next grid point not yet covered (kept in a register: checked every step)
     double y[N], k1[N];
-    float facold;
+    float lfacold;     // log2 of Hairer's facold = max(err, 1e-4)
     bool last_rejected;
     int jout, nstep;
     pv_step_stats st;
@@ -184,7 +209,7 @@ struct pv_dopri5_lane {
         st.accepted = 0;
         st.rejected = 0;
         nstep = 0;
-        facold = 1e-4f;
+        lfacold = -13.287712f;   // log2(1e-4)
         last_rejected = false;
         t = t0;
         tend = tgrid[T - 1];
@@ -197,6 +222,7 @@ struct pv_dopri5_lane {
             ++jout;
         }
         if (jout >= T) return PV_OK;
+        t_next = tgrid[jout];
         Sys::rhs(t, y, ks, k1);
         // ---- initial step (Hairer, Norsett, Wanner I, II.4) ----------------------------------
         // (fp64 here: runs once per trajectory and must survive atol -> 0 without overflow)
@@ -285,31 +311,31 @@ struct pv_dopri5_lane {
         Sys::rhs(t + h, yn, ks, k7);
 
         // ---- error estimate (fp32 norm of an fp64 difference) -----------------------------------
-        float err2 = 0.f;
-        bool finite = true;
+        double err2d = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const double e = h * fma(pv_dp5[20], k1[i],
                                      fma(pv_dp5[21], k3[i],
                                          fma(pv_dp5[22], k4[i], fma(pv_dp5[23], k5[i], fma(pv_dp5[24], k6[i], pv_dp5[25] * k7[i])))));
             const double sc = atol + rtol * fmax(fabs(y[i]), fabs(yn[i]));
-            const float r = pv_fdiv_fast((float)e, (float)sc);
-            err2 += r * r;
-            finite = finite && (fabs(yn[i]) < 1e300);
+            const double r = e * pv_rcp_approx(sc);
+            err2d = fma(r, r, err2d);
         }
-        err2 *= (1.0f / N);
-        if (!finite || !(err2 == err2)) {
-            // treat as a failed step; give up if h is already tiny
+        float err2 = (float)(err2d * (1.0 / N));
+        // a non-finite stage value makes e, hence err2, NaN or inf: treated as a failed step (give up once h is tiny)
+        if (!(err2 <= 3.0e38f)) {
             err2 = 1e10f;
             if (fabs(h) < 1e-12) return PV_ERR_NONFINITE;
         }
-        // err^(0.2 - 0.75*beta), beta = 0.04, on err^2
-        const float fac11 = pv_powf_fast(fmaxf(err2, 1e-30f), 0.085f);
+        // Hairer's PI controller in the log2 domain (one LG2 + one EX2 per step instead of two pows and a sqrt):
+        //   fac11 = err^(0.2 - 0.75 beta), beta = 0.04, err = sqrt(err2)  ->  log2 fac11 = 0.085 * log2 err2
+        const float l2 = pv_log2f_fast(fmaxf(err2, 1e-30f));
+        const float lfac11 = 0.085f * l2;
         if (err2 <= 1.0f) {
             // ---- accept: dense output for every grid point in (t, t+h] --------------------------
             ++st.accepted;
             const double tn = last ? tend : t + h;
-            if (jout < T && tgrid[jout] <= tn) {
+            if (t_next <= tn) {
                 pv_dense_rec<N> rec;
                 rec.t = t;
                 rec.h = h;
@@ -330,13 +356,14 @@ struct pv_dopri5_lane {
                     ++jout;
                 } while (jout < T && tgrid[jout] <= tn);
                 rec.j1 = jout;
+                t_next = jout < T ? tgrid[jout] : 1e300;
                 emit(rec, last || jout >= T);
             }
-            float fac = fac11 / pv_powf_fast(facold, 0.04f);
-            fac = fmaxf(0.1f, fminf(5.0f, fac * (1.0f / 0.9f)));
-            double hnew = h * (double)pv_fdiv_fast(1.0f, fac);
+            // h_new = h / clamp(fac11 / facold^beta / 0.9, 0.1, 5)  ->  multiply by 2^-(log2 of the clamped factor)
+            const float lfac = fminf(fmaxf(lfac11 - 0.04f * lfacold + 0.15200309f, -3.3219281f), 2.3219281f);
+            double hnew = h * (double)pv_exp2f_fast(-lfac);
             if (last_rejected) hnew = fmin(hnew, h);
-            facold = fmaxf(sqrtf(err2), 1e-4f);
+            lfacold = fmaxf(0.5f * l2, -13.287712f);
             last_rejected = false;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
@@ -348,7 +375,7 @@ struct pv_dopri5_lane {
             h = hnew;
         } else {
             ++st.rejected;
-            h = h * (double)pv_fdiv_fast(1.0f, fminf(5.0f, fac11 * (1.0f / 0.9f)));
+            h = h * (double)pv_exp2f_fast(-fminf(lfac11 + 0.15200309f, 2.3219281f));
             last_rejected = true;
         }
         return PV_RUNNING;

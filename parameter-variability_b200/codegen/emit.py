@@ -315,6 +315,7 @@ struct {struct_name} {{
     static constexpr int NNZ_CONST = {n_const};  // of which state independent
     static constexpr int NLU = {NLU};   // non-zeros of the filled LU
     static constexpr bool USES_TIME = {'true' if ode.uses_time else 'false'};
+    static constexpr bool OBS_UNIT = {'true' if all(e == 1 for e in hs.obs_scale_exprs) else 'false'};  // every "[sid]" is the state itself
     static constexpr int FLOPS_RHS = {rhs_flops};
     static constexpr int FLOPS_RHS_SENS = {rs_flops};
     static constexpr int FLOPS_JAC = {jac_flops};

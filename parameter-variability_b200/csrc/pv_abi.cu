@@ -308,10 +308,32 @@ extern "C" int pv_problem_set_data(pv_problem* p, int noise_model, int n_data, c
     p->sigma.assign(sigma_host, sigma_host + p->obs_idx.size());
     p->noise_model = noise_model;
     p->n_data = n_data;
+    // The kernels do not see (n, S1, S2) but the coefficients of the likelihood term as a polynomial in the model
+    // output v (v = f for normal noise, v = log f for log-normal noise):
+    //   lp(j,k) = q0 + v (q1 + q2 v),   q2 = -n/(2 sigma^2),  q1 = S1/sigma^2,
+    //   q0 = -(n/2) log(2 pi sigma^2) - S2/(2 sigma^2)            (normal)
+    //   q0 = -S1 - n (log sigma + log(2 pi)/2) - S2/(2 sigma^2)   (log-normal; -S1 = -sum log y)
+    // so an entry without measurements (n = 0) contributes exactly 0 without a branch; d lp / d v = q1 + 2 q2 v and the
+    // Fisher weight n / sigma^2 = -2 q2.
+    const double LOG_2PI = 1.8378770664093454835606594728112;
+    const size_t T = p->tgrid.size(), K = p->obs_idx.size(), D = (size_t)n_data, plane = T * K * D;
+    std::vector<double> q(3 * plane);
+    for (size_t j = 0; j < T; ++j)
+        for (size_t k = 0; k < K; ++k) {
+            const double sg = sigma_host[k], inv = 1.0 / (sg * sg);
+            for (size_t d = 0; d < D; ++d) {
+                const size_t o = (j * K + k) * D + d;
+                const double nn = stats_host[o], s1 = stats_host[plane + o], s2 = stats_host[2 * plane + o];
+                q[2 * plane + o] = -0.5 * nn * inv;
+                q[plane + o] = s1 * inv;
+                q[o] = (noise_model == PV_NOISE_NORMAL ? -0.5 * nn * (LOG_2PI + 2.0 * std::log(sg))
+                                                       : -s1 - nn * (std::log(sg) + 0.5 * LOG_2PI)) - 0.5 * s2 * inv;
+            }
+        }
     cudaFree(p->d_stats);
     p->d_stats = nullptr;
     CUDA_OK(cudaMalloc(&p->d_stats, sizeof(double) * n));
-    CUDA_OK(cudaMemcpy(p->d_stats, stats_host, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(p->d_stats, q.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -435,14 +457,6 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     lp.counter = p->d_counters + p->counter_next;
     p->counter_next = (p->counter_next + 1) % PV_COUNTER_RING;
     CUDA_OK(cudaMemsetAsync(lp.counter, 0, sizeof(unsigned long long), s));
-    if (need_logp) {
-        const double LOG_2PI = 1.8378770664093454835606594728112;
-        for (int k = 0; k < lp.n_obs; ++k) {
-            const double sg = p->sigma[k];
-            lp.inv_sigma2[k] = 1.0 / (sg * sg);
-            lp.log_norm[k] = (p->noise_model == PV_NOISE_NORMAL) ? LOG_2PI + 2.0 * std::log(sg) : std::log(sg) + 0.5 * LOG_2PI;
-        }
-    }
     int method = p->method;
     if (method == PV_METHOD_AUTO) method = p->tab->stiff ? PV_METHOD_RODAS4 : PV_METHOD_DOPRI5;
     // explicit first pass with a step budget, implicit second pass for what did not finish (stiff parameter values)

@@ -36,7 +36,7 @@ struct pv_launch_params {
     const double* theta_base;  // [NTH]
     const double* y0_base;     // [NX], NaN = use the model's initial value
     const double* tgrid;       // [T]
-    const double* stats;       // [3][T][n_obs][n_data]
+    const double* stats;       // [3][T][n_obs][n_data]  likelihood polynomial coefficients q0, q1, q2 (see pv_problem_set_data)
     double* Y;                 // [B][T][n_obs]
     double* S;                 // [B][T][n_obs][NS]
     double* logp;              // [B]
@@ -45,8 +45,6 @@ struct pv_launch_params {
     int32_t* status;           // [B]
     int32_t* steps;            // [2][B]
     double rtol, atol;
-    double inv_sigma2[PV_MAX_OBS];
-    double log_norm[PV_MAX_OBS];   // normal: log(2 pi sigma^2);  lognormal: log(sigma) + 0.5 log(2 pi)
     int col_target[PV_MAX_COLS];   // < NTH: theta index; >= NTH: NTH + state index (initial value)
     int obs_idx[PV_MAX_OBS];
     unsigned long long* counter;   // next unprocessed work item (lane refill)
@@ -87,10 +85,8 @@ struct pv_sink {
     double g[M::NSD];
     double fim[NFIM];         // sum over measurements of (df/dtheta)(df/dtheta)^T / sigma^2  (AMICI's FIM)
 
-    // yrow = &Y[b][j][0] (or nullptr), srow = &S[b][j][0][0]; so = index of (j, 0, d) in one statistics plane
-    PV_D void one(int k, double f, const double (&df)[M::NSD], double* yrow, double* srow, int so, int plane,
-                  double log_norm, double inv_sigma2) {
-        const int n_obs = OBSID ? M::NX : p.n_obs;
+    // yrow = &Y[b][j][0] (or nullptr), srow = &S[b][j][0][0]; so = index of (j, 0, d) in one coefficient plane
+    PV_D void one(int k, double f, const double (&df)[M::NSD], double* yrow, double* srow, int so, int plane) {
         if constexpr (TRAJ) {
             if (yrow) yrow[k] = f;
             if constexpr (SENS) {
@@ -100,28 +96,21 @@ struct pv_sink {
         }
         if constexpr (LOGP) {
             const int o = so + k * p.n_data;
-            double n, s1, s2;
+            double q0, q1, q2;
             if (sh_stats) {
-                n = sh_stats[o]; s1 = sh_stats[plane + o]; s2 = sh_stats[2 * plane + o];
+                q0 = sh_stats[o]; q1 = sh_stats[plane + o]; q2 = sh_stats[2 * plane + o];
             } else {
-                n = __ldg(p.stats + o); s1 = __ldg(p.stats + plane + o); s2 = __ldg(p.stats + 2 * plane + o);
+                q0 = __ldg(p.stats + o); q1 = __ldg(p.stats + plane + o); q2 = __ldg(p.stats + 2 * plane + o);
             }
-            if (n > 0.0) {
-                double w;   // d lp / d f
-                if (p.noise_model == 0) {
-                    lp -= 0.5 * fma(n, log_norm, fma(f, fma(n, f, -2.0 * s1), s2) * inv_sigma2);
-                    w = fma(-n, f, s1) * inv_sigma2;
-                } else {
-                    const double lf = log(f);
-                    lp -= s1 + fma(n, log_norm, 0.5 * fma(lf, fma(n, lf, -2.0 * s1), s2) * inv_sigma2);
-                    w = fma(-n, lf, s1) * inv_sigma2 / f;
-                }
+            // lp term = q0 + v (q1 + q2 v), v = f (normal) or log f (log-normal); n = 0 entries have q = 0
+            if (p.noise_model == 0) {
+                lp += fma(f, fma(q2, f, q1), q0);
                 if constexpr (SENS) {
+                    const double w = fma(2.0 * q2, f, q1);
 #pragma unroll
                     for (int s = 0; s < M::NS; ++s) g[s] = fma(w, df[s], g[s]);
                     if constexpr (FIM) {
-                        // expected information of n measurements at this point: n/sigma^2 (normal), n/(sigma f)^2 (log-normal)
-                        const double wi = (p.noise_model == 0) ? n * inv_sigma2 : n * inv_sigma2 / (f * f);
+                        const double wi = -2.0 * q2;
                         int q = 0;
 #pragma unroll
                         for (int s = 0; s < M::NS; ++s)
@@ -132,7 +121,26 @@ struct pv_sink {
                             }
                     }
                 }
-                (void)w;
+            } else if (q2 != 0.0) {
+                const double lf = log(f);
+                lp += fma(lf, fma(q2, lf, q1), q0);
+                if constexpr (SENS) {
+                    const double rf = 1.0 / f;
+                    const double w = fma(2.0 * q2, lf, q1) * rf;
+#pragma unroll
+                    for (int s = 0; s < M::NS; ++s) g[s] = fma(w, df[s], g[s]);
+                    if constexpr (FIM) {
+                        const double wi = -2.0 * q2 * rf * rf;
+                        int q = 0;
+#pragma unroll
+                        for (int s = 0; s < M::NS; ++s)
+#pragma unroll
+                            for (int r = s; r < M::NS; ++r) {
+                                fim[q] = fma(wi * df[s], df[r], fim[q]);
+                                ++q;
+                            }
+                    }
+                }
             }
         }
     }
@@ -158,9 +166,9 @@ struct pv_sink {
                 double df[M::NSD];
                 if constexpr (SENS) {
 #pragma unroll
-                    for (int s = 0; s < M::NS; ++s) df[s] = z[M::NX * (1 + s) + k] * obs[k];
+                    for (int s = 0; s < M::NS; ++s) df[s] = M::OBS_UNIT ? z[M::NX * (1 + s) + k] : z[M::NX * (1 + s) + k] * obs[k];
                 }
-                one(k, z[k] * obs[k], df, yrow, srow, so, plane, p.log_norm[k], p.inv_sigma2[k]);
+                one(k, M::OBS_UNIT ? z[k] : z[k] * obs[k], df, yrow, srow, so, plane);
             }
         } else {
             for (int k = 0; k < n_obs; ++k) {
@@ -171,7 +179,7 @@ struct pv_sink {
 #pragma unroll
                     for (int s = 0; s < M::NS; ++s) df[s] = pv_pick<M::NX>(z, 1 + s, idx) * sc;
                 }
-                one(k, pv_pick<M::NX>(z, 0, idx) * sc, df, yrow, srow, so, plane, p.log_norm[k], p.inv_sigma2[k]);
+                one(k, pv_pick<M::NX>(z, 0, idx) * sc, df, yrow, srow, so, plane);
             }
         }
     }

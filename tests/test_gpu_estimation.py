@@ -181,3 +181,51 @@ def test_optimize_experiments_writes_reference_results_tsv(cuda_lib, rt, oracle,
     bad.write_text("format_version: 2\n")
     assert drv.optimize_experiment(bad, tmp_path / "results") is False
     assert (tmp_path / "results" / "uidbad_errors.tsv").exists()
+
+
+# ---- the reference's own integration test (tests/experiments/test_factories.py): all three models, timepoints {5, 10} ------
+FACTORY = {   # sampling / exact-prior values of src/parvar/experiments/factories/{simple_chain,simple_pk,icg_body_flat}.py
+    "simple_pk": dict(observables=["y_cent", "y_gut", "y_peri"], dosage=None, n=20,
+                      groups={"MALE": {"CL": (1.0, 1.0), "k_abs": (0.5, 1.0)}, "FEMALE": {"CL": (0.5, 1.0), "k_abs": (1.0, 1.0)}}),
+    "icg_body_flat": dict(observables=["Cre_plasma_icg", "Cgi_plasma_icg"], dosage={"IVDOSE_icg": 10.0}, n=100,
+                          groups={"MALE": {"BW": (75.0, 10.0), "LI__ICGIM_Vmax": (0.0369598840327503, 0.01)},
+                                  "FEMALE": {"BW": (65.0, 10.0), "LI__ICGIM_Vmax": (0.02947, 0.01)}}),
+}
+
+
+@pytest.mark.parametrize("model", ["simple_pk", "icg_body_flat"])
+@pytest.mark.parametrize("timepoints", [5, 10])
+def test_create_petab_for_experiment_like_reference(cuda_lib, rt, oracle, tmp_path, model, timepoints):
+    """Sampling -> batched simulation -> noise -> PEtab files, against the oracle's restatement of the same flow
+    (same global RNG stream: np.random.seed(1234), lognormal per (group, parameter), then per row randint/reseed/normal)."""
+    wf = pkg("experiments.workflow")
+    io = pkg("optimization.petab_io")
+    spec = FACTORY[model]
+    cv = 0.1                                                   # model_experiment_factory default noise_cvs (:643-645)
+    groups = [wf.GroupSpec(id=g, sampling=pars, estimation=pars, n_samples=spec["n"], steps=timepoints - 1, cv=cv)
+              for g, pars in spec["groups"].items()]
+    xp = wf.ExperimentSpec(id="xp1", model=model, groups=groups, observables=spec["observables"], dosage=spec["dosage"])
+    yaml_file, dsets, frames = wf.create_petab_for_experiment(xp, tmp_path)
+    assert (tmp_path / "xp1" / "petab.yaml").exists()
+    # ---- oracle flow -------------------------------------------------------------------------------------------------
+    om = oracle.MODELS[model]
+    samples = oracle.create_samples_parameters({g: {p: (spec["n"], sc, lo) for p, (lo, sc) in pars.items()}
+                                                for g, pars in spec["groups"].items()})
+    t = np.linspace(0, 100, timepoints)
+    idx = [om.states.index(o) for o in spec["observables"]]
+    for g, pars in spec["groups"].items():
+        for p in pars:
+            np.testing.assert_array_equal(frames[g][p].to_numpy(), samples[g][p])          # sampling stream: bit identical
+        for i in range(spec["n"]):
+            over = dict(spec["dosage"] or {})
+            over.update({p: samples[g][p][i] for p in pars})
+            clean = (oracle.simple_pk_exact(over, t) if model == "simple_pk" else oracle.simulate(model, over, t))[:, idx]
+            noisy = oracle.add_noise(clean, cv)                                            # consumes the global stream like :201-213
+            got = np.stack([dsets[g][f"[{o}]"].values[i] for o in spec["observables"]], axis=1)
+            assert np.max(np.abs(got - noisy) / (2e-9 + 2e-6 * np.abs(noisy))) <= 1.0
+    # ---- the written problem loads back into the objective; literal mode reproduces quirk Q4 ----------------------------
+    obj = io.load_petab_problem(yaml_file, mode="intended", dosage=spec["dosage"])
+    x = np.array([np.mean(samples[g][p]) for p in list(spec["groups"]["MALE"]) for g in spec["groups"]])
+    assert np.isfinite(obj.fun(x))
+    lit = io.load_petab_problem(yaml_file, mode="literal")
+    assert lit.fun(x) != obj.fun(x)

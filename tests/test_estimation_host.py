@@ -110,3 +110,28 @@ def test_result_helpers():
     assert d.get_parameter_from_pid("LI__ICGIM_Vmax_FEMALE") == "LI__ICGIM_Vmax"
     assert d.get_parameter_from_pid("k1") == "k1"
     assert d.DEFAULT_SETTINGS["n_starts"] == 100 and d.DEFAULT_SETTINGS["n_samples"] == 5000 and d.DEFAULT_SETTINGS["n_chains"] == 4
+
+
+def test_batched_hmc_on_correlated_gaussian():
+    hm = pkg("optimization.hmc")
+    A = np.array([[1.0, 0.6, 0.0], [0.6, 2.0, -0.3], [0.0, -0.3, 0.5]])
+    Pm = np.linalg.inv(A)
+    mean = np.array([0.5, -1.0, 2.0])
+
+    def lg(X):
+        d = X - mean
+        return -0.5 * np.einsum("ci,ij,cj->c", d, Pm, d), -d @ Pm
+
+    res = hm.hmc(lg, x0=np.zeros((6, 3)), n_samples=1500, n_warmup=600, n_leapfrog=12, seed=3)
+    s = res.samples.reshape(-1, 3)
+    np.testing.assert_allclose(s.mean(axis=0), mean, atol=0.12)
+    np.testing.assert_allclose(np.cov(s.T), A, atol=0.25)
+    assert np.all(res.accept_rate > 0.6) and np.all(res.accept_rate < 0.98) and res.divergences.sum() == 0
+    assert res.n_grad_evals > 1500 * 8
+    # failed gradient evaluations (non-finite) count as divergences and are rejected, not propagated
+    def lg_bad(X):
+        l, g = lg(X)
+        l = np.where(X[:, 0] > 1.5, np.nan, l)
+        return l, g
+    res = hm.hmc(lg_bad, x0=np.zeros((2, 3)), n_samples=300, n_warmup=200, n_leapfrog=8, seed=4)
+    assert np.all(np.isfinite(res.samples)) and res.samples[..., 0].max() <= 1.5

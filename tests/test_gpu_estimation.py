@@ -229,3 +229,55 @@ def test_create_petab_for_experiment_like_reference(cuda_lib, rt, oracle, tmp_pa
     assert np.isfinite(obj.fun(x))
     lit = io.load_petab_problem(yaml_file, mode="literal")
     assert lit.fun(x) != obj.fun(x)
+
+
+def test_hmc_on_hierarchical_posterior(cuda_lib, rt, oracle):
+    """BASELINE config 3 in its intended use: a gradient-based sampler on the hierarchical simple_pk posterior
+    (per-individual k_abs_i, CL_i + population mu, omega), every leapfrog step = one launch over chains x individuals with
+    forward sensitivities.  All positive quantities are sampled on the log scale (Jacobian terms included)."""
+    po = pkg("optimization.petab_optimization")
+    hm = pkg("optimization.hmc")
+    t = np.linspace(0.5, 24, 10)
+    n_ind, C, P = 24, 4, 2
+    rs = np.random.RandomState(0)
+    mu_true, om_true = np.array([0.0, -0.4]), np.array([0.3, 0.25])
+    th_true = np.exp(mu_true + om_true * rs.normal(size=(n_ind, P)))
+    y = np.stack([oracle.simple_pk_exact({"k_abs": a, "CL": c}, t) for a, c in th_true])
+    y = y * (1 + 0.05 * rs.normal(size=y.shape))
+    pb = rt.Problem("simple_pk")
+    pb.set_solver(rtol=1e-8, atol=1e-12)
+    pb.set_columns(["k_abs", "CL"])
+    pb.set_timepoints(t, t0=0.0)
+    pb.set_observables(["y_gut", "y_cent", "y_peri"])
+    pb.set_data(np.stack([po.sufficient_statistics(y[i:i + 1], 0) for i in range(n_ind)], axis=-1), 0.02)
+    H = po.HierarchicalObjective(pb, n_ind, mu_prior=[(0.0, 1.0), (0.0, 1.0)], omega_prior=[0.5, 0.5])
+    dim = n_ind * P + 2 * P
+
+    def unpack(X):
+        lth = X[:, :n_ind * P].reshape(-1, n_ind, P)
+        return lth, X[:, n_ind * P:n_ind * P + P], X[:, n_ind * P + P:]
+
+    def lg(X):
+        lth, mu, lom = unpack(X)
+        theta, omega = np.exp(lth), np.exp(lom)
+        lp, dth, dmu, dom = H(theta, mu, omega)
+        # change of variables theta = exp(lth), omega = exp(lom): + sum lth + sum lom, chain rule on the gradients
+        lp = lp + lth.sum(axis=(1, 2)) + lom.sum(axis=1)
+        g = np.concatenate([(dth * theta + 1.0).reshape(X.shape[0], -1), dmu, dom * omega + 1.0], axis=1)
+        return lp, g
+
+    x0 = np.concatenate([np.tile(np.log(th_true).ravel(), (C, 1)) + 0.05 * rs.normal(size=(C, n_ind * P)),
+                         np.zeros((C, P)), np.log(0.3) * np.ones((C, P))], axis=1)
+    # gradient of the transformed density against central differences (one coordinate of each kind)
+    l0, g0 = lg(x0[:1])
+    for i in (0, n_ind * P, n_ind * P + P + 1):
+        e = np.zeros(dim)
+        e[i] = 1e-5
+        fd = (lg(x0[:1] + e)[0][0] - lg(x0[:1] - e)[0][0]) / 2e-5
+        assert g0[0, i] == pytest.approx(fd, rel=2e-5, abs=1e-6 * abs(l0[0]))
+    res = hm.hmc(lg, x0, n_samples=150, n_warmup=150, n_leapfrog=10, step_size=0.02, seed=5)
+    assert np.all(res.accept_rate > 0.5) and res.divergences.sum() <= 3
+    _, mu_s, lom_s = unpack(res.samples.reshape(-1, dim))
+    assert np.all(np.abs(mu_s.mean(axis=0) - np.log(th_true).mean(axis=0)) < 0.25)
+    assert np.all(np.exp(lom_s).mean(axis=0) < 0.8)
+    assert res.n_grad_evals >= 300 * 8

@@ -442,3 +442,85 @@ def test_stiff_parameter_values_switch_to_rodas4(cuda_lib, rt, oracle):
     for b in (1, 3):
         f = oracle.simple_pk_exact({"k_abs": k_abs[b], "CL": CL[b]}, t)
         assert lp[b] == pytest.approx(oracle.loglik_normal(f, truth, 0.1), rel=1e-6)
+
+
+def test_argument_errors_and_edge_cases(cuda_lib, rt, oracle):
+    """Error behaviour of the boundary: wrong ids / shapes raise with a message, never compute garbage."""
+    opt = pkg("optimization.petab_optimization")
+    pb = rt.Problem("simple_pk")
+    with pytest.raises(rt.ParvarB200Error, match="no settable id"):
+        pb.set_columns(["k_abs", "nope"])
+    with pytest.raises(rt.ParvarB200Error, match="no state"):
+        pb.set_observables(["[y_gut]", "k_abs"])            # parameters are not observables
+    with pytest.raises(rt.ParvarB200Error, match="strictly increasing"):
+        pb.set_timepoints([0.0, 1.0, 1.0])
+    with pytest.raises(rt.ParvarB200Error, match="t0 must be"):
+        pb.set_timepoints([1.0, 2.0], t0=1.5)
+    with pytest.raises(rt.ParvarB200Error, match="too many"):
+        pb.set_columns(["k_abs", "CL", "Q", "Vgut", "Vperi", "Vcent", "y_gut", "y_cent", "y_peri"])
+    with pytest.raises(rt.ParvarB200Error):
+        rt.Problem("no_such_model")
+    pb.set_columns(["k_abs"])
+    with pytest.raises(rt.ParvarB200Error, match="timepoints"):
+        pb.simulate_host(np.ones((1, 2)), 2)                  # grid not configured yet
+    pb.set_timepoints(np.linspace(0, 10, 5))
+    pb.set_observables(["y_cent"])
+    with pytest.raises(rt.ParvarB200Error, match="data not set"):
+        pb.logp_host(np.ones((1, 2)))
+    with pytest.raises(ValueError):
+        pb.simulate_host(np.ones((2, 2)), 2)                  # P has the wrong number of rows
+    with pytest.raises(rt.ParvarB200Error, match="multiple of seg_len"):
+        pb.set_data(np.ones((3, 5, 1, 1)), 1.0)
+        pb.logp_host(np.ones((1, 5)), seg_len=2)
+    with pytest.raises(rt.ParvarB200Error, match="sigma"):
+        pb.set_data(np.ones((3, 5, 1, 1)), 0.0)
+    # per-trajectory initial values and compartment sizes are settable columns as well (r.setValue on any id)
+    t = np.linspace(0, 20, 9)
+    pb.set_columns(["[y_gut]", "Vcent", "Q"])
+    pb.set_timepoints(t)
+    pb.set_observables(["y_gut", "y_cent", "y_peri"])
+    P = np.array([[2.0, 0.5], [1.0, 3.0], [1.0, 0.2]])
+    Y, nf = pb.simulate_host(P, 2)
+    assert nf == 0
+    for b in range(2):
+        ref = oracle.simple_pk_exact({"y_gut": P[0, b], "Vcent": P[1, b], "Q": P[2, b]}, t)
+        assert parity_violation(Y[b], ref) <= 1.0
+    # missing measurements (NaN) are skipped: n = 0 entries contribute nothing, also under the log-normal model
+    cols = [1, 2]
+    truth = oracle.simple_pk_exact({}, t[1:])[:, cols]
+    data = truth[None].repeat(3, axis=0) * 1.1
+    data[0, 2, 0] = np.nan
+    data[:, 5, 1] = np.nan
+    for nm, sig in ((rt.NOISE_NORMAL, 0.1), (rt.NOISE_LOGNORMAL, 0.2)):
+        pb2 = _problem(rt, "simple_pk", ["k_abs"], t[1:], ["y_cent", "y_peri"], rtol=1e-9, atol=1e-15)
+        pb2.set_timepoints(t[1:], t0=0.0)
+        pb2.set_data(opt.sufficient_statistics(data, nm)[..., None], sig, nm)
+        lp, _, _, nf = pb2.logp_host(np.array([[0.8]]))
+        f = oracle.simple_pk_exact({"k_abs": 0.8}, t[1:])[:, cols]
+        ok = np.isfinite(data)
+        ref = 0.0
+        for i in range(3):
+            m = ok[i]
+            ref += (oracle.loglik_normal(f[m], data[i][m], sig) if nm == rt.NOISE_NORMAL else oracle.loglik_lognormal(f[m], data[i][m], sig))
+        assert nf == 0 and lp[0] == pytest.approx(ref, rel=1e-6)
+
+
+def test_sweep_extremes_timepoints_and_samples(cuda_lib, rt, oracle):
+    """The corners of the reference's sweep (factories/__init__.py:12-20): 2 and 160 timepoints, 1 and 160 samples."""
+    opt = pkg("optimization.petab_optimization")
+    for T in (2, 160):
+        t = np.linspace(0, 100, T)
+        pb = _problem(rt, "simple_pk", ["k_abs", "CL"], t, ["y_cent", "y_gut", "y_peri"])
+        th = np.stack([lognormal_draws(70, 160), lognormal_draws(71, 160)])
+        Y, nf = pb.simulate_host(th, 160)
+        assert nf == 0 and Y.shape == (160, T, 3)
+        for b in (0, 1, 159):
+            ref = oracle.simple_pk_exact({"k_abs": th[0, b], "CL": th[1, b]}, t)[:, [1, 0, 2]]
+            assert parity_violation(Y[b], ref) <= 1.0
+        # pooled likelihood over 160 individuals of one group at the sweep's largest cv (1.0; values may go negative)
+        rs = np.random.RandomState(T)
+        clean = oracle.simple_pk_exact({}, t)[:, [1, 0, 2]]
+        data = clean[None] * (1 + 1.0 * rs.normal(size=(160,) + clean.shape))
+        pb.set_data(opt.sufficient_statistics(data, rt.NOISE_NORMAL)[..., None], 1.0)
+        lp, g, _, nf = pb.logp_host(np.array([[1.0], [1.0]]), grad=True)
+        assert nf == 0 and lp[0] == pytest.approx(oracle.loglik_normal(clean, data, 1.0), rel=1e-6)

@@ -76,7 +76,8 @@ int pv_problem_flops(const pv_problem* p, const char* what);
 int pv_problem_set_solver(pv_problem* p, int method, double rtol, double atol, int max_steps);
 
 /* warp scheduling of the batch kernels: a warp fetches new trajectories for its idle lanes once at least
- * refill_min (1..32, default 6) of them are idle; 32 = classic one-trajectory-per-thread behaviour per warp */
+ * refill_min (1..32) of them are idle; 32 = classic one-trajectory-per-thread behaviour per warp; 0 = the
+ * measured per-integrator default (DOPRI5: 6, RODAS4: 32) */
 int pv_problem_set_schedule(pv_problem* p, int refill_min);
 
 /* PV_METHOD_AUTO on a model classified non-stiff integrates with DOPRI5 first; trajectories that use up

@@ -202,7 +202,7 @@ class Problem:
         _check(self._lib.pv_problem_set_columns(self._h, len(ids), _cstr_array(ids) if ids else None))
         self.columns = ids
 
-    def set_schedule(self, refill_min: int = 8) -> None:
+    def set_schedule(self, refill_min: int = 0) -> None:
         _check(self._lib.pv_problem_set_schedule(self._h, int(refill_min)))
 
     def set_stiff_switch(self, switch_steps: int = 4000) -> None:

@@ -52,8 +52,6 @@ struct pv_problem {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double* stage_dev[3] = {nullptr, nullptr, nullptr};
     size_t stage_bytes[3] = {0, 0, 0};
-    double* pin[3] = {nullptr, nullptr, nullptr};
-    size_t pin_bytes[3] = {0, 0, 0};
     int* d_failed = nullptr;
     double last_kernel_ms = 0.0;
     // lane-refill work counters: one per launch in flight (ring), zeroed in-stream before each launch
@@ -62,7 +60,6 @@ struct pv_problem {
     int num_sms = 0;
     int refill_min = 0;   // 0 = per-integrator default (DOPRI5: 6, RODAS4: 32), see pv_problem_set_schedule
     double t0 = 0.0;
-    bool t0_set = false;
     // METHOD_AUTO on a non-stiff model: trajectories that exhaust switch_steps explicit steps (stiff parameter
     // values) are re-run with RODAS4.  Scratch per launch slot: 0 = caller's stream, 1..3 = internal pipeline streams.
     int switch_steps = 4000;
@@ -163,7 +160,6 @@ extern "C" void pv_problem_destroy(pv_problem* p) {
     for (int i = 0; i < 3; ++i) {
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
         cudaFree(p->stage_dev[i]);
-        if (p->pin[i]) cudaFreeHost(p->pin[i]);
     }
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);

@@ -135,3 +135,36 @@ def test_batched_hmc_on_correlated_gaussian():
         return l, g
     res = hm.hmc(lg_bad, x0=np.zeros((2, 3)), n_samples=300, n_warmup=200, n_leapfrog=8, seed=4)
     assert np.all(np.isfinite(res.samples)) and res.samples[..., 0].max() <= 1.5
+
+
+def test_batched_nuts_on_correlated_gaussian():
+    nt = pkg("optimization.nuts")
+    A = np.array([[1.0, 0.6, 0.0], [0.6, 2.0, -0.3], [0.0, -0.3, 0.5]])
+    Pm = np.linalg.inv(A)
+    mean = np.array([0.5, -1.0, 2.0])
+    calls = []
+
+    def lg(X):
+        calls.append(X.shape)
+        d = X - mean
+        return -0.5 * np.einsum("ci,ij,cj->c", d, Pm, d), -d @ Pm
+
+    res = nt.nuts(lg, x0=np.zeros((6, 3)), n_samples=1200, n_warmup=500, seed=3)
+    s = res.samples.reshape(-1, 3)
+    np.testing.assert_allclose(s.mean(axis=0), mean, atol=0.1)
+    np.testing.assert_allclose(np.cov(s.T), A, atol=0.2)
+    assert np.all(res.accept_rate > 0.65) and np.all(res.accept_rate < 0.95) and res.divergences.sum() == 0
+    assert res.tree_depth.min() >= 1 and res.tree_depth.max() <= 8 and 1.5 < res.tree_depth.mean() < 5
+    assert all(c == (6, 3) for c in calls) and res.n_grad_evals == len(calls)      # every evaluation is a full batch
+    # independent draws: lag-1 autocorrelation of NUTS on a Gaussian is small
+    c0 = res.samples[0, :, 1] - res.samples[0, :, 1].mean()
+    assert abs(np.dot(c0[1:], c0[:-1]) / np.dot(c0, c0)) < 0.35
+    # heavy ridge: a banana-shaped target exercises deeper trees without divergences
+    def banana(X):
+        a, b = X[:, 0], X[:, 1]
+        lp = -0.5 * (a * a / 4.0 + (b - 0.25 * a * a) ** 2 / 0.25)
+        g = np.stack([-(a / 4.0) + (b - 0.25 * a * a) / 0.25 * 0.5 * a, -(b - 0.25 * a * a) / 0.25], axis=1)
+        return lp, g
+    rb = nt.nuts(banana, x0=np.zeros((4, 2)), n_samples=600, n_warmup=400, seed=9, adapt_mass=False, target_accept=0.9)
+    sb = rb.samples.reshape(-1, 2)
+    assert abs(sb[:, 0].mean()) < 0.35 and abs(sb[:, 0].var() - 4.0) < 1.2 and rb.divergences.sum() <= 0.03 * sb.shape[0]

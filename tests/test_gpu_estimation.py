@@ -281,3 +281,10 @@ def test_hmc_on_hierarchical_posterior(cuda_lib, rt, oracle):
     assert np.all(np.abs(mu_s.mean(axis=0) - np.log(th_true).mean(axis=0)) < 0.25)
     assert np.all(np.exp(lom_s).mean(axis=0) < 0.8)
     assert res.n_grad_evals >= 300 * 8
+    # the no-U-turn sampler on the same posterior (north_star: NUTS calls logp + gradient at every step)
+    nt = pkg("optimization.nuts")
+    rn = nt.nuts(lg, x0, n_samples=120, n_warmup=150, step_size=0.02, max_depth=6, seed=6)
+    assert np.all(rn.accept_rate > 0.55) and rn.divergences.sum() <= 6 and rn.tree_depth.max() <= 6
+    _, mu_n, lom_n = unpack(rn.samples.reshape(-1, dim))
+    assert np.all(np.abs(mu_n.mean(axis=0) - np.log(th_true).mean(axis=0)) < 0.25)
+    assert np.all(np.abs(mu_n.mean(axis=0) - mu_s.mean(axis=0)) < 0.2)           # the two samplers agree

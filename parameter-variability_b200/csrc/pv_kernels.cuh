@@ -77,7 +77,7 @@ struct pv_sink {
     static constexpr int N = pv_system<M, SENS>::N;
     static constexpr int NFIM = FIM ? M::NSD * (M::NSD + 1) / 2 : 1;
     const pv_launch_params& p;
-    const double* sh_stats;   // shared copy when n_data == 1, else nullptr
+    const double* sh_stats;   // likelihood coefficients: the block's shared-memory copy when n_data == 1, else p.stats (global)
     int64_t b;                // trajectory
     int d;                    // data set of this trajectory (b % n_data, computed once per trajectory)
     double obs[M::NX];
@@ -96,12 +96,8 @@ struct pv_sink {
         }
         if constexpr (LOGP) {
             const int o = so + k * p.n_data;
-            double q0, q1, q2;
-            if (sh_stats) {
-                q0 = sh_stats[o]; q1 = sh_stats[plane + o]; q2 = sh_stats[2 * plane + o];
-            } else {
-                q0 = __ldg(p.stats + o); q1 = __ldg(p.stats + plane + o); q2 = __ldg(p.stats + 2 * plane + o);
-            }
+            // one generic-address load path for both homes of the coefficients (block-shared copy or global)
+            const double q0 = sh_stats[o], q1 = sh_stats[plane + o], q2 = sh_stats[2 * plane + o];
             // lp term = q0 + v (q1 + q2 v), v = f (normal) or log f (log-normal); n = 0 entries have q = 0
             if (p.noise_model == 0) {
                 lp += fma(f, fma(q2, f, q1), q0);
@@ -236,7 +232,7 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
     const int64_t n_items = p.n_items_dev ? (int64_t)*p.n_items_dev : p.B;
     typename Sys::Consts ks;
     Lane lane;
-    pv_sink<M, MODE, OBSID> sink{p, stats_shared ? sh_stats : nullptr, 0, 0, {}, 0.0, {}, {}};
+    pv_sink<M, MODE, OBSID> sink{p, stats_shared ? sh_stats : p.stats, 0, 0, {}, 0.0, {}, {}};
     bool have = false;        // this lane is integrating trajectory sink.b
     bool exhausted = false;   // the work counter ran past B
 

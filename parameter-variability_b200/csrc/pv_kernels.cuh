@@ -79,6 +79,8 @@ struct pv_sink {
     const pv_launch_params& p;
     const double* sh_stats;   // likelihood coefficients: the block's shared-memory copy when n_data == 1, else p.stats (global)
     int64_t b;                // trajectory
+    double* ybase;            // &Y[b][0][0] (nullptr: no trajectory store), set once per trajectory
+    double* sbase;            // &S[b][0][0][0]
     int d;                    // data set of this trajectory (b % n_data, computed once per trajectory)
     double obs[M::NX];
     double lp;
@@ -150,9 +152,8 @@ struct pv_sink {
             // trajectory fill whole 32-byte sectors and 128-byte lines no matter which lane integrates it (lane refill
             // scatters neighbouring trajectories over warps and time; batch-minor output made every store a partial
             // sector that was evicted half filled: 2.7x the algorithmic DRAM traffic in ncu)
-            const int64_t off = (b * p.T + j) * n_obs;
-            yrow = p.Y ? p.Y + off : nullptr;
-            if constexpr (SENS) srow = p.S + off * M::NS;
+            yrow = ybase ? ybase + j * n_obs : nullptr;
+            if constexpr (SENS) srow = sbase + j * n_obs * M::NS;
         }
         const int plane = p.T * n_obs * p.n_data;
         const int so = j * n_obs * p.n_data + d;
@@ -232,7 +233,7 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
     const int64_t n_items = p.n_items_dev ? (int64_t)*p.n_items_dev : p.B;
     typename Sys::Consts ks;
     Lane lane;
-    pv_sink<M, MODE, OBSID> sink{p, stats_shared ? sh_stats : p.stats, 0, 0, {}, 0.0, {}, {}};
+    pv_sink<M, MODE, OBSID> sink{p, stats_shared ? sh_stats : p.stats, 0, nullptr, nullptr, 0, {}, 0.0, {}, {}};
     bool have = false;        // this lane is integrating trajectory sink.b
     bool exhausted = false;   // the work counter ran past B
 
@@ -311,6 +312,12 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
                     }
                     sink.b = b;
                     sink.d = (int)(b % p.n_data);
+                    {
+                        const int n_obs = OBSID ? M::NX : p.n_obs;
+                        const int64_t off = b * p.T * n_obs;
+                        sink.ybase = p.Y ? p.Y + off : nullptr;
+                        sink.sbase = p.S ? p.S + off * M::NS : nullptr;
+                    }
                     sink.lp = 0.0;
 #pragma unroll
                     for (int s = 0; s < M::NSD; ++s) sink.g[s] = 0.0;

@@ -145,10 +145,11 @@ class ODESampleSimulator:
     """
 
     def __init__(self, model_path: Path, abs_tol: float = 1e-10, rel_tol: float = 1e-7, device: int = 0,
-                 method: int = runtime.METHOD_AUTO):
+                 method: int = runtime.METHOD_AUTO, max_steps: int = 20000):
         self.model_name = resolve_model(model_path)
         self.problem = runtime.Problem(self.model_name, device=device)
-        self.problem.set_solver(method=method, rtol=rel_tol, atol=abs_tol)
+        # 20000 = roadrunner's CVODE default `maximum_num_steps`; rows that need more raise like the reference does
+        self.problem.set_solver(method=method, rtol=rel_tol, atol=abs_tol, max_steps=max_steps)
         # roadrunner getIds() analogue (:190): concentrations, parameters
         self.ids: list[str] = [f"[{s}]" for s in self.problem.state_ids] + list(self.problem.theta_ids)
         self.last_status: Optional[np.ndarray] = None

@@ -71,7 +71,7 @@ class PetabObjective:
                  priors: Optional[dict[str, tuple[float, float]]] = None, noise_model: int = runtime.NOISE_NORMAL,
                  mode: str = "intended", dosage: Optional[dict[str, float]] = None, device: int = 0,
                  rtol: float = 1e-8, atol: float = 1e-11, method: int = runtime.METHOD_AUTO,
-                 prior_constant: bool = True):
+                 prior_constant: bool = True, max_steps: int = 10000):
         if mode not in ("intended", "literal"):
             raise ValueError("mode must be 'intended' or 'literal'")
         self.model = model
@@ -94,7 +94,9 @@ class PetabObjective:
         self._has_prior = np.isfinite(self.prior_loc)
 
         pb = runtime.Problem(model, device=device)
-        pb.set_solver(method=method, rtol=rtol, atol=atol)
+        # max_steps = 10000 is AMICI's default step budget: a parameter vector that needs more (start points and tempered
+        # chains roam the PEtab bounds [0, 1e8]) is a failed evaluation (fval = inf), not a minutes-long integration
+        pb.set_solver(method=method, rtol=rtol, atol=atol, max_steps=max_steps)
         if mode == "literal":
             for o in self.observables:
                 pb.set_value(o, 0.0)
@@ -195,7 +197,7 @@ class PetabObjectiveBatch:
                  priors: Optional[Sequence[dict[str, tuple[float, float]]]] = None,
                  noise_model: int = runtime.NOISE_NORMAL, mode: str = "intended",
                  dosage: Optional[dict[str, float]] = None, device: int = 0, rtol: float = 1e-8, atol: float = 1e-11,
-                 method: int = runtime.METHOD_AUTO, t0: float = 0.0):
+                 method: int = runtime.METHOD_AUTO, t0: float = 0.0, max_steps: int = 10000):
         self.model = model
         self.parameters = list(parameters)
         self.Q = len(problems)
@@ -219,7 +221,7 @@ class PetabObjectiveBatch:
         self.has_prior = np.isfinite(self.prior_loc)
 
         pb = runtime.Problem(model, device=device)
-        pb.set_solver(method=method, rtol=rtol, atol=atol)
+        pb.set_solver(method=method, rtol=rtol, atol=atol, max_steps=max_steps)      # AMICI's default budget, see PetabObjective
         if mode == "literal":
             for o in self.observables:
                 pb.set_value(o, 0.0)

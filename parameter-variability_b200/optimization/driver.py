@@ -173,3 +173,34 @@ def optimize_experiments(results_dir: Path, yaml_paths: Sequence[Path], caching:
 def optimize_experiment(yaml_path: Path, results_dir: Path, caching: bool = True, **kwargs) -> bool:
     """Reference ``optimize_experiment`` (:272-348) for a single PEtab problem."""
     return optimize_experiments(results_dir, [Path(yaml_path)], caching=caching, **kwargs)[0]
+
+
+def definitions_dataframe(experiments: Sequence[dict]) -> pd.DataFrame:
+    """``definitions.tsv`` in the reference's schema: ``PETabExperimentList.to_dataframe`` (src/parvar/experiments/
+    experiment.py:170-204) with the timepoints column as ``create_petabs`` stores it (steps + 1, petab_factory.py:541-543).
+
+    ``experiments``: dicts with id, model, prior_type, samples, timepoints, noise_cv and
+    ``sampling = {group: {parameter: (loc, scale)}}``."""
+    rows = []
+    for xp in experiments:
+        for group, pars in xp["sampling"].items():
+            for par, (loc, scale) in pars.items():
+                rows.append({"id": xp["id"], "model": xp["model"], "prior_type": xp["prior_type"], "n_groups": len(xp["sampling"]),
+                             "group": group, "samples": xp["samples"], "timepoints": xp["timepoints"], "noise_cv": xp["noise_cv"],
+                             "parameter": par, "dsn_type": "DistributionType.LOGNORMAL",
+                             "dsn_par": str({"loc": loc, "scale": scale})})
+    return pd.DataFrame(rows)
+
+
+def write_reference_layout(results_path: Path, xp_type: str, experiments: Sequence[dict], result_frames: dict[str, pd.DataFrame]) -> Path:
+    """Write what the reference's analysis reads (``join_optimization_results``, src/parvar/analysis/utils.py:28-98):
+    ``<results_path>/xps/<xp_type>/definitions.tsv`` and ``.../optimization_results/<uid>_results.tsv`` (one per
+    experiment, ``values`` as a JSON list, petab_optimization.py:334-336)."""
+    base = Path(results_path) / "xps" / xp_type
+    (base / "optimization_results").mkdir(parents=True, exist_ok=True)
+    definitions_dataframe(experiments).to_csv(base / "definitions.tsv", sep="\t", index=False)
+    for uid, df in result_frames.items():
+        df = df.copy()
+        df["values"] = df["values"].apply(lambda x: x if isinstance(x, str) else json.dumps(np.asarray(x).tolist()))
+        df.to_csv(base / "optimization_results" / f"{uid}_results.tsv", sep="\t", index=False)
+    return base

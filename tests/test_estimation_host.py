@@ -168,3 +168,34 @@ def test_batched_nuts_on_correlated_gaussian():
     rb = nt.nuts(banana, x0=np.zeros((4, 2)), n_samples=600, n_warmup=400, seed=9, adapt_mass=False, target_accept=0.9)
     sb = rb.samples.reshape(-1, 2)
     assert abs(sb[:, 0].mean()) < 0.35 and abs(sb[:, 0].var() - 4.0) < 1.2 and rb.divergences.sum() <= 0.03 * sb.shape[0]
+
+
+def test_reference_analysis_layout(tmp_path):
+    """The files the reference's ``join_optimization_results`` (analysis/utils.py:28-98) reads: same paths, same columns;
+    the merge it performs (on id, group, parameter) must give one row per (experiment, group, parameter)."""
+    import ast
+    import json
+    d = pkg("optimization.driver")
+    xps = [{"id": f"uid{k}", "model": "simple_pk", "prior_type": "exact_prior", "samples": 20, "timepoints": 10 + k, "noise_cv": 0.05,
+            "sampling": {"MALE": {"CL": (1.0, 1.0), "k_abs": (0.5, 1.0)}, "FEMALE": {"CL": (0.5, 1.0), "k_abs": (1.0, 1.0)}}} for k in range(3)]
+    frames = {}
+    for xp in xps:
+        rows = []
+        for pid in ("k_abs_MALE", "k_abs_FEMALE", "CL_MALE", "CL_FEMALE"):
+            rows.append({"id": xp["id"], "group": d.get_group_from_pid(pid), "parameter": d.get_parameter_from_pid(pid), "pid": pid,
+                         "mean": 1.0, "std": 0.1, "median": 1.0, "ess": 100.0, "n_samples": 50, "optim_duration": 0.1,
+                         "sampler_duration": 0.2, "values": np.ones((4, 51)), "hdi_low": 0.8, "hdi_high": 1.2})
+        frames[xp["id"]] = pd.DataFrame(rows)
+    base = d.write_reference_layout(tmp_path, "all", xps, frames)
+    # --- what join_optimization_results does -------------------------------------------------------------------------
+    df_bayes = pd.concat(pd.read_csv(f, sep="\\t") for f in sorted((base / "optimization_results").glob("*.tsv")))
+    df_bayes["values"] = df_bayes["values"].apply(lambda x: np.array(json.loads(x)))
+    df_xp = pd.read_csv(base / "definitions.tsv", sep="\\t")
+    assert list(df_xp.columns) == ["id", "model", "prior_type", "n_groups", "group", "samples", "timepoints", "noise_cv",
+                                   "parameter", "dsn_type", "dsn_par"]
+    df_join = df_xp.merge(df_bayes, on=["id", "group", "parameter"], how="inner")
+    assert len(df_join) == 3 * 4
+    assert df_join["dsn_par"].apply(lambda s: ast.literal_eval(s)["loc"]).notna().all()
+    for col in ("optim_duration", "mean", "median", "n_samples", "values", "ess", "hdi_high", "hdi_low"):
+        assert col in df_join.columns
+    assert df_join["values"].iloc[0].shape == (4, 51)

@@ -311,25 +311,29 @@ extern "C" int pv_problem_set_data(pv_problem* p, int noise_model, int n_data, c
     //   q0 = -S1 - n (log sigma + log(2 pi)/2) - S2/(2 sigma^2)   (log-normal; -S1 = -sum log y)
     // so an entry without measurements (n = 0) contributes exactly 0 without a branch; d lp / d v = q1 + 2 q2 v and the
     // Fisher weight n / sigma^2 = -2 q2.
+    // Device layout: one record (q0, q1, q2, pad) per (data set, time, observable), data-set-major [n_data][T][n_obs][4]:
+    // a lane reads the records of its trajectory's data set front to back (two 16-byte loads each) as it crosses the grid.
     const double LOG_2PI = 1.8378770664093454835606594728112;
     const size_t T = p->tgrid.size(), K = p->obs_idx.size(), D = (size_t)n_data, plane = T * K * D;
-    std::vector<double> q(3 * plane);
+    const size_t nq = PV_QSTRIDE * plane;
+    std::vector<double> q(nq, 0.0);
     for (size_t j = 0; j < T; ++j)
         for (size_t k = 0; k < K; ++k) {
             const double sg = sigma_host[k], inv = 1.0 / (sg * sg);
             for (size_t d = 0; d < D; ++d) {
                 const size_t o = (j * K + k) * D + d;
                 const double nn = stats_host[o], s1 = stats_host[plane + o], s2 = stats_host[2 * plane + o];
-                q[2 * plane + o] = -0.5 * nn * inv;
-                q[plane + o] = s1 * inv;
-                q[o] = (noise_model == PV_NOISE_NORMAL ? -0.5 * nn * (LOG_2PI + 2.0 * std::log(sg))
+                double* r = q.data() + ((d * T + j) * K + k) * PV_QSTRIDE;
+                r[2] = -0.5 * nn * inv;
+                r[1] = s1 * inv;
+                r[0] = (noise_model == PV_NOISE_NORMAL ? -0.5 * nn * (LOG_2PI + 2.0 * std::log(sg))
                                                        : -s1 - nn * (std::log(sg) + 0.5 * LOG_2PI)) - 0.5 * s2 * inv;
             }
         }
     cudaFree(p->d_stats);
     p->d_stats = nullptr;
-    CUDA_OK(cudaMalloc(&p->d_stats, sizeof(double) * n));
-    CUDA_OK(cudaMemcpy(p->d_stats, q.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&p->d_stats, sizeof(double) * nq));
+    CUDA_OK(cudaMemcpy(p->d_stats, q.data(), sizeof(double) * nq, cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -415,6 +419,7 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
         return fail(PV_E_ARG, "T * n_obs * n_data too large (< 2^29)");
     if (!p->col_target.empty() && !P) return fail(PV_E_ARG, "P is NULL but columns are configured");
     if (sens && p->tab->n_sens == 0) return fail(PV_E_MODEL, "model was generated without sensitivity parameters");
+    if ((mode & PV_MODE_TRAJ) && !Y) return fail(PV_E_ARG, "Y is NULL");
     if (mode == PV_MODE_TRAJ_SENS && !S) return fail(PV_E_ARG, "S is NULL");
     if (need_logp && !logp) return fail(PV_E_ARG, "logp is NULL");
     if ((mode & PV_MODE_LOGP) && (mode & PV_MODE_SENS) && !grad) return fail(PV_E_ARG, "grad is NULL");
@@ -466,7 +471,7 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
         if (!lp.status) lp.status = p->d_scratch_status[slot];
     }
     size_t shmem = sizeof(double) * (lp.T + p->tab->n_theta + p->tab->n_states);
-    if (need_logp && lp.n_data == 1) shmem += sizeof(double) * 3 * lp.T * lp.n_obs;
+    if (need_logp && lp.n_data == 1) shmem += sizeof(double) * PV_QSTRIDE * lp.T * lp.n_obs;
     if (shmem > 200 * 1024) return fail(PV_E_ARG, "time grid / data too large for shared memory");
     bool obsid = lp.n_obs == p->tab->n_states;
     for (int k = 0; k < lp.n_obs && obsid; ++k) obsid = (lp.obs_idx[k] == k);

@@ -91,6 +91,19 @@ PV_HD double pv_rcp_approx(double x) {
     return 1.0 / x;
 #endif
 }
+// full-precision reciprocal of a normal, finite x without the slow path of __drcp_rn: MUFU.RCP64H seed (~20 bits) and
+// two Newton steps
+PV_HD double pv_rcp_newton(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
 PV_HD double pv_drcp(double x) {
 #if defined(__CUDA_ARCH__)
     return __drcp_rn(x);
@@ -144,44 +157,6 @@ struct pv_dopri5_cost {
 
 // status of a lane that still has work to do
 #define PV_RUNNING (-1)
-
-// Dense-output record of one accepted DOPRI5 step: everything needed to evaluate the 4th-order interpolant at
-// the grid points j0 <= j < j1 that fall into (t, tn].  The batch kernel queues these records in shared memory
-// and evaluates them 32 at a time with full warps instead of inside the (divergent) accept branch.
-template <int N>
-struct pv_dense_rec {
-    double t, h, tn;
-    int j0, j1;
-    double y[N], yn[N], bs[N], r4[N], r5[N];
-    PV_HD void eval(double tj, double hinv, double (&yo)[N]) const {
-        if (tj >= tn) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) yo[i] = yn[i];
-        } else {
-            const double th = (tj - t) * hinv, th1 = 1.0 - th;
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const double yd = yn[i] - y[i];
-                yo[i] = fma(th, fma(th1, fma(th, fma(th1, r5[i], r4[i]), bs[i]), yd), y[i]);
-            }
-        }
-    }
-};
-
-// evaluate a record right away, on the lane that produced it (host checks, Rosenbrock-free static schedule)
-template <int N, class Out>
-struct pv_emit_now {
-    const double* tgrid;
-    Out& out;
-    PV_HD void operator()(const pv_dense_rec<N>& rec, bool /*final*/) {
-        const double hinv = pv_drcp(rec.h);
-        for (int j = rec.j0; j < rec.j1; ++j) {
-            double yo[N];
-            rec.eval(tgrid[j], hinv, yo);
-            out(j, tgrid[j], yo);
-        }
-    }
-};
 
 // Per-lane DOPRI5 state machine: start() once, then step() until it returns something other than
 // PV_RUNNING.  The batch kernels drive it either one trajectory per thread for the whole launch
@@ -252,18 +227,11 @@ struct pv_dopri5_lane {
         return PV_RUNNING;
     }
 
-    // one attempted step, dense output evaluated immediately through `out`
+    // one attempted step; the 4th-order dense output of an accepted step is evaluated right away for every grid
+    // point in (t, t+h] and handed to `out`
     template <class Out>
     PV_HD int step(const typename Sys::Consts& ks, const double* tgrid, int T, double rtol, double atol,
                    int max_steps, Out& out) {
-        pv_emit_now<N, Out> emit{tgrid, out};
-        return step_emit(ks, tgrid, T, rtol, atol, max_steps, emit);
-    }
-
-    // one attempted step; an accepted step that covers grid points hands a pv_dense_rec to `emit`
-    template <class Emit>
-    PV_HD int step_emit(const typename Sys::Consts& ks, const double* tgrid, int T, double rtol, double atol,
-                        int max_steps, Emit& emit) {
         if (nstep >= max_steps) return PV_ERR_MAX_STEPS;
         ++nstep;
         bool last = false;
@@ -271,7 +239,6 @@ struct pv_dopri5_lane {
             h = tend - t;
             last = true;
         }
-        if (!(fabs(h) > 1e-14 * fmax(fabs(t), 1.0))) return PV_ERR_STEP_TOO_SMALL;
 
         double k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], yn[N];
         // ---- stages ----------------------------------------------------------------------------
@@ -332,28 +299,28 @@ struct pv_dopri5_lane {
             ++st.accepted;
             const double tn = last ? tend : t + h;
             if (t_next <= tn) {
-                pv_dense_rec<N> rec;
-                rec.t = t;
-                rec.h = h;
-                rec.tn = tn;
+                // y(t + th h) = y + th (yd + (1 - th) (bs + th (r4 + (1 - th) r5)))   (Hairer's contd5, Horner form)
+                double yd[N], bs[N], r4[N], r5[N];
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
-                    const double yd = yn[i] - y[i];
-                    rec.y[i] = y[i];
-                    rec.yn[i] = yn[i];
-                    rec.bs[i] = fma(h, k1[i], -yd);
-                    rec.r4[i] = yd - fma(h, k7[i], rec.bs[i]);
-                    rec.r5[i] = h * fma(pv_dp5[26], k1[i],
-                                        fma(pv_dp5[27], k3[i],
-                                            fma(pv_dp5[28], k4[i], fma(pv_dp5[29], k5[i], fma(pv_dp5[30], k6[i], pv_dp5[31] * k7[i])))));
+                    yd[i] = yn[i] - y[i];
+                    bs[i] = fma(h, k1[i], -yd[i]);
+                    r4[i] = yd[i] - fma(h, k7[i], bs[i]);
+                    r5[i] = h * fma(pv_dp5[26], k1[i],
+                                    fma(pv_dp5[27], k3[i],
+                                        fma(pv_dp5[28], k4[i], fma(pv_dp5[29], k5[i], fma(pv_dp5[30], k6[i], pv_dp5[31] * k7[i])))));
                 }
-                rec.j0 = jout;
+                const double hinv = pv_rcp_newton(h);
                 do {
+                    // a grid point at the end of the step takes th = 1 (y + yd): no branch around the interpolant
+                    const double th = (t_next >= tn) ? 1.0 : (t_next - t) * hinv, th1 = 1.0 - th;
+                    double yo[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) yo[i] = fma(th, fma(th1, fma(th, fma(th1, r5[i], r4[i]), bs[i]), yd[i]), y[i]);
+                    out(jout, t_next, yo);
                     ++jout;
-                } while (jout < T && tgrid[jout] <= tn);
-                rec.j1 = jout;
-                t_next = jout < T ? tgrid[jout] : 1e300;
-                emit(rec, last || jout >= T);
+                    t_next = jout < T ? tgrid[jout] : 1e300;
+                } while (t_next <= tn);
             }
             // h_new = h / clamp(fac11 / facold^beta / 0.9, 0.1, 5)  ->  multiply by 2^-(log2 of the clamped factor)
             const float lfac = fminf(fmaxf(lfac11 - 0.04f * lfacold + 0.15200309f, -3.3219281f), 2.3219281f);
@@ -373,6 +340,8 @@ struct pv_dopri5_lane {
             ++st.rejected;
             h = h * (double)pv_exp2f_fast(-fminf(lfac11 + 0.15200309f, 2.3219281f));
             last_rejected = true;
+            // only a rejection shrinks h, so the underflow test lives here and not in front of every step
+            if (!(fabs(h) > 1e-14 * fmax(fabs(t), 1.0))) return PV_ERR_STEP_TOO_SMALL;
         }
         return PV_RUNNING;
     }

@@ -36,7 +36,7 @@ struct pv_launch_params {
     const double* theta_base;  // [NTH]
     const double* y0_base;     // [NX], NaN = use the model's initial value
     const double* tgrid;       // [T]
-    const double* stats;       // [3][T][n_obs][n_data]  likelihood polynomial coefficients q0, q1, q2 (see pv_problem_set_data)
+    const double* stats;       // [n_data][T][n_obs][4]  likelihood polynomial coefficients q0, q1, q2, pad (see pv_problem_set_data)
     double* Y;                 // [B][T][n_obs]
     double* S;                 // [B][T][n_obs][NS]
     double* logp;              // [B]
@@ -63,11 +63,12 @@ PV_D double pv_pick(const double (&a)[N], int block, int idx) {
 }
 
 // ---- per-grid-point sink: stores the observables and / or folds them into the likelihood ---------------------
+// The integrators call it once per grid point in increasing j, so a lane walks three running pointers (its row of Y,
+// of S and of the likelihood coefficients) instead of rebuilding addresses from (b, j, k) at every point.
 // OBSID = true: the observables are exactly the model's states in order (n_obs == NX, obs_idx[k] == k), so the
 // selection chains, the indexed constant loads and the k-loop overhead disappear (the common case of the
 // cheap non-stiff models, where the per-output code is a sizeable share of a step).
-// Index arithmetic is kept in 32 bits wherever the host has checked the ranges (T * n_obs * n_data < 2^31,
-// B < 2^31); only the final row offset into Y / S is 64-bit, one IMAD.WIDE per grid point.
+#define PV_QSTRIDE 4   // doubles per likelihood coefficient record (q0, q1, q2, pad): two 16-byte loads
 template <class M, int MODE, bool OBSID>
 struct pv_sink {
     static constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
@@ -77,31 +78,52 @@ struct pv_sink {
     static constexpr int N = pv_system<M, SENS>::N;
     static constexpr int NFIM = FIM ? M::NSD * (M::NSD + 1) / 2 : 1;
     const pv_launch_params& p;
-    const double* sh_stats;   // likelihood coefficients: the block's shared-memory copy when n_data == 1, else p.stats (global)
     int64_t b;                // trajectory
-    double* ybase;            // &Y[b][0][0] (nullptr: no trajectory store), set once per trajectory
-    double* sbase;            // &S[b][0][0][0]
-    int d;                    // data set of this trajectory (b % n_data, computed once per trajectory)
+    double* yrow;             // &Y[b][j][0] of the next grid point (trajectory-major: see below)
+    double* srow;             // &S[b][j][0][0]
+    const double* qrow;       // &q[d][j][0][0]: coefficients of the trajectory's data set d = b % n_data, either in the
+                              // block's shared-memory copy (n_data == 1) or in global memory (generic address)
     double obs[M::NX];
     double lp;
     double g[M::NSD];
     double fim[NFIM];         // sum over measurements of (df/dtheta)(df/dtheta)^T / sigma^2  (AMICI's FIM)
 
-    // yrow = &Y[b][j][0] (or nullptr), srow = &S[b][j][0][0]; so = index of (j, 0, d) in one coefficient plane
-    PV_D void one(int k, double f, const double (&df)[M::NSD], double* yrow, double* srow, int so, int plane) {
+    // first grid point of trajectory b_
+    PV_D void begin(int64_t b_, const double* qbase) {
+        const int n_obs = OBSID ? M::NX : p.n_obs;
+        b = b_;
         if constexpr (TRAJ) {
-            if (yrow) yrow[k] = f;
+            const int64_t off = b_ * p.T * n_obs;
+            yrow = p.Y + off;
+            if constexpr (SENS) srow = p.S + off * M::NS;
+        }
+        if constexpr (LOGP) qrow = qbase + (int64_t)(b_ % p.n_data) * (p.T * n_obs * PV_QSTRIDE);
+        lp = 0.0;
+#pragma unroll
+        for (int s = 0; s < M::NSD; ++s) g[s] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NFIM; ++q) fim[q] = 0.0;
+    }
+
+    template <bool LOGNORMAL>
+    PV_D void one(int k, double f, const double (&df)[M::NSD]) {
+        if constexpr (TRAJ) {
+            // trajectory-major: a lane writes its own contiguous [T][n_obs] block, so consecutive grid points of one
+            // trajectory fill whole 32-byte sectors and 128-byte lines no matter which lane integrates it (lane refill
+            // scatters neighbouring trajectories over warps and time; batch-minor output made every store a partial
+            // sector that was evicted half filled: 2.7x the algorithmic DRAM traffic in ncu)
+            yrow[k] = f;
             if constexpr (SENS) {
 #pragma unroll
                 for (int s = 0; s < M::NS; ++s) srow[k * M::NS + s] = df[s];
             }
         }
         if constexpr (LOGP) {
-            const int o = so + k * p.n_data;
-            // one generic-address load path for both homes of the coefficients (block-shared copy or global)
-            const double q0 = sh_stats[o], q1 = sh_stats[plane + o], q2 = sh_stats[2 * plane + o];
             // lp term = q0 + v (q1 + q2 v), v = f (normal) or log f (log-normal); n = 0 entries have q = 0
-            if (p.noise_model == 0) {
+            const double2 q01 = *reinterpret_cast<const double2*>(qrow + k * PV_QSTRIDE);
+            const double q2 = qrow[k * PV_QSTRIDE + 2];
+            const double q0 = q01.x, q1 = q01.y;
+            if constexpr (!LOGNORMAL) {
                 lp += fma(f, fma(q2, f, q1), q0);
                 if constexpr (SENS) {
                     const double w = fma(2.0 * q2, f, q1);
@@ -143,20 +165,8 @@ struct pv_sink {
         }
     }
 
-    PV_D void operator()(int j, double, const double (&z)[N]) {
-        const int n_obs = OBSID ? M::NX : p.n_obs;
-        double* yrow = nullptr;
-        double* srow = nullptr;
-        if constexpr (TRAJ) {
-            // trajectory-major: a lane writes its own contiguous [T][n_obs] block, so consecutive grid points of one
-            // trajectory fill whole 32-byte sectors and 128-byte lines no matter which lane integrates it (lane refill
-            // scatters neighbouring trajectories over warps and time; batch-minor output made every store a partial
-            // sector that was evicted half filled: 2.7x the algorithmic DRAM traffic in ncu)
-            yrow = ybase ? ybase + j * n_obs : nullptr;
-            if constexpr (SENS) srow = sbase + j * n_obs * M::NS;
-        }
-        const int plane = p.T * n_obs * p.n_data;
-        const int so = j * n_obs * p.n_data + d;
+    template <bool LOGNORMAL>
+    PV_D void row(const double (&z)[N]) {
         if constexpr (OBSID) {
 #pragma unroll
             for (int k = 0; k < M::NX; ++k) {
@@ -165,10 +175,10 @@ struct pv_sink {
 #pragma unroll
                     for (int s = 0; s < M::NS; ++s) df[s] = M::OBS_UNIT ? z[M::NX * (1 + s) + k] : z[M::NX * (1 + s) + k] * obs[k];
                 }
-                one(k, M::OBS_UNIT ? z[k] : z[k] * obs[k], df, yrow, srow, so, plane);
+                one<LOGNORMAL>(k, M::OBS_UNIT ? z[k] : z[k] * obs[k], df);
             }
         } else {
-            for (int k = 0; k < n_obs; ++k) {
+            for (int k = 0; k < p.n_obs; ++k) {
                 const int idx = p.obs_idx[k];
                 const double sc = pv_pick<M::NX>(obs, 0, idx);
                 double df[M::NSD];
@@ -176,9 +186,23 @@ struct pv_sink {
 #pragma unroll
                     for (int s = 0; s < M::NS; ++s) df[s] = pv_pick<M::NX>(z, 1 + s, idx) * sc;
                 }
-                one(k, pv_pick<M::NX>(z, 0, idx) * sc, df, yrow, srow, so, plane);
+                one<LOGNORMAL>(k, pv_pick<M::NX>(z, 0, idx) * sc, df);
             }
         }
+    }
+
+    PV_D void operator()(int, double, const double (&z)[N]) {
+        // the noise model is a launch-wide constant: one uniform branch per grid point, not one per observable
+        if (LOGP && p.noise_model != 0)
+            row<true>(z);
+        else
+            row<false>(z);
+        const int n_obs = OBSID ? M::NX : p.n_obs;
+        if constexpr (TRAJ) {
+            yrow += n_obs;
+            if constexpr (SENS) srow += n_obs * M::NS;
+        }
+        if constexpr (LOGP) qrow += n_obs * PV_QSTRIDE;
     }
 };
 
@@ -215,17 +239,18 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
     constexpr bool LOGP = (MODE & PV_MODE_LOGP) != 0;
     using Sys = pv_system<M, SENS>;
     using Lane = typename pv_lane_of<M, METHOD, SENS>::type;
-    extern __shared__ double sh[];
-    double* sh_t = sh;                    // [T]
-    double* sh_theta = sh_t + p.T;        // [NTH]
-    double* sh_y0 = sh_theta + M::NTH;    // [NX]
-    double* sh_stats = sh_y0 + M::NX;     // [3][T][n_obs] when LOGP && n_data == 1
+    extern __shared__ __align__(16) double sh[];
+    // the coefficient records come first: they are read with 16-byte loads, and their size is a multiple of 32 bytes
+    const bool stats_shared = LOGP && p.n_data == 1;
+    double* sh_stats = sh;                                                    // [T][n_obs][4] when stats_shared
+    double* sh_t = sh + (stats_shared ? PV_QSTRIDE * p.T * p.n_obs : 0);      // [T]
+    double* sh_theta = sh_t + p.T;                                            // [NTH]
+    double* sh_y0 = sh_theta + M::NTH;                                        // [NX]
     for (int i = threadIdx.x; i < p.T; i += blockDim.x) sh_t[i] = p.tgrid[i];
     for (int i = threadIdx.x; i < M::NTH; i += blockDim.x) sh_theta[i] = p.theta_base[i];
     for (int i = threadIdx.x; i < M::NX; i += blockDim.x) sh_y0[i] = p.y0_base[i];
-    const bool stats_shared = LOGP && p.n_data == 1;
     if (stats_shared)
-        for (int i = threadIdx.x; i < 3 * p.T * p.n_obs; i += blockDim.x) sh_stats[i] = p.stats[i];
+        for (int i = threadIdx.x; i < PV_QSTRIDE * p.T * p.n_obs; i += blockDim.x) sh_stats[i] = p.stats[i];
     __syncthreads();
 
     const unsigned FULL = 0xffffffffu;
@@ -233,7 +258,8 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
     const int64_t n_items = p.n_items_dev ? (int64_t)*p.n_items_dev : p.B;
     typename Sys::Consts ks;
     Lane lane;
-    pv_sink<M, MODE, OBSID> sink{p, stats_shared ? sh_stats : p.stats, 0, nullptr, nullptr, 0, {}, 0.0, {}, {}};
+    pv_sink<M, MODE, OBSID> sink{p, 0, nullptr, nullptr, nullptr, {}, 0.0, {}, {}};
+    const double* qbase = stats_shared ? sh_stats : p.stats;
     bool have = false;        // this lane is integrating trajectory sink.b
     bool exhausted = false;   // the work counter ran past B
 
@@ -310,19 +336,7 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
 #pragma unroll
                             for (int i = 0; i < M::NX; ++i) z[M::NX * (1 + s) + i] = over[i] ? 0.0 : dy0[s][i];
                     }
-                    sink.b = b;
-                    sink.d = (int)(b % p.n_data);
-                    {
-                        const int n_obs = OBSID ? M::NX : p.n_obs;
-                        const int64_t off = b * p.T * n_obs;
-                        sink.ybase = p.Y ? p.Y + off : nullptr;
-                        sink.sbase = p.S ? p.S + off * M::NS : nullptr;
-                    }
-                    sink.lp = 0.0;
-#pragma unroll
-                    for (int s = 0; s < M::NSD; ++s) sink.g[s] = 0.0;
-#pragma unroll
-                    for (int q = 0; q < pv_sink<M, MODE, OBSID>::NFIM; ++q) sink.fim[q] = 0.0;
+                    sink.begin(b, qbase);
                     have = true;
                     const int rc = lane.start(ks, z, p.t0, sh_t, p.T, p.rtol, p.atol, sink);
                     if (rc != PV_RUNNING) finish(rc);

@@ -58,13 +58,21 @@ struct pv_system<M, true> {
 // ---- controller helpers -------------------------------------------------------------------
 PV_HD float pv_log2f_fast(float x) {
 #if defined(__CUDA_ARCH__)
-    return __log2f(x);           // MUFU.LG2
+    float r;                     // bare MUFU.LG2: callers clamp the argument away from the denormal range
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #else
     return log2f(x);
 #endif
 }
 PV_HD float pv_exp2f_fast(float x) {
-    return exp2f(x);             // device: MUFU.EX2 plus range scaling; the argument here is clamped to [-3.4, 2.4]
+#if defined(__CUDA_ARCH__)
+    float r;                     // bare MUFU.EX2: the argument here is clamped to [-3.4, 2.4], no range scaling needed
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return exp2f(x);
+#endif
 }
 PV_HD float pv_powf_fast(float x, float a) {
 #if defined(__CUDA_ARCH__)
@@ -242,34 +250,37 @@ struct pv_dopri5_lane {
 
         double k2[N], k3[N], k4[N], k5[N], k6[N], k7[N], yn[N];
         // ---- stages ----------------------------------------------------------------------------
+        // The newest stage derivative enters each sum LAST (outermost fma): everything else of the sum is
+        // independent of it and overlaps with the preceding RHS evaluation, so the dependent chain per stage is
+        // RHS -> one fma -> fma(h, sum, y) instead of one fma per stage derivative.
 #pragma unroll
         for (int i = 0; i < N; ++i) yn[i] = fma(h * pv_dp5[0], k1[i], y[i]);
         Sys::rhs(t + 0.2 * h, yn, ks, k2);
 #pragma unroll
-        for (int i = 0; i < N; ++i) yn[i] = fma(h, fma(pv_dp5[1], k1[i], pv_dp5[2] * k2[i]), y[i]);
+        for (int i = 0; i < N; ++i) yn[i] = fma(h, fma(pv_dp5[2], k2[i], pv_dp5[1] * k1[i]), y[i]);
         Sys::rhs(t + 0.3 * h, yn, ks, k3);
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            yn[i] = fma(h, fma(pv_dp5[3], k1[i], fma(pv_dp5[4], k2[i], pv_dp5[5] * k3[i])), y[i]);
+            yn[i] = fma(h, fma(pv_dp5[5], k3[i], fma(pv_dp5[4], k2[i], pv_dp5[3] * k1[i])), y[i]);
         Sys::rhs(t + 0.8 * h, yn, ks, k4);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             yn[i] = fma(h,
-                        fma(pv_dp5[6], k1[i], fma(pv_dp5[7], k2[i], fma(pv_dp5[8], k3[i], pv_dp5[9] * k4[i]))),
+                        fma(pv_dp5[9], k4[i], fma(pv_dp5[8], k3[i], fma(pv_dp5[7], k2[i], pv_dp5[6] * k1[i]))),
                         y[i]);
         Sys::rhs(t + (8.0 / 9.0) * h, yn, ks, k5);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             yn[i] = fma(h,
-                        fma(pv_dp5[10], k1[i],
-                            fma(pv_dp5[11], k2[i], fma(pv_dp5[12], k3[i], fma(pv_dp5[13], k4[i], pv_dp5[14] * k5[i])))),
+                        fma(pv_dp5[14], k5[i],
+                            fma(pv_dp5[13], k4[i], fma(pv_dp5[12], k3[i], fma(pv_dp5[11], k2[i], pv_dp5[10] * k1[i])))),
                         y[i]);
         Sys::rhs(t + h, yn, ks, k6);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             yn[i] = fma(h,
-                        fma(pv_dp5[15], k1[i],
-                            fma(pv_dp5[16], k3[i], fma(pv_dp5[17], k4[i], fma(pv_dp5[18], k5[i], pv_dp5[19] * k6[i])))),
+                        fma(pv_dp5[19], k6[i],
+                            fma(pv_dp5[18], k5[i], fma(pv_dp5[17], k4[i], fma(pv_dp5[16], k3[i], pv_dp5[15] * k1[i])))),
                         y[i]);
         Sys::rhs(t + h, yn, ks, k7);
 
@@ -277,9 +288,9 @@ struct pv_dopri5_lane {
         double err2d = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double e = h * fma(pv_dp5[20], k1[i],
-                                     fma(pv_dp5[21], k3[i],
-                                         fma(pv_dp5[22], k4[i], fma(pv_dp5[23], k5[i], fma(pv_dp5[24], k6[i], pv_dp5[25] * k7[i])))));
+            const double e = h * fma(pv_dp5[25], k7[i],
+                                     fma(pv_dp5[24], k6[i],
+                                         fma(pv_dp5[23], k5[i], fma(pv_dp5[22], k4[i], fma(pv_dp5[21], k3[i], pv_dp5[20] * k1[i])))));
             const double sc = atol + rtol * fmax(fabs(y[i]), fabs(yn[i]));
             const double r = e * pv_rcp_approx(sc);
             err2d = fma(r, r, err2d);
@@ -306,9 +317,9 @@ struct pv_dopri5_lane {
                     yd[i] = yn[i] - y[i];
                     bs[i] = fma(h, k1[i], -yd[i]);
                     r4[i] = yd[i] - fma(h, k7[i], bs[i]);
-                    r5[i] = h * fma(pv_dp5[26], k1[i],
-                                    fma(pv_dp5[27], k3[i],
-                                        fma(pv_dp5[28], k4[i], fma(pv_dp5[29], k5[i], fma(pv_dp5[30], k6[i], pv_dp5[31] * k7[i])))));
+                    r5[i] = h * fma(pv_dp5[31], k7[i],
+                                    fma(pv_dp5[30], k6[i],
+                                        fma(pv_dp5[29], k5[i], fma(pv_dp5[28], k4[i], fma(pv_dp5[27], k3[i], pv_dp5[26] * k1[i])))));
                 }
                 const double hinv = pv_rcp_newton(h);
                 do {
@@ -323,9 +334,9 @@ struct pv_dopri5_lane {
                 } while (t_next <= tn);
             }
             // h_new = h / clamp(fac11 / facold^beta / 0.9, 0.1, 5)  ->  multiply by 2^-(log2 of the clamped factor)
-            const float lfac = fminf(fmaxf(lfac11 - 0.04f * lfacold + 0.15200309f, -3.3219281f), 2.3219281f);
-            double hnew = h * (double)pv_exp2f_fast(-lfac);
-            if (last_rejected) hnew = fmin(hnew, h);
+            // (a step that follows a rejection must not grow: lower bound 0 instead of log2(1/5))
+            const float lfac = fminf(fmaxf(lfac11 - 0.04f * lfacold + 0.15200309f, last_rejected ? 0.0f : -3.3219281f), 2.3219281f);
+            const double hnew = h * (double)pv_exp2f_fast(-lfac);
             lfacold = fmaxf(0.5f * l2, -13.287712f);
             last_rejected = false;
 #pragma unroll

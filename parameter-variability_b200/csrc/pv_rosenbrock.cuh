@@ -178,6 +178,7 @@ struct pv_rodas4_lane {
             M::lu_assemble(hi * (1.0 / GAMMA), J, W);
             M::lu_factor(W);
         }
+        // (in every stage sum below the newest K enters last, as the outermost fma: the rest of the sum does not wait for it)
         // ---- stage 1 ----------------------------------------------------------------------------------
         eval_F(t, z, ks, K1);
         solve_stage(ks, W, K1);
@@ -196,25 +197,25 @@ struct pv_rodas4_lane {
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int i = 0; i < NX; ++i) zs[b * NX + i] = fma(A31, K1[b][i], fma(A32, K2[b][i], z[b * NX + i]));
+            for (int i = 0; i < NX; ++i) zs[b * NX + i] = fma(A32, K2[b][i], fma(A31, K1[b][i], z[b * NX + i]));
         eval_F(t + C3 * h, zs, ks, K3);
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int i = 0; i < NX; ++i) K3[b][i] = fma(hi, fma(C31, K1[b][i], C32 * K2[b][i]), K3[b][i]);
+            for (int i = 0; i < NX; ++i) K3[b][i] = fma(hi, fma(C32, K2[b][i], C31 * K1[b][i]), K3[b][i]);
         solve_stage(ks, W, K3);
         // ---- stage 4 ----------------------------------------------------------------------------------
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i)
-                zs[b * NX + i] = fma(A41, K1[b][i], fma(A42, K2[b][i], fma(A43, K3[b][i], z[b * NX + i])));
+                zs[b * NX + i] = fma(A43, K3[b][i], fma(A42, K2[b][i], fma(A41, K1[b][i], z[b * NX + i])));
         eval_F(t + C4 * h, zs, ks, K4);
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i)
-                K4[b][i] = fma(hi, fma(C41, K1[b][i], fma(C42, K2[b][i], C43 * K3[b][i])), K4[b][i]);
+                K4[b][i] = fma(hi, fma(C43, K3[b][i], fma(C42, K2[b][i], C41 * K1[b][i])), K4[b][i]);
         solve_stage(ks, W, K4);
         // ---- stage 5 ----------------------------------------------------------------------------------
 #pragma unroll
@@ -222,14 +223,14 @@ struct pv_rodas4_lane {
 #pragma unroll
             for (int i = 0; i < NX; ++i)
                 zs[b * NX + i] =
-                    fma(A51, K1[b][i], fma(A52, K2[b][i], fma(A53, K3[b][i], fma(A54, K4[b][i], z[b * NX + i]))));
+                    fma(A54, K4[b][i], fma(A53, K3[b][i], fma(A52, K2[b][i], fma(A51, K1[b][i], z[b * NX + i]))));
         eval_F(t + h, zs, ks, K5);
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i)
                 K5[b][i] =
-                    fma(hi, fma(C51, K1[b][i], fma(C52, K2[b][i], fma(C53, K3[b][i], C54 * K4[b][i]))), K5[b][i]);
+                    fma(hi, fma(C54, K4[b][i], fma(C53, K3[b][i], fma(C52, K2[b][i], C51 * K1[b][i]))), K5[b][i]);
         solve_stage(ks, W, K5);
         // ---- stage 6 (the embedded solution zs + K5 is the evaluation point) -------------------------------
 #pragma unroll
@@ -242,8 +243,8 @@ struct pv_rodas4_lane {
 #pragma unroll
             for (int i = 0; i < NX; ++i)
                 K6[b][i] = fma(hi,
-                               fma(C61, K1[b][i],
-                                   fma(C62, K2[b][i], fma(C63, K3[b][i], fma(C64, K4[b][i], C65 * K5[b][i])))),
+                               fma(C65, K5[b][i],
+                                   fma(C64, K4[b][i], fma(C63, K3[b][i], fma(C62, K2[b][i], C61 * K1[b][i])))),
                                K6[b][i]);
         solve_stage(ks, W, K6);
         // new solution = zs + K6, error estimate = K6

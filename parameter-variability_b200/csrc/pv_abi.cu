@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -351,6 +352,12 @@ static cudaError_t launch_persistent(KernelT kern, const pv_launch_params& lp, s
     cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PV_BLOCK, shmem);
     if (eo != cudaSuccess) return eo;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    // tuning knob for tools/sweep_schedule*.py: cap the resident CTAs per SM (e.g. to keep the local-memory
+    // footprint of the spilling Rosenbrock sensitivity kernels inside the L2)
+    if (const char* cap = getenv("PV_MAX_CTAS_PER_SM")) {
+        const int c = atoi(cap);
+        if (c >= 1 && c < per_sm) per_sm = c;
+    }
     const int64_t want = (lp.B + PV_BLOCK - 1) / PV_BLOCK;
     const int64_t blocks = std::min<int64_t>(want, (int64_t)num_sms * per_sm);
     kern<<<(unsigned)blocks, PV_BLOCK, shmem, s>>>(lp);

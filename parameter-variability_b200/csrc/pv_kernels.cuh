@@ -10,7 +10,9 @@
 
 #define PV_MAX_COLS 8
 #define PV_MAX_OBS 16
+#ifndef PV_BLOCK
 #define PV_BLOCK 128
+#endif
 #ifndef PV_MINB_SMALL
 #define PV_MINB_SMALL 4
 #endif

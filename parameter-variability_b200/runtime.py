@@ -7,6 +7,7 @@ CPU fallback: if the library or a CUDA device is missing, construction fails lou
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional, Sequence
 
@@ -81,7 +82,8 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = Path(path or LIB_PATH)
+    # PARVAR_B200_LIB: an alternative build of the same library (tuning variants, tools/sweep_variants.sh)
+    path = Path(path or os.environ.get("PARVAR_B200_LIB") or LIB_PATH)
     if not path.exists():
         raise ParvarB200Error(
             f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

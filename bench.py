@@ -191,6 +191,8 @@ def main() -> None:
     if lib.pv_device_count() <= 0:
         raise SystemExit("bench.py needs a CUDA device: parvar_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    # one process per GPU: run next to it (pinned pages land on the NUMA node of the thread that touches them first)
+    importlib.import_module(PKG + ".numa").bind_to_gpu_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)

@@ -50,6 +50,9 @@ struct pv_problem {
     bool dirty_values = true;
     // host pipeline
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;                               // all device->host copies of the host pipeline, FIFO
+    cudaEvent_t ev_ready[3] = {nullptr, nullptr, nullptr};            // slot's kernels done
+    cudaEvent_t ev_drained[3] = {nullptr, nullptr, nullptr};          // slot's results copied out
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double* stage_dev[3] = {nullptr, nullptr, nullptr};
     size_t stage_bytes[3] = {0, 0, 0};
@@ -134,7 +137,11 @@ extern "C" pv_problem* pv_problem_create(const char* model_name, int device) {
               cudaMalloc(&p->d_failed, sizeof(int)) == cudaSuccess &&
               cudaMalloc(&p->d_counters, sizeof(unsigned long long) * PV_COUNTER_RING) == cudaSuccess &&
               cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
-    for (int i = 0; i < 3 && ok; ++i) ok = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 3 && ok; ++i)
+        ok = cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&p->ev_ready[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&p->ev_drained[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&p->ev0) == cudaSuccess && cudaEventCreate(&p->ev1) == cudaSuccess;
     if (!ok) {
         fail(PV_E_CUDA, std::string("problem setup: ") + cudaGetErrorString(cudaGetLastError()));
@@ -160,8 +167,11 @@ extern "C" void pv_problem_destroy(pv_problem* p) {
     }
     for (int i = 0; i < 3; ++i) {
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
+        if (p->ev_ready[i]) cudaEventDestroy(p->ev_ready[i]);
+        if (p->ev_drained[i]) cudaEventDestroy(p->ev_drained[i]);
         cudaFree(p->stage_dev[i]);
     }
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     delete p;
@@ -578,7 +588,14 @@ extern "C" int pv_simulate_host(pv_problem* p, int64_t B, const double* P_host, 
     const int n_cols = (int)p->col_target.size();
     const int64_t rows = (int64_t)p->tgrid.size() * (int64_t)p->obs_idx.size();
     // chunks sized so that copy-out of chunk i overlaps the kernel of chunk i+1
-    const int64_t chunk = std::min<int64_t>(B, (int64_t)1 << 17);
+    // measured on the C2 workload (tools/time_e2e.py; raw pinned D2H of this box: 57 GB/s, one unchunked copy of the
+    // results alone: 21.9 ms): 16 Ki rows 23.6 ms, 32 Ki 23.0 ms, 64 Ki 23.4 ms, 128 Ki 24.4 ms per 10^6 trajectories
+    int64_t chunk_rows = (int64_t)1 << 15;
+    if (const char* e = getenv("PV_HOST_CHUNK")) {   // tuning knob (tools/time_e2e.py)
+        const long long v = atoll(e);
+        if (v >= 1024) chunk_rows = v;
+    }
+    const int64_t chunk = std::min<int64_t>(B, chunk_rows);
     // per slot: P [n_cols][chunk], Y [chunk][rows], logp [chunk], status [chunk] + steps [2][chunk] (int32)
     const size_t bytesP = sizeof(double) * (size_t)std::max(n_cols, 1) * chunk;
     const size_t bytesY = sizeof(double) * (size_t)rows * chunk;
@@ -591,6 +608,10 @@ extern "C" int pv_simulate_host(pv_problem* p, int64_t B, const double* P_host, 
     CUDA_OK(cudaMemsetAsync(p->d_failed, 0, sizeof(int), p->streams[0]));
     CUDA_OK(cudaStreamSynchronize(p->streams[0]));
     CUDA_OK(cudaEventRecord(p->ev0, p->streams[0]));
+    // Slot pipeline: H2D + kernels of chunk k run on the slot's own stream; every device->host copy goes through ONE copy
+    // stream in chunk order (events hand the slot over and back), so the copy engine drains the results back to back
+    // instead of arbitrating between three streams.
+    cudaStream_t cs = p->copy_stream;
     int k = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk, ++k) {
         const int slot = k % n_slots;
@@ -601,6 +622,7 @@ extern "C" int pv_simulate_host(pv_problem* p, int64_t B, const double* P_host, 
         double* dL = (double*)((char*)dY + bytesY);
         int32_t* dStatus = (int32_t*)((char*)dL + bytesL);
         int32_t* dSteps = dStatus + chunk;
+        if (k >= n_slots) CUDA_OK(cudaStreamWaitEvent(s, p->ev_drained[slot], 0));   // slot buffers are free again
         if (n_cols > 0)
             CUDA_OK(cudaMemcpy2DAsync(dP, sizeof(double) * nb, P_host + b0, sizeof(double) * B, sizeof(double) * nb, n_cols,
                                       cudaMemcpyHostToDevice, s));
@@ -609,13 +631,17 @@ extern "C" int pv_simulate_host(pv_problem* p, int64_t B, const double* P_host, 
             return rc;
         pv_count_failed_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(dStatus, nb, p->d_failed);
         g_launches.fetch_add(1);
-        CUDA_OK(cudaMemcpyAsync(Y_host + b0 * rows, dY, sizeof(double) * rows * nb, cudaMemcpyDeviceToHost, s));
-        if (logp_host) CUDA_OK(cudaMemcpyAsync(logp_host + b0, dL, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
-        if (status_host) CUDA_OK(cudaMemcpyAsync(status_host + b0, dStatus, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaEventRecord(p->ev_ready[slot], s));
+        CUDA_OK(cudaStreamWaitEvent(cs, p->ev_ready[slot], 0));
+        CUDA_OK(cudaMemcpyAsync(Y_host + b0 * rows, dY, sizeof(double) * rows * nb, cudaMemcpyDeviceToHost, cs));
+        if (logp_host) CUDA_OK(cudaMemcpyAsync(logp_host + b0, dL, sizeof(double) * nb, cudaMemcpyDeviceToHost, cs));
+        if (status_host) CUDA_OK(cudaMemcpyAsync(status_host + b0, dStatus, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, cs));
         if (steps_host)
             CUDA_OK(cudaMemcpy2DAsync(steps_host + b0, sizeof(int32_t) * B, dSteps, sizeof(int32_t) * nb, sizeof(int32_t) * nb, 2,
-                                      cudaMemcpyDeviceToHost, s));
+                                      cudaMemcpyDeviceToHost, cs));
+        CUDA_OK(cudaEventRecord(p->ev_drained[slot], cs));
     }
+    CUDA_OK(cudaStreamSynchronize(cs));
     for (int s = 0; s < n_slots; ++s) CUDA_OK(cudaStreamSynchronize(p->streams[s]));
     int failed = 0;
     CUDA_OK(cudaMemcpy(&failed, p->d_failed, sizeof(int), cudaMemcpyDeviceToHost));

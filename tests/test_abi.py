@@ -62,3 +62,15 @@ def test_host_mirror_without_gpu():
     y = np.array([[[1.0, np.nan], [2.0, 3.0]], [[3.0, 1.0], [4.0, 5.0]]])
     st = opt.sufficient_statistics(y, 0)
     assert st.shape == (3, 2, 2) and st[0, 0, 1] == 1 and st[1, 0, 0] == 4 and st[2, 1, 1] == 34
+
+
+def test_numa_helper_parses_cpulists_and_degrades_without_a_gpu():
+    import importlib
+    numa = importlib.import_module("parameter-variability_b200.numa")
+    assert numa._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert numa._parse_cpulist("") == set()
+    info = numa.gpu_numa_info(0)
+    assert set(info) == {"bus", "node", "cpus", "allowed"}
+    import torch
+    if not torch.cuda.is_available():
+        assert numa.bind_to_gpu_node(0) is None     # nothing to bind to: the process affinity is left alone

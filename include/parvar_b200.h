@@ -80,6 +80,21 @@ int pv_problem_set_solver(pv_problem* p, int method, double rtol, double atol, i
  * measured per-integrator default (DOPRI5: 6, RODAS4: 32) */
 int pv_problem_set_schedule(pv_problem* p, int refill_min);
 
+/* Data layout of the Rosenbrock sensitivity kernels (logp + gradient, + Fisher information) of the large models
+ * (augmented system of more than 16 components; of the built-in models: icg_body_flat):
+ *   PV_LAYOUT_LANE   one trajectory per lane (all blocks of the augmented system in one thread)
+ *   PV_LAYOUT_SPLIT  one warp per block: a CTA of 1 + n_sens warps integrates 32 trajectories, the stage vectors of a
+ *                    block stay in its lane's registers, coefficients and the LU are shared through shared memory
+ *   PV_LAYOUT_AUTO   (default) SPLIT while the whole batch is resident at once (latency regime: 9472 trajectories on
+ *                    a B200), LANE beyond.  Both layouts integrate the same method with the same tolerances; their
+ *                    results agree within the integration tolerance, not bit for bit (different summation order of
+ *                    the error norm).  Choose one layout explicitly where bit-reproducibility across batch sizes
+ *                    matters. */
+#define PV_LAYOUT_AUTO 0
+#define PV_LAYOUT_LANE 1
+#define PV_LAYOUT_SPLIT 2
+int pv_problem_set_layout(pv_problem* p, int layout);
+
 /* PV_METHOD_AUTO on a model classified non-stiff integrates with DOPRI5 first; trajectories that use up
  * switch_steps (default 4000) explicit steps - stiff parameter values, e.g. rate constants near the PEtab upper bound
  * 1e8 that a tempered chain or a uniform start point visits - are re-run with RODAS4 in a second launch on the

@@ -294,6 +294,92 @@ def emit_model(hs: HoistedSystem, struct_name: str | None = None) -> EmittedMode
             fp_exprs.append((f"fp[{k}][{i}]", e))
     fp_code, fp_flops = _emit_block(fp_exprs, symmap, "p")
 
+    # ---- per-block forms (one sensitivity parameter at a time) for the block-per-warp Rosenbrock kernel -----
+    # s[j] / v[j] are the block's own vectors; c, dc, W may be any indexable container (registers or shared memory)
+    bsyms = [sp.Symbol(f"sb_{j}") for j in range(NX)]
+    symmap_b = dict(symmap)
+    for j in range(NX):
+        symmap_b[bsyms[j]] = f"s[{j}]"
+    blk_rhs, blk_term, blk_prep, blk_apply = [], [], [], []
+    blk_rhs_flops, blk_term_flops, blk_prep_flops, blk_apply_flops, blk_nhc = [], [], [], [], []
+
+    def kw_of(k):
+        return "if" if k == 0 else "else if"
+    for k in range(NS):
+        exprs_r, exprs_t = [], []
+        for i in range(NX):
+            e = sp.Integer(0)
+            base = sp.Integer(0)
+            for j in range(NX):
+                if (i, j) in hs.jac:
+                    e += hs.jac[(i, j)] * bsyms[j]
+                    if not hs.jac_const[(i, j)]:
+                        base += hs.jac[(i, j)] * bsyms[j]
+            for m in range(NC):
+                if (i, m) in hs.dfdc and (k, m) in dc_syms:
+                    e += hs.dfdc[(i, m)] * dc_syms[(k, m)]
+                    base += hs.dfdc[(i, m)] * dc_syms[(k, m)]
+            exprs_r.append((f"out[{i}]", e))
+            d = sp.Integer(0)
+            for l, yl in enumerate(ysyms):
+                if yl in base.free_symbols:
+                    d += sp.diff(base, yl) * vsyms[l]
+            exprs_t.append((f"out[{i}]", d))
+        code_r, fl_r = _emit_block(exprs_r, symmap_b, f"a{k}_", indent="            ")
+        # the stage term is linear in v: out_i += sum_l H_il v_l.  Entries that are more than a (signed, scaled) symbol are
+        # evaluated once per step (sens_term_prep -> hc[]); sens_term_apply does the sparse product at every stage.
+        prep_assign, apply_lines, n_mul = [], [], 0
+        pr_b = _Printer(symmap_b)
+        for i in range(NX):
+            base = sp.Integer(0)
+            for j in range(NX):
+                if (i, j) in hs.jac and not hs.jac_const[(i, j)]:
+                    base += hs.jac[(i, j)] * bsyms[j]
+            for m in range(NC):
+                if (i, m) in hs.dfdc and (k, m) in dc_syms:
+                    base += hs.dfdc[(i, m)] * dc_syms[(k, m)]
+            terms = []
+            for l, yl in enumerate(ysyms):
+                if yl not in base.free_symbols:
+                    continue
+                ent = sp.diff(base, yl)
+                if ent == 0:
+                    continue
+                coeff, rest = ent.as_coeff_Mul()
+                if rest.is_Symbol or rest == 1:
+                    terms.append(f"({pr_b.doprint(ent)})*v[{l}]")
+                else:
+                    terms.append(f"hc[{len(prep_assign)}]*v[{l}]")
+                    prep_assign.append((f"hc[{len(prep_assign)}]", ent))
+                n_mul += 1
+            if terms:
+                apply_lines.append(f"            out[{i}] += {' + '.join(terms)};")
+        code_p, fl_p = _emit_block(prep_assign, symmap_b, f"e{k}_", indent="            ")
+        blk_prep.append(f"        {kw_of(k)} constexpr (K == {k}) {{\n{code_p if code_p else '            (void)hc;'}\n        }}")
+        blk_apply.append(f"        {kw_of(k)} constexpr (K == {k}) {{\n" + ("\n".join(apply_lines) if apply_lines else "            (void)out;") + "\n        }")
+        blk_prep_flops.append(fl_p)
+        blk_apply_flops.append(2 * n_mul)
+        blk_nhc.append(len(prep_assign))
+        # the stage term ACCUMULATES into out (it is added to the stage right-hand side); zero rows are skipped
+        exprs_t = [(lhs.replace("out[", "acc["), e) for lhs, e in exprs_t if e != 0]
+        code_t, fl_t = _emit_block(exprs_t, symmap_b, f"b{k}_", indent="            ")
+        code_t = code_t.replace("acc[", "out[").replace("] = ", "] += ") if code_t else "            (void)out;"
+        fl_t += len(exprs_t)
+        kw = "if" if k == 0 else "else if"
+        blk_rhs.append(f"        {kw} constexpr (K == {k}) {{\n{code_r}\n        }}")
+        blk_term.append(f"        {kw} constexpr (K == {k}) {{\n{code_t}\n        }}")
+        blk_rhs_flops.append(fl_r)
+        blk_term_flops.append(fl_t)
+    blk_rhs_code = "\n".join(blk_rhs) if blk_rhs else "        (void)out;"
+    blk_term_code = "\n".join(blk_term) if blk_term else "        (void)out;"
+    blk_prep_code = "\n".join(blk_prep) if blk_prep else "        (void)hc;"
+    blk_apply_code = "\n".join(blk_apply) if blk_apply else "        (void)out;"
+    NHC = max(max(blk_nhc, default=0), 1)
+    blk_prep_max = max(blk_prep_flops, default=0)
+    blk_apply_max = max(blk_apply_flops, default=0)
+    blk_rhs_max = max(blk_rhs_flops, default=0)
+    blk_term_max = max(blk_term_flops, default=0)
+
     unused = "(void)t; (void)y; (void)c;"
     NSd = max(NS, 1)
     header = f"""// GENERATED by parameter-variability_b200/codegen (emit.py) from SBML model '{name}'. Do not edit.
@@ -335,7 +421,8 @@ struct {struct_name} {{
 {hs_code}
     }}
 
-    PV_HD static void rhs(double t, const double (&y)[NX], const double (&c)[NC], double (&f)[NX]) {{
+    template <class CV>
+    PV_HD static void rhs(double t, const double (&y)[NX], const CV& c, double (&f)[NX]) {{
         {unused}
 {rhs_code}
     }}
@@ -348,7 +435,8 @@ struct {struct_name} {{
     }}
 
     // sparse Jacobian values, pattern (row,col): {' '.join(f'({i},{j})' for i, j in pattern)}
-    PV_HD static void jac(double t, const double (&y)[NX], const double (&c)[NC], double (&J)[NNZ]) {{
+    template <class CV>
+    PV_HD static void jac(double t, const double (&y)[NX], const CV& c, double (&J)[NNZ]) {{
         {unused} (void)J;
 {jac_code}
     }}
@@ -370,8 +458,9 @@ struct {struct_name} {{
 {chr(10).join(fac)}
     }}
 
-    // b <- W^-1 b
-    PV_HD static void lu_solve(const double (&W)[NLU], double (&b)[NX]) {{
+    // b <- W^-1 b   (W: any indexable container of the NLU factor entries)
+    template <class WV>
+    PV_HD static void lu_solve(const WV& W, double (&b)[NX]) {{
 {chr(10).join(sol)}
     }}
 
@@ -388,6 +477,42 @@ struct {struct_name} {{
                                       double (&out)[NSD][NX]) {{
         {unused} (void)s; (void)v; (void)dc; (void)out;
 {st_code}
+    }}
+
+    // ---- one sensitivity block at a time (block-per-warp Rosenbrock kernel): s, v, out are the block's own vectors;
+    // c and dc may live in registers or in shared memory (any indexable container) ----
+    static constexpr int FLOPS_SENS_RHS_BLOCK = {blk_rhs_max};    // max over K
+    static constexpr int FLOPS_SENS_TERM_BLOCK = {blk_term_max};  // max over K
+    // out = J(y) s + (df/dc) dc_K
+    template <int K, class YV, class CV, class DV>
+    PV_HD static void sens_rhs_block(double t, const YV& y, const double (&s)[NX], const CV& c, const DV& dc,
+                                     double (&out)[NX]) {{
+        {unused} (void)s; (void)dc; (void)out;
+{blk_rhs_code}
+    }}
+    // out += (d/dy [J s + f_theta_K]) v
+    template <int K, class YV, class VV, class CV, class DV>
+    PV_HD static void sens_stage_term_block(double t, const YV& y, const double (&s)[NX], const VV& v,
+                                            const CV& c, const DV& dc, double (&out)[NX]) {{
+        {unused} (void)s; (void)v; (void)dc; (void)out;
+{blk_term_code}
+    }}
+    // the same term in two parts: the entries of H_K = d/dy [J s + f_theta_K] that cost more than a coefficient read,
+    // evaluated once per step (y, s at the start of the step) ...
+    static constexpr int NHC = {NHC};
+    static constexpr int FLOPS_SENS_TERM_PREP = {blk_prep_max};    // max over K
+    static constexpr int FLOPS_SENS_TERM_APPLY = {blk_apply_max};  // max over K
+    template <int K, class YV, class CV, class DV>
+    PV_HD static void sens_term_prep(double t, const YV& y, const double (&s)[NX], const CV& c, const DV& dc,
+                                     double (&hc)[NHC]) {{
+        {unused} (void)s; (void)dc; (void)hc;
+{blk_prep_code}
+    }}
+    // ... and the sparse product out += H_K v at every stage
+    template <int K, class VV, class CV, class DV>
+    PV_HD static void sens_term_apply(const double (&hc)[NHC], const VV& v, const CV& c, const DV& dc, double (&out)[NX]) {{
+        (void)hc; (void)v; (void)c; (void)dc; (void)out;
+{blk_apply_code}
     }}
 }};
 """

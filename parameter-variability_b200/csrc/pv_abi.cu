@@ -15,6 +15,7 @@
 
 #include "../../include/parvar_b200.h"
 #include "pv_kernels.cuh"
+#include "pv_rosenbrock_split.cuh"
 #include "generated/simple_chain.cuh"
 #include "generated/simple_pk.cuh"
 #include "generated/icg_body_flat.cuh"
@@ -63,6 +64,7 @@ struct pv_problem {
     int counter_next = 0;
     int num_sms = 0;
     int refill_min = 0;   // 0 = per-integrator default (DOPRI5: 6, RODAS4: 32), see pv_problem_set_schedule
+    int layout = PV_LAYOUT_AUTO;   // see pv_problem_set_layout
     double t0 = 0.0;
     // METHOD_AUTO on a non-stiff model: trajectories that exhaust switch_steps explicit steps (stiff parameter
     // values) are re-run with RODAS4.  Scratch per launch slot: 0 = caller's stream, 1..3 = internal pipeline streams.
@@ -207,6 +209,13 @@ extern "C" int pv_problem_set_schedule(pv_problem* p, int refill_min) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
     if (refill_min < 0 || refill_min > 32) return fail(PV_E_ARG, "refill_min must be in [0, 32] (0 = default)");
     p->refill_min = refill_min;
+    return 0;
+}
+
+extern "C" int pv_problem_set_layout(pv_problem* p, int layout) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (layout < PV_LAYOUT_AUTO || layout > PV_LAYOUT_SPLIT) return fail(PV_E_ARG, "unknown layout");
+    p->layout = layout;
     return 0;
 }
 
@@ -380,9 +389,61 @@ static cudaError_t launch_one(const pv_launch_params& lp, size_t shmem, int num_
     return launch_persistent(pv_batch_kernel<M, METHOD, MODE, OBSID>, lp, shmem, num_sms, s);
 }
 
+// RODAS4 + sensitivities of the large models: one warp per block of the augmented system (pv_rosenbrock_split.cuh)
+template <class M>
+constexpr bool pv_use_split = M::NS >= 1 && M::NS <= 2 && M::NX * (1 + M::NS) > 16;
+
+// `declined` = the layout rule chose the one-lane-per-trajectory kernel instead (nothing was launched)
+template <class M, int MODE>
+static cudaError_t launch_split(const pv_launch_params& lp, int num_sms, int layout, bool& declined, cudaStream_t s) {
+    declined = false;
+    if constexpr (pv_use_split<M>) {
+        auto kern = pv_rodas4_split_kernel<M, MODE>;
+        const int threads = 32 * (1 + M::NS);
+        const size_t shmem = pv_split_layout<M>::bytes(lp.T, lp.n_obs);
+        if (shmem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+            if (e != cudaSuccess) return e;
+        }
+        int per_sm = 0;
+        cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, shmem);
+        if (eo != cudaSuccess) return eo;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        if (const char* cap = getenv("PV_MAX_CTAS_PER_SM")) {
+            const int c = atoi(cap);
+            if (c >= 1 && c < per_sm) per_sm = c;
+        }
+        const int64_t want = (lp.B + 31) / 32;
+        // measured (tools/bench_configs.py, icg_body_flat logp + gradient): 8000 trajectories 9.3 ms split vs 13.8 ms lane;
+        // 128 000 trajectories 124 ms split vs 97 ms lane (the split grid holds 64 trajectories per SM, the lane grid 256)
+        if (layout == PV_LAYOUT_AUTO && want > (int64_t)num_sms * per_sm) {
+            declined = true;
+            return cudaSuccess;
+        }
+        const int64_t blocks = std::min<int64_t>(want, (int64_t)num_sms * per_sm);
+        kern<<<(unsigned)blocks, threads, shmem, s>>>(lp);
+        g_launches.fetch_add(1);
+        return cudaGetLastError();
+    } else {
+        (void)lp; (void)num_sms; (void)layout; (void)s;
+        declined = true;
+        return cudaSuccess;
+    }
+}
+
 template <class M>
 static cudaError_t launch_model(int method, int mode, bool obsid, const pv_launch_params& lp, size_t shmem, int num_sms,
-                                cudaStream_t s) {
+                                int layout, cudaStream_t s) {
+    if constexpr (pv_use_split<M>) {
+        if (method == 2 && (mode == PV_MODE_LOGP_GRAD || mode == PV_MODE_LOGP_GRAD_FIM) && layout != PV_LAYOUT_LANE &&
+            pv_split_layout<M>::bytes(lp.T, lp.n_obs) <= 100 * 1024) {
+            bool declined = false;
+            const cudaError_t e = mode == PV_MODE_LOGP_GRAD
+                                      ? launch_split<M, PV_MODE_LOGP_GRAD>(lp, num_sms, layout, declined, s)
+                                      : launch_split<M, PV_MODE_LOGP_GRAD_FIM>(lp, num_sms, layout, declined, s);
+            if (!declined) return e;
+        }
+    }
     // the all-states-in-order specialisation is compiled for the explicit integrator only (cheap steps, where the
     // per-output code matters); the Rosenbrock kernels always use the generic sink
 #define PV_CASE(METH, MODE)                                                                      \
@@ -494,7 +555,7 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     for (int k = 0; k < lp.n_obs && obsid; ++k) obsid = (lp.obs_idx[k] == k);
     cudaError_t e = cudaErrorInvalidValue;
     switch (p->model) {
-        PV_MODEL_DISPATCH(e = launch_model, (method, mode, obsid, lp, shmem, p->num_sms, s))
+        PV_MODEL_DISPATCH(e = launch_model, (method, mode, obsid, lp, shmem, p->num_sms, p->layout, s))
     }
     if (e != cudaSuccess) return fail(PV_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     if (two_pass) {
@@ -513,7 +574,7 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
         CUDA_OK(cudaMemsetAsync(lp.counter, 0, sizeof(unsigned long long), s));
         e = cudaErrorInvalidValue;
         switch (p->model) {
-            PV_MODEL_DISPATCH(e = launch_model, (PV_METHOD_RODAS4, mode, false, lp, shmem, p->num_sms, s))
+            PV_MODEL_DISPATCH(e = launch_model, (PV_METHOD_RODAS4, mode, false, lp, shmem, p->num_sms, p->layout, s))
         }
         if (e != cudaSuccess) return fail(PV_E_CUDA, std::string("kernel launch (stiff re-run): ") + cudaGetErrorString(e));
     }

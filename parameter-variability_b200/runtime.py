@@ -18,6 +18,7 @@ LIB_PATH = Path(__import__("os").environ.get("PARVAR_B200_LIB", PKG_DIR / "lib" 
 
 METHOD_AUTO, METHOD_DOPRI5, METHOD_RODAS4 = 0, 1, 2
 NOISE_NORMAL, NOISE_LOGNORMAL = 0, 1
+LAYOUT_AUTO, LAYOUT_LANE, LAYOUT_SPLIT = 0, 1, 2
 STATUS_TEXT = {0: "ok", 1: "max_steps", 2: "step_too_small", 3: "nonfinite"}
 
 _dp = C.POINTER(C.c_double)
@@ -44,6 +45,7 @@ ABI = {
     "pv_problem_set_columns": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]),
     "pv_problem_set_timepoints": (C.c_int, [C.c_void_p, C.c_double, C.c_int, _dp]),
     "pv_problem_set_schedule": (C.c_int, [C.c_void_p, C.c_int]),
+    "pv_problem_set_layout": (C.c_int, [C.c_void_p, C.c_int]),
     "pv_problem_set_stiff_switch": (C.c_int, [C.c_void_p, C.c_int]),
     "pv_problem_set_observables": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]),
     "pv_problem_set_data": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
@@ -206,6 +208,10 @@ class Problem:
 
     def set_schedule(self, refill_min: int = 0) -> None:
         _check(self._lib.pv_problem_set_schedule(self._h, int(refill_min)))
+
+    def set_layout(self, layout: int = 0) -> None:
+        """LAYOUT_AUTO / LAYOUT_LANE / LAYOUT_SPLIT of the Rosenbrock sensitivity kernels (``pv_problem_set_layout``)."""
+        _check(self._lib.pv_problem_set_layout(self._h, int(layout)))
 
     def set_stiff_switch(self, switch_steps: int = 4000) -> None:
         _check(self._lib.pv_problem_set_stiff_switch(self._h, int(switch_steps)))

@@ -192,6 +192,55 @@ def test_icg_logp_grad_vs_oracle(cuda_lib, rt, oracle):
         np.testing.assert_allclose(g[:, b], ref_g, rtol=1e-5)
 
 
+@pytest.mark.parametrize("noise", ["normal", "lognormal"])
+@pytest.mark.parametrize("n_data", [1, 7])
+def test_icg_sensitivity_layouts_agree(cuda_lib, rt, oracle, noise, n_data):
+    """The two layouts of the Rosenbrock sensitivity kernels (one trajectory per lane / one warp per block of the
+    augmented system, include/parvar_b200.h pv_problem_set_layout) integrate the same method: logp, gradient, Fisher
+    information and step counts agree on a ragged batch, for pooled and per-individual data, both noise models."""
+    B = 77
+    nm = rt.NOISE_NORMAL if noise == "normal" else rt.NOISE_LOGNORMAL
+    t = np.linspace(0, 40, 9)
+    if nm == rt.NOISE_LOGNORMAL:
+        t = t[1:]                      # log y needs y > 0: the observed compartments are empty at t = 0
+    obs = ["Cgi_plasma_icg", "Cre_plasma_icg", "LI__icg"]
+    idx = [oracle.ICG_STATES.index(o) for o in obs]
+    tt = np.unique(np.concatenate([[0.0], t]))        # the oracle integrates from its first time point
+    truth = oracle.simulate("icg_body_flat", {"IVDOSE_icg": 10.0}, tt)[len(tt) - len(t):, idx]
+    opt = pkg("optimization.petab_optimization")
+    rs = np.random.RandomState(5)
+    data = np.abs(truth[None] * (1 + 0.05 * rs.normal(size=(n_data,) + truth.shape))) + 1e-12
+    stats = np.stack([opt.sufficient_statistics(data[i:i + 1], nm) for i in range(n_data)], axis=-1)
+    sigma = [0.1, 0.2, 0.15] if nm == rt.NOISE_LOGNORMAL else [1e-4, 2e-4, 1e-3]
+    P = np.stack([lognormal_draws(51, B, 75.0, 10.0), lognormal_draws(52, B, 0.0369598840327503, 0.01)])
+    res = {}
+    for layout in (rt.LAYOUT_LANE, rt.LAYOUT_SPLIT):
+        pb = _problem(rt, "icg_body_flat", ["BW", "LI__ICGIM_Vmax"], t, obs, dosage={"IVDOSE_icg": 10.0}, rtol=1e-9, atol=1e-14)
+        pb.set_layout(layout)
+        pb.set_timepoints(t, t0=0.0)
+        pb.set_data(stats, sigma, nm)
+        lp, g, _, nf = pb.logp_host(P, grad=True)
+        lp2, g2, f2, _, nf2 = pb.logp_fim_host(P)
+        assert nf == 0 and nf2 == 0
+        np.testing.assert_array_equal(lp, lp2)       # the FIM variant of a layout reproduces its logp / gradient exactly
+        np.testing.assert_array_equal(g, g2)
+        res[layout] = (lp, g, f2)
+        pb.close()
+    (lp_a, g_a, f_a), (lp_b, g_b, f_b) = res[rt.LAYOUT_LANE], res[rt.LAYOUT_SPLIT]
+    assert np.all(np.isfinite(lp_b)) and np.all(np.isfinite(g_b)) and np.all(np.isfinite(f_b))
+    np.testing.assert_allclose(lp_b, lp_a, rtol=1e-7)
+    np.testing.assert_allclose(g_b, g_a, rtol=1e-6, atol=1e-7 * np.abs(g_a).max())
+    np.testing.assert_allclose(f_b, f_a, rtol=1e-6, atol=1e-7 * np.abs(f_a).max())
+
+
+def test_icg_layout_auto_rule_and_errors(cuda_lib, rt):
+    pb = _problem(rt, "icg_body_flat", ["BW"], np.linspace(0, 10, 3), ["Cre_plasma_icg"], dosage={"IVDOSE_icg": 10.0})
+    with pytest.raises(rt.ParvarB200Error):
+        pb.set_layout(7)
+    pb.set_layout(rt.LAYOUT_AUTO)
+    pb.close()
+
+
 def test_empty_and_ragged_batches(cuda_lib, rt):
     t = np.linspace(0, 10, 5)
     pb = _problem(rt, "simple_pk", ["k_abs"], t, ["y_cent"])

@@ -29,7 +29,7 @@ from .symbolic import HoistedSystem, count_flops
 
 class _Printer(C99CodePrinter):
     def __init__(self, symmap: dict[sp.Symbol, str]):
-        super().__init__({"precision": 17})
+        super().__init__({"precision": 17, "user_functions": {"pv_rcp_newton": "pv_rcp_newton"}})
         self._symmap = symmap
 
     def _print_Symbol(self, expr):
@@ -56,12 +56,26 @@ class _Printer(C99CodePrinter):
         return f"pow({self._print(b)}, {self._print(e)})"
 
 
+_RCP = sp.Function("pv_rcp_newton")
+
+
+def _fast_rcp(e: sp.Expr) -> sp.Expr:
+    """b**-n -> pv_rcp_newton(b)**n (before CSE, so 1/b and 1/b^2 share one reciprocal): the per-stage functions divide by Michaelis-Menten denominators, which are normal
+    finite numbers; the branch-free reciprocal (MUFU.RCP64H + two Newton steps, pv_common.cuh) replaces the IEEE
+    division, whose slow-path branch is a scheduling barrier in the middle of straight-line code."""
+    return e.replace(lambda x: x.is_Pow and x.exp.is_Integer and x.exp < 0 and not x.base.is_Number,
+                     lambda x: _RCP(x.base) ** (-x.exp))
+
+
 def _emit_block(assignments: Sequence[tuple[str, sp.Expr]], symmap: dict[sp.Symbol, str],
-                tmp_prefix: str, indent: str = "    ") -> tuple[str, int]:
-    """CSE + print ``lhs = expr;`` lines.  Returns (code, flops)."""
+                tmp_prefix: str, indent: str = "    ", fast_rcp: bool = False) -> tuple[str, int]:
+    """CSE + print ``lhs = expr;`` lines.  Returns (code, flops); a division counts one flop either way."""
     exprs = [sp.sympify(e) for _, e in assignments]
     if not exprs:
         return "", 0
+    flops = count_flops(exprs)
+    if fast_rcp:
+        exprs = [_fast_rcp(e) for e in exprs]
     repl, reduced = sp.cse(exprs, symbols=sp.numbered_symbols(tmp_prefix), optimizations="basic")
     pr = _Printer(symmap)
     lines = []
@@ -69,7 +83,7 @@ def _emit_block(assignments: Sequence[tuple[str, sp.Expr]], symmap: dict[sp.Symb
         lines.append(f"{indent}const double {sym.name} = {pr.doprint(e)};")
     for (lhs, _), e in zip(assignments, reduced):
         lines.append(f"{indent}{lhs} = {pr.doprint(e)};")
-    return "\n".join(lines), count_flops(exprs)
+    return "\n".join(lines), flops
 
 
 # ----------------------------------------------------------------------------------------
@@ -170,7 +184,7 @@ def emit_model(hs: HoistedSystem, struct_name: str | None = None) -> EmittedMode
 
     # ---- rhs -----------------------------------------------------------------------------
     rhs_assign = [(f"f[{i}]", e) for i, e in enumerate(hs.f)]
-    rhs_code, rhs_flops = _emit_block(rhs_assign, symmap, "r")
+    rhs_code, rhs_flops = _emit_block(rhs_assign, symmap, "r", fast_rcp=True)
 
     # ---- rhs_sens ------------------------------------------------------------------------
     ssyms = [[sp.Symbol(f"s_{k}_{j}") for j in range(NX)] for k in range(NS)]
@@ -188,13 +202,13 @@ def emit_model(hs: HoistedSystem, struct_name: str | None = None) -> EmittedMode
                 if (i, m) in hs.dfdc and (k, m) in dc_syms:
                     e += hs.dfdc[(i, m)] * dc_syms[(k, m)]
             fs_exprs.append((f"fs[{k}][{i}]", e))
-    rs_code, rs_flops = _emit_block(rhs_assign + fs_exprs, symmap, "q")
+    rs_code, rs_flops = _emit_block(rhs_assign + fs_exprs, symmap, "q", fast_rcp=True)
 
     # ---- jacobian (sparse, row-major pattern) ------------------------------------------------
     pattern = sorted(hs.jac.keys())
     NNZ = max(len(pattern), 1)
     jac_assign = [(f"J[{n}]", hs.jac[ij]) for n, ij in enumerate(pattern)]
-    jac_code, jac_flops = _emit_block(jac_assign, symmap, "j")
+    jac_code, jac_flops = _emit_block(jac_assign, symmap, "j", fast_rcp=True)
     n_const = sum(1 for ij in pattern if hs.jac_const[ij])
 
     # ---- LU of W = d*I - J --------------------------------------------------------------------
@@ -221,7 +235,7 @@ def emit_model(hs: HoistedSystem, struct_name: str | None = None) -> EmittedMode
             _, ik, kk = op
             k = kk[0]
             if k not in done_diag:
-                fac.append(f"    W[{lu_pos[kk]}] = 1.0 / W[{lu_pos[kk]}];")
+                fac.append(f"    W[{lu_pos[kk]}] = pv_rcp_newton(W[{lu_pos[kk]}]);")
                 done_diag.add(k)
                 lu_flops += 1
             fac.append(f"    W[{lu_pos[ik]}] *= W[{lu_pos[kk]}];")
@@ -232,7 +246,7 @@ def emit_model(hs: HoistedSystem, struct_name: str | None = None) -> EmittedMode
             lu_flops += 2
     for k in range(NX):
         if k not in done_diag:
-            fac.append(f"    W[{lu_pos[(k, k)]}] = 1.0 / W[{lu_pos[(k, k)]}];")
+            fac.append(f"    W[{lu_pos[(k, k)]}] = pv_rcp_newton(W[{lu_pos[(k, k)]}]);")
             lu_flops += 1
     sol = []
     sol_flops = 0
@@ -274,7 +288,7 @@ def emit_model(hs: HoistedSystem, struct_name: str | None = None) -> EmittedMode
                 if yl in base.free_symbols:
                     e += sp.diff(base, yl) * vsyms[l]
             st_exprs.append((f"out[{k}][{i}]", e))
-    st_code, st_flops = _emit_block(st_exprs, symmap, "w")
+    st_code, st_flops = _emit_block(st_exprs, symmap, "w", fast_rcp=True)
 
     # ---- J*v product (used by Rosenbrock sensitivities: J s) ------------------------------------
     jv_lines = []
@@ -292,7 +306,7 @@ def emit_model(hs: HoistedSystem, struct_name: str | None = None) -> EmittedMode
                 if (i, m) in hs.dfdc and (k, m) in dc_syms:
                     e += hs.dfdc[(i, m)] * dc_syms[(k, m)]
             fp_exprs.append((f"fp[{k}][{i}]", e))
-    fp_code, fp_flops = _emit_block(fp_exprs, symmap, "p")
+    fp_code, fp_flops = _emit_block(fp_exprs, symmap, "p", fast_rcp=True)
 
     # ---- per-block forms (one sensitivity parameter at a time) for the block-per-warp Rosenbrock kernel -----
     # s[j] / v[j] are the block's own vectors; c, dc, W may be any indexable container (registers or shared memory)
@@ -325,7 +339,7 @@ def emit_model(hs: HoistedSystem, struct_name: str | None = None) -> EmittedMode
                 if yl in base.free_symbols:
                     d += sp.diff(base, yl) * vsyms[l]
             exprs_t.append((f"out[{i}]", d))
-        code_r, fl_r = _emit_block(exprs_r, symmap_b, f"a{k}_", indent="            ")
+        code_r, fl_r = _emit_block(exprs_r, symmap_b, f"a{k}_", indent="            ", fast_rcp=True)
         # the stage term is linear in v: out_i += sum_l H_il v_l.  Entries that are more than a (signed, scaled) symbol are
         # evaluated once per step (sens_term_prep -> hc[]); sens_term_apply does the sparse product at every stage.
         prep_assign, apply_lines, n_mul = [], [], 0
@@ -354,7 +368,7 @@ def emit_model(hs: HoistedSystem, struct_name: str | None = None) -> EmittedMode
                 n_mul += 1
             if terms:
                 apply_lines.append(f"            out[{i}] += {' + '.join(terms)};")
-        code_p, fl_p = _emit_block(prep_assign, symmap_b, f"e{k}_", indent="            ")
+        code_p, fl_p = _emit_block(prep_assign, symmap_b, f"e{k}_", indent="            ", fast_rcp=True)
         blk_prep.append(f"        {kw_of(k)} constexpr (K == {k}) {{\n{code_p if code_p else '            (void)hc;'}\n        }}")
         blk_apply.append(f"        {kw_of(k)} constexpr (K == {k}) {{\n" + ("\n".join(apply_lines) if apply_lines else "            (void)out;") + "\n        }")
         blk_prep_flops.append(fl_p)
@@ -362,7 +376,7 @@ def emit_model(hs: HoistedSystem, struct_name: str | None = None) -> EmittedMode
         blk_nhc.append(len(prep_assign))
         # the stage term ACCUMULATES into out (it is added to the stage right-hand side); zero rows are skipped
         exprs_t = [(lhs.replace("out[", "acc["), e) for lhs, e in exprs_t if e != 0]
-        code_t, fl_t = _emit_block(exprs_t, symmap_b, f"b{k}_", indent="            ")
+        code_t, fl_t = _emit_block(exprs_t, symmap_b, f"b{k}_", indent="            ", fast_rcp=True)
         code_t = code_t.replace("acc[", "out[").replace("] = ", "] += ") if code_t else "            (void)out;"
         fl_t += len(exprs_t)
         kw = "if" if k == 0 else "else if"

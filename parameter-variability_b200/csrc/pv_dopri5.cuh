@@ -82,36 +82,6 @@ PV_HD float pv_powf_fast(float x, float a) {
 #endif
 }
 
-PV_HD float pv_fdiv_fast(float a, float b) {
-#if defined(__CUDA_ARCH__)
-    return __fdividef(a, b);     // MUFU.RCP + FMUL: the controller needs two digits, not IEEE division
-#else
-    return a / b;
-#endif
-}
-// ~20-bit reciprocal (one MUFU.RCP64H): enough for the error *norm*, which only steers the step size
-PV_HD double pv_rcp_approx(double x) {
-#if defined(__CUDA_ARCH__)
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    return r;
-#else
-    return 1.0 / x;
-#endif
-}
-// full-precision reciprocal of a normal, finite x without the slow path of __drcp_rn: MUFU.RCP64H seed (~20 bits) and
-// two Newton steps
-PV_HD double pv_rcp_newton(double x) {
-#if defined(__CUDA_ARCH__)
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
-    return r;
-#else
-    return 1.0 / x;
-#endif
-}
 PV_HD double pv_drcp(double x) {
 #if defined(__CUDA_ARCH__)
     return __drcp_rn(x);

@@ -164,7 +164,7 @@ struct pv_rodas4_lane {
             last = true;
         }
         if (!(fabs(h) > 1e-14 * fmax(fabs(t), 1.0))) return PV_ERR_STEP_TOO_SMALL;
-        const double hi = 1.0 / h;
+        const double hi = pv_rcp_newton(h);   // h is a normal number here (checked above): no IEEE slow path
 
         double K1[NB][NX], K2[NB][NX], K3[NB][NX], K4[NB][NX], K5[NB][NX], K6[NB][NX];
         double zs[N];
@@ -248,21 +248,22 @@ struct pv_rodas4_lane {
                                K6[b][i]);
         solve_stage(ks, W, K6);
         // new solution = zs + K6, error estimate = K6
-        float err2 = 0.f;
+        // error norm with a ~20-bit reciprocal of the scale (one MUFU.RCP64H, no division slow path): it only steers h
+        double err2d = 0.0;
         bool finite = true;
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
                 const double znew = zs[b * NX + i] + K6[b][i];
-                const double sc = atol + rtol * fmax(fabs(z[b * NX + i]), fabs(znew));
-                const float r = (float)K6[b][i] / (float)sc;
-                err2 += r * r;
+                const double sc = fma(rtol, fmax(fabs(z[b * NX + i]), fabs(znew)), atol);
+                const double r = K6[b][i] * pv_rcp_approx(sc);
+                err2d = fma(r, r, err2d);
                 finite = finite && (fabs(znew) < 1e300);
                 zs[b * NX + i] = znew;
             }
-        err2 *= (1.0f / N);
-        if (!finite || !(err2 == err2)) {
+        float err2 = (float)(err2d * (1.0 / N));
+        if (!finite || !(err2 <= 3.0e38f)) {
             err2 = 1e10f;
             if (fabs(h) < 1e-12) return PV_ERR_NONFINITE;
         }
@@ -296,13 +297,13 @@ struct pv_rodas4_lane {
             }
             // Gustafsson predictive controller (rodas.f, PRED)
             if (st.accepted > 1) {
-                float facgus = (float)(h_acc / h) * pv_powf_fast(fmaxf(err2, 1e-30f) / err_acc, 0.25f) * (1.0f / 0.9f);
+                float facgus = (float)(h_acc * hi) * pv_powf_fast(pv_fdiv_fast(fmaxf(err2, 1e-30f), err_acc), 0.25f) * (1.0f / 0.9f);
                 facgus = fmaxf(1.0f / 6.0f, fminf(5.0f, facgus));
                 fac = fmaxf(fac, facgus);
             }
             h_acc = h;
             err_acc = fmaxf(1e-2f, sqrtf(err2));
-            double hnew = h / (double)fac;
+            double hnew = h * (double)pv_fdiv_fast(1.0f, fac);
             if (last_rejected) hnew = fmin(hnew, h);
             last_rejected = false;
 #pragma unroll
@@ -312,7 +313,7 @@ struct pv_rodas4_lane {
             h = hnew;
         } else {
             ++st.rejected;
-            h = (st.accepted == 0 && st.rejected >= 2) ? h * 0.1 : h / (double)fac;
+            h = (st.accepted == 0 && st.rejected >= 2) ? h * 0.1 : h * (double)pv_fdiv_fast(1.0f, fac);
             last_rejected = true;
         }
         return PV_RUNNING;

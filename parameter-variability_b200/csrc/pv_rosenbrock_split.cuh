@@ -258,7 +258,7 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params p) {
                         rc = PV_ERR_STEP_TOO_SMALL;
                         running = false;
                     }
-                    hi = 1.0 / h;
+                    hi = pv_rcp_newton(h);
                 }
             }
             // tick 0: state at the start of the step, Jacobian, LU of W = I/(gamma h) - J
@@ -395,26 +395,27 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params p) {
             }
 
             // ---- new solution zs + K6 (r holds K6), error partial of this block ----------------------------------
-            float e2 = 0.f;
+            double e2 = 0.0;
             bool finite = true;
             if (running) {
 #pragma unroll
                 for (int i = 0; i < NX; ++i) {
                     const double znew = zs[i] + r[i];
-                    const double sc = p.atol + p.rtol * fmax(fabs(z[i]), fabs(znew));
-                    const float q = (float)r[i] / (float)sc;
-                    e2 += q * q;
+                    const double sc = fma(p.rtol, fmax(fabs(z[i]), fabs(znew)), p.atol);
+                    const double q = r[i] * pv_rcp_approx(sc);
+                    e2 = fma(q, q, e2);
                     finite = finite && (fabs(znew) < 1e300);
                     zs[i] = znew;
                 }
-                if (!finite || !(e2 == e2)) e2 = __int_as_float(0x7fc00000);   // NaN marks a non-finite block
+                if (!finite || !(e2 == e2)) e2 = __longlong_as_double(0x7ff8000000000000LL);   // NaN marks a non-finite block
             }
-            err_sh[warp * 32] = (double)e2;
+            err_sh[warp * 32] = e2;
             __syncthreads();
-            float err2 = 0.f;
+            double err2d = 0.0;
 #pragma unroll
-            for (int w = 0; w < NB; ++w) err2 += (float)err_sh[w * 32];
-            err2 *= inv_n;
+            for (int w = 0; w < NB; ++w) err2d += err_sh[w * 32];
+            float err2 = (float)(err2d * (1.0 / N));
+            if (!(err2 <= 3.0e38f)) err2 = __int_as_float(0x7fc00000);
             bool accept = false;
             double tn = t;
             float fac = 1.f;
@@ -465,13 +466,13 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params p) {
             if (running) {
                 if (accept) {
                     if (n_acc > 1) {
-                        float facgus = (float)(h_acc / h) * pv_powf_fast(fmaxf(err2, 1e-30f) / err_acc, 0.25f) * (1.0f / 0.9f);
+                        float facgus = (float)(h_acc * hi) * pv_powf_fast(pv_fdiv_fast(fmaxf(err2, 1e-30f), err_acc), 0.25f) * (1.0f / 0.9f);
                         facgus = fmaxf(1.0f / 6.0f, fminf(5.0f, facgus));
                         fac = fmaxf(fac, facgus);
                     }
                     h_acc = h;
                     err_acc = fmaxf(1e-2f, sqrtf(err2));
-                    double hnew = h / (double)fac;
+                    double hnew = h * (double)pv_fdiv_fast(1.0f, fac);
                     if (last_rejected) hnew = fmin(hnew, h);
                     last_rejected = false;
 #pragma unroll
@@ -484,7 +485,7 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params p) {
                     h = hnew;
                 } else {
                     ++n_rej;
-                    h = (n_acc == 0 && n_rej >= 2) ? h * 0.1 : h / (double)fac;
+                    h = (n_acc == 0 && n_rej >= 2) ? h * 0.1 : h * (double)pv_fdiv_fast(1.0f, fac);
                     last_rejected = true;
                 }
             }

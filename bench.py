@@ -49,11 +49,10 @@ def draws(rank: int, B: int) -> np.ndarray:
     return np.stack([k_abs, CL])
 
 
-def c1_data(tgrid: np.ndarray) -> np.ndarray:
-    """C1's synthetic data vector: default-parameter trajectory x (1 + 0.05 eps), eps ~ seed 1234."""
-    sys.path.insert(0, str(ROOT / "oracle"))
-    import parvar_oracle as oracle     # used to *make the fixed data vector*, outside every timed region
-    truth = oracle.simple_pk_exact({}, tgrid)
+def c1_data(truth: np.ndarray) -> np.ndarray:
+    """C1's synthetic data vector: default-parameter trajectory x (1 + 0.05 eps), eps ~ seed 1234.
+    `truth` [T, 3] comes from the arm that is being timed (GPU arm: one trajectory through the CUDA path; CPU arm: the
+    oracle's closed form), so the GPU arm never touches oracle/."""
     rs = np.random.RandomState(1234)
     return truth * (1.0 + 0.05 * rs.normal(size=truth.shape))
 
@@ -120,7 +119,8 @@ def cpu_baseline(sample: int, threads: int | None = None) -> dict:
     tgrid = np.linspace(0.0, 100.0, T_POINTS)
     th = draws(0, sample)
     cores = threads or os.cpu_count() or 1
-    data = c1_data(tgrid)
+    import parvar_oracle as oracle
+    data = c1_data(oracle.simple_pk_exact({}, tgrid))
     oracle_c.load()
     t0 = time.perf_counter()
     _, lp, nf, st = oracle_c.simulate_batch("simple_pk", {"k_abs": th[0], "CL": th[1]}, tgrid, OBS, rtol=1e-6, atol=1e-6,
@@ -165,6 +165,86 @@ def workload_config(n_gpus: int) -> dict:
 
 
 # ----------------------------------------------------------------------------------------------------------
+def logp_grad_leg(rt, torch, dist, rank: int, world: int, local: int, evals: int = 20) -> dict:
+    """Second half of BASELINE.json's metric: logp + gradient evaluations/s (configs[2] and [3]).
+
+    Hierarchical objective over 8 chains x (1000 individuals per GPU), individuals sharded over the ranks (weak
+    scaling), ONE all-reduce of [chains, 1 + 2P] per evaluation; per-individual gradients stay on their rank.
+    Each evaluation goes through the public host API (`HierarchicalObjective.local_terms` -> `pv_logp_grad_host`):
+    host theta -> H2D -> sensitivity kernel -> D2H of logp / gradient -> population terms -> all-reduce.  Data are
+    synthetic: the model's default trajectory (through the CUDA path) x (1 + 0.05 eps) per individual.
+    """
+    po = importlib.import_module(PKG + ".optimization.petab_optimization")
+    dd = importlib.import_module(PKG + ".distributed")
+    pf = importlib.import_module(PKG + ".experiments.petab_factory")
+    C, n_loc, T = 8, 1000, 20
+    n_ind = n_loc * world
+    first, stop = dd.shard_range(n_ind, rank, world)
+    t = np.linspace(0.0, 100.0, T)
+    out = {}
+    cases = [("C3 simple_pk", "simple_pk", ["k_abs", "CL"], OBS, {}, (1.0, 1.0), (1.0, 1.0), 0.05, (1e-8, 1e-11), "DOPRI5"),
+             ("C4 icg_body_flat", "icg_body_flat", ["BW", "LI__ICGIM_Vmax"], ["Cre_plasma_icg", "Cgi_plasma_icg"],
+              {"IVDOSE_icg": 10.0}, (75.0, 10.0), (0.0369598840327503, 0.01), 1e-4, (1e-7, 1e-11), "RODAS4")]
+    for name, model, cols, obs, fixed, ms1, ms2, sigma, (rtol, atol), method in cases:
+        pb = rt.Problem(model, device=local)
+        pb.set_solver(rtol=rtol, atol=atol)
+        for k, v in fixed.items():
+            pb.set_value(k, v)
+        pb.set_columns(cols)
+        pb.set_timepoints(t)
+        pb.set_observables(obs)
+        mean = torch.tensor([[ms1[0]], [ms2[0]]], dtype=torch.float64, device="cuda")
+        Y1 = torch.empty((1, T, len(obs)), dtype=torch.float64, device="cuda")
+        pb.simulate(mean, Y1)
+        torch.cuda.synchronize()
+        truth = Y1[0].cpu().numpy()
+        rs = np.random.RandomState(1234)                 # every rank draws the full set and keeps its slice
+        y = (truth[None] * (1 + 0.05 * rs.normal(size=(n_ind,) + truth.shape)))[first:stop]
+        (m1, s1), (m2, s2) = pf.lognorm_par_transform(*ms1), pf.lognorm_par_transform(*ms2)
+        theta = np.stack([rs.lognormal(m1, s1, size=(C, n_ind)), rs.lognormal(m2, s2, size=(C, n_ind))], axis=2)
+        theta = np.ascontiguousarray(theta[:, first:stop])
+        pb.set_data(np.stack([po.sufficient_statistics(y[i:i + 1], 0) for i in range(len(y))], axis=-1), sigma)
+        H = po.HierarchicalObjective(pb, n_ind, mu_prior=[(m1, 0.5), (m2, 0.5)], omega_prior=[0.5, 0.5],
+                                     first_individual=first, n_local=stop - first)
+        mu = np.tile(np.array([m1, m2]), (C, 1))
+        omega = np.tile(np.array([s1, s2]), (C, 1))
+
+        def evaluate():
+            lp, dth, dmu, dom = H.local_terms(theta, mu, omega)
+            buf = np.concatenate([lp[:, None], dmu, dom], axis=1)          # [C, 1 + 2P]
+            if world > 1:
+                tb = torch.from_numpy(buf).cuda()
+                dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+                buf = tb.cpu().numpy()
+            return H.finish(buf[:, 0], buf[:, 1:3], buf[:, 3:5], mu, omega) + (dth,)
+
+        for _ in range(3):
+            res = evaluate()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(evals):
+            res = evaluate()
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        if not (np.all(np.isfinite(res[0])) and np.all(np.isfinite(res[3]))):
+            raise SystemExit(f"{name}: non-finite logp / gradient")
+        out[name] = {"logp_grad_evals_per_s": C * evals / dt, "ms_per_batched_eval": 1e3 * dt / evals,
+                     "kernel_ms": pb.last_kernel_ms, "trajectories_per_eval": C * n_ind, "chains": C,
+                     "individuals_per_gpu": n_loc, "timepoints": T, "integrator": method + " + forward sensitivities",
+                     "rtol": rtol, "atol": atol, "collective": "1 all-reduce of [8, 5] fp64 per evaluation" if world > 1 else "none (1 rank)",
+                     "logp_chain0": float(res[0][0])}
+        pb.close()
+    out["note"] = ("one batched evaluation = logp + gradient of all 8 chains (each over every individual); "
+                   "logp_grad_evals_per_s counts chain evaluations; timed through the host API, max over ranks")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,7 +285,10 @@ def main() -> None:
     pb.set_columns(["k_abs", "CL"])
     pb.set_timepoints(tgrid)
     pb.set_observables(OBS)
-    data = c1_data(tgrid)
+    Y1 = torch.empty((1, T, 3), dtype=torch.float64, device=dev)
+    pb.simulate(torch.ones((2, 1), dtype=torch.float64, device=dev), Y1)       # defaults: k_abs = CL = 1
+    torch.cuda.synchronize()
+    data = c1_data(Y1[0].cpu().numpy())
     stats = np.stack([np.ones_like(data), data, data * data])[..., None]
     pb.set_data(stats, 1.0, rt.NOISE_NORMAL)
 
@@ -287,6 +370,8 @@ def main() -> None:
     e2e_value = world * B * e2e_steps / float(t_e.item())
     e2e_ok = bool(np.allclose(lp_pin[:1000], logp[:1000].cpu().numpy(), rtol=0, atol=0))
 
+    lg = logp_grad_leg(rt, torch, dist, rank, world, local)
+
     if rank == 0:
         peak64 = rt.fma_peak_tflops(local, fp64=True)
         peak32 = rt.fma_peak_tflops(local, fp64=False)
@@ -328,6 +413,7 @@ def main() -> None:
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "peak_source": hbm_src, "bytes_per_launch": bytes_per_launch}},
             "cpu_baseline": cpu,
+            "logp_grad": lg,
             "logp_checksum": checksum,
         }
         print(json.dumps(line))

@@ -37,6 +37,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--layout", type=int, default=0, help="pv_problem_set_layout for the Rosenbrock sensitivity kernels: 0 auto, 1 lane, 2 split")
+    ap.add_argument("--sizes", default="1000,16000", help="individuals per chain for the icg cases")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     import torch
@@ -100,7 +102,7 @@ def main():
         rs = np.random.RandomState(1234)
         m1, s1 = oracle.lognorm_par_transform(75.0, 10.0)
         m2, s2 = oracle.lognorm_par_transform(0.0369598840327503, 0.01)
-        for n_chains, n_ind in ((8, 1000), (8, 16000)):
+        for n_chains, n_ind in [(8, int(x)) for x in args.sizes.split(",")]:
             B = n_chains * n_ind
             th = np.stack([rs.lognormal(m1, s1, B), rs.lognormal(m2, s2, B)])
             y = truth[None] * (1 + 0.05 * rs.normal(size=(n_ind,) + truth.shape))
@@ -112,6 +114,7 @@ def main():
             pb.set_timepoints(t)
             pb.set_observables(obs)
             pb.set_data(stats, 1e-4)
+            pb.set_layout(args.layout)
             P = torch.from_numpy(th).cuda()
             Y = torch.empty((B, T, 2), dtype=torch.float64, device="cuda")
             lp = torch.empty(B, dtype=torch.float64, device="cuda")

@@ -234,7 +234,8 @@ def logp_grad_leg(rt, torch, dist, rank: int, world: int, local: int, evals: int
         if not (np.all(np.isfinite(res[0])) and np.all(np.isfinite(res[3]))):
             raise SystemExit(f"{name}: non-finite logp / gradient")
         out[name] = {"logp_grad_evals_per_s": C * evals / dt, "ms_per_batched_eval": 1e3 * dt / evals,
-                     "kernel_ms": pb.last_kernel_ms, "trajectories_per_eval": C * n_ind, "chains": C,
+                     "kernel_ms": pb.last_kernel_ms, "trajectories_per_eval": C * n_ind,
+                     "trajectories_per_s": C * n_ind * evals / dt, "chains": C,
                      "individuals_per_gpu": n_loc, "timepoints": T, "integrator": method + " + forward sensitivities",
                      "rtol": rtol, "atol": atol, "collective": "1 all-reduce of [8, 5] fp64 per evaluation" if world > 1 else "none (1 rank)",
                      "logp_chain0": float(res[0][0])}

@@ -414,12 +414,9 @@ static cudaError_t launch_split(const pv_launch_params& lp, int num_sms, int lay
             if (c >= 1 && c < per_sm) per_sm = c;
         }
         const int64_t want = (lp.B + 31) / 32;
-        // measured (tools/bench_configs.py, icg_body_flat logp + gradient): 8000 trajectories 9.3 ms split vs 13.8 ms lane;
-        // 128 000 trajectories 124 ms split vs 97 ms lane (the split grid holds 64 trajectories per SM, the lane grid 256)
-        if (layout == PV_LAYOUT_AUTO && want > (int64_t)num_sms * per_sm) {
-            declined = true;
-            return cudaSuccess;
-        }
+        // measured (tools/bench_configs.py, icg_body_flat logp + gradient, stage vectors in shared memory): 8000
+        // trajectories 3.6 ms split vs 11 ms lane; 128 000 trajectories 49 ms split vs 68 ms lane -> AUTO = split
+        (void)layout;
         const int64_t blocks = std::min<int64_t>(want, (int64_t)num_sms * per_sm);
         kern<<<(unsigned)blocks, threads, shmem, s>>>(lp);
         g_launches.fetch_add(1);

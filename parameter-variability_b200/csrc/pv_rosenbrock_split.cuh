@@ -10,12 +10,16 @@
 //
 // Here a CTA of (1 + NS) warps integrates 32 trajectories: lane l of warp 0 owns the state block of trajectory l,
 // lane l of warp k its k-th sensitivity block.  The augmented Jacobian is block lower triangular, [[J,0],[H_k,J]], so
-//   * every block's 6 stage vectors stay in its own lane's registers (72 doubles for 12 states),
+//   * every block's stage vectors K1..K5 live in shared memory, [block][stage][state][32] lane-minor (conflict free),
+//     indexed by the RUN-TIME stage: the stage loop is a real loop (its body - RHS, H-term, LU solve - exists once and
+//     stays in the instruction cache) and the stage sums are short loops over a coefficient table in constant memory.
+//     (First version: K1..K5 in registers, selected by a switch on the stage - 23 % of its instructions were the
+//     register moves of that switch and 10 % spills, profiles/r01_icg_c4_logp_grad_split_ncu_full.txt.)
 //   * what the blocks share - hoisted coefficients c, dc, the LU of W = I/(gamma h) - J, the state at the start of the
-//     step - lives in shared memory, lane-minor ([index][32]: conflict free), written once per trajectory / step,
+//     step - lives in shared memory too, written once per trajectory / step,
 //   * warp 0 runs one stage AHEAD: in tick i it computes stage i of the state block and publishes the stage point
-//     Y_i and K_i^y (double buffered), while the sensitivity warps compute stage i-1 from what it published in the
-//     previous tick; one __syncthreads per tick,
+//     Y_i (double buffered) and K_i^y (its own stage-vector slot), while the sensitivity warps compute stage i-1 from
+//     what it published in the previous tick; one __syncthreads per tick,
 //   * every warp executes only its own role's code: no intra-warp role divergence and a third of the code per warp,
 //   * the step-size controller runs replicated in all warps from the same shared error partials, so all warps take
 //     identical accept / reject / output decisions without further communication.
@@ -27,6 +31,23 @@
 #ifndef PV_MINB_SPLIT
 #define PV_MINB_SPLIT 2
 #endif
+
+// RODAS4 stage coefficients by run-time stage (row st - 1, column j = index of K_{j+1}); stage 6 evaluates at the embedded
+// solution z + sum_j A5j K_j + K5, hence the 1 in its A row
+__constant__ double pv_rodas4_A[6][5] = {
+    {0, 0, 0, 0, 0},
+    {pv_rodas4::A21, 0, 0, 0, 0},
+    {pv_rodas4::A31, pv_rodas4::A32, 0, 0, 0},
+    {pv_rodas4::A41, pv_rodas4::A42, pv_rodas4::A43, 0, 0},
+    {pv_rodas4::A51, pv_rodas4::A52, pv_rodas4::A53, pv_rodas4::A54, 0},
+    {pv_rodas4::A51, pv_rodas4::A52, pv_rodas4::A53, pv_rodas4::A54, 1.0}};
+__constant__ double pv_rodas4_C[6][5] = {
+    {0, 0, 0, 0, 0},
+    {pv_rodas4::C21, 0, 0, 0, 0},
+    {pv_rodas4::C31, pv_rodas4::C32, 0, 0, 0},
+    {pv_rodas4::C41, pv_rodas4::C42, pv_rodas4::C43, 0, 0},
+    {pv_rodas4::C51, pv_rodas4::C52, pv_rodas4::C53, pv_rodas4::C54, 0},
+    {pv_rodas4::C61, pv_rodas4::C62, pv_rodas4::C63, pv_rodas4::C64, pv_rodas4::C65}};
 
 // element i of this lane's trajectory in a lane-minor shared-memory array [n][32]
 struct pv_smem_vec {
@@ -44,9 +65,10 @@ struct pv_split_layout {
     static constexpr int W = DC + M::NDC * 32;
     static constexpr int YN = W + M::NLU * 32;
     static constexpr int YS = YN + M::NX * 32;            // [2][NX][32] stage point of the state block
-    static constexpr int KY = YS + 2 * M::NX * 32;        // [2][NX][32] K_i of the state block
-    static constexpr int Z0 = KY + 2 * M::NX * 32;        // [NB][NX][32] initial blocks (set-up hand-over)
-    static constexpr int ERR = Z0 + NB * M::NX * 32;      // [2][NB][32] error-norm / initial-step partials
+    static constexpr int KS = YS + 2 * M::NX * 32;        // [NB][5][NX][32] stage vectors K1..K5 of every block
+    static constexpr int Z0 = KS;                         // [NB][NX][32] initial blocks (set-up hand-over; aliases KS)
+    static constexpr int K6Y = KS + NB * 5 * M::NX * 32;  // [NX][32] K6 of the state block
+    static constexpr int ERR = K6Y + M::NX * 32;          // [2][NB][32] error-norm / initial-step partials
     static constexpr int FIXED = ERR + 2 * NB * 32;
     // then, sized at launch: OW [n_obs][32], OWI [n_obs][32], DF [NS][n_obs][32], tgrid [T], theta [NTH], y0 [NX]
     static size_t bytes(int T, int n_obs) {
@@ -133,9 +155,10 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params p) {
         __syncthreads();
 
         // ---- per-lane state: the control variables are replicated in every warp and evolve identically ----------
-        double z[NX], K1[NX], K2[NX], K3[NX], K4[NX], K5[NX];
+        double z[NX];
 #pragma unroll
         for (int i = 0; i < NX; ++i) z[i] = valid ? Z0[warp * NX + i] : 0.0;
+        double* const kmine = sh + L::KS + (warp * 5 * NX) * 32 + lane;   // this block's K_{j+1}[i] = kmine[(j * NX + i) * 32]
         double t = p.t0, h = 0.0, h_acc = 0.0;
         float err_acc = 1e-2f;
         bool last_rejected = false, running = valid;
@@ -283,45 +306,35 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params p) {
                     if (warp == 2) M::template sens_term_prep<(NS > 1 ? 1 : 0)>(t, YN, z, C, DC, hc);
             }
             // Ticks 1..7: warp 0 does stage `tick`, the sensitivity warps stage `tick - 1`.  A real loop (the stage is a
-            // run-time value): the heavy role code - RHS, H_k K^y, LU solve - exists once and stays in the instruction
-            // cache; only the short stage sums, which name K1..K5 (registers), are switched per stage.
+            // run-time value): the role code - stage sums, RHS, H_k K^y, LU solve - exists once and stays in the
+            // instruction cache.
 #pragma unroll 1
             for (int tick = 1; tick <= 7; ++tick) {
                 const int st = (warp == 0) ? tick : tick - 1;
                 if (running && st >= 1 && st <= 6) {
-                    const pv_smem_vec YS{sh + L::YS + ((st & 1) * NX) * 32 + lane}, KY{sh + L::KY + ((st & 1) * NX) * 32 + lane};
-                    double ts = t + h;   // stage time (only non-autonomous models read it; same convention as pv_rodas4_lane)
-                    // stage point (the newest K enters last: see pv_rosenbrock.cuh)
-                    switch (st) {
-                        case 1:
-                            ts = t;
+                    const pv_smem_vec YS{sh + L::YS + ((st & 1) * NX) * 32 + lane};
+                    // K_st of the state block: where warp 0 puts it and the sensitivity warps read it one tick later
+                    double* const kyp = (st <= 5) ? sh + L::KS + ((st - 1) * NX) * 32 + lane : sh + L::K6Y + lane;
+                    const pv_smem_vec KY{kyp};
+                    const double ts = (st == 1) ? t : (st == 2) ? t + C2 * h : (st == 3) ? t + C3 * h : (st == 4) ? t + C4 * h : t + h;
+                    // stage point zs = z + sum_j A[st][j] K_j and right-hand-side combination cs = sum_j C[st][j] K_j in one pass
+                    // over this block's stage vectors (the newest K enters last)
+                    double cs[NX];
 #pragma unroll
-                            for (int i = 0; i < NX; ++i) zs[i] = z[i];
-                            break;
-                        case 2:
-                            ts = t + C2 * h;
+                    for (int i = 0; i < NX; ++i) {
+                        zs[i] = z[i];
+                        cs[i] = 0.0;
+                    }
+#pragma unroll 1
+                    for (int j = 0; j < st - 1; ++j) {
+                        const double a = pv_rodas4_A[st - 1][j], cc = pv_rodas4_C[st - 1][j];
+                        const double* kj = kmine + (j * NX) * 32;
 #pragma unroll
-                            for (int i = 0; i < NX; ++i) zs[i] = fma(A21, K1[i], z[i]);
-                            break;
-                        case 3:
-                            ts = t + C3 * h;
-#pragma unroll
-                            for (int i = 0; i < NX; ++i) zs[i] = fma(A32, K2[i], fma(A31, K1[i], z[i]));
-                            break;
-                        case 4:
-                            ts = t + C4 * h;
-#pragma unroll
-                            for (int i = 0; i < NX; ++i) zs[i] = fma(A43, K3[i], fma(A42, K2[i], fma(A41, K1[i], z[i])));
-                            break;
-                        case 5:
-#pragma unroll
-                            for (int i = 0; i < NX; ++i)
-                                zs[i] = fma(A54, K4[i], fma(A53, K3[i], fma(A52, K2[i], fma(A51, K1[i], z[i]))));
-                            break;
-                        default:
-#pragma unroll
-                            for (int i = 0; i < NX; ++i) zs[i] += K5[i];
-                            break;
+                        for (int i = 0; i < NX; ++i) {
+                            const double k = kj[i * 32];
+                            zs[i] = fma(a, k, zs[i]);
+                            cs[i] = fma(cc, k, cs[i]);
+                        }
                     }
                     if (warp == 0) {
 #pragma unroll
@@ -332,64 +345,23 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params p) {
                         if constexpr (NS > 1)
                             if (warp == 2) M::template sens_rhs_block<(NS > 1 ? 1 : 0)>(ts, YS, zs, C, DC, r);
                     }
-                    switch (st) {
-                        case 1: break;
-                        case 2:
 #pragma unroll
-                            for (int i = 0; i < NX; ++i) r[i] = fma(hi * C21, K1[i], r[i]);
-                            break;
-                        case 3:
-#pragma unroll
-                            for (int i = 0; i < NX; ++i) r[i] = fma(hi, fma(C32, K2[i], C31 * K1[i]), r[i]);
-                            break;
-                        case 4:
-#pragma unroll
-                            for (int i = 0; i < NX; ++i) r[i] = fma(hi, fma(C43, K3[i], fma(C42, K2[i], C41 * K1[i])), r[i]);
-                            break;
-                        case 5:
-#pragma unroll
-                            for (int i = 0; i < NX; ++i)
-                                r[i] = fma(hi, fma(C54, K4[i], fma(C53, K3[i], fma(C52, K2[i], C51 * K1[i]))), r[i]);
-                            break;
-                        default:
-#pragma unroll
-                            for (int i = 0; i < NX; ++i)
-                                r[i] = fma(hi, fma(C65, K5[i], fma(C64, K4[i], fma(C63, K3[i], fma(C62, K2[i], C61 * K1[i])))), r[i]);
-                            break;
-                    }
+                    for (int i = 0; i < NX; ++i) r[i] = fma(hi, cs[i], r[i]);
                     if (warp > 0) {
                         if (warp == 1) M::template sens_term_apply<0>(hc, KY, C, DC, r);
                         if constexpr (NS > 1)
                             if (warp == 2) M::template sens_term_apply<(NS > 1 ? 1 : 0)>(hc, KY, C, DC, r);
                     }
                     M::lu_solve(Wsm, r);
-                    if (warp == 0) {
+                    if (st <= 5) {
+                        double* kst = kmine + ((st - 1) * NX) * 32;   // for warp 0 this is kyp
+#pragma unroll
+                        for (int i = 0; i < NX; ++i) kst[i * 32] = r[i];
+                    } else if (warp == 0) {
 #pragma unroll
                         for (int i = 0; i < NX; ++i) KY.set(i, r[i]);
                     }
-                    switch (st) {
-                        case 1:
-#pragma unroll
-                            for (int i = 0; i < NX; ++i) K1[i] = r[i];
-                            break;
-                        case 2:
-#pragma unroll
-                            for (int i = 0; i < NX; ++i) K2[i] = r[i];
-                            break;
-                        case 3:
-#pragma unroll
-                            for (int i = 0; i < NX; ++i) K3[i] = r[i];
-                            break;
-                        case 4:
-#pragma unroll
-                            for (int i = 0; i < NX; ++i) K4[i] = r[i];
-                            break;
-                        case 5:
-#pragma unroll
-                            for (int i = 0; i < NX; ++i) K5[i] = r[i];
-                            break;
-                        default: break;   // K6 stays in r: new solution = stage point + K6, error estimate = K6
-                    }
+                    // K6 stays in r: new solution = stage point + K6, error estimate = K6
                 }
                 __syncthreads();
             }
@@ -450,8 +422,10 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params p) {
                         const double s = (tj - t) * hi, s1 = 1.0 - s;
 #pragma unroll
                         for (int i = 0; i < NX; ++i) {
-                            const double c2 = fma(D21, K1[i], fma(D22, K2[i], fma(D23, K3[i], fma(D24, K4[i], D25 * K5[i]))));
-                            const double c3 = fma(D31, K1[i], fma(D32, K2[i], fma(D33, K3[i], fma(D34, K4[i], D35 * K5[i]))));
+                            const double k1 = kmine[i * 32], k2 = kmine[(NX + i) * 32], k3 = kmine[(2 * NX + i) * 32],
+                                         k4 = kmine[(3 * NX + i) * 32], k5 = kmine[(4 * NX + i) * 32];
+                            const double c2 = fma(D21, k1, fma(D22, k2, fma(D23, k3, fma(D24, k4, D25 * k5))));
+                            const double c3 = fma(D31, k1, fma(D32, k2, fma(D33, k3, fma(D34, k4, D35 * k5))));
                             zo[i] = fma(s1, z[i], s * fma(s1, fma(s, c3, c2), zs[i]));
                         }
                     }

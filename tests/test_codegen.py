@@ -104,3 +104,22 @@ def test_unsupported_sbml_is_rejected(tmp_path):
                    '<listOfEvents><event id="e"/></listOfEvents></model></sbml>')
     with pytest.raises(NotImplementedError):
         cg.read_sbml(bad)
+
+
+def test_no_ieee_division_inside_a_step():
+    """The per-stage functions and the LU factorisation of the generated headers multiply by pv_rcp_newton(d) instead of
+    dividing: an IEEE fp64 division carries a slow-path branch that splits the straight-line step.
+    hoist / hoist_sens run once per trajectory and keep the IEEE division."""
+    import re
+    gen = pkg("build").CSRC / "generated"
+    for name in ("simple_chain", "simple_pk", "icg_body_flat"):
+        text = (gen / f"{name}.cuh").read_text()
+        for fn in ("rhs", "rhs_sens", "jac", "lu_factor", "lu_solve", "sens_stage_term", "sens_rhs_block", "sens_term_prep",
+                   "sens_term_apply"):
+            m = re.search(r"PV_HD static void " + fn + r"\(.*?\n    \}\n", text, flags=re.S)
+            assert m, (name, fn)
+            body = re.sub(r"//.*", "", m.group(0))
+            body = re.sub(r"\(\d+\.0/\d+\.0\)", "", body)       # rational constants fold at compile time
+            assert "/" not in body, (name, fn)
+    icg = (gen / "icg_body_flat.cuh").read_text()
+    assert icg.count("pv_rcp_newton") >= 12 + 4          # 12 pivots + the Michaelis-Menten denominators

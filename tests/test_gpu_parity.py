@@ -296,6 +296,42 @@ def test_full_size_properties_c2(cuda_lib, rt):
     assert float(((Y2 - 2 * Y).abs() / (2e-9 + 2e-6 * Y.abs())).max()) <= 1.0
 
 
+def test_full_size_properties_icg(cuda_lib, rt, oracle):
+    """BASELINE C4-sized forward batch of the stiff PBPK model (128 000 draws of BW and Vmax): size-independent
+    properties.  The model conserves ICG: injected dose / Mr = sum of compartment amounts + remaining dose at every grid
+    point (volumes depend on the sampled BW); concentrations stay non-negative; a trajectory does not depend on which
+    lane integrated it (permuting the batch permutes the output bit for bit)."""
+    torch = _torch()
+    B, T = 128_000, 20
+    t = np.linspace(0, 100, T)
+    BW = lognormal_draws(21, B, 75.0, 10.0)
+    Vm = lognormal_draws(22, B, 0.0369598840327503, 0.01)
+    pb = _problem(rt, "icg_body_flat", ["BW", "LI__ICGIM_Vmax"], t, list(oracle.ICG_STATES), dosage={"IVDOSE_icg": 10.0})
+    P = torch.from_numpy(np.stack([BW, Vm])).cuda()
+    Y = torch.empty((B, T, len(oracle.ICG_STATES)), dtype=torch.float64, device="cuda")
+    status = torch.empty(B, dtype=torch.int32, device="cuda")
+    pb.simulate(P, Y, status=status)
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0
+    Yh = Y.cpu().numpy()
+    par = dict(oracle.ICG_DEFAULTS)
+    par["BW"] = BW
+    v = oracle._icg_volumes_flows(par)
+    vol = {"Afeces_icg": 1.0, "Car_icg": v["Var"], "Cgi_plasma_icg": v["Vgi_plasma"], "Chv_icg": v["Vhv"],
+           "Cli_plasma_icg": v["Vli_plasma"], "Clu_plasma_icg": v["Vlu_plasma"], "Cpo_icg": v["Vpo"],
+           "Cre_plasma_icg": v["Vre_plasma"], "Cve_icg": v["Vve"], "LI__icg": v["Vli_tissue"], "LI__icg_bi": v["Vbi"]}
+    i = oracle.ICG_STATES.index
+    amount = sum(Yh[:, :, i(sid)] * (np.asarray(V) * np.ones(B))[:, None] for sid, V in vol.items())
+    amount = amount + Yh[:, :, i("IVDOSE_icg")] / par["Mr_icg"]
+    np.testing.assert_allclose(amount, 10.0 / par["Mr_icg"], rtol=2e-6)
+    assert Yh.min() >= -1e-9
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(3)).cuda()
+    Y2 = torch.empty_like(Y)
+    pb.simulate(P[:, perm].contiguous(), Y2)
+    torch.cuda.synchronize()
+    assert torch.equal(Y2, Y[perm])
+
+
 def test_ode_sample_simulator_drop_in(cuda_lib, oracle):
     """The reference-facing class: DataFrame in, (sim x time) dataset out, noise stream identical to the oracle's
     restatement of petab_factory.py:192-219."""

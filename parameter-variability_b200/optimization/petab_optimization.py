@@ -325,15 +325,23 @@ class HierarchicalObjective:
         """theta [C, n_local, P], mu / omega [C, P] -> (logp_local [C], dtheta [C, n_local, P], dmu [C, P], domega [C, P])
         for this rank's individuals (likelihood + population density); hyper-priors are added once by ``finish``."""
         C, L, P = theta.shape
-        Pm = np.ascontiguousarray(theta.transpose(2, 0, 1).reshape(P, C * L))
-        lp, g, seg, nf = self.problem.logp_host(Pm, seg_len=L, grad=True)
-        dth = g[self._sens_row].reshape(P, C, L).transpose(1, 2, 0).copy()
-        z = (np.log(theta) - mu[:, None, :]) / omega[:, None, :]
-        pop = np.sum(-np.log(theta) - np.log(omega)[:, None, :] - 0.5 * LOG_2PI - 0.5 * z * z, axis=(1, 2))
-        dth += (-1.0 - z / omega[:, None, :]) / theta
-        dmu = np.sum(z / omega[:, None, :], axis=1)
-        domega = np.sum((z * z - 1.0) / omega[:, None, :], axis=1)
-        return seg + pop, dth, dmu, domega
+        # parameter-major [P, C, L] throughout: it is the kernel's own layout, so nothing is transposed around the launch
+        thp = np.ascontiguousarray(theta.transpose(2, 0, 1))
+        lp, g, seg, nf = self.problem.logp_host(thp.reshape(P, C * L), seg_len=L, grad=True)
+        g = g[self._sens_row].reshape(P, C, L)
+        iw = (1.0 / omega).T[:, :, None]                               # [P, C, 1]
+        lt = np.log(thp)
+        z = lt - mu.T[:, :, None]
+        z *= iw
+        s_lt, s_z, s_zz = lt.sum(axis=2), z.sum(axis=2), np.einsum("pcl,pcl->pc", z, z)     # [P, C]
+        pop = -s_lt.sum(axis=0) - L * np.log(omega).sum(axis=1) - 0.5 * LOG_2PI * L * P - 0.5 * s_zz.sum(axis=0)
+        z *= iw
+        z += 1.0
+        z /= thp
+        g -= z                                                         # d/dtheta of the population density: -(1 + z/omega)/theta
+        dmu = (s_z * iw[:, :, 0]).T
+        domega = ((s_zz - L) * iw[:, :, 0]).T
+        return seg + pop, g.transpose(1, 2, 0), dmu, domega
 
     def finish(self, logp: np.ndarray, dmu: np.ndarray, domega: np.ndarray, mu: np.ndarray, omega: np.ndarray):
         """Add the hyper-priors (after the cross-rank reduction)."""

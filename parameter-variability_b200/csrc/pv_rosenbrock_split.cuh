@@ -69,7 +69,8 @@ struct pv_split_layout {
     static constexpr int Z0 = KS;                         // [NB][NX][32] initial blocks (set-up hand-over; aliases KS)
     static constexpr int K6Y = KS + NB * 5 * M::NX * 32;  // [NX][32] K6 of the state block
     static constexpr int ERR = K6Y + M::NX * 32;          // [2][NB][32] error-norm / initial-step partials
-    static constexpr int FIXED = ERR + 2 * NB * 32;
+    static constexpr int ZERO = ERR + 2 * NB * 32;        // [NX][32] zeros: the "K_1" stage 1 sums over (see the stage sums)
+    static constexpr int FIXED = ZERO + M::NX * 32;
     // then, sized at launch: OW [n_obs][32], OWI [n_obs][32], DF [NS][n_obs][32], tgrid [T], theta [NTH], y0 [NX]
     static size_t bytes(int T, int n_obs) {
         return sizeof(double) * ((size_t)FIXED + (size_t)(2 + M::NS) * n_obs * 32 + T + M::NTH + M::NX);
@@ -98,6 +99,7 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params p) {
     for (int i = threadIdx.x; i < T; i += blockDim.x) sh_t[i] = p.tgrid[i];
     for (int i = threadIdx.x; i < M::NTH; i += blockDim.x) sh_theta[i] = p.theta_base[i];
     for (int i = threadIdx.x; i < NX; i += blockDim.x) sh_y0[i] = p.y0_base[i];
+    for (int i = threadIdx.x; i < NX * 32; i += blockDim.x) sh[L::ZERO + i] = 0.0;
     const pv_smem_vec C{sh + L::C + lane}, DC{sh + L::DC + lane}, Wsm{sh + L::W + lane}, YN{sh + L::YN + lane};
     const pv_smem_vec Z0{sh + L::Z0 + lane};
     double* const err_sh = sh + L::ERR + lane;     // [2][NB] partials of this lane's trajectory, stride 32
@@ -319,14 +321,21 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params p) {
                     const double ts = (st == 1) ? t : (st == 2) ? t + C2 * h : (st == 3) ? t + C3 * h : (st == 4) ? t + C4 * h : t + h;
                     // stage point zs = z + sum_j A[st][j] K_j and right-hand-side combination cs = sum_j C[st][j] K_j in one pass
                     // over this block's stage vectors (the newest K enters last)
+                    // The first term initialises both sums (no copy of z, no zeroing); stage 1 has no K yet and sums over a
+                    // row of zeros with zero coefficients instead: zs = z, cs = 0 exactly.
                     double cs[NX];
+                    {
+                        const double a = pv_rodas4_A[st - 1][0], cc = pv_rodas4_C[st - 1][0];
+                        const double* k0 = (st == 1) ? sh + L::ZERO + lane : kmine;
 #pragma unroll
-                    for (int i = 0; i < NX; ++i) {
-                        zs[i] = z[i];
-                        cs[i] = 0.0;
+                        for (int i = 0; i < NX; ++i) {
+                            const double k = k0[i * 32];
+                            zs[i] = fma(a, k, z[i]);
+                            cs[i] = cc * k;
+                        }
                     }
 #pragma unroll 1
-                    for (int j = 0; j < st - 1; ++j) {
+                    for (int j = 1; j < st - 1; ++j) {
                         const double a = pv_rodas4_A[st - 1][j], cc = pv_rodas4_C[st - 1][j];
                         const double* kj = kmine + (j * NX) * 32;
 #pragma unroll

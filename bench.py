@@ -211,7 +211,7 @@ def logp_grad_leg(rt, torch, dist, rank: int, world: int, local: int, evals: int
 
         def evaluate():
             lp, dth, dmu, dom = H.local_terms(theta, mu, omega)
-            buf = np.concatenate([lp[:, None], dmu, dom], axis=1)          # [C, 1 + 2P]
+            buf = np.ascontiguousarray(np.concatenate([lp[:, None], dmu, dom], axis=1))          # [C, 1 + 2P]
             if world > 1:
                 tb = torch.from_numpy(buf).cuda()
                 dist.all_reduce(tb, op=dist.ReduceOp.SUM)

@@ -339,9 +339,9 @@ class HierarchicalObjective:
         z += 1.0
         z /= thp
         g -= z                                                         # d/dtheta of the population density: -(1 + z/omega)/theta
-        dmu = (s_z * iw[:, :, 0]).T
-        domega = ((s_zz - L) * iw[:, :, 0]).T
-        return seg + pop, g.transpose(1, 2, 0), dmu, domega
+        dmu = np.ascontiguousarray((s_z * iw[:, :, 0]).T)            # C-contiguous results: callers pack them into
+        domega = np.ascontiguousarray(((s_zz - L) * iw[:, :, 0]).T)  # all-reduce buffers
+        return seg + pop, np.ascontiguousarray(g.transpose(1, 2, 0)), dmu, domega
 
     def finish(self, logp: np.ndarray, dmu: np.ndarray, domega: np.ndarray, mu: np.ndarray, omega: np.ndarray):
         """Add the hyper-priors (after the cross-rank reduction)."""

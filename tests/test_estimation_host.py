@@ -199,3 +199,53 @@ def test_reference_analysis_layout(tmp_path):
     for col in ("optim_duration", "mean", "median", "n_samples", "values", "ess", "hdi_high", "hdi_low"):
         assert col in df_join.columns
     assert df_join["values"].iloc[0].shape == (4, 51)
+
+
+def test_hierarchical_population_terms_host_algebra():
+    """HierarchicalObjective.local_terms (host part, kernel replaced by a stub): the population density of
+    theta_ip ~ LogNormal(mu_p, omega_p) and its derivatives against the plain formula and central differences;
+    outputs are C-contiguous (they are packed into all-reduce buffers)."""
+    po = pkg("optimization.petab_optimization")
+
+    class Stub:                                   # stands in for runtime.Problem: zero likelihood
+        columns = ["a", "b"]
+        sens_ids = ["b", "a"]                     # kernel's sensitivity order differs from the column order
+        n_sens = 2
+
+        def logp_host(self, Pm, seg_len=0, grad=False):
+            B = Pm.shape[1]
+            self.last_P = Pm.copy()
+            return np.zeros(B), np.zeros((2, B)), np.zeros(B // seg_len), 0
+
+    C, L, P = 3, 7, 2
+    rs = np.random.RandomState(5)
+    theta = rs.lognormal(size=(C, L, P))
+    mu, omega = rs.normal(size=(C, P)), rs.uniform(0.5, 2.0, size=(C, P))
+    stub = Stub()
+    H = po.HierarchicalObjective(stub, L, mu_prior=[(0.0, 0.5)] * P, omega_prior=[0.5] * P)
+
+    def pop(th, m, w):
+        z = (np.log(th) - m[:, None, :]) / w[:, None, :]
+        return np.sum(-np.log(th) - np.log(w)[:, None, :] - 0.5 * np.log(2 * np.pi) - 0.5 * z * z, axis=(1, 2))
+
+    lp, dth, dmu, dom = H.local_terms(theta, mu, omega)
+    for a in (lp, dth, dmu, dom):
+        assert a.flags["C_CONTIGUOUS"]
+    assert dth.shape == (C, L, P) and dmu.shape == (C, P) and dom.shape == (C, P)
+    np.testing.assert_array_equal(stub.last_P, theta.transpose(2, 0, 1).reshape(P, C * L))    # parameter-major rows
+    np.testing.assert_allclose(lp, pop(theta, mu, omega), rtol=1e-13)
+    eps = 1e-6
+    for c, l, p in [(0, 0, 0), (2, 6, 1), (1, 3, 0)]:
+        tp, tm = theta.copy(), theta.copy()
+        tp[c, l, p] += eps
+        tm[c, l, p] -= eps
+        np.testing.assert_allclose(dth[c, l, p], (pop(tp, mu, omega)[c] - pop(tm, mu, omega)[c]) / (2 * eps), rtol=1e-6)
+    for c, p in [(0, 0), (2, 1)]:
+        mp, mm = mu.copy(), mu.copy()
+        mp[c, p] += eps
+        mm[c, p] -= eps
+        np.testing.assert_allclose(dmu[c, p], (pop(theta, mp, omega)[c] - pop(theta, mm, omega)[c]) / (2 * eps), rtol=1e-6)
+        wp, wm = omega.copy(), omega.copy()
+        wp[c, p] += eps
+        wm[c, p] -= eps
+        np.testing.assert_allclose(dom[c, p], (pop(theta, mu, wp)[c] - pop(theta, mu, wm)[c]) / (2 * eps), rtol=1e-6)

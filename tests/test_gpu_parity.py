@@ -268,6 +268,44 @@ def test_failed_trajectories_are_reported(cuda_lib, rt):
     assert nf == 1 and status[1] != 0 and status[0] == 0
 
 
+@pytest.mark.parametrize("layout", ["lane", "split"])
+def test_rosenbrock_failures_are_reported_per_trajectory(cuda_lib, rt, layout):
+    """Stiff path, logp + gradient: a NaN parameter row or an exhausted step budget fails ITS trajectory (status != 0,
+    logp = NaN, counted in the return value) and leaves its neighbours in the same CTA untouched - in the split layout
+    32 trajectories share a CTA and its barriers, so a failed one must keep walking through them."""
+    T = 6
+    t = np.linspace(0, 30, T)
+    obs = ["Cre_plasma_icg", "Cgi_plasma_icg"]
+    B = 45
+    BW = lognormal_draws(31, B, 75.0, 10.0)
+    Vm = lognormal_draws(32, B, 0.0369598840327503, 0.01)
+    stats = np.stack([np.ones((T, 2)), np.full((T, 2), 1e-3), np.full((T, 2), 1e-6)])[..., None]
+
+    def run(P, max_steps=1_000_000):
+        pb = _problem(rt, "icg_body_flat", ["BW", "LI__ICGIM_Vmax"], t, obs, dosage={"IVDOSE_icg": 10.0})
+        pb.set_solver(method=rt.METHOD_RODAS4, rtol=1e-7, atol=1e-11, max_steps=max_steps)
+        pb.set_layout(rt.LAYOUT_LANE if layout == "lane" else rt.LAYOUT_SPLIT)
+        pb.set_data(stats, 1e-4)
+        out = pb.logp_host(P, grad=True)
+        pb.close()
+        return out
+
+    good = np.stack([BW, Vm])
+    lp0, g0, _, nf0 = run(good)
+    assert nf0 == 0 and np.all(np.isfinite(lp0)) and np.all(np.isfinite(g0))
+    bad = good.copy()
+    bad[0, 3] = np.nan
+    bad[1, 40] = np.nan
+    lp1, g1, _, nf1 = run(bad)
+    assert nf1 == 2 and np.isnan(lp1[3]) and np.isnan(lp1[40])
+    keep = np.ones(B, bool)
+    keep[[3, 40]] = False
+    np.testing.assert_array_equal(lp1[keep], lp0[keep])          # neighbours are bit-identical
+    np.testing.assert_array_equal(g1[:, keep], g0[:, keep])
+    lp2, g2, _, nf2 = run(good, max_steps=20)                    # nobody finishes in 20 steps
+    assert nf2 == B and np.all(np.isnan(lp2))
+
+
 def test_full_size_properties_c2(cuda_lib, rt):
     """BASELINE C2 at full size (1e6 draws x 50 timepoints): size-independent properties.
     simple_pk is linear: mass only leaves through clearance, so 0 <= y_gut+y_cent+y_peri <= 1 and y_gut is

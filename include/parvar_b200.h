@@ -179,6 +179,30 @@ int pv_logp_grad_fim_host(pv_problem* p, int64_t B, const double* P_host, double
 void* pv_host_alloc(size_t bytes);
 void pv_host_free(void* ptr);
 
+/* ---- host bookkeeping of the batched sampler ------------------------------------------------------------
+ * Adaptive Metropolis inside adaptive parallel tempering for Q problems x C temperatures at once; replaces, for all
+ * problems together, the per-problem pyPESTO sampler loop behind `pypesto.sample.sample(...)`
+ * (src/parvar/optimization/petab_optimization.py:158-173).  Plain host arrays, row-major [Q][C][...]; the objective of
+ * the proposals is evaluated by the caller between the two calls (one GPU launch for all of them); random numbers are
+ * the caller's (xi ~ N(0,1) [Q][C][dim], u_acc ~ U(0,1) [Q][C], u_swap ~ U(0,1) [Q][C-1]). */
+typedef struct pv_sampler_options {
+    double decay_constant, target_acceptance_rate, reg_factor, nu, eta;
+    int64_t threshold_sample;
+    int32_t adapt_betas;
+} pv_sampler_options;
+/* x_new = x + chol(cov) xi; inside = (lb <= x_new <= ub); x_eval = inside ? x_new : x.  Returns the number of
+ * covariance matrices that were not positive definite (their proposal is x), < 0 on argument errors. */
+int64_t pv_sampler_propose(int64_t Q, int C, int dim, const double* cov, const double* x, const double* xi,
+                           const double* lb, const double* ub, double* x_new, uint8_t* inside, double* x_eval);
+/* accept / reject, proposal adaptation (Haario), swaps (hottest pair first), ladder adaptation (Vousden), trace row
+ * `it` (1-based, < n_trace) of trace_x [n_trace][Q][C][dim], trace_neglogpost / trace_neglogprior [n_trace][Q][C].
+ * In/out: x, llh, lpr, betas, mean_hist, cov_hist, cov_scale, cov, n_acc [Q][C], n_swap / n_swap_try [Q][max(C-1,1)]. */
+int pv_sampler_step(int64_t Q, int C, int dim, int64_t it, int64_t n_trace, const pv_sampler_options* options, double* x,
+                    double* llh, double* lpr, const double* x_new, const double* llh_new, const double* lpr_new,
+                    const uint8_t* inside, const double* u_acc, const double* u_swap, double* betas, double* mean_hist,
+                    double* cov_hist, double* cov_scale, double* cov, double* n_acc, double* n_swap, double* n_swap_try,
+                    double* trace_x, double* trace_neglogpost, double* trace_neglogprior);
+
 /* ---- measurement helpers ------------------------------------------------------------------------------ */
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t pv_launch_count(void);

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/parvar_b200.h"
+#include "pv_sampler_host.cuh"
 #include "pv_kernels.cuh"
 #include "pv_rosenbrock_split.cuh"
 #include "generated/simple_chain.cuh"
@@ -781,6 +782,30 @@ extern "C" int pv_logp_grad_fim_host(pv_problem* p, int64_t B, const double* P_h
                                      double* fim_host, int64_t seg_len, double* logp_seg_host) {
     if (!fim_host) return fail(PV_E_ARG, "fim_host is NULL");
     return logp_host_impl(p, true, B, P_host, logp_host, grad_host, seg_len, logp_seg_host, fim_host);
+}
+
+// ---- host bookkeeping of the batched sampler (pv_sampler_host.cuh) ----------------------------------------------------
+extern "C" int64_t pv_sampler_propose(int64_t Q, int C, int dim, const double* cov, const double* x, const double* xi,
+                                      const double* lb, const double* ub, double* x_new, uint8_t* inside, double* x_eval) {
+    if (Q < 0 || C < 1 || dim < 1 || !cov || !x || !xi || !lb || !ub || !x_new || !inside || !x_eval)
+        return fail(PV_E_ARG, "pv_sampler_propose: bad arguments");
+    const int64_t r = pv_sampler_propose_impl(Q, C, dim, cov, x, xi, lb, ub, x_new, inside, x_eval);
+    if (r < 0) return fail(PV_E_ARG, "pv_sampler_propose: dim too large");
+    return r;
+}
+extern "C" int pv_sampler_step(int64_t Q, int C, int dim, int64_t it, int64_t n_trace, const pv_sampler_options* o, double* x,
+                               double* llh, double* lpr, const double* x_new, const double* llh_new, const double* lpr_new,
+                               const uint8_t* inside, const double* u_acc, const double* u_swap, double* betas,
+                               double* mean_hist, double* cov_hist, double* cov_scale, double* cov, double* n_acc,
+                               double* n_swap, double* n_swap_try, double* trace_x, double* trace_lp, double* trace_pr) {
+    if (Q < 0 || C < 1 || dim < 1 || it < 1 || it >= n_trace || !o || !x || !llh || !lpr || !x_new || !llh_new || !lpr_new ||
+        !inside || !u_acc || (C > 1 && !u_swap) || !betas || !mean_hist || !cov_hist || !cov_scale || !cov || !n_acc ||
+        !n_swap || !n_swap_try || !trace_x || !trace_lp || !trace_pr)
+        return fail(PV_E_ARG, "pv_sampler_step: bad arguments");
+    if (pv_sampler_step_impl(Q, C, dim, it, n_trace, o, x, llh, lpr, x_new, llh_new, lpr_new, inside, u_acc, u_swap, betas,
+                             mean_hist, cov_hist, cov_scale, cov, n_acc, n_swap, n_swap_try, trace_x, trace_lp, trace_pr))
+        return fail(PV_E_ARG, "pv_sampler_step: dim or number of temperatures too large");
+    return 0;
 }
 
 extern "C" double pv_last_kernel_ms(const pv_problem* p) { return p ? p->last_kernel_ms : -1.0; }

@@ -5,7 +5,8 @@ The reference samples each PEtab problem with
 5000 samples (src/parvar/optimization/petab_optimization.py:158-173, settings :294-306): 4 x 5000 sequential Python ->
 AMICI objective calls per problem, problems spread over a process pool.  Here every iteration evaluates the proposals
 of ALL chains of ALL problems in one kernel launch (``PetabObjectiveBatch.evaluate``); the bookkeeping around it is
-vectorised numpy over [problems, chains].
+compiled host code over [problems, chains] (``pv_sampler_propose`` / ``pv_sampler_step`` of the C ABI; the numpy
+statement of the same loop is kept as ``native=False``: same random stream, same chain up to round-off).
 
 Algorithms (restated from the publications pyPESTO implements; pyPESTO 0.6.0 is not in /root/reference):
   * adaptive Metropolis: Haario, Saksman, Tamminen (2001) with the decaying update of the running mean / covariance
@@ -86,9 +87,14 @@ class SampleResult:
 def sample(evaluate: Callable[[np.ndarray], tuple[np.ndarray, np.ndarray]], x0: np.ndarray, lb: np.ndarray, ub: np.ndarray,
            n_samples: int = 5000, n_chains: int = 4, seed: int = 1234, cov0: Optional[np.ndarray] = None,
            decay_constant: float = 0.51, target_acceptance_rate: float = 0.234, reg_factor: float = 1e-6,
-           threshold_sample: int = 1, nu: float = 1e3, eta: float = 100.0, adapt_betas: bool = True) -> SampleResult:
+           threshold_sample: int = 1, nu: float = 1e3, eta: float = 100.0, adapt_betas: bool = True,
+           native: Optional[bool] = None) -> SampleResult:
     """``evaluate(X [Q, C, dim]) -> (llh [Q, C], lprior [Q, C])``; ``x0`` [Q, dim] (start of every chain, as pyPESTO
-    starts all tempered chains at the best optimisation result)."""
+    starts all tempered chains at the best optimisation result).  ``native``: bookkeeping in the library's compiled host
+    code (default) or in numpy."""
+    if native is None or native:
+        return _sample_native(evaluate, x0, lb, ub, n_samples, n_chains, seed, cov0, decay_constant, target_acceptance_rate,
+                              reg_factor, threshold_sample, nu, eta, adapt_betas)
     rs = np.random.RandomState(seed)
     x0 = np.atleast_2d(np.asarray(x0, dtype=np.float64))
     Q, dim = x0.shape
@@ -162,6 +168,61 @@ def sample(evaluate: Callable[[np.ndarray], tuple[np.ndarray, np.ndarray]], x0: 
         trace_x[:, :, it], trace_lp[:, :, it], trace_pr[:, :, it] = x, -(llh + lpr), -lpr
 
     return SampleResult(trace_x=trace_x, trace_neglogpost=trace_lp, trace_neglogprior=trace_pr, betas=betas,
+                        acceptance_rate=n_acc / n_samples, swap_rate=n_swap / np.maximum(n_swap_try, 1), n_evals=n_evals)
+
+
+def _sample_native(evaluate, x0, lb, ub, n_samples, n_chains, seed, cov0, decay_constant, target_acceptance_rate, reg_factor,
+                   threshold_sample, nu, eta, adapt_betas) -> SampleResult:
+    """The loop of ``sample`` with the per-iteration bookkeeping in ``pv_sampler_propose`` / ``pv_sampler_step``.
+    Random numbers are drawn here, in the order the numpy loop draws them."""
+    from .. import runtime
+    lib = runtime.load_library()
+    rs = np.random.RandomState(seed)
+    x0 = np.atleast_2d(np.asarray(x0, dtype=np.float64))
+    Q, dim = x0.shape
+    C = n_chains
+    S = max(C - 1, 1)
+    lb = np.ascontiguousarray(np.broadcast_to(np.asarray(lb, dtype=np.float64), (dim,)))
+    ub = np.ascontiguousarray(np.broadcast_to(np.asarray(ub, dtype=np.float64), (dim,)))
+    x = np.ascontiguousarray(np.repeat(x0[:, None, :], C, axis=1))
+    llh, lpr = (np.array(a, dtype=np.float64) for a in evaluate(x))       # own copies: updated in place
+    n_evals = Q * C
+    betas = np.ascontiguousarray(np.repeat(near_exponential_decay_betas(C)[None, :], Q, axis=0))
+    cov = np.broadcast_to(np.eye(dim) if cov0 is None else np.asarray(cov0, dtype=np.float64), (Q, C, dim, dim)).copy()
+    cov = np.ascontiguousarray(_regularize(cov, reg_factor))
+    mean_hist, cov_hist, cov_scale = x.copy(), cov.copy(), np.ones((Q, C))
+    n_tr = n_samples + 1
+    # iteration-major while sampling (contiguous row per iteration), [Q, C, n, ...] in the result
+    trace_x, trace_lp, trace_pr = np.empty((n_tr, Q, C, dim)), np.empty((n_tr, Q, C)), np.empty((n_tr, Q, C))
+    trace_x[0], trace_lp[0], trace_pr[0] = x, -(llh + lpr), -lpr
+    n_acc, n_swap, n_swap_try = np.zeros((Q, C)), np.zeros((Q, S)), np.zeros((Q, S))
+    x_new, x_eval, inside = np.empty_like(x), np.empty_like(x), np.empty((Q, C), dtype=np.uint8)
+    u_swap = np.zeros((Q, S))
+    opts = runtime.SamplerOptions(decay_constant, target_acceptance_rate, reg_factor, nu, eta, int(threshold_sample),
+                                  int(bool(adapt_betas)))
+    import ctypes
+    p_opts = ctypes.addressof(opts)
+    ptr = lambda a: a.ctypes.data
+    # every array the library updates in place keeps its address for the whole run
+    a_propose = (ptr(lb), ptr(ub), ptr(x_new), ptr(inside), ptr(x_eval))
+    a_state = (ptr(x), ptr(llh), ptr(lpr), ptr(x_new))
+    a_rest = (ptr(u_swap), ptr(betas), ptr(mean_hist), ptr(cov_hist), ptr(cov_scale), ptr(cov), ptr(n_acc), ptr(n_swap),
+              ptr(n_swap_try), ptr(trace_x), ptr(trace_lp), ptr(trace_pr))
+    p_cov, p_x, p_inside = ptr(cov), ptr(x), ptr(inside)
+    for it in range(1, n_samples + 1):
+        xi = rs.normal(size=(Q, C, dim))
+        if lib.pv_sampler_propose(Q, C, dim, p_cov, p_x, ptr(xi), *a_propose) < 0:
+            raise runtime.ParvarB200Error(runtime.last_error())
+        llh_new, lpr_new = (np.ascontiguousarray(a, dtype=np.float64) for a in evaluate(x_eval))
+        n_evals += Q * C
+        u_acc = rs.uniform(size=(Q, C))
+        for k in range(C - 1, 0, -1):
+            u_swap[:, k - 1] = rs.uniform(size=Q)
+        if lib.pv_sampler_step(Q, C, dim, it, n_tr, p_opts, *a_state, ptr(llh_new), ptr(lpr_new), p_inside, ptr(u_acc), *a_rest):
+            raise runtime.ParvarB200Error(runtime.last_error())
+    return SampleResult(trace_x=np.ascontiguousarray(trace_x.transpose(1, 2, 0, 3)),
+                        trace_neglogpost=np.ascontiguousarray(trace_lp.transpose(1, 2, 0)),
+                        trace_neglogprior=np.ascontiguousarray(trace_pr.transpose(1, 2, 0)), betas=betas,
                         acceptance_rate=n_acc / n_samples, swap_rate=n_swap / np.maximum(n_swap_try, 1), n_evals=n_evals)
 
 

@@ -66,6 +66,8 @@ ABI = {
     "pv_logp_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pv_logp_grad_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pv_launch_count": (C.c_int64, []),
+    "pv_sampler_propose": (C.c_int64, [C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 8),
+    "pv_sampler_step": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 21),
     "pv_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "pv_fma_peak_tflops": (C.c_double, [C.c_int, C.c_int, C.c_int]),
     "pv_host_alloc": (C.c_void_p, [C.c_size_t]),
@@ -312,6 +314,12 @@ class Problem:
     @property
     def last_kernel_ms(self) -> float:
         return self._lib.pv_last_kernel_ms(self._h)
+
+
+class SamplerOptions(C.Structure):
+    """``pv_sampler_options`` (include/parvar_b200.h)."""
+    _fields_ = [("decay_constant", C.c_double), ("target_acceptance_rate", C.c_double), ("reg_factor", C.c_double),
+                ("nu", C.c_double), ("eta", C.c_double), ("threshold_sample", C.c_int64), ("adapt_betas", C.c_int32)]
 
 
 def launch_count() -> int:

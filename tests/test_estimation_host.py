@@ -249,3 +249,41 @@ def test_hierarchical_population_terms_host_algebra():
         wp[c, p] += eps
         wm[c, p] -= eps
         np.testing.assert_allclose(dom[c, p], (pop(theta, mu, wp)[c] - pop(theta, mu, wm)[c]) / (2 * eps), rtol=1e-6)
+
+
+def test_native_sampler_bookkeeping_matches_numpy():
+    """The compiled host loop of the sampler (pv_sampler_propose / pv_sampler_step, include/parvar_b200.h) and its numpy
+    statement draw the same random numbers in the same order and must walk the same chains: identical accept / swap
+    decisions, positions equal up to round-off - including proposals outside the bounds, failed evaluations (NaN),
+    a single temperature, and covariance matrices that need the eigenvalue floor."""
+    smp = pkg("optimization.sampler")
+    A = np.array([[2.0, 0.6, 0.1], [0.6, 1.0, 0.3], [0.1, 0.3, 0.5]])
+    Ai = np.linalg.inv(A)
+
+    def evaluate(X):
+        d = X - 0.3
+        llh = -0.5 * np.einsum("qci,ij,qcj->qc", d, Ai, d) * 40
+        llh = np.where(X[..., 0] > 1.2, np.nan, llh)                      # a region where the "simulation fails"
+        return llh, -0.5 * np.sum((X - 0.5) ** 2, axis=2)
+
+    Q, dim = 24, 3
+    x0 = np.full((Q, dim), 0.25)
+    lb, ub = np.zeros(dim), np.array([2.0, 1e8, 1e8])                     # tight lower bound: many rejected proposals
+    for chains in (4, 1):
+        r0 = smp.sample(evaluate, x0, lb, ub, n_samples=300, n_chains=chains, native=False)
+        r1 = smp.sample(evaluate, x0, lb, ub, n_samples=300, n_chains=chains, native=True)
+        np.testing.assert_array_equal(r0.acceptance_rate, r1.acceptance_rate)
+        np.testing.assert_array_equal(r0.swap_rate, r1.swap_rate)
+        np.testing.assert_allclose(r1.trace_x, r0.trace_x, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(r1.trace_neglogpost, r0.trace_neglogpost, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(r1.trace_neglogprior, r0.trace_neglogprior, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(r1.betas, r0.betas, rtol=1e-12)
+        assert r1.trace_x.shape == (Q, chains, 301, dim) and r1.trace_x.flags["C_CONTIGUOUS"]
+        assert 0.05 < r1.acceptance_rate[:, 0].mean() < 0.9
+    # degenerate start covariance (rank 1, scale 1e15): the eigenvalue floor of _regularize / pv_sampler::regularize
+    v = np.array([1.0, 1.0, 1.0])
+    cov0 = 1e15 * np.outer(v, v)
+    ra = smp.sample(evaluate, x0, lb, np.full(dim, 1e8), n_samples=50, cov0=cov0, native=False)
+    rb = smp.sample(evaluate, x0, lb, np.full(dim, 1e8), n_samples=50, cov0=cov0, native=True)
+    np.testing.assert_array_equal(ra.acceptance_rate, rb.acceptance_rate)
+    np.testing.assert_allclose(rb.trace_x, ra.trace_x, rtol=1e-6, atol=1e-6)

@@ -361,10 +361,15 @@ extern "C" int pv_problem_set_data(pv_problem* p, int noise_model, int n_data, c
 // ---------------------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------------------
+constexpr int PV_MAX_DYN_SMEM = 200 * 1024;   // pv_launch refuses time grids / data that need more
+
 template <class KernelT>
 static cudaError_t launch_persistent(KernelT kern, const pv_launch_params& lp, size_t shmem, int num_sms, cudaStream_t s) {
+    // The opt-in limit is a property of the FUNCTION, shared by every problem and host thread that launches it: it is set to
+    // one constant (the largest size pv_launch accepts), never to this launch's size - otherwise a thread with a short
+    // time grid could lower it between another thread's cudaFuncSetAttribute and its launch ("invalid argument").
     if (shmem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_MAX_DYN_SMEM);
         if (e != cudaSuccess) return e;
     }
     // persistent grid: as many CTAs as are resident at once (a multiple of the SM count), never more than the work
@@ -402,8 +407,8 @@ static cudaError_t launch_split(const pv_launch_params& lp, int num_sms, int lay
         auto kern = pv_rodas4_split_kernel<M, MODE>;
         const int threads = 32 * (1 + M::NS);
         const size_t shmem = pv_split_layout<M>::bytes(lp.T, lp.n_obs);
-        if (shmem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+        if (shmem > 48 * 1024) {   // constant, see launch_persistent
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_MAX_DYN_SMEM);
             if (e != cudaSuccess) return e;
         }
         int per_sm = 0;

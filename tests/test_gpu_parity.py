@@ -306,6 +306,45 @@ def test_rosenbrock_failures_are_reported_per_trajectory(cuda_lib, rt, layout):
     assert nf2 == B and np.all(np.isnan(lp2))
 
 
+def test_concurrent_problems_with_different_time_grids(cuda_lib, rt):
+    """Host threads with their own Problem (the study driver runs one per time grid) launch the same kernels with
+    different dynamic shared-memory sizes at the same time.  The opt-in shared-memory limit is a per-function attribute:
+    it must not depend on who launched last (regression: 'kernel launch: invalid argument' from the Rosenbrock
+    sensitivity kernel when a short-grid thread lowered the limit under a long-grid thread)."""
+    from concurrent.futures import ThreadPoolExecutor
+    obs = ["Cre_plasma_icg", "Cgi_plasma_icg"]
+    B = 40
+    P = np.stack([lognormal_draws(61, B, 75.0, 10.0), lognormal_draws(62, B, 0.0369598840327503, 0.01)])
+
+    def make(T):
+        t = np.linspace(0, 100, T)
+        pb = _problem(rt, "icg_body_flat", ["BW", "LI__ICGIM_Vmax"], t, obs, dosage={"IVDOSE_icg": 10.0})
+        stats = np.stack([np.ones((T, 2)), np.full((T, 2), 1e-3), np.full((T, 2), 1e-6)])[..., None]
+        pb.set_data(stats, 1e-4)
+        return pb
+
+    grids = [2, 160, 5, 80, 3, 40]
+    ref = {}
+    for T in grids:
+        pb = make(T)
+        ref[T] = pb.logp_fim_host(P)
+        pb.close()
+
+    def work(T):
+        pb = make(T)
+        out = [pb.logp_fim_host(P) for _ in range(15)]
+        pb.close()
+        return T, out
+
+    with ThreadPoolExecutor(max_workers=len(grids)) as pool:
+        for T, outs in pool.map(work, grids):
+            for lp, g, f, _, nf in outs:
+                assert nf == 0
+                np.testing.assert_array_equal(lp, ref[T][0])
+                np.testing.assert_array_equal(g, ref[T][1])
+                np.testing.assert_array_equal(f, ref[T][2])
+
+
 def test_full_size_properties_c2(cuda_lib, rt):
     """BASELINE C2 at full size (1e6 draws x 50 timepoints): size-independent properties.
     simple_pk is linear: mass only leaves through clearance, so 0 <= y_gut+y_cent+y_peri <= 1 and y_gut is

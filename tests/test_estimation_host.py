@@ -287,3 +287,48 @@ def test_native_sampler_bookkeeping_matches_numpy():
     rb = smp.sample(evaluate, x0, lb, np.full(dim, 1e8), n_samples=50, cov0=cov0, native=True)
     np.testing.assert_array_equal(ra.acceptance_rate, rb.acceptance_rate)
     np.testing.assert_allclose(rb.trace_x, ra.trace_x, rtol=1e-6, atol=1e-6)
+
+
+def test_covariance_regularisation_and_sampler_abi_errors():
+    """_regularize: symmetric output, eigenvalues >= max(reg, 1e-12 lambda_max), good matrices untouched; the batched
+    Cholesky test agrees with the eigenvalues.  pv_sampler_propose: proposals outside the box are flagged and replaced
+    by the current point in x_eval, a covariance that is not positive definite is counted and proposes x itself;
+    argument errors come back as negative codes with a message."""
+    smp = pkg("optimization.sampler")
+    rt = pkg("runtime")
+    rs = np.random.RandomState(3)
+    A = rs.normal(size=(30, 4, 5, 5))
+    S = A @ np.swapaxes(A, -1, -2)
+    S[3, 1] = np.diag([1, 1, 0, 1, 1.0])
+    S[7, 2] = -np.eye(5)
+    S[9, 0] = 1e15 * np.ones((5, 5))
+    ok = smp._positive_definite(S)
+    np.testing.assert_array_equal(ok, np.linalg.eigvalsh(S).min(axis=-1) > 0)
+    R = smp._regularize(S.copy(), 1e-6)
+    np.testing.assert_allclose(R, np.swapaxes(R, -1, -2), rtol=1e-12, atol=0)     # symmetric up to round-off
+    w = np.linalg.eigvalsh(R)
+    assert np.all(w[..., 0] >= np.maximum(1e-6, 1e-12 * w[..., -1]) * (1 - 1e-3))
+    np.testing.assert_array_equal(R[ok], (0.5 * (S + np.swapaxes(S, -1, -2)))[ok])
+
+    lib = rt.load_library()
+    Q, C, dim = 2, 2, 3
+    x = np.full((Q, C, dim), 0.5)
+    cov = np.broadcast_to(np.eye(dim), (Q, C, dim, dim)).copy()
+    cov[1, 1] = -np.eye(dim)                                            # not positive definite
+    xi = np.zeros((Q, C, dim))
+    xi[0, 0] = [-1.0, 0.0, 0.0]                                         # x_new = (-0.5, .5, .5): below lb
+    xi[0, 1] = [0.25, 0.5, -0.25]
+    lb, ub = np.zeros(dim), np.ones(dim)
+    x_new, x_eval, inside = np.empty_like(x), np.empty_like(x), np.empty((Q, C), np.uint8)
+    p = lambda a: a.ctypes.data
+    bad = lib.pv_sampler_propose(Q, C, dim, p(cov), p(x), p(xi), p(lb), p(ub), p(x_new), p(inside), p(x_eval))
+    assert bad == 1
+    np.testing.assert_array_equal(inside, [[0, 1], [1, 1]])
+    np.testing.assert_allclose(x_new[0, 0], [-0.5, 0.5, 0.5])
+    np.testing.assert_allclose(x_eval[0, 0], x[0, 0])                   # outside: the objective is asked for x
+    np.testing.assert_allclose(x_eval[0, 1], [0.75, 1.0, 0.25])
+    np.testing.assert_allclose(x_new[1, 1], x[1, 1])                    # failed Cholesky: proposal = x
+    assert lib.pv_sampler_propose(Q, C, 17, p(cov), p(x), p(xi), p(lb), p(ub), p(x_new), p(inside), p(x_eval)) < 0
+    assert "dim" in rt.last_error()
+    assert lib.pv_sampler_propose(Q, C, dim, None, p(x), p(xi), p(lb), p(ub), p(x_new), p(inside), p(x_eval)) < 0
+    assert "pv_sampler_propose" in rt.last_error()

@@ -3,7 +3,8 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import
 this file.  The product (``parameter-variability_b200``) never does and has no CPU fallback.
 
-PARITY UNPINNED.  The arithmetic of the reference's path lives in two third-party native
+PARITY UNPINNED FOR THE ODE ROWS (the sampling / noise rows below are pinned by the reference's own code).
+The arithmetic of the reference's path lives in two third-party native
 libraries that are absent from /root/reference and cannot be installed here (no network):
   * libroadrunner 2.9.2 (uv.lock:961-962)  - forward simulation, SUNDIALS CVODE (BDF, Newton,
     dense LU), called at src/parvar/experiments/petab_factory.py:185-189, 229-246;
@@ -22,6 +23,10 @@ against.  What this oracle is anchored on instead:
     rtol 1e-12) - checked in tests/test_oracle.py;
   * numpy's frozen legacy MT19937 stream for the sampling / noise call sites
     (petab_factory.py:101-121, 192-219), which is bit-reproducible.
+PINNED: lognorm_par_transform, create_samples_parameters and add_noise are plain numpy / pandas in the reference;
+tools/make_golden_reference.py executes those three definitions out of the reference file's syntax tree and commits
+their outputs (tests/golden/reference_sampling_noise.npz); tests/test_golden.py holds this file's restatements (and
+the product's host mirror) to them bit for bit.
 
 Every function cites the reference lines it follows.
 """

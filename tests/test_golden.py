@@ -137,3 +137,64 @@ def test_cuda_reproduces_golden_chain_and_icg(cuda_lib, rt):
     assert nf == 0
     np.testing.assert_allclose(lp, g["logp"], rtol=1e-6)
     np.testing.assert_allclose(gr[:, :4], g["grad"], rtol=1e-5)
+
+
+# ---- vectors produced by the reference's own code (tools/make_golden_reference.py: the pure numpy / pandas functions of
+# src/parvar/experiments/petab_factory.py executed out of its syntax tree) ---------------------------------------------
+REF_FACTORIES = {
+    "simple_chain": {"MALE": {"k1": (1.0, 1)}, "FEMALE": {"k1": (2.0, 1)}},
+    "simple_pk": {"MALE": {"k_abs": (0.5, 1), "CL": (1.0, 1)}, "FEMALE": {"k_abs": (1.0, 1), "CL": (0.5, 1)}},
+    "icg_body_flat": {"MALE": {"BW": (75.0, 10), "LI__ICGIM_Vmax": (0.0369598840327503, 0.01)},
+                      "FEMALE": {"BW": (65.0, 10), "LI__ICGIM_Vmax": (0.02947, 0.01)}},
+}
+
+
+def test_oracle_sampling_and_noise_match_the_reference_code(oracle):
+    """Rows a1 / a4 of SURVEY.md section 8a are pinned by the reference itself: lognorm_par_transform (:94-98),
+    create_samples_parameters (:101-121, with the loc / scale swap and the global seed) and add_noise (:192-219, with the
+    per-individual reseeding) of the oracle reproduce the outputs of the reference's functions bit for bit."""
+    g = np.load(G / "reference_sampling_noise.npz")
+    for (a, b), want in zip(g["lpt_in"], g["lpt_out"]):
+        np.testing.assert_array_equal(np.array(oracle.lognorm_par_transform(a, b)), want)
+    for model, groups in REF_FACTORIES.items():
+        for n in (7, 160):
+            s = oracle.create_samples_parameters({grp: {p: (n, sc, lo) for p, (lo, sc) in d.items()} for grp, d in groups.items()})
+            for grp, d in groups.items():
+                for p in d:
+                    np.testing.assert_array_equal(s[grp][p], g[f"samples/{model}/{n}/{grp}/{p}"])
+    s = oracle.create_samples_parameters({grp: {p: (5, sc, lo) for p, (lo, sc) in d.items()}
+                                          for grp, d in REF_FACTORIES["simple_pk"].items()}, seed=99)
+    np.testing.assert_array_equal(s["MALE"]["CL"], g["samples_seed99/simple_pk/MALE/CL"])
+    table = g["noise_in"]
+    np.testing.assert_array_equal(oracle.add_noise(table[:, 1:], 0.1, seed=17), g["noise_seed17_cv0.1"][:, 1:])
+    oracle.create_samples_parameters({grp: {p: (3, sc, lo) for p, (lo, sc) in d.items()}
+                                      for grp, d in REF_FACTORIES["simple_pk"].items()})
+    for k in range(4):
+        np.testing.assert_array_equal(oracle.add_noise(table[:, 1:], 0.05), g["noise_sequence_cv0.05"][k][:, 1:])
+
+
+def test_host_mirror_sampling_and_noise_match_the_reference_code():
+    """The product's host mirror (experiments/petab_factory.py) against the same reference-generated vectors."""
+    import pandas as pd
+    pf = pkg("experiments.petab_factory")
+    g = np.load(G / "reference_sampling_noise.npz")
+    L = pf.LognormParameters
+    for (a, b), want in zip(g["lpt_in"], g["lpt_out"]):
+        np.testing.assert_array_equal(np.array(pf.lognorm_par_transform(a, b)), want)
+    for model, groups in REF_FACTORIES.items():
+        for n in (7, 160):
+            s = pf.create_samples_parameters({grp: {p: L(n=n, sigma=sc, mu=lo) for p, (lo, sc) in d.items()}
+                                              for grp, d in groups.items()})
+            for grp, d in groups.items():
+                for p in d:
+                    np.testing.assert_array_equal(s[grp][p], g[f"samples/{model}/{n}/{grp}/{p}"])
+    table = g["noise_in"]
+    cols = ["time", "[y_cent]", "[y_gut]", "[y_peri]"]
+    df = pd.DataFrame(table, columns=cols).set_index("time")
+    noisy = pf.ODESampleSimulator.add_noise(df, 0.1, seed=17)
+    np.testing.assert_array_equal(noisy.reset_index().to_numpy(), g["noise_seed17_cv0.1"])
+    pf.create_samples_parameters({grp: {p: L(n=3, sigma=sc, mu=lo) for p, (lo, sc) in d.items()}
+                                  for grp, d in REF_FACTORIES["simple_pk"].items()})
+    for k in range(4):
+        noisy = pf.ODESampleSimulator.add_noise(pd.DataFrame(table, columns=cols).set_index("time"), 0.05)
+        np.testing.assert_array_equal(noisy.reset_index().to_numpy(), g["noise_sequence_cv0.05"][k])

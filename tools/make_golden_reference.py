@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Golden vectors produced by the REFERENCE'S OWN CODE for the rows of the hot path that are plain numpy / pandas.
+
+`src/parvar/experiments/petab_factory.py` cannot be imported here (it imports roadrunner, xarray, pymetadata ... at module
+level, none installed), but three of its functions on the path do not touch any of that:
+
+    lognorm_par_transform          :94-98     
+    create_samples_parameters      :101-121   (row a1; includes the loc / scale swap, quirk Q1, and the global seed, Q2)
+    ODESampleSimulator.add_noise   :192-219   (row a4; reseeds the global generator per individual, quirks Q2 / Q3)
+
+This script reads the reference file, takes exactly those definitions (and the LognormParameters dataclass, :71-77) out
+of its syntax tree, executes them unmodified, and stores their inputs and outputs in tests/golden/reference_sampling_noise.npz.
+tests/test_golden.py then holds the oracle's restatement AND the product's host mirror to these vectors bit for bit - these
+rows are pinned by the reference itself, not by the oracle.  (The ODE rows a3 / a5-a9 stay unpinned: their arithmetic is
+libroadrunner's and AMICI's.)
+
+Runs in the build container only (/root/reference does not exist on the GPU box); the .npz is committed.
+
+usage: python tools/make_golden_reference.py [/root/reference]
+"""
+import ast
+import sys
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+import pandas as pd
+
+ROOT = Path(__file__).resolve().parent.parent
+OUT = ROOT / "tests" / "golden" / "reference_sampling_noise.npz"
+
+
+def load_reference_functions(ref_root: Path) -> dict:
+    src_file = ref_root / "src" / "parvar" / "experiments" / "petab_factory.py"
+    tree = ast.parse(src_file.read_text())
+    wanted: list[ast.stmt] = []
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("lognorm_par_transform", "create_samples_parameters"):
+            wanted.append(node)
+        elif isinstance(node, ast.ClassDef) and node.name == "LognormParameters":
+            wanted.append(node)
+        elif isinstance(node, ast.ClassDef) and node.name == "ODESampleSimulator":
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and sub.name == "add_noise":
+                    sub.decorator_list = []          # a plain function here; the body is untouched
+                    wanted.append(sub)
+    names = sorted(n.name for n in wanted)
+    assert names == ["LognormParameters", "add_noise", "create_samples_parameters", "lognorm_par_transform"], names
+    # names the definitions refer to in annotations / at run time; the enums are only dictionary keys and type hints
+    ns = {"np": np, "pd": pd, "dataclass": dataclass, "Optional": Optional, "Category": str, "PKPDParameters": str,
+          "DistributionType": str}
+    module = ast.Module(body=wanted, type_ignores=[])
+    exec(compile(module, str(src_file), "exec"), ns)
+    return ns
+
+
+# sampling definitions of the three reference factories: (group, parameter) -> (loc, scale) of `pars_true`
+FACTORIES = {
+    "simple_chain": {"MALE": {"k1": (1.0, 1)}, "FEMALE": {"k1": (2.0, 1)}},                               # factories/simple_chain.py:12-25
+    "simple_pk": {"MALE": {"k_abs": (0.5, 1), "CL": (1.0, 1)}, "FEMALE": {"k_abs": (1.0, 1), "CL": (0.5, 1)}},   # simple_pk.py:19-44
+    "icg_body_flat": {"MALE": {"BW": (75.0, 10), "LI__ICGIM_Vmax": (0.0369598840327503, 0.01)},             # icg_body_flat.py:23-49
+                      "FEMALE": {"BW": (65.0, 10), "LI__ICGIM_Vmax": (0.02947, 0.01)}},
+}
+
+
+def main():
+    ref_root = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    ref = load_reference_functions(ref_root)
+    L = ref["LognormParameters"]
+    out: dict[str, np.ndarray] = {}
+
+    # ---- lognorm_par_transform -------------------------------------------------------------------------------------------
+    pairs = np.array([(1.0, 1.0), (0.5, 1.0), (1.0, 0.5), (75.0, 10.0), (10.0, 75.0), (0.0369598840327503, 0.01), (2.0, 3.0)])
+    out["lpt_in"] = pairs
+    out["lpt_out"] = np.array([ref["lognorm_par_transform"](a, b) for a, b in pairs])
+
+    # ---- create_samples_parameters: every factory at n = 7 and n = 160 (the largest sweep value), default seed; and one
+    # call with another seed.  LognormParameters(mu=loc, sigma=scale, n=...) as the reference builds them (:567-571) ----------
+    for model, groups in FACTORIES.items():
+        for n in (7, 160):
+            pars = {g: {p: L(n=n, sigma=sc, mu=lo) for p, (lo, sc) in d.items()} for g, d in groups.items()}
+            s = ref["create_samples_parameters"](pars)
+            for g, d in s.items():
+                for p, v in d.items():
+                    out[f"samples/{model}/{n}/{g}/{p}"] = np.asarray(v)
+    pars = {g: {p: L(n=5, sigma=sc, mu=lo) for p, (lo, sc) in d.items()} for g, d in FACTORIES["simple_pk"].items()}
+    s = ref["create_samples_parameters"](pars, seed=99)
+    out["samples_seed99/simple_pk/MALE/CL"] = np.asarray(s["MALE"]["CL"])
+
+    # ---- add_noise: a small trajectory table, explicit seed; then the reference's per-individual pattern - the global stream
+    # left behind by create_samples_parameters decides the seeds (seed=None -> np.random.randint(0, 2001)) --------------------
+    t = np.linspace(0.0, 100.0, 6)
+    table = pd.DataFrame({"time": t, "[y_cent]": np.exp(-0.1 * t) * 0.3, "[y_gut]": np.exp(-t), "[y_peri]": 0.1 * t * np.exp(-0.05 * t)})
+    out["noise_in"] = table.to_numpy()
+    noisy = ref["add_noise"](table.set_index("time"), 0.1, "normal", seed=17)
+    out["noise_seed17_cv0.1"] = noisy.reset_index().to_numpy()
+    pars = {g: {p: L(n=3, sigma=sc, mu=lo) for p, (lo, sc) in d.items()} for g, d in FACTORIES["simple_pk"].items()}
+    ref["create_samples_parameters"](pars)                       # seeds the global generator (1234) and draws
+    seq = []
+    for _ in range(4):                                           # four individuals, cv = 0.05 (factories/simple_pk.py:108)
+        seq.append(ref["add_noise"](table.set_index("time"), 0.05, "normal").reset_index().to_numpy())
+    out["noise_sequence_cv0.05"] = np.stack(seq)
+
+    np.savez_compressed(OUT, **out)
+    print(f"wrote {OUT} ({len(out)} arrays) from {ref_root}")
+
+
+if __name__ == "__main__":
+    main()

@@ -48,7 +48,8 @@ def read_petab_tables(yaml_path: str | Path) -> PetabTables:
     prob = cfg["problems"][0]
 
     def tsv(rel):
-        return pd.read_csv(base / rel, sep="\t")
+        # round_trip: pandas' default float parser is off by a few ulp; the reference writes repr() floats, read them exactly
+        return pd.read_csv(base / rel, sep="\t", float_precision="round_trip")
 
     return PetabTables(
         yaml_path=yaml_path,

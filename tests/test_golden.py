@@ -198,3 +198,55 @@ def test_host_mirror_sampling_and_noise_match_the_reference_code():
     for k in range(4):
         noisy = pf.ODESampleSimulator.add_noise(pd.DataFrame(table, columns=cols).set_index("time"), 0.05)
         np.testing.assert_array_equal(noisy.reset_index().to_numpy(), g["noise_sequence_cv0.05"][k])
+
+
+def _petab_fixture_data():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_reference", G.parent.parent / "tools" / "make_golden_reference.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.petab_fixture_data()
+
+
+def test_petab_reader_and_writer_against_reference_written_directory(tmp_path, monkeypatch):
+    """tests/golden/petab_reference_simple_pk/ was written by the reference's own create_petab_example
+    (petab_factory.py:320-517, executed by tools/make_golden_reference.py with the product's SimDataset as its data set).
+    The product's reader must turn it back into exactly the data it was written from - parameters, groups, individuals,
+    time grid, observables, priors, bounds, and the literal-mode species overrides (quirk Q4) - and the product's own
+    writer must produce the same files byte for byte."""
+    import shutil
+    io = pkg("optimization.petab_io")
+    P = pkg()
+    t, species, data, priors = _petab_fixture_data()
+    xp = tmp_path / "refuid"
+    shutil.copytree(G / "petab_reference_simple_pk", xp)
+    shutil.copy(P.MODELS["simple_pk"], xp / "petab" / "simple_pk.xml")      # the writer copies the model next to the tables
+    seen = {}
+
+    class ObjectiveStub:                      # PetabObjective's constructor needs a GPU; the reader's output is its arguments
+        def __init__(self, model, pars, groups, times, spec_, **kw):
+            seen.update(model=model, pars=list(pars), groups=groups, times=np.asarray(times), species=list(spec_), kw=kw, set=[])
+            self.x_names = [f"{p}_{g.id}" for p in pars for g in groups]
+            self.problem = type("PB", (), {"set_value": lambda _s, k, v: seen["set"].append((k, v))})()
+
+    monkeypatch.setattr(io, "PetabObjective", ObjectiveStub)
+    obj = io.load_petab_problem(xp / "petab.yaml", mode="literal")
+    assert seen["model"] == "simple_pk" and seen["pars"] == ["k_abs", "CL"] and seen["species"] == species
+    np.testing.assert_array_equal(seen["times"], t)
+    assert [g.id for g in seen["groups"]] == ["MALE", "FEMALE"]
+    for g in seen["groups"]:
+        np.testing.assert_array_equal(g.y, data[g.id])                      # [individual, time, observable], bit for bit
+    assert seen["kw"]["priors"] == priors
+    np.testing.assert_array_equal(seen["kw"]["sigma"], [1.0, 1.0, 1.0])     # noiseFormula = 1 (quirk Q5)
+    assert sorted(seen["set"]) == [("y_cent", 0.0), ("y_gut", 0.0), ("y_peri", 0.0)]     # quirk Q4, literal mode
+    assert obj.x_names == ["k_abs_MALE", "k_abs_FEMALE", "CL_MALE", "CL_FEMALE"]
+    np.testing.assert_array_equal(obj.lb, np.zeros(4))
+    np.testing.assert_array_equal(obj.ub, np.full(4, 1e8))
+    np.testing.assert_array_equal(obj.x_nominal, np.ones(4))
+
+    mine = tmp_path / "mine"
+    groups = [io.GroupData("MALE", data["MALE"]), io.GroupData("FEMALE", data["FEMALE"])]
+    io.write_petab_like_reference(mine, P.MODELS["simple_pk"], groups, t, species, ["k_abs", "CL"], priors)
+    for rel in ("petab.yaml", "petab/measurements_simple_pk.tsv", "petab/conditions_simple_pk.tsv",
+                "petab/parameters_simple_pk.tsv", "petab/observables_simple_pk.tsv"):
+        assert (mine / rel).read_bytes() == (G / "petab_reference_simple_pk" / rel).read_bytes(), rel

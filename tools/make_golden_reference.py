@@ -14,12 +14,22 @@ tests/test_golden.py then holds the oracle's restatement AND the product's host 
 rows are pinned by the reference itself, not by the oracle.  (The ODE rows a3 / a5-a9 stay unpinned: their arithmetic is
 libroadrunner's and AMICI's.)
 
-Runs in the build container only (/root/reference does not exist on the GPU box); the .npz is committed.
+A second fixture pins the on-disk format either side of the path: the reference's PEtab
+writer `create_petab_example` (:320-517) is plain pandas / yaml too.  It is executed the same way on a small data set
+(2 groups x 3 individuals x 4 time points x 3 observables; the product's xarray-free `SimDataset` stands in for the
+xr.Dataset argument, it offers the four members the writer touches) and the directory it writes is committed as
+tests/golden/petab_reference_simple_pk/ (without the SBML file it copies).  tests/test_golden.py checks that the
+product's reader parses it and that the product's own writer produces the same tables.
+
+Runs in the build container only (/root/reference does not exist on the GPU box); the fixtures are committed.
 
 usage: python tools/make_golden_reference.py [/root/reference]
 """
 import ast
+import importlib
+import shutil
 import sys
+import tempfile
 from dataclasses import dataclass
 from pathlib import Path
 from typing import Optional
@@ -64,8 +74,70 @@ FACTORIES = {
 }
 
 
+def petab_fixture_data():
+    """The small data set of the PEtab fixture: deterministic numbers, no simulator involved."""
+    t = np.array([0.0, 10.0, 50.0, 100.0])
+    species = ["y_cent", "y_gut", "y_peri"]
+    data = {}
+    for gi, grp in enumerate(("MALE", "FEMALE")):
+        y = np.empty((3, len(t), len(species)))
+        for i in range(3):
+            for k in range(len(species)):
+                y[i, :, k] = (0.1 + 0.05 * k + 0.01 * i + 0.2 * gi) * np.exp(-(0.01 + 0.005 * k) * t) * (1 + 0.03 * ((i + k) % 3))
+        data[grp] = y
+    priors = {"k_abs_MALE": (0.5, 1.0), "k_abs_FEMALE": (1.0, 1.0), "CL_MALE": (1.0, 1.0), "CL_FEMALE": (0.5, 1.0)}
+    return t, species, data, priors
+
+
+def write_petab_with_reference_code(ref_root: Path, out_dir: Path) -> None:
+    sys.path.insert(0, str(ROOT))
+    ds = importlib.import_module("parameter-variability_b200.experiments.dataset")
+    pkg = importlib.import_module("parameter-variability_b200")
+    src_file = ref_root / "src" / "parvar" / "experiments" / "petab_factory.py"
+    tree = ast.parse(src_file.read_text())
+    wanted = [n for n in tree.body
+              if (isinstance(n, ast.FunctionDef) and n.name == "create_petab_example")
+              or (isinstance(n, ast.ClassDef) and n.name == "Category")
+              or (isinstance(n, ast.Assign) and any(isinstance(tg, ast.Name) and tg.id in ("MEASUREMENT_UNIT_COLUMN", "MEASUREMENT_TIME_UNIT_COLUMN")
+                                                    for tg in n.targets))]
+    assert len(wanted) == 4, [getattr(n, "name", "assign") for n in wanted]
+    import enum
+    import typing
+    import yaml
+    ns = {"np": np, "pd": pd, "yaml": yaml, "shutil": shutil, "Path": Path, "Enum": enum.Enum, "Optional": Optional,
+          "Union": typing.Union, "xr": type("xr", (), {"Dataset": object}), "Group": object}
+    exec(compile(ast.Module(body=wanted, type_ignores=[]), str(src_file), "exec"), ns)
+    Category = ns["Category"]
+    t, species, data, priors = petab_fixture_data()
+
+    class Estimation:                      # the two members of parvar.experiments.experiment.Group the writer uses (:439-444)
+        parameters = True
+
+    class GroupStub:
+        estimation = Estimation()
+
+        def __init__(self, gid):
+            self.gid = gid
+
+        def get_parameter(self, kind, par, key):
+            assert kind == "estimation"
+            return priors[f"{par}_{self.gid}"][0 if key == "loc" else 1]
+
+    dfs = {Category[g]: ds.SimDataset(t, {f"[{sp}]": y[:, :, k] for k, sp in enumerate(species)}) for g, y in data.items()}
+    with tempfile.TemporaryDirectory() as tmp:
+        xp = Path(tmp) / "refuid"
+        ns["create_petab_example"](dfs, [GroupStub("MALE"), GroupStub("FEMALE")], xp / "petab", ["k_abs", "CL"],
+                                   Path(pkg.MODELS["simple_pk"]))
+        (xp / "petab" / Path(pkg.MODELS["simple_pk"]).name).unlink()        # the copied model is not part of the fixture
+        if out_dir.exists():
+            shutil.rmtree(out_dir)
+        shutil.copytree(xp, out_dir)
+    print(f"wrote {out_dir} with the reference's create_petab_example")
+
+
 def main():
     ref_root = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    write_petab_with_reference_code(ref_root, ROOT / "tests" / "golden" / "petab_reference_simple_pk")
     ref = load_reference_functions(ref_root)
     L = ref["LognormParameters"]
     out: dict[str, np.ndarray] = {}

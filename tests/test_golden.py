@@ -143,7 +143,7 @@ def test_cuda_reproduces_golden_chain_and_icg(cuda_lib, rt):
 # src/parvar/experiments/petab_factory.py executed out of its syntax tree) ---------------------------------------------
 REF_FACTORIES = {
     "simple_chain": {"MALE": {"k1": (1.0, 1)}, "FEMALE": {"k1": (2.0, 1)}},
-    "simple_pk": {"MALE": {"k_abs": (0.5, 1), "CL": (1.0, 1)}, "FEMALE": {"k_abs": (1.0, 1), "CL": (0.5, 1)}},
+    "simple_pk": {"MALE": {"CL": (1.0, 1), "k_abs": (0.5, 1)}, "FEMALE": {"CL": (0.5, 1), "k_abs": (1.0, 1)}},
     "icg_body_flat": {"MALE": {"BW": (75.0, 10), "LI__ICGIM_Vmax": (0.0369598840327503, 0.01)},
                       "FEMALE": {"BW": (65.0, 10), "LI__ICGIM_Vmax": (0.02947, 0.01)}},
 }
@@ -250,3 +250,41 @@ def test_petab_reader_and_writer_against_reference_written_directory(tmp_path, m
     for rel in ("petab.yaml", "petab/measurements_simple_pk.tsv", "petab/conditions_simple_pk.tsv",
                 "petab/parameters_simple_pk.tsv", "petab/observables_simple_pk.tsv"):
         assert (mine / rel).read_bytes() == (G / "petab_reference_simple_pk" / rel).read_bytes(), rel
+
+
+def test_study_definitions_match_the_reference_factories():
+    """tests/golden/reference_study_definitions.json is a dump of the objects the reference's own experiment.py and
+    factories/*.py build (tools/make_golden_reference.py executes those modules).  The study driver's transcription of them
+    (tools/run_study.py: sweep grid, sampling and prior distributions, parameter order, observables, dose) and the sampling
+    definitions used by the fixtures above must say the same."""
+    import importlib.util
+    import json
+    ref = json.loads((G / "reference_study_definitions.json").read_text())
+    spec = importlib.util.spec_from_file_location("run_study", G.parent.parent / "tools" / "run_study.py")
+    rs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rs)
+    assert rs.DEFINITIONS_ALL == ref["definitions_all"]
+    assert len(ref["definitions_all"]["prior_types"]) * len(ref["definitions_all"]["samples"]) * \
+        len(ref["definitions_all"]["timepoints"]) * len(ref["definitions_all"]["noise_cvs"]) == 2160
+
+    def ls(p):
+        return (p["distribution"]["parameters"]["loc"], p["distribution"]["parameters"]["scale"])
+
+    for model, mine in rs.MODELS.items():
+        r = ref[model]
+        xb = r["exp_base"]
+        assert xb["model"] == model
+        assert (xb["dosage"] or None) == mine["dosage"]
+        assert [g["id"] for g in xb["groups"]] == list(mine["sampling"])
+        for g in xb["groups"]:
+            smp = g["sampling"]
+            assert list(mine["sampling"][g["id"]].items()) == [(p["id"], ls(p)) for p in smp["parameters"]]     # draw order
+            assert list(REF_FACTORIES[model][g["id"]].items()) == [(p["id"], ls(p)) for p in smp["parameters"]]
+            assert [o["id"] for o in smp["observables"]] == mine["observables"]
+            assert smp["tend"] == 100.0 and smp["noise"]["type"] == "normal"                                    # quirks Q3, Q8
+            assert [p["id"] for p in g["estimation"]["parameters"]] == mine["params"]
+            for p in mine["params"]:
+                key = f"{p}_{g['id']}" if f"{p}_{g['id']}" in r["pars_true"] else g["id"]     # simple_chain keys by group only
+                assert mine["priors"]["exact_prior"][g["id"]][p] == ls(r["pars_true"][key])
+                for kind in ("prior_biased", "prior_incorrect"):
+                    assert mine["priors"][kind][g["id"]][p] == ls(r["pars_biased"][kind][key])

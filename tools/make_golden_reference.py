@@ -68,7 +68,7 @@ def load_reference_functions(ref_root: Path) -> dict:
 # sampling definitions of the three reference factories: (group, parameter) -> (loc, scale) of `pars_true`
 FACTORIES = {
     "simple_chain": {"MALE": {"k1": (1.0, 1)}, "FEMALE": {"k1": (2.0, 1)}},                               # factories/simple_chain.py:12-25
-    "simple_pk": {"MALE": {"k_abs": (0.5, 1), "CL": (1.0, 1)}, "FEMALE": {"k_abs": (1.0, 1), "CL": (0.5, 1)}},   # simple_pk.py:19-44
+    "simple_pk": {"MALE": {"CL": (1.0, 1), "k_abs": (0.5, 1)}, "FEMALE": {"CL": (0.5, 1), "k_abs": (1.0, 1)}},   # simple_pk.py:19-44, order :100-121
     "icg_body_flat": {"MALE": {"BW": (75.0, 10), "LI__ICGIM_Vmax": (0.0369598840327503, 0.01)},             # icg_body_flat.py:23-49
                       "FEMALE": {"BW": (65.0, 10), "LI__ICGIM_Vmax": (0.02947, 0.01)}},
 }
@@ -135,8 +135,59 @@ def write_petab_with_reference_code(ref_root: Path, out_dir: Path) -> None:
     print(f"wrote {out_dir} with the reference's create_petab_example")
 
 
+def study_definitions(ref_root: Path, out_file: Path) -> None:
+    """The sweep grid (factories/__init__.py:12-20) and the three factories' experiment definitions - sampling and prior
+    distributions, sample counts, steps, noise, observables, parameter order - as the reference's own modules build them.
+    experiment.py (pydantic models) and factories/*.py are executed unmodified; only the two missing I/O dependencies of
+    experiment.py (pydantic_yaml, pymetadata.console - YAML round trip and printing) are stubbed, and `parvar/__init__.py`
+    (which creates result directories at import) is bypassed."""
+    import json
+    import types
+    saved = dict(sys.modules)
+    try:
+        for name in ("parvar", "parvar.experiments"):
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+        py = types.ModuleType("pydantic_yaml")
+        py.parse_yaml_raw_as = py.to_yaml_str = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stub"))
+        sys.modules["pydantic_yaml"] = py
+        pm, pmc = types.ModuleType("pymetadata"), types.ModuleType("pymetadata.console")
+        pmc.console = types.SimpleNamespace(print=lambda *a, **k: None, rule=lambda *a, **k: None)
+        pm.console = pmc
+        sys.modules["pymetadata"], sys.modules["pymetadata.console"] = pm, pmc
+        base = ref_root / "src" / "parvar" / "experiments"
+        xm = types.ModuleType("parvar.experiments.experiment")
+        xm.__file__ = str(base / "experiment.py")
+        sys.modules["parvar.experiments.experiment"] = xm
+        exec(compile((base / "experiment.py").read_text(), xm.__file__, "exec"), xm.__dict__)
+        for cls in list(vars(xm).values()):                      # `from __future__ import annotations`: resolve forward refs
+            if isinstance(cls, type) and cls.__module__ == xm.__name__ and hasattr(cls, "model_rebuild"):
+                cls.model_rebuild(_types_namespace=vars(xm))
+        out = {}
+        ns: dict = {}
+        exec(compile((base / "factories" / "__init__.py").read_text(), "factories/__init__.py", "exec"), ns)
+        out["definitions_all"] = ns["definitions_all"]["all"]
+        out["definitions_minimal"] = ns["definitions_minimal"]
+        for model in ("simple_chain", "simple_pk", "icg_body_flat"):
+            ns = {}
+            f = base / "factories" / f"{model}.py"
+            exec(compile(f.read_text(), str(f), "exec"), ns)
+            fd = ns["factory_data"]
+            dump = lambda pars: {k: v.model_dump(mode="json") for k, v in pars.items()}
+            out[model] = {"exp_base": fd["exp_base"].model_dump(mode="json"), "pars_true": dump(fd["pars_true"]),
+                          "pars_biased": {k: dump(v) for k, v in fd["pars_biased"].items()}}
+    finally:
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
+    out_file.write_text(json.dumps(out, indent=1, sort_keys=True) + "\n")
+    print(f"wrote {out_file} from the reference's experiment.py and factories/")
+
+
 def main():
     ref_root = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    study_definitions(ref_root, ROOT / "tests" / "golden" / "reference_study_definitions.json")
     write_petab_with_reference_code(ref_root, ROOT / "tests" / "golden" / "petab_reference_simple_pk")
     ref = load_reference_functions(ref_root)
     L = ref["LognormParameters"]

@@ -185,8 +185,122 @@ def study_definitions(ref_root: Path, out_file: Path) -> None:
     print(f"wrote {out_file} from the reference's experiment.py and factories/")
 
 
+def workflow_fixture(ref_root: Path, out_file: Path) -> None:
+    """The reference's whole data-generation workflow - `create_petab_for_experiment` (:548-621) with the real
+    `ODESampleSimulator.simulate_samples` (:221-272), `create_samples_parameters`, `add_noise`, `create_petab_example` - run
+    from the reference's own module source for a small simple_pk experiment (its factory's `exp_base` with 4 individuals per
+    group, 5 time points, cv 0.1).  Only the ODE solve is not the reference's: `roadrunner.RoadRunner` is a stand-in that
+    answers `simulate()` with the oracle's exact solution (matrix exponential); xarray is a stand-in that builds the
+    product's `SimDataset`; plotting is switched off.  What the fixture pins is everything AROUND the solve: which random
+    numbers are drawn in which order (one global legacy stream: seed 1234, log-normal draws per group and parameter, then per
+    individual randint -> reseed -> normal), dose / parameter hand-over to the simulator, bracketed observable ids, the
+    start / end / steps -> time grid convention, and the table assembly."""
+    import types
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import parvar_oracle as oracle
+    ds = importlib.import_module("parameter-variability_b200.experiments.dataset")
+    pkg = importlib.import_module("parameter-variability_b200")
+    captured: dict = {}
+
+    class FakeIntegrator:
+        def setSetting(self, key, value):
+            captured.setdefault("integrator", {})[key] = value
+
+    class SimResult(np.ndarray):            # roadrunner's NamedArray: a 2-D array with .colnames
+        colnames: list
+
+    class FakeRoadRunner:
+        def __init__(self, path):
+            assert Path(path).stem == "simple_pk"
+            self.integrator = FakeIntegrator()
+            self.values: dict = {}
+
+        def getIds(self):
+            return ["y_gut", "y_cent", "y_peri", "k_abs", "CL", "Q"]
+
+        def resetAll(self):
+            self.values = {}
+
+        def setValue(self, key, value):
+            self.values[key] = float(value)
+
+        def simulate(self, start, end, steps):
+            t = np.linspace(start, end, steps + 1)
+            y = oracle.simple_pk_exact(dict(self.values), t)
+            res = np.column_stack([t, y]).view(SimResult)
+            res.colnames = ["time"] + [f"[{sid}]" for sid in oracle.SIMPLE_PK.states]
+            return res
+
+    class Dataset(ds.SimDataset):
+        def to_netcdf(self, path):
+            captured.setdefault("dsets", {})[Path(path).stem] = self
+
+    def concat(frames, dim):
+        return Dataset(frames[0].index.to_numpy(), {c: np.stack([f[c].to_numpy() for f in frames]) for c in frames[0].columns},
+                       sim=np.asarray(dim))
+
+    saved = dict(sys.modules)
+    saved_to_xarray = pd.DataFrame.to_xarray
+    try:
+        def mod(name, **attrs):
+            m = types.ModuleType(name)
+            m.__path__ = []
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+            return m
+        mod("roadrunner", RoadRunner=FakeRoadRunner, Integrator=FakeIntegrator)
+        mod("xarray", Dataset=Dataset, concat=concat)
+        mpl = mod("matplotlib")
+        mpl.pyplot = mod("matplotlib.pyplot")
+        mod("pymetadata").console = mod("pymetadata.console", console=types.SimpleNamespace(print=lambda *a, **k: None,
+                                                                                           rule=lambda *a, **k: None))
+        mod("rich").progress = mod("rich.progress", track=lambda it, **k: it)
+        py = mod("pydantic_yaml")
+        py.parse_yaml_raw_as = py.to_yaml_str = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stub"))
+        mod("parvar", MODELS={"simple_pk": Path(pkg.MODELS["simple_pk"])})
+        mod("parvar.experiments")
+        base = ref_root / "src" / "parvar" / "experiments"
+        for name in ("utils", "experiment", "petab_factory"):
+            m = types.ModuleType(f"parvar.experiments.{name}")
+            m.__file__ = str(base / f"{name}.py")
+            sys.modules[m.__name__] = m
+            exec(compile((base / f"{name}.py").read_text(), m.__file__, "exec"), m.__dict__)
+        pfm = sys.modules["parvar.experiments.petab_factory"]
+        pfm.plot_samples = pfm.plot_simulations = lambda *a, **k: None
+        pd.DataFrame.to_xarray = lambda self: self           # consumed by the xarray stand-in's concat only
+        ns: dict = {}
+        f = base / "factories" / "simple_pk.py"
+        exec(compile(f.read_text(), str(f), "exec"), ns)
+        xp = ns["factory_data"]["exp_base"].model_copy(deep=True)
+        xp.id = "wf"
+        for g in xp.groups:
+            g.sampling.n_samples, g.sampling.steps, g.sampling.noise.cv = 4, 4, 0.1
+        with tempfile.TemporaryDirectory() as tmp:
+            yaml_file = pfm.create_petab_for_experiment(xp, Path(tmp), show_plot=False)
+            meas = pd.read_csv(Path(yaml_file).parent / "petab" / "measurements_simple_pk.tsv", sep="\t", float_precision="round_trip")
+    finally:
+        pd.DataFrame.to_xarray = saved_to_xarray
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
+    keys = list(captured["dsets"])
+    out = {"time": captured["dsets"][keys[0]]["time"].values, "groups": np.array(keys),
+           "abs_tol": captured["integrator"]["absolute_tolerance"], "rel_tol": captured["integrator"]["relative_tolerance"]}
+    for key, dset in captured["dsets"].items():
+        out[f"vars/{key}"] = np.array(list(dset.data_vars))
+        out[f"noisy/{key}"] = np.stack([dset.data_vars[v] for v in dset.data_vars], axis=2)       # [sim, time, observable]
+    out["measurement"] = meas["measurement"].to_numpy()
+    out["measurement_condition"] = meas["simulationConditionId"].to_numpy().astype(str)
+    out["measurement_observable"] = meas["observableId"].to_numpy().astype(str)
+    out["measurement_time"] = meas["time"].to_numpy()
+    np.savez_compressed(out_file, **out)
+    print(f"wrote {out_file} from the reference's create_petab_for_experiment (groups {keys})")
+
+
 def main():
     ref_root = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    workflow_fixture(ref_root, ROOT / "tests" / "golden" / "reference_workflow_simple_pk.npz")
     study_definitions(ref_root, ROOT / "tests" / "golden" / "reference_study_definitions.json")
     write_petab_with_reference_code(ref_root, ROOT / "tests" / "golden" / "petab_reference_simple_pk")
     ref = load_reference_functions(ref_root)

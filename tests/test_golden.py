@@ -388,3 +388,14 @@ def test_product_workflow_host_logic_reproduces_the_reference_workflow(oracle, t
     np.testing.assert_array_equal(meas["time"].to_numpy(), g["measurement_time"])
     assert list(meas["simulationConditionId"]) == [str(c) for c in g["measurement_condition"]]
     assert list(meas["observableId"]) == [str(c) for c in g["measurement_observable"]]
+
+
+def test_pid_helpers_match_the_reference_utils():
+    """get_group_from_pid / get_parameter_from_pid of the results writer (optimization/driver.py) against the outputs of the
+    reference's experiments/utils.py functions (tests/golden/reference_pid_helpers.json), edge cases included."""
+    import json
+    drv = pkg("optimization.driver")
+    ref = json.loads((G / "reference_pid_helpers.json").read_text())
+    for pid, grp, par in zip(ref["pids"], ref["group"], ref["parameter"]):
+        assert drv.get_group_from_pid(pid) == grp, pid
+        assert drv.get_parameter_from_pid(pid) == par, pid

@@ -298,8 +298,27 @@ def workflow_fixture(ref_root: Path, out_file: Path) -> None:
     print(f"wrote {out_file} from the reference's create_petab_for_experiment (groups {keys})")
 
 
+PIDS = ["k_abs_MALE", "CL_FEMALE", "LI__ICGIM_Vmax_MALE", "BW_OLD", "k1", "k1_", "_MALE", "a_b_c", "par_gr\u00fcn", "x__y", "",
+        "k_abs_MALE\n", "UPPER_lower_123"]
+
+
+def pid_helpers(ref_root: Path, out_file: Path) -> None:
+    """experiments/utils.py (importable as is): how a PEtab parameter id splits into (parameter, group) in the results table
+    (`get_parameter_from_pid`, `get_group_from_pid`, used at petab_optimization.py:254-262)."""
+    import json
+    ns: dict = {"__name__": "ref_utils"}
+    f = ref_root / "src" / "parvar" / "experiments" / "utils.py"
+    exec(compile(f.read_text(), str(f), "exec"), ns)
+    out = {"pids": PIDS, "group": [ns["get_group_from_pid"](p) for p in PIDS],
+           "parameter": [ns["get_parameter_from_pid"](p) for p in PIDS],
+           "uuid_lengths": {str(n): len(ns["uuid_alphanumeric"](n)) for n in (1, 20, 45)}}
+    out_file.write_text(json.dumps(out, indent=1) + "\n")
+    print(f"wrote {out_file} from the reference's experiments/utils.py")
+
+
 def main():
     ref_root = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    pid_helpers(ref_root, ROOT / "tests" / "golden" / "reference_pid_helpers.json")
     workflow_fixture(ref_root, ROOT / "tests" / "golden" / "reference_workflow_simple_pk.npz")
     study_definitions(ref_root, ROOT / "tests" / "golden" / "reference_study_definitions.json")
     write_petab_with_reference_code(ref_root, ROOT / "tests" / "golden" / "petab_reference_simple_pk")

@@ -399,3 +399,31 @@ def test_pid_helpers_match_the_reference_utils():
     for pid, grp, par in zip(ref["pids"], ref["group"], ref["parameter"]):
         assert drv.get_group_from_pid(pid) == grp, pid
         assert drv.get_parameter_from_pid(pid) == par, pid
+
+
+def test_results_files_are_what_the_reference_analysis_joined(tmp_path):
+    """tests/golden/analysis_reference_join/: results files written by the product (driver.write_reference_layout) and the
+    table the reference's own join_optimization_results (analysis/utils.py:28-98) made of them
+    (tools/make_golden_reference.py).  The product must still write exactly those files, and the joined table carries the
+    sampling distribution and the posterior summaries where the reference's plots look for them."""
+    import importlib.util
+    import pandas as pd
+    spec = importlib.util.spec_from_file_location("make_golden_reference", G.parent.parent / "tools" / "make_golden_reference.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    drv = pkg("optimization.driver")
+    xps, frames = mod.analysis_inputs()
+    base = drv.write_reference_layout(tmp_path, "all", xps, frames)
+    ref = G / "analysis_reference_join"
+    for rel in ["definitions.tsv"] + [f"optimization_results/uid{k}_results.tsv" for k in range(3)]:
+        assert (base / rel).read_bytes() == (ref / rel).read_bytes(), rel
+    joined = pd.read_csv(ref / "definitions_results.tsv", sep="\t")
+    assert len(joined) == 8 and set(joined["prior_type"]) == {"exact_prior", "prior_biased"}       # no_prior rows are dropped (:91)
+    for _, row in joined.iterrows():
+        xp = next(x for x in xps if x["id"] == row["id"])
+        loc, scale = xp["sampling"][row["group"]][row["parameter"]]
+        assert (row["sample_loc"], row["sample_scale"]) == (loc, scale)
+        src = frames[row["id"]]
+        src = src[(src["group"] == row["group"]) & (src["parameter"] == row["parameter"])].iloc[0]
+        assert row["bayes_sampler_mean"] == src["mean"] and row["bayes_sampler_median"] == src["median"]
+        assert row["ess"] == src["ess"] and row["hdi_low"] == src["hdi_low"] and row["hdi_high"] == src["hdi_high"]

@@ -316,8 +316,59 @@ def pid_helpers(ref_root: Path, out_file: Path) -> None:
     print(f"wrote {out_file} from the reference's experiments/utils.py")
 
 
+def analysis_inputs():
+    """Deterministic result frames in the product's results schema (driver.results_df) for three small experiments."""
+    xps = [{"id": f"uid{k}", "model": "simple_pk", "prior_type": ["exact_prior", "prior_biased", "no_prior"][k], "samples": 20,
+            "timepoints": 10 + k, "noise_cv": 0.05,
+            "sampling": {"MALE": {"CL": (1.0, 1.0), "k_abs": (0.5, 1.0)}, "FEMALE": {"CL": (0.5, 1.0), "k_abs": (1.0, 1.0)}}} for k in range(3)]
+    frames = {}
+    for k, xp in enumerate(xps):
+        rows = []
+        for j, pid in enumerate(("k_abs_MALE", "k_abs_FEMALE", "CL_MALE", "CL_FEMALE")):
+            grp = pid.rsplit("_", 1)[1]
+            rows.append({"id": xp["id"], "group": grp, "parameter": pid[: -len(grp) - 1], "pid": pid, "mean": 1.0 + 0.1 * j + k,
+                         "std": 0.1 + 0.01 * j, "median": 0.9 + 0.1 * j + k, "ess": 100.0 + j, "n_samples": 50,
+                         "optim_duration": 0.1 * (k + 1), "sampler_duration": 0.2, "values": (np.arange(8.0).reshape(2, 4) + j) / 7.0,
+                         "hdi_low": 0.8 + k, "hdi_high": 1.2 + k})
+        frames[xp["id"]] = pd.DataFrame(rows)
+    return xps, frames
+
+
+def analysis_fixture(ref_root: Path, out_dir: Path) -> None:
+    """The other end of the path: the results files.  The PRODUCT writes `definitions.tsv` + `<uid>_results.tsv`
+    (optimization/driver.py::write_reference_layout), and the reference's own `join_optimization_results`
+    (src/parvar/analysis/utils.py:28-98, executed from its source, console stubbed) reads and joins them.  The files that
+    went in and the table that came out are committed; the test checks that the product still writes exactly these files."""
+    import types
+    sys.path.insert(0, str(ROOT))
+    drv = importlib.import_module("parameter-variability_b200.optimization.driver")
+    saved = dict(sys.modules)
+    try:
+        pm, pmc = types.ModuleType("pymetadata"), types.ModuleType("pymetadata.console")
+        pmc.console = types.SimpleNamespace(print=lambda *a, **k: None, rule=lambda *a, **k: None)
+        sys.modules["pymetadata"], sys.modules["pymetadata.console"] = pm, pmc
+        ns: dict = {"__name__": "ref_analysis_utils"}
+        f = ref_root / "src" / "parvar" / "analysis" / "utils.py"
+        exec(compile(f.read_text(), str(f), "exec"), ns)
+        xps, frames = analysis_inputs()
+        with tempfile.TemporaryDirectory() as tmp:
+            base = drv.write_reference_layout(Path(tmp), "all", xps, frames)
+            joined = ns["join_optimization_results"](Path(tmp), "all")
+            assert len(joined) == 2 * 4, len(joined)          # the no_prior experiment is dropped by the reference (:91)
+            (base / "definitions_results.parquet").unlink()
+            if out_dir.exists():
+                shutil.rmtree(out_dir)
+            shutil.copytree(base, out_dir)
+    finally:
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
+    print(f"wrote {out_dir}: product-written results joined by the reference's join_optimization_results")
+
+
 def main():
     ref_root = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    analysis_fixture(ref_root, ROOT / "tests" / "golden" / "analysis_reference_join")
     pid_helpers(ref_root, ROOT / "tests" / "golden" / "reference_pid_helpers.json")
     workflow_fixture(ref_root, ROOT / "tests" / "golden" / "reference_workflow_simple_pk.npz")
     study_definitions(ref_root, ROOT / "tests" / "golden" / "reference_study_definitions.json")

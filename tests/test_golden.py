@@ -282,7 +282,7 @@ def test_study_definitions_match_the_reference_factories():
             assert list(REF_FACTORIES[model][g["id"]].items()) == [(p["id"], ls(p)) for p in smp["parameters"]]
             assert [o["id"] for o in smp["observables"]] == mine["observables"]
             assert smp["tend"] == 100.0 and smp["noise"]["type"] == "normal"                                    # quirks Q3, Q8
-            assert [p["id"] for p in g["estimation"]["parameters"]] == mine["params"]
+            assert [p["id"] for p in smp["parameters"]] == mine["params"]       # PEtab parameter order = sampling order (:611)
             for p in mine["params"]:
                 key = f"{p}_{g['id']}" if f"{p}_{g['id']}" in r["pars_true"] else g["id"]     # simple_chain keys by group only
                 assert mine["priors"]["exact_prior"][g["id"]][p] == ls(r["pars_true"][key])
@@ -427,3 +427,30 @@ def test_results_files_are_what_the_reference_analysis_joined(tmp_path):
         src = src[(src["group"] == row["group"]) & (src["parameter"] == row["parameter"])].iloc[0]
         assert row["bayes_sampler_mean"] == src["mean"] and row["bayes_sampler_median"] == src["median"]
         assert row["ess"] == src["ess"] and row["hdi_low"] == src["hdi_low"] and row["hdi_high"] == src["hdi_high"]
+
+
+def test_study_enumeration_matches_the_reference_experiment_factory():
+    """tests/golden/reference_experiment_factory.npz: the 3 x 2160 experiments the reference's own model_experiment_factory
+    (petab_factory.py:623-700) builds from definitions_all.  The study driver (tools/run_study.py) must enumerate the same
+    experiments in the same order - prior type, samples, steps = timepoints - 1 (quirk Q8), noise cv - with the same PEtab
+    parameter order and the same prior (loc, scale) per (group, parameter)."""
+    import importlib.util
+    import itertools
+    g = np.load(G / "reference_experiment_factory.npz")
+    spec = importlib.util.spec_from_file_location("run_study", G.parent.parent / "tools" / "run_study.py")
+    rs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rs)
+    D = rs.DEFINITIONS_ALL
+    defs = list(itertools.product(D["prior_types"], D["samples"], D["timepoints"], D["noise_cvs"]))     # run_study.py:main
+    assert len(defs) == 2160
+    for model, mine in rs.MODELS.items():
+        groups = [str(x) for x in g[f"{model}/groups"]]
+        params = [str(x) for x in g[f"{model}/params"]]
+        assert groups == list(mine["sampling"]) and params == mine["params"]
+        assert [d[0] for d in defs] == [str(x) for x in g[f"{model}/prior_type"]]
+        for k in range(len(groups)):
+            np.testing.assert_array_equal([d[1] for d in defs], g[f"{model}/samples"][:, k])
+            np.testing.assert_array_equal([d[2] - 1 for d in defs], g[f"{model}/steps"][:, k])
+            np.testing.assert_array_equal([d[3] for d in defs], g[f"{model}/cv"][:, k])
+        prior = np.array([[[mine["priors"][d[0]][grp][p] for p in params] for grp in groups] for d in defs], dtype=float)
+        np.testing.assert_array_equal(prior, g[f"{model}/prior"])

@@ -366,8 +366,68 @@ def analysis_fixture(ref_root: Path, out_dir: Path) -> None:
     print(f"wrote {out_dir}: product-written results joined by the reference's join_optimization_results")
 
 
+def experiment_factory_fixture(ref_root: Path, out_file: Path) -> None:
+    """All 3 x 2160 experiments of the study as the reference's own `model_experiment_factory` (:623-700) builds them from
+    `definitions_all` and each factory's data: per experiment the prior type, samples, steps (= timepoints - 1), noise cv and
+    the prior (loc, scale) that `create_petab_example` would write for every (group, parameter) - looked up the reference's
+    way, `group.get_parameter("estimation", par, ...)` = first match in the group's estimation list (which for MALE also holds
+    the FEMALE entries: `g.id in par` is a substring test, :686-693)."""
+    import types
+    saved = dict(sys.modules)
+    out: dict = {}
+    try:
+        def mod(name, **attrs):
+            m = types.ModuleType(name)
+            m.__path__ = []
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+            return m
+        mod("roadrunner", RoadRunner=object, Integrator=object)
+        mod("xarray", Dataset=object)
+        mod("matplotlib").pyplot = mod("matplotlib.pyplot")
+        quiet = types.SimpleNamespace(print=lambda *a, **k: None, rule=lambda *a, **k: None)
+        mod("pymetadata").console = mod("pymetadata.console", console=quiet)
+        mod("rich").progress = mod("rich.progress", track=lambda it, **k: it)
+        py = mod("pydantic_yaml")
+        py.parse_yaml_raw_as = py.to_yaml_str = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stub"))
+        mod("parvar", MODELS={})
+        mod("parvar.experiments")
+        base = ref_root / "src" / "parvar" / "experiments"
+        for name in ("utils", "experiment", "petab_factory"):
+            m = types.ModuleType(f"parvar.experiments.{name}")
+            m.__file__ = str(base / f"{name}.py")
+            sys.modules[m.__name__] = m
+            exec(compile((base / f"{name}.py").read_text(), m.__file__, "exec"), m.__dict__)
+        pfm = sys.modules["parvar.experiments.petab_factory"]
+        ns: dict = {}
+        exec(compile((base / "factories" / "__init__.py").read_text(), "factories/__init__.py", "exec"), ns)
+        definition = ns["definitions_all"]["all"]
+        for model in ("simple_chain", "simple_pk", "icg_body_flat"):
+            fns: dict = {}
+            f = base / "factories" / f"{model}.py"
+            exec(compile(f.read_text(), str(f), "exec"), fns)
+            xps = pfm.model_experiment_factory(**definition, **fns["factory_data"]).experiments
+            params = [p.id for p in xps[0].groups[0].get_parameter_list("sampling")]          # create_petab_for_experiment :611
+            out[f"{model}/params"] = np.array(params)
+            out[f"{model}/groups"] = np.array([g.id for g in xps[0].groups])
+            out[f"{model}/prior_type"] = np.array([x.prior_type for x in xps])
+            out[f"{model}/samples"] = np.array([[g.sampling.n_samples for g in x.groups] for x in xps])
+            out[f"{model}/steps"] = np.array([[g.sampling.steps for g in x.groups] for x in xps])
+            out[f"{model}/cv"] = np.array([[g.sampling.noise.cv for g in x.groups] for x in xps])
+            out[f"{model}/prior"] = np.array([[[[g.get_parameter("estimation", p, k) for k in ("loc", "scale")] for p in params]
+                                               for g in x.groups] for x in xps])                # [experiment, group, parameter, 2]
+            out[f"{model}/n_estimation_entries"] = np.array([[len(g.estimation.parameters) for g in x.groups] for x in xps])
+    finally:
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
+    np.savez_compressed(out_file, **out)
+    print(f"wrote {out_file}: {len(out['simple_pk/prior_type'])} experiments per model from the reference's model_experiment_factory")
+
+
 def main():
     ref_root = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    experiment_factory_fixture(ref_root, ROOT / "tests" / "golden" / "reference_experiment_factory.npz")
     analysis_fixture(ref_root, ROOT / "tests" / "golden" / "analysis_reference_join")
     pid_helpers(ref_root, ROOT / "tests" / "golden" / "reference_pid_helpers.json")
     workflow_fixture(ref_root, ROOT / "tests" / "golden" / "reference_workflow_simple_pk.npz")

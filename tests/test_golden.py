@@ -454,3 +454,16 @@ def test_study_enumeration_matches_the_reference_experiment_factory():
             np.testing.assert_array_equal([d[3] for d in defs], g[f"{model}/cv"][:, k])
         prior = np.array([[[mine["priors"][d[0]][grp][p] for p in params] for grp in groups] for d in defs], dtype=float)
         np.testing.assert_array_equal(prior, g[f"{model}/prior"])
+
+
+def test_estimation_settings_match_the_reference():
+    """optimize_experiment's settings (petab_optimization.py:294-306, read out of the reference's syntax tree): multistart and
+    sampler sizes, tolerances, seed.  Plot creation and the engine name are the two the GPU driver sets differently on purpose."""
+    import json
+    ref = json.loads((G / "reference_study_definitions.json").read_text())["optimization_settings"]
+    mine = pkg("optimization.driver").DEFAULT_SETTINGS
+    assert set(ref) - {"create_optimization_plots"} <= set(mine)
+    for key, value in ref.items():
+        if key != "create_optimization_plots":
+            assert mine[key] == value, key
+    assert (ref["n_starts"], ref["n_samples"], ref["n_chains"]) == (100, 5000, 4)

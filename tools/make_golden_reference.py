@@ -181,6 +181,14 @@ def study_definitions(ref_root: Path, out_file: Path) -> None:
         for k in list(sys.modules):
             if k not in saved:
                 del sys.modules[k]
+    # the estimation settings: the constant keywords of `settings = dict(...)` in optimize_experiment (petab_optimization.py:294-306)
+    tree = ast.parse((ref_root / "src" / "parvar" / "optimization" / "petab_optimization.py").read_text())
+    for node in ast.walk(tree):
+        if (isinstance(node, ast.Assign) and isinstance(node.targets[0], ast.Name) and node.targets[0].id == "settings"
+                and isinstance(node.value, ast.Call) and getattr(node.value.func, "id", "") == "dict"):
+            out["optimization_settings"] = {kw.arg: ast.literal_eval(kw.value) for kw in node.value.keywords
+                                            if isinstance(kw.value, ast.Constant)}
+    assert out["optimization_settings"]["n_starts"] == 100
     out_file.write_text(json.dumps(out, indent=1, sort_keys=True) + "\n")
     print(f"wrote {out_file} from the reference's experiment.py and factories/")
 

@@ -41,6 +41,58 @@ ROOT = Path(__file__).resolve().parent.parent
 OUT = ROOT / "tests" / "golden" / "reference_sampling_noise.npz"
 
 
+import contextlib
+import types
+
+
+@contextlib.contextmanager
+def reference_modules(ref_root: Path, models: Optional[dict] = None, roadrunner_cls=object, dataset_cls=object, concat=None):
+    """Execute the reference's `parvar.experiments.{utils, experiment, petab_factory}` from their source files and yield
+    the petab_factory module.  What cannot be imported in this container is replaced by inert stand-ins: `roadrunner`
+    (`roadrunner_cls`), `xarray` (`dataset_cls`, `concat`), matplotlib, `pymetadata.console`, `rich.progress.track`,
+    `pydantic_yaml` (YAML round trip of experiments, unused here); `parvar/__init__.py` (creates result directories at
+    import) is bypassed, `parvar.MODELS` is `models`.  sys.modules is restored on exit."""
+    saved = dict(sys.modules)
+    try:
+        def mod(name, **attrs):
+            m = types.ModuleType(name)
+            m.__path__ = []
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+            return m
+        mod("roadrunner", RoadRunner=roadrunner_cls, Integrator=object)
+        mod("xarray", Dataset=dataset_cls, concat=concat)
+        mod("matplotlib").pyplot = mod("matplotlib.pyplot")
+        quiet = types.SimpleNamespace(print=lambda *a, **k: None, rule=lambda *a, **k: None)
+        mod("pymetadata").console = mod("pymetadata.console", console=quiet)
+        mod("rich").progress = mod("rich.progress", track=lambda it, **k: it)
+        py = mod("pydantic_yaml")
+        py.parse_yaml_raw_as = py.to_yaml_str = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stub"))
+        mod("parvar", MODELS=models or {})
+        mod("parvar.experiments")
+        base = ref_root / "src" / "parvar" / "experiments"
+        for name in ("utils", "experiment", "petab_factory"):
+            m = types.ModuleType(f"parvar.experiments.{name}")
+            m.__file__ = str(base / f"{name}.py")
+            sys.modules[m.__name__] = m
+            exec(compile((base / f"{name}.py").read_text(), m.__file__, "exec"), m.__dict__)
+        pfm = sys.modules["parvar.experiments.petab_factory"]
+        pfm.plot_samples = pfm.plot_simulations = lambda *a, **k: None
+        yield pfm
+    finally:
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
+
+
+def reference_factory(ref_root: Path, model: str) -> dict:
+    """`factory_data` of src/parvar/experiments/factories/<model>.py (inside `reference_modules`)."""
+    ns: dict = {}
+    f = ref_root / "src" / "parvar" / "experiments" / "factories" / f"{model}.py"
+    exec(compile(f.read_text(), str(f), "exec"), ns)
+    return ns["factory_data"]
+
+
 def load_reference_functions(ref_root: Path) -> dict:
     src_file = ref_root / "src" / "parvar" / "experiments" / "petab_factory.py"
     tree = ast.parse(src_file.read_text())
@@ -138,49 +190,20 @@ def write_petab_with_reference_code(ref_root: Path, out_dir: Path) -> None:
 def study_definitions(ref_root: Path, out_file: Path) -> None:
     """The sweep grid (factories/__init__.py:12-20) and the three factories' experiment definitions - sampling and prior
     distributions, sample counts, steps, noise, observables, parameter order - as the reference's own modules build them.
-    experiment.py (pydantic models) and factories/*.py are executed unmodified; only the two missing I/O dependencies of
-    experiment.py (pydantic_yaml, pymetadata.console - YAML round trip and printing) are stubbed, and `parvar/__init__.py`
-    (which creates result directories at import) is bypassed."""
+    experiment.py (pydantic models) and factories/*.py are executed unmodified (`reference_modules`)."""
     import json
-    import types
-    saved = dict(sys.modules)
-    try:
-        for name in ("parvar", "parvar.experiments"):
-            m = types.ModuleType(name)
-            m.__path__ = []
-            sys.modules[name] = m
-        py = types.ModuleType("pydantic_yaml")
-        py.parse_yaml_raw_as = py.to_yaml_str = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stub"))
-        sys.modules["pydantic_yaml"] = py
-        pm, pmc = types.ModuleType("pymetadata"), types.ModuleType("pymetadata.console")
-        pmc.console = types.SimpleNamespace(print=lambda *a, **k: None, rule=lambda *a, **k: None)
-        pm.console = pmc
-        sys.modules["pymetadata"], sys.modules["pymetadata.console"] = pm, pmc
-        base = ref_root / "src" / "parvar" / "experiments"
-        xm = types.ModuleType("parvar.experiments.experiment")
-        xm.__file__ = str(base / "experiment.py")
-        sys.modules["parvar.experiments.experiment"] = xm
-        exec(compile((base / "experiment.py").read_text(), xm.__file__, "exec"), xm.__dict__)
-        for cls in list(vars(xm).values()):                      # `from __future__ import annotations`: resolve forward refs
-            if isinstance(cls, type) and cls.__module__ == xm.__name__ and hasattr(cls, "model_rebuild"):
-                cls.model_rebuild(_types_namespace=vars(xm))
-        out = {}
+    out = {}
+    with reference_modules(ref_root):
         ns: dict = {}
-        exec(compile((base / "factories" / "__init__.py").read_text(), "factories/__init__.py", "exec"), ns)
+        f = ref_root / "src" / "parvar" / "experiments" / "factories" / "__init__.py"
+        exec(compile(f.read_text(), str(f), "exec"), ns)
         out["definitions_all"] = ns["definitions_all"]["all"]
         out["definitions_minimal"] = ns["definitions_minimal"]
         for model in ("simple_chain", "simple_pk", "icg_body_flat"):
-            ns = {}
-            f = base / "factories" / f"{model}.py"
-            exec(compile(f.read_text(), str(f), "exec"), ns)
-            fd = ns["factory_data"]
+            fd = reference_factory(ref_root, model)
             dump = lambda pars: {k: v.model_dump(mode="json") for k, v in pars.items()}
             out[model] = {"exp_base": fd["exp_base"].model_dump(mode="json"), "pars_true": dump(fd["pars_true"]),
                           "pars_biased": {k: dump(v) for k, v in fd["pars_biased"].items()}}
-    finally:
-        for k in list(sys.modules):
-            if k not in saved:
-                del sys.modules[k]
     # the estimation settings: the constant keywords of `settings = dict(...)` in optimize_experiment (petab_optimization.py:294-306)
     tree = ast.parse((ref_root / "src" / "parvar" / "optimization" / "petab_optimization.py").read_text())
     for node in ast.walk(tree):
@@ -203,7 +226,6 @@ def workflow_fixture(ref_root: Path, out_file: Path) -> None:
     numbers are drawn in which order (one global legacy stream: seed 1234, log-normal draws per group and parameter, then per
     individual randint -> reseed -> normal), dose / parameter hand-over to the simulator, bracketed observable ids, the
     start / end / steps -> time grid convention, and the table assembly."""
-    import types
     sys.path.insert(0, str(ROOT))
     sys.path.insert(0, str(ROOT / "oracle"))
     import parvar_oracle as oracle
@@ -248,50 +270,21 @@ def workflow_fixture(ref_root: Path, out_file: Path) -> None:
         return Dataset(frames[0].index.to_numpy(), {c: np.stack([f[c].to_numpy() for f in frames]) for c in frames[0].columns},
                        sim=np.asarray(dim))
 
-    saved = dict(sys.modules)
     saved_to_xarray = pd.DataFrame.to_xarray
     try:
-        def mod(name, **attrs):
-            m = types.ModuleType(name)
-            m.__path__ = []
-            m.__dict__.update(attrs)
-            sys.modules[name] = m
-            return m
-        mod("roadrunner", RoadRunner=FakeRoadRunner, Integrator=FakeIntegrator)
-        mod("xarray", Dataset=Dataset, concat=concat)
-        mpl = mod("matplotlib")
-        mpl.pyplot = mod("matplotlib.pyplot")
-        mod("pymetadata").console = mod("pymetadata.console", console=types.SimpleNamespace(print=lambda *a, **k: None,
-                                                                                           rule=lambda *a, **k: None))
-        mod("rich").progress = mod("rich.progress", track=lambda it, **k: it)
-        py = mod("pydantic_yaml")
-        py.parse_yaml_raw_as = py.to_yaml_str = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stub"))
-        mod("parvar", MODELS={"simple_pk": Path(pkg.MODELS["simple_pk"])})
-        mod("parvar.experiments")
-        base = ref_root / "src" / "parvar" / "experiments"
-        for name in ("utils", "experiment", "petab_factory"):
-            m = types.ModuleType(f"parvar.experiments.{name}")
-            m.__file__ = str(base / f"{name}.py")
-            sys.modules[m.__name__] = m
-            exec(compile((base / f"{name}.py").read_text(), m.__file__, "exec"), m.__dict__)
-        pfm = sys.modules["parvar.experiments.petab_factory"]
-        pfm.plot_samples = pfm.plot_simulations = lambda *a, **k: None
         pd.DataFrame.to_xarray = lambda self: self           # consumed by the xarray stand-in's concat only
-        ns: dict = {}
-        f = base / "factories" / "simple_pk.py"
-        exec(compile(f.read_text(), str(f), "exec"), ns)
-        xp = ns["factory_data"]["exp_base"].model_copy(deep=True)
-        xp.id = "wf"
-        for g in xp.groups:
-            g.sampling.n_samples, g.sampling.steps, g.sampling.noise.cv = 4, 4, 0.1
-        with tempfile.TemporaryDirectory() as tmp:
-            yaml_file = pfm.create_petab_for_experiment(xp, Path(tmp), show_plot=False)
-            meas = pd.read_csv(Path(yaml_file).parent / "petab" / "measurements_simple_pk.tsv", sep="\t", float_precision="round_trip")
+        with reference_modules(ref_root, models={"simple_pk": Path(pkg.MODELS["simple_pk"])}, roadrunner_cls=FakeRoadRunner,
+                               dataset_cls=Dataset, concat=concat) as pfm:
+            xp = reference_factory(ref_root, "simple_pk")["exp_base"].model_copy(deep=True)
+            xp.id = "wf"
+            for g in xp.groups:
+                g.sampling.n_samples, g.sampling.steps, g.sampling.noise.cv = 4, 4, 0.1
+            with tempfile.TemporaryDirectory() as tmp:
+                yaml_file = pfm.create_petab_for_experiment(xp, Path(tmp), show_plot=False)
+                meas = pd.read_csv(Path(yaml_file).parent / "petab" / "measurements_simple_pk.tsv", sep="\t",
+                                   float_precision="round_trip")
     finally:
         pd.DataFrame.to_xarray = saved_to_xarray
-        for k in list(sys.modules):
-            if k not in saved:
-                del sys.modules[k]
     keys = list(captured["dsets"])
     out = {"time": captured["dsets"][keys[0]]["time"].values, "groups": np.array(keys),
            "abs_tol": captured["integrator"]["absolute_tolerance"], "rel_tol": captured["integrator"]["relative_tolerance"]}
@@ -380,41 +373,14 @@ def experiment_factory_fixture(ref_root: Path, out_file: Path) -> None:
     the prior (loc, scale) that `create_petab_example` would write for every (group, parameter) - looked up the reference's
     way, `group.get_parameter("estimation", par, ...)` = first match in the group's estimation list (which for MALE also holds
     the FEMALE entries: `g.id in par` is a substring test, :686-693)."""
-    import types
-    saved = dict(sys.modules)
     out: dict = {}
-    try:
-        def mod(name, **attrs):
-            m = types.ModuleType(name)
-            m.__path__ = []
-            m.__dict__.update(attrs)
-            sys.modules[name] = m
-            return m
-        mod("roadrunner", RoadRunner=object, Integrator=object)
-        mod("xarray", Dataset=object)
-        mod("matplotlib").pyplot = mod("matplotlib.pyplot")
-        quiet = types.SimpleNamespace(print=lambda *a, **k: None, rule=lambda *a, **k: None)
-        mod("pymetadata").console = mod("pymetadata.console", console=quiet)
-        mod("rich").progress = mod("rich.progress", track=lambda it, **k: it)
-        py = mod("pydantic_yaml")
-        py.parse_yaml_raw_as = py.to_yaml_str = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stub"))
-        mod("parvar", MODELS={})
-        mod("parvar.experiments")
-        base = ref_root / "src" / "parvar" / "experiments"
-        for name in ("utils", "experiment", "petab_factory"):
-            m = types.ModuleType(f"parvar.experiments.{name}")
-            m.__file__ = str(base / f"{name}.py")
-            sys.modules[m.__name__] = m
-            exec(compile((base / f"{name}.py").read_text(), m.__file__, "exec"), m.__dict__)
-        pfm = sys.modules["parvar.experiments.petab_factory"]
+    with reference_modules(ref_root) as pfm:
         ns: dict = {}
-        exec(compile((base / "factories" / "__init__.py").read_text(), "factories/__init__.py", "exec"), ns)
+        f = ref_root / "src" / "parvar" / "experiments" / "factories" / "__init__.py"
+        exec(compile(f.read_text(), str(f), "exec"), ns)
         definition = ns["definitions_all"]["all"]
         for model in ("simple_chain", "simple_pk", "icg_body_flat"):
-            fns: dict = {}
-            f = base / "factories" / f"{model}.py"
-            exec(compile(f.read_text(), str(f), "exec"), fns)
-            xps = pfm.model_experiment_factory(**definition, **fns["factory_data"]).experiments
+            xps = pfm.model_experiment_factory(**definition, **reference_factory(ref_root, model)).experiments
             params = [p.id for p in xps[0].groups[0].get_parameter_list("sampling")]          # create_petab_for_experiment :611
             out[f"{model}/params"] = np.array(params)
             out[f"{model}/groups"] = np.array([g.id for g in xps[0].groups])
@@ -425,10 +391,6 @@ def experiment_factory_fixture(ref_root: Path, out_file: Path) -> None:
             out[f"{model}/prior"] = np.array([[[[g.get_parameter("estimation", p, k) for k in ("loc", "scale")] for p in params]
                                                for g in x.groups] for x in xps])                # [experiment, group, parameter, 2]
             out[f"{model}/n_estimation_entries"] = np.array([[len(g.estimation.parameters) for g in x.groups] for x in xps])
-    finally:
-        for k in list(sys.modules):
-            if k not in saved:
-                del sys.modules[k]
     np.savez_compressed(out_file, **out)
     print(f"wrote {out_file}: {len(out['simple_pk/prior_type'])} experiments per model from the reference's model_experiment_factory")
 

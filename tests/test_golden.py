@@ -290,32 +290,52 @@ def test_study_definitions_match_the_reference_factories():
                     assert mine["priors"][kind][g["id"]][p] == ls(r["pars_biased"][kind][key])
 
 
-def test_oracle_flow_reproduces_the_reference_workflow(oracle):
-    """tests/golden/reference_workflow_simple_pk.npz: the reference's own create_petab_for_experiment (:548-621), with its
-    real simulate_samples / create_samples_parameters / add_noise / create_petab_example, run by
-    tools/make_golden_reference.py for a 2 x 4-individual, 5-time-point simple_pk experiment; only the ODE solve inside
-    RoadRunner.simulate was answered by the oracle's exact solution.  The oracle's restatement of that flow - the checker of
-    tests/test_gpu_estimation.py::test_create_petab_for_experiment_like_reference - must reproduce it bit for bit: same
-    draws from the one global stream in the same order, same grid, same observable order, same table order."""
-    g = np.load(G / "reference_workflow_simple_pk.npz")
+def _golden_tools():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_reference", G.parent.parent / "tools" / "make_golden_reference.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+WORKFLOW_CASES = [("simple_pk", 4), ("simple_chain", 3), ("icg_body_flat", 3)]
+
+
+@pytest.mark.parametrize("model,n", WORKFLOW_CASES)
+def test_oracle_flow_reproduces_the_reference_workflow(oracle, model, n):
+    """tests/golden/reference_workflow_<model>.npz: the reference's own create_petab_for_experiment (:548-621), with its real
+    simulate_samples / create_samples_parameters / add_noise / create_petab_example, run by tools/make_golden_reference.py for
+    a 2-group, n-individual, 5-time-point experiment of every model; only the ODE solve inside RoadRunner.simulate was answered
+    by the oracle.  The oracle's restatement of that flow - the checker of
+    tests/test_gpu_estimation.py::test_create_petab_for_experiment_like_reference - must reproduce it bit for bit: same draws
+    from the one global stream in the same order, dose before parameters, same grid, observable order and table order."""
+    import json
+    traj = _golden_tools().oracle_trajectory
+    g = np.load(G / f"reference_workflow_{model}.npz")
+    xb = json.loads((G / "reference_study_definitions.json").read_text())[model]["exp_base"]
     assert float(g["abs_tol"]) == 1e-6 and float(g["rel_tol"]) == 1e-6             # quirk Q9: the reference's data tolerances
     t = np.linspace(0.0, 100.0, 5)                                                 # start 0, end tend = 100, steps 4 (quirk Q8)
     np.testing.assert_array_equal(g["time"], t)
-    groups = REF_FACTORIES["simple_pk"]
+    groups = REF_FACTORIES[model]
     assert [str(k) for k in g["groups"]] == [f"Category.{k}" for k in groups]
-    samples = oracle.create_samples_parameters({grp: {p: (4, sc, lo) for p, (lo, sc) in d.items()} for grp, d in groups.items()})
+    dosage = xb["dosage"] or {}
+    assert [str(k) for k in g["set_order_first_row"]] == list(dosage) + list(groups["MALE"])      # setValue order (:231-239)
+    observed = [o["id"] for o in xb["groups"][0]["sampling"]["observables"]]
+    assert [str(c) for c in g["condition_columns"]] == ["conditionId", "conditionName"] + list(groups["MALE"]) + observed   # Q4: no dose
+    samples = oracle.create_samples_parameters({grp: {p: (n, sc, lo) for p, (lo, sc) in d.items()} for grp, d in groups.items()})
+    states = oracle.MODELS[model].states
     rows = []
     for grp in groups:
         names = [str(v) for v in g[f"vars/Category.{grp}"]]
-        assert names == ["[y_cent]", "[y_gut]", "[y_peri]"]                        # bracketed ids, factory order (:250-258)
-        idx = [oracle.SIMPLE_PK.states.index(n.strip("[]")) for n in names]
+        assert names == [f"[{o}]" for o in observed]                               # bracketed ids, factory order (:250-258)
+        idx = [states.index(o) for o in observed]
         want = g[f"noisy/Category.{grp}"]
-        for i in range(4):
-            clean = oracle.simple_pk_exact({p: samples[grp][p][i] for p in groups[grp]}, t)[:, idx]
+        for i in range(n):
+            clean = traj(oracle, model, {**dosage, **{p: samples[grp][p][i] for p in groups[grp]}}, t)[:, idx]
             noisy = oracle.add_noise(clean, 0.1)                                   # randint -> reseed -> normal, per individual
             np.testing.assert_array_equal(noisy, want[i])
-            for k, n in enumerate(names):
-                rows += [(grp, n.strip("[]") + "_observable", tj, noisy[j, k]) for j, tj in enumerate(t)]
+            for k, o in enumerate(observed):
+                rows += [(grp, o + "_observable", tj, noisy[j, k]) for j, tj in enumerate(t)]
     # the measurement table: group, individual, observable, time (petab_factory.py:378-417)
     assert [r[0] for r in rows] == [str(c) for c in g["measurement_condition"]]
     assert [r[1] for r in rows] == [str(c) for c in g["measurement_observable"]]
@@ -323,21 +343,23 @@ def test_oracle_flow_reproduces_the_reference_workflow(oracle):
     np.testing.assert_array_equal([r[3] for r in rows], g["measurement"])
 
 
-def test_product_workflow_host_logic_reproduces_the_reference_workflow(oracle, tmp_path, monkeypatch):
+@pytest.mark.parametrize("model,n", WORKFLOW_CASES)
+def test_product_workflow_host_logic_reproduces_the_reference_workflow(oracle, tmp_path, monkeypatch, model, n):
     """The product's data-generation workflow (experiments/workflow.py::create_petab_for_experiment with the mirror's real
     ODESampleSimulator.simulate_samples: sampling, hand-over of dose / columns / grid / observables to the kernel wrapper,
-    per-row host noise, PEtab tables) against the reference's own workflow (reference_workflow_simple_pk.npz).  Only the
-    kernel call is replaced - `Problem.simulate_host` answers with the oracle's exact solution, as RoadRunner.simulate did
-    when the fixture was made - so the two must agree bit for bit, measurement table included."""
+    per-row host noise, PEtab tables) against the reference's own workflow (reference_workflow_<model>.npz).  Only the
+    kernel call is replaced - `Problem.simulate_host` answers with the oracle, as RoadRunner.simulate did when the fixture
+    was made - so the two must agree bit for bit, measurement table included."""
     import json
     import pandas as pd
+    traj = _golden_tools().oracle_trajectory
     wf = pkg("experiments.workflow")
     pf = pkg("experiments.petab_factory")
-    g = np.load(G / "reference_workflow_simple_pk.npz")
-    xb = json.loads((G / "reference_study_definitions.json").read_text())["simple_pk"]["exp_base"]
+    g = np.load(G / f"reference_workflow_{model}.npz")
+    xb = json.loads((G / "reference_study_definitions.json").read_text())[model]["exp_base"]
 
     class FakeProblem:                                       # the members of runtime.Problem simulate_samples touches
-        state_ids = list(oracle.SIMPLE_PK.states)
+        state_ids = list(oracle.MODELS[model].states)
 
         def reset_values(self):
             self.over = {}
@@ -354,16 +376,16 @@ def test_product_workflow_host_logic_reproduces_the_reference_workflow(oracle, t
         def set_observables(self, obs):
             self.idx = [self.state_ids.index(o.strip("[]")) for o in obs]
 
-        def simulate_host(self, P, n, status=None, steps=None):
-            Y = np.stack([oracle.simple_pk_exact({**self.over, **{c: P[j, i] for j, c in enumerate(self.cols)}}, self.t)[:, self.idx]
-                          for i in range(n)])
+        def simulate_host(self, P, n_rows, status=None, steps=None):
+            Y = np.stack([traj(oracle, model, {**self.over, **{c: P[j, i] for j, c in enumerate(self.cols)}}, self.t)[:, self.idx]
+                          for i in range(n_rows)])
             status[:] = 0
             steps[:] = 0
             return Y, 0
 
     def make_simulator(model_path, device=0):
         sim = pf.ODESampleSimulator.__new__(pf.ODESampleSimulator)      # no GPU: skip the constructor, keep the methods
-        sim.model_name, sim.problem = "simple_pk", FakeProblem()
+        sim.model_name, sim.problem = model, FakeProblem()
         return sim
 
     monkeypatch.setattr(wf, "ODESampleSimulator", make_simulator)
@@ -373,21 +395,23 @@ def test_product_workflow_host_logic_reproduces_the_reference_workflow(oracle, t
 
     groups = [wf.GroupSpec(id=grp["id"], sampling={p["id"]: ls(p) for p in grp["sampling"]["parameters"]},
                            estimation={p["id"]: ls(p) for p in grp["estimation"]["parameters"]},
-                           n_samples=4, steps=4, tend=grp["sampling"]["tend"], cv=0.1) for grp in xb["groups"]]
-    xp = wf.ExperimentSpec(id="wf", model="simple_pk", groups=groups,
+                           n_samples=n, steps=4, tend=grp["sampling"]["tend"], cv=0.1) for grp in xb["groups"]]
+    xp = wf.ExperimentSpec(id="wf", model=model, groups=groups,
                            observables=[o["id"] for o in xb["groups"][0]["sampling"]["observables"]], dosage=xb["dosage"])
     yaml_file, dsets, frames = wf.create_petab_for_experiment(xp, tmp_path)
     for grp in groups:
         names = [str(v) for v in g[f"vars/Category.{grp.id}"]]
         assert list(dsets[grp.id].data_vars) == names
-        got = np.stack([dsets[grp.id][n].values for n in names], axis=2)
+        got = np.stack([dsets[grp.id][v].values for v in names], axis=2)
         np.testing.assert_array_equal(got, g[f"noisy/Category.{grp.id}"])
         np.testing.assert_array_equal(dsets[grp.id]["time"].values, g["time"])
-    meas = pd.read_csv(tmp_path / "wf" / "petab" / "measurements_simple_pk.tsv", sep="\t", float_precision="round_trip")
+    meas = pd.read_csv(tmp_path / "wf" / "petab" / f"measurements_{model}.tsv", sep="\t", float_precision="round_trip")
     np.testing.assert_array_equal(meas["measurement"].to_numpy(), g["measurement"])
     np.testing.assert_array_equal(meas["time"].to_numpy(), g["measurement_time"])
     assert list(meas["simulationConditionId"]) == [str(c) for c in g["measurement_condition"]]
     assert list(meas["observableId"]) == [str(c) for c in g["measurement_observable"]]
+    cond = pd.read_csv(tmp_path / "wf" / "petab" / f"conditions_{model}.tsv", sep="\t")
+    assert list(cond.columns) == [str(c) for c in g["condition_columns"]]
 
 
 def test_pid_helpers_match_the_reference_utils():

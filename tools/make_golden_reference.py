@@ -126,6 +126,13 @@ FACTORIES = {
 }
 
 
+def oracle_trajectory(oracle, model: str, overrides: dict, t: np.ndarray) -> np.ndarray:
+    """What stands in for the ODE solve when the reference's workflow is executed (and when the tests replay it)."""
+    if model == "simple_pk":
+        return oracle.simple_pk_exact(overrides, t)
+    return oracle.simulate(model, overrides, t)
+
+
 def petab_fixture_data():
     """The small data set of the PEtab fixture: deterministic numbers, no simulator involved."""
     t = np.array([0.0, 10.0, 50.0, 100.0])
@@ -216,12 +223,13 @@ def study_definitions(ref_root: Path, out_file: Path) -> None:
     print(f"wrote {out_file} from the reference's experiment.py and factories/")
 
 
-def workflow_fixture(ref_root: Path, out_file: Path) -> None:
+def workflow_fixture(ref_root: Path, out_file: Path, model: str = "simple_pk", n_samples: int = 4) -> None:
     """The reference's whole data-generation workflow - `create_petab_for_experiment` (:548-621) with the real
     `ODESampleSimulator.simulate_samples` (:221-272), `create_samples_parameters`, `add_noise`, `create_petab_example` - run
-    from the reference's own module source for a small simple_pk experiment (its factory's `exp_base` with 4 individuals per
-    group, 5 time points, cv 0.1).  Only the ODE solve is not the reference's: `roadrunner.RoadRunner` is a stand-in that
-    answers `simulate()` with the oracle's exact solution (matrix exponential); xarray is a stand-in that builds the
+    from the reference's own module source for a small experiment per model (its factory's `exp_base` with a few individuals
+    per group, 5 time points, cv 0.1).  Only the ODE solve is not the reference's: `roadrunner.RoadRunner` is a stand-in that
+    answers `simulate()` with the oracle (exact matrix exponential for simple_pk, scipy at rtol 1e-12 for the other two -
+    `oracle_trajectory` below, which the tests call as well); xarray is a stand-in that builds the
     product's `SimDataset`; plotting is switched off.  What the fixture pins is everything AROUND the solve: which random
     numbers are drawn in which order (one global legacy stream: seed 1234, log-normal draws per group and parameter, then per
     individual randint -> reseed -> normal), dose / parameter hand-over to the simulator, bracketed observable ids, the
@@ -242,24 +250,26 @@ def workflow_fixture(ref_root: Path, out_file: Path) -> None:
 
     class FakeRoadRunner:
         def __init__(self, path):
-            assert Path(path).stem == "simple_pk"
+            assert Path(path).stem == model
             self.integrator = FakeIntegrator()
             self.values: dict = {}
+            self.calls: list = []
 
         def getIds(self):
-            return ["y_gut", "y_cent", "y_peri", "k_abs", "CL", "Q"]
+            return list(oracle.MODELS[model].states)
 
         def resetAll(self):
             self.values = {}
 
         def setValue(self, key, value):
             self.values[key] = float(value)
+            captured.setdefault("set_order", []).append(key)
 
         def simulate(self, start, end, steps):
             t = np.linspace(start, end, steps + 1)
-            y = oracle.simple_pk_exact(dict(self.values), t)
+            y = oracle_trajectory(oracle, model, dict(self.values), t)
             res = np.column_stack([t, y]).view(SimResult)
-            res.colnames = ["time"] + [f"[{sid}]" for sid in oracle.SIMPLE_PK.states]
+            res.colnames = ["time"] + [f"[{sid}]" for sid in oracle.MODELS[model].states]
             return res
 
     class Dataset(ds.SimDataset):
@@ -273,16 +283,17 @@ def workflow_fixture(ref_root: Path, out_file: Path) -> None:
     saved_to_xarray = pd.DataFrame.to_xarray
     try:
         pd.DataFrame.to_xarray = lambda self: self           # consumed by the xarray stand-in's concat only
-        with reference_modules(ref_root, models={"simple_pk": Path(pkg.MODELS["simple_pk"])}, roadrunner_cls=FakeRoadRunner,
+        with reference_modules(ref_root, models={model: Path(pkg.MODELS[model])}, roadrunner_cls=FakeRoadRunner,
                                dataset_cls=Dataset, concat=concat) as pfm:
-            xp = reference_factory(ref_root, "simple_pk")["exp_base"].model_copy(deep=True)
+            xp = reference_factory(ref_root, model)["exp_base"].model_copy(deep=True)
             xp.id = "wf"
             for g in xp.groups:
-                g.sampling.n_samples, g.sampling.steps, g.sampling.noise.cv = 4, 4, 0.1
+                g.sampling.n_samples, g.sampling.steps, g.sampling.noise.cv = n_samples, 4, 0.1
             with tempfile.TemporaryDirectory() as tmp:
                 yaml_file = pfm.create_petab_for_experiment(xp, Path(tmp), show_plot=False)
-                meas = pd.read_csv(Path(yaml_file).parent / "petab" / "measurements_simple_pk.tsv", sep="\t",
+                meas = pd.read_csv(Path(yaml_file).parent / "petab" / f"measurements_{model}.tsv", sep="\t",
                                    float_precision="round_trip")
+                cond = pd.read_csv(Path(yaml_file).parent / "petab" / f"conditions_{model}.tsv", sep="\t")
     finally:
         pd.DataFrame.to_xarray = saved_to_xarray
     keys = list(captured["dsets"])
@@ -291,6 +302,9 @@ def workflow_fixture(ref_root: Path, out_file: Path) -> None:
     for key, dset in captured["dsets"].items():
         out[f"vars/{key}"] = np.array(list(dset.data_vars))
         out[f"noisy/{key}"] = np.stack([dset.data_vars[v] for v in dset.data_vars], axis=2)       # [sim, time, observable]
+    n_set = len(captured["set_order"]) // (len(keys) * n_samples)            # setValue calls per simulated row, in order (:231-239)
+    out["set_order_first_row"] = np.array(captured["set_order"][:n_set])
+    out["condition_columns"] = np.array(list(cond.columns))
     out["measurement"] = meas["measurement"].to_numpy()
     out["measurement_condition"] = meas["simulationConditionId"].to_numpy().astype(str)
     out["measurement_observable"] = meas["observableId"].to_numpy().astype(str)
@@ -401,6 +415,8 @@ def main():
     analysis_fixture(ref_root, ROOT / "tests" / "golden" / "analysis_reference_join")
     pid_helpers(ref_root, ROOT / "tests" / "golden" / "reference_pid_helpers.json")
     workflow_fixture(ref_root, ROOT / "tests" / "golden" / "reference_workflow_simple_pk.npz")
+    workflow_fixture(ref_root, ROOT / "tests" / "golden" / "reference_workflow_simple_chain.npz", model="simple_chain", n_samples=3)
+    workflow_fixture(ref_root, ROOT / "tests" / "golden" / "reference_workflow_icg_body_flat.npz", model="icg_body_flat", n_samples=3)
     study_definitions(ref_root, ROOT / "tests" / "golden" / "reference_study_definitions.json")
     write_petab_with_reference_code(ref_root, ROOT / "tests" / "golden" / "petab_reference_simple_pk")
     ref = load_reference_functions(ref_root)

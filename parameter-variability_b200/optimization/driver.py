@@ -188,7 +188,7 @@ def definitions_dataframe(experiments: Sequence[dict]) -> pd.DataFrame:
                 rows.append({"id": xp["id"], "model": xp["model"], "prior_type": xp["prior_type"], "n_groups": len(xp["sampling"]),
                              "group": group, "samples": xp["samples"], "timepoints": xp["timepoints"], "noise_cv": xp["noise_cv"],
                              "parameter": par, "dsn_type": "DistributionType.LOGNORMAL",
-                             "dsn_par": str({"loc": loc, "scale": scale})})
+                             "dsn_par": str({"loc": float(loc), "scale": float(scale)})})     # pydantic stores floats
     return pd.DataFrame(rows)
 
 

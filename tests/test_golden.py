@@ -491,3 +491,21 @@ def test_estimation_settings_match_the_reference():
         if key != "create_optimization_plots":
             assert mine[key] == value, key
     assert (ref["n_starts"], ref["n_samples"], ref["n_chains"]) == (100, 5000, 4)
+
+
+def test_definitions_table_matches_the_reference_writer():
+    """tests/golden/reference_definitions_minimal_simple_pk.tsv was written by the reference's own
+    create_petabs_for_definitions -> create_petabs -> PETabExperimentList.to_dataframe for `definitions_minimal` (the scenario
+    of the reference's tests/experiments/test_factories.py).  The product's definitions_dataframe must write the same bytes."""
+    import io
+    import itertools
+    import json
+    drv = pkg("optimization.driver")
+    ref_bytes = (G / "reference_definitions_minimal_simple_pk.tsv").read_bytes()
+    minimal = json.loads((G / "reference_study_definitions.json").read_text())["definitions_minimal"]["timepoints"]
+    xps = [{"id": f"xp{k:018d}", "model": "simple_pk", "prior_type": prior, "samples": 20, "timepoints": n_t, "noise_cv": 0.1,
+            "sampling": REF_FACTORIES["simple_pk"]}                       # defaults of model_experiment_factory: 20 samples, cv 0.1
+           for k, (prior, n_t) in enumerate(itertools.product(minimal["prior_types"], minimal["timepoints"]))]
+    buf = io.StringIO()
+    drv.definitions_dataframe(xps).to_csv(buf, sep="\t", index=False)
+    assert buf.getvalue().encode() == ref_bytes

@@ -409,8 +409,74 @@ def experiment_factory_fixture(ref_root: Path, out_file: Path) -> None:
     print(f"wrote {out_file}: {len(out['simple_pk/prior_type'])} experiments per model from the reference's model_experiment_factory")
 
 
+def definitions_table_fixture(ref_root: Path, out_file: Path) -> None:
+    """`definitions.tsv` as the reference writes it: `create_petabs_for_definitions` (:702-716) -> `create_petabs` (:520-546)
+    -> `PETabExperimentList.to_dataframe` (experiment.py:170-204), run on `definitions_minimal` for simple_pk (3 prior types x
+    {5, 10} time points; what the reference's own tests/experiments/test_factories.py runs) with the stand-ins of
+    `workflow_fixture`.  Only the table is kept."""
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import parvar_oracle as oracle
+    ds = importlib.import_module("parameter-variability_b200.experiments.dataset")
+    pkg = importlib.import_module("parameter-variability_b200")
+
+    class SimResult(np.ndarray):
+        colnames: list
+
+    class Integrator:
+        def setSetting(self, key, value):
+            pass
+
+    class RoadRunner:
+        def __init__(self, path):
+            self.integrator, self.values = Integrator(), {}
+
+        def getIds(self):
+            return list(oracle.SIMPLE_PK.states)
+
+        def resetAll(self):
+            self.values = {}
+
+        def setValue(self, key, value):
+            self.values[key] = float(value)
+
+        def simulate(self, start, end, steps):
+            t = np.linspace(start, end, steps + 1)
+            res = np.column_stack([t, oracle.simple_pk_exact(dict(self.values), t)]).view(SimResult)
+            res.colnames = ["time"] + [f"[{sid}]" for sid in oracle.SIMPLE_PK.states]
+            return res
+
+    class Dataset(ds.SimDataset):
+        def to_netcdf(self, path):
+            pass
+
+    def concat(frames, dim):
+        return Dataset(frames[0].index.to_numpy(), {c: np.stack([f[c].to_numpy() for f in frames]) for c in frames[0].columns},
+                       sim=np.asarray(dim))
+
+    saved_to_xarray = pd.DataFrame.to_xarray
+    try:
+        pd.DataFrame.to_xarray = lambda self: self
+        with reference_modules(ref_root, models={"simple_pk": Path(pkg.MODELS["simple_pk"])}, roadrunner_cls=RoadRunner,
+                               dataset_cls=Dataset, concat=concat) as pfm:
+            ns: dict = {}
+            f = ref_root / "src" / "parvar" / "experiments" / "factories" / "__init__.py"
+            exec(compile(f.read_text(), str(f), "exec"), ns)
+            counter = iter(range(10 ** 6))
+            pfm.uuid_alphanumeric = lambda length=20: f"xp{next(counter):0{length - 2}d}"     # reproducible ids (uuid4 in the reference)
+            with tempfile.TemporaryDirectory() as tmp:
+                pfm.create_petabs_for_definitions(ns["definitions_minimal"], Path(tmp), reference_factory(ref_root, "simple_pk"))
+                table = Path(tmp) / "xps" / "timepoints" / pfm.DEFINITIONS_FILENAME
+                out_file.write_bytes(table.read_bytes())
+                n_dirs = len([d for d in table.parent.iterdir() if d.is_dir()])
+    finally:
+        pd.DataFrame.to_xarray = saved_to_xarray
+    print(f"wrote {out_file}: definitions.tsv of {n_dirs} experiments written by the reference's create_petabs")
+
+
 def main():
     ref_root = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+    definitions_table_fixture(ref_root, ROOT / "tests" / "golden" / "reference_definitions_minimal_simple_pk.tsv")
     experiment_factory_fixture(ref_root, ROOT / "tests" / "golden" / "reference_experiment_factory.npz")
     analysis_fixture(ref_root, ROOT / "tests" / "golden" / "analysis_reference_join")
     pid_helpers(ref_root, ROOT / "tests" / "golden" / "reference_pid_helpers.json")

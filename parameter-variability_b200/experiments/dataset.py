@@ -70,6 +70,22 @@ class SimDataset:
             df = df.droplevel("sim")
         return df
 
+    def to_netcdf(self, path) -> None:
+        """``xr.Dataset.to_netcdf`` for the call in the reference's workflow (``dset.to_netcdf(xp_path / f"{category}.nc")``,
+        petab_factory.py:601-602): a NetCDF-3 classic file with dims (sim, time), the two coordinates and one float64
+        variable per observable, written with scipy (no netCDF4 / h5netcdf needed); xarray opens it as the same Dataset."""
+        from scipy.io import netcdf_file
+        with netcdf_file(str(path), "w") as f:
+            f.createDimension("sim", self.dims["sim"])
+            f.createDimension("time", self.dims["time"])
+            sim = f.createVariable("sim", "i4", ("sim",))
+            sim[:] = np.asarray(self.coords["sim"], dtype=np.int32)
+            time = f.createVariable("time", "d", ("time",))
+            time[:] = self.coords["time"]
+            for name, values in self.data_vars.items():
+                var = f.createVariable(name, "d", ("sim", "time"))
+                var[:] = values
+
     def to_xarray(self):
         import xarray as xr   # optional
         return xr.Dataset({k: (("sim", "time"), v) for k, v in self.data_vars.items()},

@@ -509,3 +509,21 @@ def test_definitions_table_matches_the_reference_writer():
     buf = io.StringIO()
     drv.definitions_dataframe(xps).to_csv(buf, sep="\t", index=False)
     assert buf.getvalue().encode() == ref_bytes
+
+
+def test_simdataset_netcdf_roundtrip(tmp_path):
+    """SimDataset.to_netcdf (the reference's workflow calls dset.to_netcdf, petab_factory.py:601-602): NetCDF-3 via scipy,
+    bracketed variable names, dims (sim, time)."""
+    from scipy.io import netcdf_file
+    ds = pkg("experiments.dataset")
+    t = np.linspace(0.0, 100.0, 5)
+    data = {"[y_cent]": np.arange(15.0).reshape(3, 5) / 7.0, "[y_gut]": np.exp(-np.arange(15.0).reshape(3, 5))}
+    d = ds.SimDataset(t, data)
+    d.to_netcdf(tmp_path / "MALE.nc")
+    with netcdf_file(str(tmp_path / "MALE.nc"), "r", mmap=False) as f:
+        assert f.dimensions == {"sim": 3, "time": 5}
+        np.testing.assert_array_equal(f.variables["time"][:], t)
+        np.testing.assert_array_equal(f.variables["sim"][:], [0, 1, 2])
+        for name, values in data.items():
+            assert f.variables[name].dimensions == ("sim", "time")
+            np.testing.assert_array_equal(f.variables[name][:], values)

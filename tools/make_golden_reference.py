@@ -312,6 +312,64 @@ def workflow_fixture(ref_root: Path, out_file: Path, model: str = "simple_pk", n
     np.savez_compressed(out_file, **out)
     print(f"wrote {out_file} from the reference's create_petab_for_experiment (groups {keys})")
 
+    # ---- drop-in check of boundary B1 (not a fixture): the SAME reference workflow once more, now with the reference's
+    # ODESampleSimulator class replaced by the product's mirror (its real simulate_samples; the kernel wrapper answered by the
+    # oracle like RoadRunner above).  The reference's code must run unchanged and produce the same data.
+    pf = importlib.import_module("parameter-variability_b200.experiments.petab_factory")
+
+    class FakeProblem:
+        state_ids = list(oracle.MODELS[model].states)
+
+        def reset_values(self):
+            self.over = {}
+
+        def set_value(self, key, value):
+            self.over[key] = value
+
+        def set_columns(self, ids):
+            self.cols = list(ids)
+
+        def set_timepoints(self, t):
+            self.t = np.asarray(t, dtype=float)
+
+        def set_observables(self, obs):
+            self.idx = [self.state_ids.index(o.strip("[]")) for o in obs]
+
+        def simulate_host(self, P, n_rows, status=None, steps=None):
+            Y = np.stack([oracle_trajectory(oracle, model, {**self.over, **{c: P[j, i] for j, c in enumerate(self.cols)}}, self.t)[:, self.idx]
+                          for i in range(n_rows)])
+            status[:] = 0
+            steps[:] = 0
+            return Y, 0
+
+    second: dict = {}
+
+    class MirrorSimulator(pf.ODESampleSimulator):
+        def __init__(self, model_path, abs_tol=1e-6, rel_tol=1e-6):          # the reference's call: ODESampleSimulator(model_path=...)
+            self.model_name, self.problem = model, FakeProblem()
+
+        def simulate_samples(self, parameters, simulation_settings):
+            dset = super().simulate_samples(parameters, simulation_settings)
+            second[len(second)] = dset          # the reference goes on to call dset.to_netcdf(...): SimDataset's own (scipy, NetCDF-3)
+            return dset
+
+    with reference_modules(ref_root, models={model: Path(pkg.MODELS[model])}) as pfm:
+        pfm.ODESampleSimulator = MirrorSimulator
+        xp = reference_factory(ref_root, model)["exp_base"].model_copy(deep=True)
+        xp.id = "wf"
+        for g in xp.groups:
+            g.sampling.n_samples, g.sampling.steps, g.sampling.noise.cv = n_samples, 4, 0.1
+        with tempfile.TemporaryDirectory() as tmp:
+            yaml_file = pfm.create_petab_for_experiment(xp, Path(tmp), show_plot=False)
+            meas2 = pd.read_csv(Path(yaml_file).parent / "petab" / f"measurements_{model}.tsv", sep="\t", float_precision="round_trip")
+    assert len(second) == len(keys)
+    for k, key in enumerate(keys):
+        assert list(second[k].data_vars) == list(captured["dsets"][key].data_vars)
+        for v in second[k].data_vars:
+            assert np.array_equal(second[k].data_vars[v], captured["dsets"][key].data_vars[v]), (key, v)
+    assert meas2.equals(meas)
+    print(f"  drop-in check: the reference workflow with the product's ODESampleSimulator class gives the same {model} data")
+
 
 PIDS = ["k_abs_MALE", "CL_FEMALE", "LI__ICGIM_Vmax_MALE", "BW_OLD", "k1", "k1_", "_MALE", "a_b_c", "par_gr\u00fcn", "x__y", "",
         "k_abs_MALE\n", "UPPER_lower_123"]

@@ -165,83 +165,178 @@ def workload_config(n_gpus: int) -> dict:
 
 
 # ----------------------------------------------------------------------------------------------------------
-def logp_grad_leg(rt, torch, dist, rank: int, world: int, local: int, evals: int = 20) -> dict:
-    """Second half of BASELINE.json's metric: logp + gradient evaluations/s (configs[2] and [3]).
+def _timed(torch, dist, world, fn, reps):
+    """reps calls of fn between barrier + synchronize, CUDA events on the current stream, max over ranks -> ms per call."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
-    Hierarchical objective over 8 chains x (1000 individuals per GPU), individuals sharded over the ranks (weak
-    scaling), ONE all-reduce of [chains, 1 + 2P] per evaluation; per-individual gradients stay on their rank.
-    Each evaluation goes through the public host API (`HierarchicalObjective.local_terms` -> `pv_logp_grad_host`):
-    host theta -> H2D -> sensitivity kernel -> D2H of logp / gradient -> population terms -> all-reduce.  Data are
-    synthetic: the model's default trajectory (through the CUDA path) x (1 + 0.05 eps) per individual.
+
+def logp_grad_leg(rt, torch, dist, rank: int, world: int, local: int) -> dict:
+    """Second half of BASELINE.json's metric: logp + gradient evaluations/s (configs[2] "C3" and [3] "C4"), at exactly the
+    settings of ``bench_cases`` (the ones tests/test_gpu_parity.py::test_bench_logp_grad_settings_meet_the_bar verifies).
+
+    Hierarchical objective over 8 chains x n individuals, individuals sharded over the ranks, device resident
+    (``HierarchicalObjectiveDevice``): sensitivity kernel -> epilogue kernel writing [8, 5] -> ONE NCCL all-reduce of that
+    buffer on the same stream -> hyper-prior kernel; theta, gradients and results never leave the GPU.
+      weak             1000 individuals per GPU (the config BASELINE names, per GPU)
+      strong_8x1000    the config BASELINE literally names, 8 x 1000 individuals in total, split over the ranks
+      strong_8x16000   a size that fills the GPUs: 8 x 16 000 individuals in total, split over the ranks
+      e2e              weak size through host buffers: pinned theta -> H2D, evaluation, D2H of [8, 5] and the gradients
+    Data are synthetic: the trajectory at the population means (through the CUDA path) x (1 + 0.05 eps) per individual.
     """
     po = importlib.import_module(PKG + ".optimization.petab_optimization")
     dd = importlib.import_module(PKG + ".distributed")
-    pf = importlib.import_module(PKG + ".experiments.petab_factory")
-    C, n_loc, T = 8, 1000, 20
-    n_ind = n_loc * world
-    first, stop = dd.shard_range(n_ind, rank, world)
-    t = np.linspace(0.0, 100.0, T)
+    bc = importlib.import_module(PKG + ".bench_cases")
+    C = bc.N_CHAINS
+    dev = torch.device("cuda", local)
     out = {}
-    cases = [("C3 simple_pk", "simple_pk", ["k_abs", "CL"], OBS, {}, (1.0, 1.0), (1.0, 1.0), 0.05, (1e-8, 1e-11), "DOPRI5"),
-             ("C4 icg_body_flat", "icg_body_flat", ["BW", "LI__ICGIM_Vmax"], ["Cre_plasma_icg", "Cgi_plasma_icg"],
-              {"IVDOSE_icg": 10.0}, (75.0, 10.0), (0.0369598840327503, 0.01), 1e-4, (1e-7, 1e-11), "RODAS4")]
-    for name, model, cols, obs, fixed, ms1, ms2, sigma, (rtol, atol), method in cases:
-        pb = rt.Problem(model, device=local)
-        pb.set_solver(rtol=rtol, atol=atol)
-        for k, v in fixed.items():
+    for case in bc.CASES:
+        P = len(case.columns)
+        t = case.tgrid
+        pb = rt.Problem(case.model, device=local)
+        pb.set_solver(rtol=case.rtol, atol=case.atol)
+        for k, v in case.fixed.items():
             pb.set_value(k, v)
-        pb.set_columns(cols)
+        pb.set_columns(list(case.columns))
         pb.set_timepoints(t)
-        pb.set_observables(obs)
-        mean = torch.tensor([[ms1[0]], [ms2[0]]], dtype=torch.float64, device="cuda")
-        Y1 = torch.empty((1, T, len(obs)), dtype=torch.float64, device="cuda")
+        pb.set_observables(list(case.observables))
+        mean = torch.tensor([[m] for m, _ in case.population], dtype=torch.float64, device=dev)
+        Y1 = torch.empty((1, len(t), len(case.observables)), dtype=torch.float64, device=dev)
         pb.simulate(mean, Y1)
         torch.cuda.synchronize()
         truth = Y1[0].cpu().numpy()
-        rs = np.random.RandomState(1234)                 # every rank draws the full set and keeps its slice
-        y = (truth[None] * (1 + 0.05 * rs.normal(size=(n_ind,) + truth.shape)))[first:stop]
-        (m1, s1), (m2, s2) = pf.lognorm_par_transform(*ms1), pf.lognorm_par_transform(*ms2)
-        theta = np.stack([rs.lognormal(m1, s1, size=(C, n_ind)), rs.lognormal(m2, s2, size=(C, n_ind))], axis=2)
-        theta = np.ascontiguousarray(theta[:, first:stop])
-        pb.set_data(np.stack([po.sufficient_statistics(y[i:i + 1], 0) for i in range(len(y))], axis=-1), sigma)
-        H = po.HierarchicalObjective(pb, n_ind, mu_prior=[(m1, 0.5), (m2, 0.5)], omega_prior=[0.5, 0.5],
-                                     first_individual=first, n_local=stop - first)
-        mu = np.tile(np.array([m1, m2]), (C, 1))
-        omega = np.tile(np.array([s1, s2]), (C, 1))
-
-        def evaluate():
-            lp, dth, dmu, dom = H.local_terms(theta, mu, omega)
-            buf = np.ascontiguousarray(np.concatenate([lp[:, None], dmu, dom], axis=1))          # [C, 1 + 2P]
-            if world > 1:
-                tb = torch.from_numpy(buf).cuda()
-                dist.all_reduce(tb, op=dist.ReduceOp.SUM)
-                buf = tb.cpu().numpy()
-            return H.finish(buf[:, 0], buf[:, 1:3], buf[:, 3:5], mu, omega) + (dth,)
-
-        for _ in range(3):
-            res = evaluate()
-        torch.cuda.synchronize()
+        pop = case.population_ln()
+        mu_prior, omega_prior = [(m, 0.5) for m, _ in pop], [0.5] * P
+        mu = torch.tensor([[m for m, _ in pop]] * C, dtype=torch.float64, device=dev)
+        omega = torch.tensor([[s for _, s in pop]] * C, dtype=torch.float64, device=dev)
+        rec = {"chains": C, "timepoints": len(t), "integrator": case.method + " + forward sensitivities",
+               "rtol": case.rtol, "atol": case.atol,
+               "collective": "1 ncclAllReduce of [8, 5] fp64 per evaluation, on the kernels' stream" if world > 1 else "none (1 rank)"}
+        sizes = [("weak", bc.N_INDIVIDUALS_PER_GPU * world, 50)]
         if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(evals):
-            res = evaluate()
-        torch.cuda.synchronize()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        if not (np.all(np.isfinite(res[0])) and np.all(np.isfinite(res[3]))):
-            raise SystemExit(f"{name}: non-finite logp / gradient")
-        out[name] = {"logp_grad_evals_per_s": C * evals / dt, "ms_per_batched_eval": 1e3 * dt / evals,
-                     "kernel_ms": pb.last_kernel_ms, "trajectories_per_eval": C * n_ind,
-                     "trajectories_per_s": C * n_ind * evals / dt, "chains": C,
-                     "individuals_per_gpu": n_loc, "timepoints": T, "integrator": method + " + forward sensitivities",
-                     "rtol": rtol, "atol": atol, "collective": "1 all-reduce of [8, 5] fp64 per evaluation" if world > 1 else "none (1 rank)",
-                     "logp_chain0": float(res[0][0])}
+            sizes.append(("strong_8x1000", 1000, 50))
+        sizes.append(("strong_8x16000", 16000, 10))
+        for label, n_ind, reps in sizes:
+            first, stop = dd.shard_range(n_ind, rank, world)
+            L = stop - first
+            y, theta = case.inputs(truth, n_ind)
+            pb.set_data(np.stack([po.sufficient_statistics(y[i:i + 1], 0) for i in range(first, stop)], axis=-1), case.sigma)
+            th = torch.from_numpy(np.ascontiguousarray(theta[:, first:stop].transpose(2, 0, 1))).to(dev)     # [P, C, L]
+            H = po.HierarchicalObjectiveDevice(pb, C, n_ind, mu_prior, omega_prior, first_individual=first, n_local=L, world=world)
+            for _ in range(3):
+                H(th, mu, omega)
+            ms = _timed(torch, dist, world, lambda: H(th, mu, omega), reps)
+            red = H.red.cpu().numpy()
+            if not (np.all(np.isfinite(red)) and bool(torch.isfinite(H.dtheta).all()) and int(H.status.abs().sum()) == 0):
+                raise SystemExit(f"{case.name} {label}: non-finite logp / gradient or failed trajectories")
+            r = {"individuals_total": n_ind, "individuals_this_rank": L, "trajectories_per_eval": C * n_ind,
+                 "ms_per_batched_eval": ms, "logp_grad_evals_per_s": C / (ms * 1e-3),
+                 "trajectories_per_s": C * n_ind / (ms * 1e-3), "logp_chain0": float(red[0, 0])}
+            if label == "weak":
+                # the same evaluation through host buffers (what a host-side sampler would pay per step)
+                th_pin = torch.empty(th.shape, dtype=torch.float64).pin_memory()
+                th_pin.copy_(th)
+                out_red = torch.empty(H.red.shape, dtype=torch.float64).pin_memory()
+                out_g = torch.empty(H.dtheta.shape, dtype=torch.float64).pin_memory()
+
+                def host_eval():
+                    th.copy_(th_pin, non_blocking=True)
+                    H(th, mu, omega)
+                    out_red.copy_(H.red, non_blocking=True)
+                    out_g.copy_(H.dtheta, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                ms_h = _timed(torch, dist, world, host_eval, reps)
+                r["e2e"] = {"ms_per_batched_eval": ms_h, "logp_grad_evals_per_s": C / (ms_h * 1e-3),
+                            "h2d_bytes_per_eval": int(th.numel() * 8), "d2h_bytes_per_eval": int((H.red.numel() + H.dtheta.numel()) * 8)}
+            if label == "strong_8x1000" and world > 1:
+                # every rank also evaluates ALL individuals alone: the sharded sums must agree with the unsharded ones
+                pb.set_data(np.stack([po.sufficient_statistics(y[i:i + 1], 0) for i in range(n_ind)], axis=-1), case.sigma)
+                th_all = torch.from_numpy(np.ascontiguousarray(theta.transpose(2, 0, 1))).to(dev)
+                H1 = po.HierarchicalObjectiveDevice(pb, C, n_ind, mu_prior, omega_prior)
+                ref = H1(th_all, mu, omega)[0].cpu().numpy()
+                r["sharded_vs_unsharded_max_rel"] = float(np.max(np.abs(red - ref) / np.abs(ref)))
+                if r["sharded_vs_unsharded_max_rel"] > 1e-11:
+                    raise SystemExit(f"{case.name}: sharded evaluation differs from the unsharded one: {r}")
+            rec[label] = r
+        rec["logp_grad_evals_per_s"] = rec["weak"]["logp_grad_evals_per_s"]
+        rec["ms_per_batched_eval"] = rec["weak"]["ms_per_batched_eval"]
+        out[case.name] = rec
         pb.close()
-    out["note"] = ("one batched evaluation = logp + gradient of all 8 chains (each over every individual); "
-                   "logp_grad_evals_per_s counts chain evaluations; timed through the host API, max over ranks")
+    out["note"] = ("one batched evaluation = logp + gradient of all 8 chains (each over every individual); logp_grad_evals_per_s "
+                   "counts chain evaluations; device resident, CUDA events, max over ranks; settings = bench_cases.py, verified "
+                   "against the oracle by tests/test_gpu_parity.py::test_bench_logp_grad_settings_meet_the_bar")
+    return out
+
+
+def extra_measurements(rt, torch, pb, P, logp, status, steps, stream, B, T, th_host) -> dict:
+    """SURVEY.md section 8d rows besides the headline: C2 "fused logp, no trajectory store" (device and through host
+    buffers) and the C1 single-parameter-set latency (forward simulation and logp through the host API)."""
+    out = {}
+    for _ in range(3):
+        pb.logp(P, logp, status=status, steps=steps, stream=stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    reps = 10
+    for _ in range(reps):
+        pb.logp(P, logp, status=status, steps=steps, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    P_pin = rt.pinned_empty((2, B))
+    P_pin[:] = th_host
+    lp_pin = rt.pinned_empty((B,))
+    for _ in range(2):
+        pb.logp_host(P_pin, out=lp_pin)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        lp_h, _, _, nf = pb.logp_host(P_pin, out=lp_pin)
+    dt = (time.perf_counter() - t0) / reps
+    out["c2_fused_logp"] = {"what": "C2 with the likelihood folded into the integrator and NO trajectory store (pv_logp)",
+                            "trajectories_per_s": B / (ms * 1e-3), "ms_per_step": ms,
+                            "e2e_trajectories_per_s": B / dt, "e2e_ms_per_step": dt * 1e3, "e2e_api": "pv_logp_host",
+                            "h2d_bytes_per_step": int(16 * B), "d2h_bytes_per_step": int(8 * B),
+                            "e2e_matches_device": bool(np.array_equal(lp_h[:1000], logp[:1000].cpu().numpy()))}
+    # C1: one parameter set (defaults), the reference's own CPU-runnable case: latency of one call through the host API
+    c1 = {}
+    for Tn in (21, 50):
+        p1 = rt.Problem("simple_pk", device=pb.device)
+        p1.set_solver(rtol=RTOL, atol=ATOL)
+        p1.set_columns([])
+        p1.set_timepoints(np.linspace(0.0, 100.0, Tn))
+        p1.set_observables(OBS)
+        Y1, _ = p1.simulate_host(None, 1)
+        d = c1_data(Y1[0])
+        p1.set_data(np.stack([np.ones_like(d), d, d * d])[..., None], 1.0, rt.NOISE_NORMAL)
+        for _ in range(20):
+            p1.simulate_host(None, 1)
+        n = 300
+        t0 = time.perf_counter()
+        for _ in range(n):
+            p1.simulate_host(None, 1)
+        us_sim = (time.perf_counter() - t0) / n * 1e6
+        for _ in range(20):
+            p1.logp_host(np.empty((0, 1)))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            p1.logp_host(np.empty((0, 1)))
+        us_lp = (time.perf_counter() - t0) / n * 1e6
+        c1[f"T{Tn}"] = {"simulate_host_us": us_sim, "logp_host_us": us_lp}
+        p1.close()
+    c1["what"] = "C1: simple_pk, one parameter set, host call -> result on the host (launch + integration + copies), microseconds"
+    out["c1_latency"] = c1
     return out
 
 
@@ -372,6 +467,9 @@ def main() -> None:
     e2e_ok = bool(np.allclose(lp_pin[:1000], logp[:1000].cpu().numpy(), rtol=0, atol=0))
 
     lg = logp_grad_leg(rt, torch, dist, rank, world, local)
+    extra = extra_measurements(rt, torch, pb, P, logp, status, steps, stream, B, T, th_host) if rank == 0 else {}
+    if world > 1:
+        dist.barrier()
 
     if rank == 0:
         peak64 = rt.fma_peak_tflops(local, fp64=True)
@@ -415,6 +513,7 @@ def main() -> None:
                                  "peak_source": hbm_src, "bytes_per_launch": bytes_per_launch}},
             "cpu_baseline": cpu,
             "logp_grad": lg,
+            **extra,
             "logp_checksum": checksum,
         }
         print(json.dumps(line))

@@ -94,6 +94,12 @@ int pv_problem_set_schedule(pv_problem* p, int refill_min);
 #define PV_LAYOUT_SPLIT 2
 int pv_problem_set_layout(pv_problem* p, int layout);
 
+/* Tuning knobs of the launch configuration (tools/sweep_schedule*.py, tools/time_e2e.py):
+ *   max_ctas_per_sm  > 0 caps the resident CTAs per SM of the persistent grids (0 = what the occupancy calculator allows)
+ *   host_chunk_rows  rows per chunk of the pv_simulate_host pipeline (0 = default 32 768; measured optimum on the C2
+ *                    workload at 57 GB/s pinned D2H) */
+int pv_problem_set_tuning(pv_problem* p, int max_ctas_per_sm, int64_t host_chunk_rows);
+
 /* PV_METHOD_AUTO on a model classified non-stiff integrates with DOPRI5 first; trajectories that use up
  * switch_steps (default 4000) explicit steps - stiff parameter values, e.g. rate constants near the PEtab upper bound
  * 1e8 that a tempered chain or a uniform start point visits - are re-run with RODAS4 in a second launch on the
@@ -118,7 +124,7 @@ int pv_problem_set_observables(pv_problem* p, int n_obs, const char* const* ids)
 /* ---- B1: batched forward simulation --------------------------------------------------------------------
  * Replaces the loop `for _, row in parameters.iterrows(): ... s = self.r.simulate(...)` (:228-246).
  *   P_dev      [n_cols][B]   per-trajectory values of the configured columns
- *   Y_dev      [B][n_t][n_obs] concentrations of the selected observables (may be NULL: integrate only)
+ *   Y_dev      [B][n_t][n_obs] concentrations of the selected observables (required)
  *   status_dev [B] int32     PV_TRAJ_* (may be NULL)
  *   steps_dev  [2][B] int32  accepted / rejected step counts (may be NULL)                               */
 int pv_simulate(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, int32_t* status_dev,
@@ -163,7 +169,7 @@ int pv_logp_grad_fim(pv_problem* p, int64_t B, const double* P_dev, double* logp
 int pv_simulate_logp(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, double* logp_dev,
                      int32_t* status_dev, int32_t* steps_dev, void* stream);
 
-/* trajectories and their sensitivities (AMICI `rdata.sy`): S_dev [B][n_t][n_obs][n_sens] (Y_dev may be NULL) */
+/* trajectories and their sensitivities (AMICI `rdata.sy`): Y_dev as above, S_dev [B][n_t][n_obs][n_sens] (both required) */
 int pv_simulate_sens(pv_problem* p, int64_t B, const double* P_dev, double* Y_dev, double* S_dev,
                      int32_t* status_dev, int32_t* steps_dev, void* stream);
 
@@ -174,6 +180,30 @@ int pv_logp_grad_host(pv_problem* p, int64_t B, const double* P_host, double* lo
                       int64_t seg_len, double* logp_seg_host);
 int pv_logp_grad_fim_host(pv_problem* p, int64_t B, const double* P_host, double* logp_host, double* grad_host,
                           double* fim_host, int64_t seg_len, double* logp_seg_host);
+
+/* ---- hierarchical (population) objective, device resident (BASELINE configs 3-4) -----------
+ * Every individual i of chain c has its own theta_ci (the configured columns, which must be compiled sensitivity
+ * parameters) and its own data set (individual i of this GPU's shard <-> data set i: n_data == n_local);
+ * theta_cip ~ LogNormal(mu_cp, omega_cp).  One call = sensitivity kernel over n_chains * n_local trajectories +
+ * an epilogue kernel, both on `stream`, nothing synchronises and nothing touches the host:
+ *   theta_dev  [n_cols][n_chains * n_local]   chain-major columns (c * n_local + i)
+ *   mu_dev, omega_dev [n_chains][n_cols]      log-scale population mean / sd of every chain
+ *   dtheta_dev [n_cols][n_chains * n_local]   out: d/d theta_ci of (log-likelihood + population density)
+ *   red_dev    [n_chains][1 + 2 n_cols]       out: this GPU's partial (logp, d/d mu, d/d omega) - the send buffer of
+ *                                             the ONE all-reduce (sum) per evaluation when a chain's individuals are
+ *                                             sharded over GPUs (ncclAllReduce on the same stream; none on one GPU)
+ * A failed integration or theta <= 0 makes the chain's logp NaN.  n_local = 0 (a rank without individuals) writes zeros.
+ * Replaces, for all chains at once, what a NUTS / HMC step of the north-star configuration evaluates; the reference's
+ * own parallel strategy is a process pool over problems (petab_optimization.py:381-391). */
+int pv_hier_logp_grad(pv_problem* p, int n_chains, int64_t n_local, const double* theta_dev, const double* mu_dev,
+                      const double* omega_dev, double* dtheta_dev, double* red_dev, int32_t* status_dev,
+                      int32_t* steps_dev, void* stream);
+/* hyper-priors mu_p ~ Normal(m_p, s_p), omega_p ~ HalfNormal(h_p), added in place AFTER the reduction:
+ * red_dev becomes (log posterior, d/d mu, d/d omega) per chain.  The three prior arrays [n_cols] are host memory
+ * (they travel in the kernel parameters). */
+int pv_hier_finish(int n_chains, int n_cols, double* red_dev, const double* mu_dev, const double* omega_dev,
+                   const double* mu_prior_mean_host, const double* mu_prior_sd_host, const double* omega_prior_host,
+                   void* stream);
 
 /* page-locked host memory for the *_host calls (cudaHostAlloc / cudaFreeHost); NULL on failure */
 void* pv_host_alloc(size_t bytes);
@@ -206,7 +236,8 @@ int pv_sampler_step(int64_t Q, int C, int dim, int64_t it, int64_t n_trace, cons
 /* ---- measurement helpers ------------------------------------------------------------------------------ */
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t pv_launch_count(void);
-/* device time of the most recent hot kernel launched through the *_host calls, in ms (CUDA events) */
+/* device time of the kernels of the most recent pv_logp*_host call, in ms (CUDA events); pv_simulate_host pipelines
+ * several chunks over three streams and does not update it */
 double pv_last_kernel_ms(const pv_problem* p);
 /* fp64 / fp32 FMA-pipe peak microbenchmark: returns TFLOP/s achieved by a register-resident FMA chain kernel */
 double pv_fma_peak_tflops(int device, int use_fp64, int iters);

@@ -10,13 +10,18 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <string>
+#include <tuple>
+#include <utility>
 #include <vector>
 
 #include "../../include/parvar_b200.h"
 #include "pv_sampler_host.cuh"
 #include "pv_kernels.cuh"
 #include "pv_rosenbrock_split.cuh"
+#include "pv_hier.cuh"
 #include "generated/simple_chain.cuh"
 #include "generated/simple_pk.cuh"
 #include "generated/icg_body_flat.cuh"
@@ -48,8 +53,7 @@ struct pv_problem {
     int noise_model = PV_NOISE_NORMAL;
     int n_data = 0;
     // device copies
-    double *d_theta = nullptr, *d_y0 = nullptr, *d_tgrid = nullptr, *d_stats = nullptr;
-    bool dirty_values = true;
+    double *d_tgrid = nullptr, *d_stats = nullptr;   // (batch-wide values travel in the kernel parameters)
     // host pipeline
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;                               // all device->host copies of the host pipeline, FIFO
@@ -66,6 +70,10 @@ struct pv_problem {
     int num_sms = 0;
     int refill_min = 0;   // 0 = per-integrator default (DOPRI5: 6, RODAS4: 32), see pv_problem_set_schedule
     int layout = PV_LAYOUT_AUTO;   // see pv_problem_set_layout
+    int max_ctas_per_sm = 0;       // 0 = what the occupancy calculator allows (pv_problem_set_tuning)
+    int64_t host_chunk_rows = (int64_t)1 << 15;
+    double* d_hier = nullptr;      // logp [B] + grad [NS][B] scratch of pv_hier_logp_grad
+    size_t hier_bytes = 0;
     double t0 = 0.0;
     // METHOD_AUTO on a non-stiff model: trajectories that exhaust switch_steps explicit steps (stiff parameter
     // values) are re-run with RODAS4.  Scratch per launch slot: 0 = caller's stream, 1..3 = internal pipeline streams.
@@ -135,9 +143,7 @@ extern "C" pv_problem* pv_problem_create(const char* model_name, int device) {
     p->tab = &pv_model_tables[m];
     p->theta_base.assign(p->tab->theta_default, p->tab->theta_default + p->tab->n_theta);
     p->y0_base.assign(p->tab->n_states, std::numeric_limits<double>::quiet_NaN());
-    bool ok = cudaMalloc(&p->d_theta, sizeof(double) * p->tab->n_theta) == cudaSuccess &&
-              cudaMalloc(&p->d_y0, sizeof(double) * p->tab->n_states) == cudaSuccess &&
-              cudaMalloc(&p->d_failed, sizeof(int)) == cudaSuccess &&
+    bool ok = cudaMalloc(&p->d_failed, sizeof(int)) == cudaSuccess &&
               cudaMalloc(&p->d_counters, sizeof(unsigned long long) * PV_COUNTER_RING) == cudaSuccess &&
               cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
     for (int i = 0; i < 3 && ok; ++i)
@@ -157,8 +163,7 @@ extern "C" pv_problem* pv_problem_create(const char* model_name, int device) {
 extern "C" void pv_problem_destroy(pv_problem* p) {
     if (!p) return;
     cudaSetDevice(p->device);
-    cudaFree(p->d_theta);
-    cudaFree(p->d_y0);
+    cudaFree(p->d_hier);
     cudaFree(p->d_tgrid);
     cudaFree(p->d_stats);
     cudaFree(p->d_failed);
@@ -220,6 +225,15 @@ extern "C" int pv_problem_set_layout(pv_problem* p, int layout) {
     return 0;
 }
 
+extern "C" int pv_problem_set_tuning(pv_problem* p, int max_ctas_per_sm, int64_t host_chunk_rows) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (max_ctas_per_sm < 0) return fail(PV_E_ARG, "max_ctas_per_sm must be >= 0 (0 = no cap)");
+    if (host_chunk_rows != 0 && host_chunk_rows < 1024) return fail(PV_E_ARG, "host_chunk_rows must be 0 (default) or >= 1024");
+    p->max_ctas_per_sm = max_ctas_per_sm;
+    p->host_chunk_rows = host_chunk_rows ? host_chunk_rows : ((int64_t)1 << 15);
+    return 0;
+}
+
 extern "C" int pv_problem_set_stiff_switch(pv_problem* p, int switch_steps) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
     if (switch_steps < 1) return fail(PV_E_ARG, "switch_steps must be >= 1");
@@ -256,14 +270,12 @@ extern "C" int pv_problem_set_value(pv_problem* p, const char* id, double value)
         p->theta_base[t] = value;
     else
         p->y0_base[t - p->tab->n_theta] = value;
-    p->dirty_values = true;
     return 0;
 }
 extern "C" int pv_problem_reset_values(pv_problem* p) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
     p->theta_base.assign(p->tab->theta_default, p->tab->theta_default + p->tab->n_theta);
     p->y0_base.assign(p->tab->n_states, std::numeric_limits<double>::quiet_NaN());
-    p->dirty_values = true;
     return 0;
 }
 
@@ -292,6 +304,9 @@ extern "C" int pv_problem_set_timepoints(pv_problem* p, double t0, int n_t, cons
     p->d_tgrid = nullptr;
     CUDA_OK(cudaMalloc(&p->d_tgrid, sizeof(double) * n_t));
     CUDA_OK(cudaMemcpy(p->d_tgrid, t_host, sizeof(double) * n_t, cudaMemcpyHostToDevice));
+    // a pageable-source copy may return once the data are staged: wait for the DMA itself, because the kernels run on
+    // non-blocking streams that do not order against the legacy stream (configuration time, not the hot loop)
+    CUDA_OK(cudaStreamSynchronize(0));
     p->stats.clear();   // data are tied to the grid
     p->n_data = 0;
     return 0;
@@ -355,6 +370,7 @@ extern "C" int pv_problem_set_data(pv_problem* p, int noise_model, int n_data, c
     p->d_stats = nullptr;
     CUDA_OK(cudaMalloc(&p->d_stats, sizeof(double) * nq));
     CUDA_OK(cudaMemcpy(p->d_stats, q.data(), sizeof(double) * nq, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaStreamSynchronize(0));   // see pv_problem_set_timepoints
     return 0;
 }
 
@@ -363,96 +379,99 @@ extern "C" int pv_problem_set_data(pv_problem* p, int noise_model, int n_data, c
 // ---------------------------------------------------------------------------------------------------------
 constexpr int PV_MAX_DYN_SMEM = 200 * 1024;   // pv_launch refuses time grids / data that need more
 
-template <class KernelT>
-static cudaError_t launch_persistent(KernelT kern, const pv_launch_params& lp, size_t shmem, int num_sms, cudaStream_t s) {
+// resident CTAs per SM of (kernel, block size, dynamic shared memory): asked once, then cached - the occupancy query
+// and the opt-in attribute cost several microseconds each, which the small latency-bound launches of the sampler
+// loops would pay at every iteration
+static int resident_ctas(const void* kern, int threads, size_t shmem, cudaError_t& err) {
+    static std::mutex mu;
+    static std::map<std::tuple<const void*, int, size_t, int>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const auto key = std::make_tuple(kern, threads, shmem, dev);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        err = cudaSuccess;
+        return it->second;
+    }
     // The opt-in limit is a property of the FUNCTION, shared by every problem and host thread that launches it: it is set to
     // one constant (the largest size pv_launch accepts), never to this launch's size - otherwise a thread with a short
     // time grid could lower it between another thread's cudaFuncSetAttribute and its launch ("invalid argument").
     if (shmem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_MAX_DYN_SMEM);
-        if (e != cudaSuccess) return e;
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_MAX_DYN_SMEM);
+        if (err != cudaSuccess) return 0;
     }
-    // persistent grid: as many CTAs as are resident at once (a multiple of the SM count), never more than the work
     int per_sm = 0;
-    cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PV_BLOCK, shmem);
-    if (eo != cudaSuccess) return eo;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    // tuning knob for tools/sweep_schedule*.py: cap the resident CTAs per SM (e.g. to keep the local-memory
-    // footprint of the spilling Rosenbrock sensitivity kernels inside the L2)
-    if (const char* cap = getenv("PV_MAX_CTAS_PER_SM")) {
-        const int c = atoi(cap);
-        if (c >= 1 && c < per_sm) per_sm = c;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, shmem);
+    if (err != cudaSuccess) return 0;
+    if (per_sm < 1) {
+        err = cudaErrorLaunchOutOfResources;
+        return 0;
     }
-    const int64_t want = (lp.B + PV_BLOCK - 1) / PV_BLOCK;
-    const int64_t blocks = std::min<int64_t>(want, (int64_t)num_sms * per_sm);
-    kern<<<(unsigned)blocks, PV_BLOCK, shmem, s>>>(lp);
+    cache[key] = per_sm;
+    return per_sm;
+}
+
+struct pv_launch_ctx {
+    int num_sms, layout, max_ctas_per_sm;
+    const double* theta;   // host [NTH]
+    const double* y0;      // host [NX]
+};
+
+template <class M>
+static pv_launch_params_m<M> with_values(const pv_launch_params& lp, const pv_launch_ctx& cx) {
+    pv_launch_params_m<M> out;
+    static_cast<pv_launch_params&>(out) = lp;
+    for (int i = 0; i < M::NTH; ++i) out.theta_base[i] = cx.theta[i];
+    for (int i = 0; i < M::NX; ++i) out.y0_base[i] = cx.y0[i];
+    return out;
+}
+
+template <class M, class KernelT>
+static cudaError_t launch_persistent(KernelT kern, const pv_launch_params& lp, const pv_launch_ctx& cx, int threads,
+                                     int64_t items_per_cta, size_t shmem, cudaStream_t s) {
+    // persistent grid: as many CTAs as are resident at once (a multiple of the SM count), never more than the work
+    cudaError_t e = cudaSuccess;
+    int per_sm = resident_ctas((const void*)kern, threads, shmem, e);
+    if (e != cudaSuccess) return e;
+    if (cx.max_ctas_per_sm >= 1 && cx.max_ctas_per_sm < per_sm) per_sm = cx.max_ctas_per_sm;
+    const int64_t want = (lp.B + items_per_cta - 1) / items_per_cta;
+    const int64_t blocks = std::min<int64_t>(want, (int64_t)cx.num_sms * per_sm);
+    kern<<<(unsigned)blocks, threads, shmem, s>>>(with_values<M>(lp, cx));
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
 
 template <class M, int METHOD, int MODE, bool OBSID>
-static cudaError_t launch_one(const pv_launch_params& lp, size_t shmem, int num_sms, cudaStream_t s) {
-    return launch_persistent(pv_batch_kernel<M, METHOD, MODE, OBSID>, lp, shmem, num_sms, s);
+static cudaError_t launch_one(const pv_launch_params& lp, const pv_launch_ctx& cx, size_t shmem, cudaStream_t s) {
+    return launch_persistent<M>(pv_batch_kernel<M, METHOD, MODE, OBSID>, lp, cx, PV_BLOCK, PV_BLOCK, shmem, s);
 }
 
 // RODAS4 + sensitivities of the large models: one warp per block of the augmented system (pv_rosenbrock_split.cuh)
 template <class M>
 constexpr bool pv_use_split = M::NS >= 1 && M::NS <= 2 && M::NX * (1 + M::NS) > 16;
 
-// `declined` = the layout rule chose the one-lane-per-trajectory kernel instead (nothing was launched)
-template <class M, int MODE>
-static cudaError_t launch_split(const pv_launch_params& lp, int num_sms, int layout, bool& declined, cudaStream_t s) {
-    declined = false;
+template <class M>
+static cudaError_t launch_model(int method, int mode, bool obsid, const pv_launch_params& lp, const pv_launch_ctx& cx,
+                                size_t shmem, cudaStream_t s) {
     if constexpr (pv_use_split<M>) {
-        auto kern = pv_rodas4_split_kernel<M, MODE>;
-        const int threads = 32 * (1 + M::NS);
-        const size_t shmem = pv_split_layout<M>::bytes(lp.T, lp.n_obs);
-        if (shmem > 48 * 1024) {   // constant, see launch_persistent
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PV_MAX_DYN_SMEM);
-            if (e != cudaSuccess) return e;
-        }
-        int per_sm = 0;
-        cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, shmem);
-        if (eo != cudaSuccess) return eo;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        if (const char* cap = getenv("PV_MAX_CTAS_PER_SM")) {
-            const int c = atoi(cap);
-            if (c >= 1 && c < per_sm) per_sm = c;
-        }
-        const int64_t want = (lp.B + 31) / 32;
         // measured (tools/bench_configs.py, icg_body_flat logp + gradient, stage vectors in shared memory): 8000
         // trajectories 3.6 ms split vs 11 ms lane; 128 000 trajectories 49 ms split vs 68 ms lane -> AUTO = split
-        (void)layout;
-        const int64_t blocks = std::min<int64_t>(want, (int64_t)num_sms * per_sm);
-        kern<<<(unsigned)blocks, threads, shmem, s>>>(lp);
-        g_launches.fetch_add(1);
-        return cudaGetLastError();
-    } else {
-        (void)lp; (void)num_sms; (void)layout; (void)s;
-        declined = true;
-        return cudaSuccess;
-    }
-}
-
-template <class M>
-static cudaError_t launch_model(int method, int mode, bool obsid, const pv_launch_params& lp, size_t shmem, int num_sms,
-                                int layout, cudaStream_t s) {
-    if constexpr (pv_use_split<M>) {
-        if (method == 2 && (mode == PV_MODE_LOGP_GRAD || mode == PV_MODE_LOGP_GRAD_FIM) && layout != PV_LAYOUT_LANE &&
+        if (method == 2 && (mode == PV_MODE_LOGP_GRAD || mode == PV_MODE_LOGP_GRAD_FIM) && cx.layout != PV_LAYOUT_LANE &&
             pv_split_layout<M>::bytes(lp.T, lp.n_obs) <= 100 * 1024) {
-            bool declined = false;
-            const cudaError_t e = mode == PV_MODE_LOGP_GRAD
-                                      ? launch_split<M, PV_MODE_LOGP_GRAD>(lp, num_sms, layout, declined, s)
-                                      : launch_split<M, PV_MODE_LOGP_GRAD_FIM>(lp, num_sms, layout, declined, s);
-            if (!declined) return e;
+            const size_t sh = pv_split_layout<M>::bytes(lp.T, lp.n_obs);
+            const int threads = 32 * (1 + M::NS);
+            return mode == PV_MODE_LOGP_GRAD
+                       ? launch_persistent<M>(pv_rodas4_split_kernel<M, PV_MODE_LOGP_GRAD>, lp, cx, threads, 32, sh, s)
+                       : launch_persistent<M>(pv_rodas4_split_kernel<M, PV_MODE_LOGP_GRAD_FIM>, lp, cx, threads, 32, sh, s);
         }
     }
     // the all-states-in-order specialisation is compiled for the explicit integrator only (cheap steps, where the
     // per-output code matters); the Rosenbrock kernels always use the generic sink
-#define PV_CASE(METH, MODE)                                                                      \
-    if (method == METH && mode == MODE) {                                                        \
-        if (METH == 1 && obsid) return launch_one<M, METH, MODE, (METH == 1)>(lp, shmem, num_sms, s); \
-        return launch_one<M, METH, MODE, false>(lp, shmem, num_sms, s);                          \
+#define PV_CASE(METH, MODE)                                                                \
+    if (method == METH && mode == MODE) {                                                  \
+        if (METH == 1 && obsid) return launch_one<M, METH, MODE, (METH == 1)>(lp, cx, shmem, s); \
+        return launch_one<M, METH, MODE, false>(lp, cx, shmem, s);                         \
     }
     PV_CASE(1, PV_MODE_TRAJ) PV_CASE(1, PV_MODE_LOGP) PV_CASE(1, PV_MODE_TRAJ_LOGP) PV_CASE(1, PV_MODE_LOGP_GRAD) PV_CASE(1, PV_MODE_TRAJ_SENS)
     PV_CASE(1, PV_MODE_LOGP_GRAD_FIM)
@@ -460,16 +479,6 @@ static cudaError_t launch_model(int method, int mode, bool obsid, const pv_launc
     PV_CASE(2, PV_MODE_LOGP_GRAD_FIM)
 #undef PV_CASE
     return cudaErrorInvalidValue;
-}
-
-static int sync_values(pv_problem* p, cudaStream_t s) {
-    if (!p->dirty_values) return 0;
-    // small synchronous copies: configuration time, not the hot loop
-    (void)s;
-    CUDA_OK(cudaMemcpy(p->d_theta, p->theta_base.data(), sizeof(double) * p->theta_base.size(), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(p->d_y0, p->y0_base.data(), sizeof(double) * p->y0_base.size(), cudaMemcpyHostToDevice));
-    p->dirty_values = false;
-    return 0;
 }
 
 static int ensure_scratch(pv_problem* p, int slot, int64_t B) {
@@ -506,14 +515,11 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     if ((mode & PV_MODE_LOGP) && (mode & PV_MODE_SENS) && !grad) return fail(PV_E_ARG, "grad is NULL");
     if ((mode & PV_MODE_FIM) && !fim) return fail(PV_E_ARG, "fim is NULL");
     CUDA_OK(cudaSetDevice(p->device));
-    if (int rc = sync_values(p, s)) return rc;
 
     pv_launch_params lp;
     memset(&lp, 0, sizeof(lp));
     lp.B = B;
     lp.P = P;
-    lp.theta_base = p->d_theta;
-    lp.y0_base = p->d_y0;
     lp.tgrid = p->d_tgrid;
     lp.stats = p->d_stats;
     lp.Y = Y;
@@ -556,9 +562,10 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     if (shmem > 200 * 1024) return fail(PV_E_ARG, "time grid / data too large for shared memory");
     bool obsid = lp.n_obs == p->tab->n_states;
     for (int k = 0; k < lp.n_obs && obsid; ++k) obsid = (lp.obs_idx[k] == k);
+    const pv_launch_ctx cx{p->num_sms, p->layout, p->max_ctas_per_sm, p->theta_base.data(), p->y0_base.data()};
     cudaError_t e = cudaErrorInvalidValue;
     switch (p->model) {
-        PV_MODEL_DISPATCH(e = launch_model, (method, mode, obsid, lp, shmem, p->num_sms, p->layout, s))
+        PV_MODEL_DISPATCH(e = launch_model, (method, mode, obsid, lp, cx, shmem, s))
     }
     if (e != cudaSuccess) return fail(PV_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
     if (two_pass) {
@@ -577,7 +584,7 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
         CUDA_OK(cudaMemsetAsync(lp.counter, 0, sizeof(unsigned long long), s));
         e = cudaErrorInvalidValue;
         switch (p->model) {
-            PV_MODEL_DISPATCH(e = launch_model, (PV_METHOD_RODAS4, mode, false, lp, shmem, p->num_sms, p->layout, s))
+            PV_MODEL_DISPATCH(e = launch_model, (PV_METHOD_RODAS4, mode, false, lp, cx, shmem, s))
         }
         if (e != cudaSuccess) return fail(PV_E_CUDA, std::string("kernel launch (stiff re-run): ") + cudaGetErrorString(e));
     }
@@ -629,6 +636,81 @@ extern "C" int pv_logp_grad_fim(pv_problem* p, int64_t B, const double* P_dev, d
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// hierarchical objective, device resident (pv_hier.cuh)
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int pv_hier_logp_grad(pv_problem* p, int n_chains, int64_t n_local, const double* theta_dev, const double* mu_dev,
+                                 const double* omega_dev, double* dtheta_dev, double* red_dev, int32_t* status_dev,
+                                 int32_t* steps_dev, void* stream) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (n_chains <= 0 || n_local < 0) return fail(PV_E_ARG, "n_chains > 0 and n_local >= 0 required");
+    if (!mu_dev || !omega_dev || !red_dev) return fail(PV_E_ARG, "mu / omega / red is NULL");
+    const int P = (int)p->col_target.size();
+    if (P < 1 || P > PV_HIER_MAX_P) return fail(PV_E_STATE, "configure 1..8 per-individual columns first");
+    const int64_t B = (int64_t)n_chains * n_local;
+    if (B > 0 && (!theta_dev || !dtheta_dev)) return fail(PV_E_ARG, "theta / dtheta is NULL");
+    CUDA_OK(cudaSetDevice(p->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    pv_hier_params hp;
+    memset(&hp, 0, sizeof(hp));
+    for (int j = 0; j < P; ++j) {
+        int row = -1;
+        for (int k = 0; k < p->tab->n_sens; ++k)
+            if (p->tab->sens_index[k] == p->col_target[j]) row = k;
+        if (row < 0)
+            return fail(PV_E_MODEL, std::string("column '") + p->tab->theta_ids[std::min(p->col_target[j], p->tab->n_theta - 1)] +
+                                        "' is not a compiled sensitivity parameter of model '" + p->tab->name + "'");
+        hp.sens_row[j] = row;
+    }
+    const int ns = p->tab->n_sens;
+    const size_t need = sizeof(double) * (size_t)(1 + ns) * (size_t)std::max<int64_t>(B, 1);
+    if (p->hier_bytes < need) {       // grows on the first call of a given size only
+        cudaFree(p->d_hier);
+        p->d_hier = nullptr;
+        p->hier_bytes = 0;
+        CUDA_OK(cudaMalloc(&p->d_hier, need));
+        p->hier_bytes = need;
+    }
+    double* d_logp = p->d_hier;
+    double* d_grad = p->d_hier + std::max<int64_t>(B, 1);
+    if (B > 0)
+        if (int rc = launch(p, PV_MODE_LOGP_GRAD, B, theta_dev, nullptr, nullptr, d_logp, d_grad, status_dev, steps_dev, s)) return rc;
+    hp.n_chains = n_chains;
+    hp.n_local = n_local;
+    hp.n_par = P;
+    hp.theta = theta_dev;
+    hp.mu = mu_dev;
+    hp.omega = omega_dev;
+    hp.logp = d_logp;
+    hp.grad = d_grad;
+    hp.dtheta = dtheta_dev;
+    hp.red = red_dev;
+    pv_hier_epilogue_kernel<<<n_chains, PV_HIER_THREADS, 0, s>>>(hp);
+    g_launches.fetch_add(1);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pv_hier_finish(int n_chains, int n_par, double* red_dev, const double* mu_dev, const double* omega_dev,
+                              const double* mu_prior_mean_host, const double* mu_prior_sd_host,
+                              const double* omega_prior_host, void* stream) {
+    if (n_chains <= 0 || n_par < 1 || n_par > PV_HIER_MAX_P) return fail(PV_E_ARG, "n_chains > 0 and 1 <= n_par <= 8 required");
+    if (!red_dev || !mu_dev || !omega_dev || !mu_prior_mean_host || !mu_prior_sd_host || !omega_prior_host)
+        return fail(PV_E_ARG, "NULL argument");
+    pv_hier_prior pr;
+    memset(&pr, 0, sizeof(pr));
+    for (int q = 0; q < n_par; ++q) {
+        if (!(mu_prior_sd_host[q] > 0) || !(omega_prior_host[q] > 0)) return fail(PV_E_ARG, "prior scales must be > 0");
+        pr.m[q] = mu_prior_mean_host[q];
+        pr.s[q] = mu_prior_sd_host[q];
+        pr.h[q] = omega_prior_host[q];
+    }
+    pv_hier_finish_kernel<<<(n_chains + 63) / 64, 64, 0, (cudaStream_t)stream>>>(n_chains, n_par, red_dev, mu_dev, omega_dev, pr);
+    g_launches.fetch_add(1);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host-buffer pipelines
 // ---------------------------------------------------------------------------------------------------------
 static int ensure_dev(pv_problem* p, int slot, size_t bytes) {
@@ -654,12 +736,7 @@ extern "C" int pv_simulate_host(pv_problem* p, int64_t B, const double* P_host, 
     // chunks sized so that copy-out of chunk i overlaps the kernel of chunk i+1
     // measured on the C2 workload (tools/time_e2e.py; raw pinned D2H of this box: 57 GB/s, one unchunked copy of the
     // results alone: 21.9 ms): 16 Ki rows 23.6 ms, 32 Ki 23.0 ms, 64 Ki 23.4 ms, 128 Ki 24.4 ms per 10^6 trajectories
-    int64_t chunk_rows = (int64_t)1 << 15;
-    if (const char* e = getenv("PV_HOST_CHUNK")) {   // tuning knob (tools/time_e2e.py)
-        const long long v = atoll(e);
-        if (v >= 1024) chunk_rows = v;
-    }
-    const int64_t chunk = std::min<int64_t>(B, chunk_rows);
+    const int64_t chunk = std::min<int64_t>(B, p->host_chunk_rows);   // pv_problem_set_tuning
     // per slot: P [n_cols][chunk], Y [chunk][rows], logp [chunk], status [chunk] + steps [2][chunk] (int32)
     const size_t bytesP = sizeof(double) * (size_t)std::max(n_cols, 1) * chunk;
     const size_t bytesY = sizeof(double) * (size_t)rows * chunk;

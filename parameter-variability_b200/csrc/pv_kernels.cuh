@@ -35,8 +35,6 @@ enum pv_mode : int {
 struct pv_launch_params {
     int64_t B;
     const double* P;           // [n_cols][B]
-    const double* theta_base;  // [NTH]
-    const double* y0_base;     // [NX], NaN = use the model's initial value
     const double* tgrid;       // [T]
     const double* stats;       // [n_data][T][n_obs][4]  likelihood polynomial coefficients q0, q1, q2, pad (see pv_problem_set_data)
     double* Y;                 // [B][T][n_obs]
@@ -54,6 +52,15 @@ struct pv_launch_params {
     const int* n_items_dev;        // number of work items if it lives on the device (nullptr: B)
     double t0;                     // integration start (initial values hold at t0 <= tgrid[0])
     int n_cols, T, n_obs, n_data, noise_model, max_steps, refill_min;
+};
+
+// The batch-wide values (`setValue` calls shared by all rows) ride in the kernel parameters themselves: a launch
+// carries its own snapshot, so changing a value between launches cannot race with a kernel still in flight on another
+// stream, and no host->device copy of configuration data sits in front of a launch.
+template <class M>
+struct pv_launch_params_m : pv_launch_params {
+    double theta_base[M::NTH];   // batch-wide theta
+    double y0_base[M::NX];       // NaN = use the model's initial value
 };
 
 template <int NX, int N>
@@ -236,7 +243,7 @@ struct pv_kernel_traits {
 
 template <class M, int METHOD, int MODE, bool OBSID>
 __global__ void __launch_bounds__(PV_BLOCK, pv_kernel_traits<M, METHOD, MODE>::MIN_BLOCKS)
-pv_batch_kernel(const __grid_constant__ pv_launch_params p) {
+pv_batch_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
     constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
     constexpr bool LOGP = (MODE & PV_MODE_LOGP) != 0;
     using Sys = pv_system<M, SENS>;

@@ -79,7 +79,7 @@ struct pv_split_layout {
 
 template <class M, int MODE>
 __global__ void __launch_bounds__(32 * (1 + M::NS), PV_MINB_SPLIT)
-pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params p) {
+pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
     using namespace pv_rodas4;
     using L = pv_split_layout<M>;
     constexpr int NX = M::NX, NS = M::NS, NB = 1 + NS, N = NX * NB;

@@ -328,16 +328,19 @@ class HierarchicalObjective:
         # parameter-major [P, C, L] throughout: it is the kernel's own layout, so nothing is transposed around the launch
         thp = np.ascontiguousarray(theta.transpose(2, 0, 1))
         lp, g, seg, nf = self.problem.logp_host(thp.reshape(P, C * L), seg_len=L, grad=True)
+        self.n_failed = nf
         g = g[self._sens_row].reshape(P, C, L)
         iw = (1.0 / omega).T[:, :, None]                               # [P, C, 1]
-        lt = np.log(thp)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lt = np.log(thp)
         z = lt - mu.T[:, :, None]
         z *= iw
         s_lt, s_z, s_zz = lt.sum(axis=2), z.sum(axis=2), np.einsum("pcl,pcl->pc", z, z)     # [P, C]
         pop = -s_lt.sum(axis=0) - L * np.log(omega).sum(axis=1) - 0.5 * LOG_2PI * L * P - 0.5 * s_zz.sum(axis=0)
         z *= iw
         z += 1.0
-        z /= thp
+        with np.errstate(divide="ignore", invalid="ignore"):   # theta <= 0 (a leapfrog overshoot): NaN gradient, logp = NaN
+            z /= thp
         g -= z                                                         # d/dtheta of the population density: -(1 + z/omega)/theta
         dmu = np.ascontiguousarray((s_z * iw[:, :, 0]).T)            # C-contiguous results: callers pack them into
         domega = np.ascontiguousarray(((s_zz - L) * iw[:, :, 0]).T)  # all-reduce buffers
@@ -356,3 +359,53 @@ class HierarchicalObjective:
         lp, dth, dmu, dom = self.local_terms(theta, mu, omega)
         lp, dmu, dom = self.finish(lp, dmu, dom, mu, omega)
         return lp, dth, dmu, dom
+
+
+class HierarchicalObjectiveDevice:
+    """``HierarchicalObjective`` with nothing on the host: theta, mu, omega are CUDA tensors, the population terms and
+    the per-chain sums are an epilogue kernel behind the sensitivity kernel (``pv_hier_logp_grad``), the buffer
+    ``[C, 1 + 2P]`` it writes is all-reduced in place by NCCL on the same stream when the individuals of a chain are
+    sharded over ranks, and the hyper-priors are added by ``pv_hier_finish``.  An evaluation
+    is 3 launches + at most one collective, queued without a host synchronisation; the results stay on the device for
+    the sampler's next leapfrog step.
+
+    Data set i of ``problem`` must be this rank's i-th individual (``n_data == n_local``).
+    """
+
+    def __init__(self, problem: "runtime.Problem", n_chains: int, n_individuals: int,
+                 mu_prior: Sequence[tuple[float, float]], omega_prior: Sequence[float], first_individual: int = 0,
+                 n_local: Optional[int] = None, group=None, world: int = 1):
+        import torch
+        self._torch = torch
+        self.problem = problem
+        self.C = int(n_chains)
+        self.n_ind = int(n_individuals)
+        self.first = int(first_individual)
+        self.n_local = self.n_ind if n_local is None else int(n_local)
+        self.P = len(problem.columns)
+        if problem.n_data not in (0, self.n_local) and self.n_local > 0:
+            raise ValueError(f"problem holds {problem.n_data} data sets, expected one per local individual ({self.n_local})")
+        mp = np.asarray(mu_prior, dtype=np.float64).reshape(self.P, 2)
+        self.mu_prior_mean, self.mu_prior_sd = np.ascontiguousarray(mp[:, 0]), np.ascontiguousarray(mp[:, 1])
+        self.omega_prior = np.ascontiguousarray(omega_prior, dtype=np.float64)
+        self.group, self.world = group, int(world)
+        dev = torch.device("cuda", problem.device)
+        B = self.C * self.n_local
+        self.dtheta = torch.empty((self.P, self.C, self.n_local), dtype=torch.float64, device=dev)
+        self.red = torch.empty((self.C, 1 + 2 * self.P), dtype=torch.float64, device=dev)
+        self.status = torch.zeros(max(B, 1), dtype=torch.int32, device=dev)
+
+    def __call__(self, theta, mu, omega):
+        """theta [P, C, n_local] (parameter-major: the kernel's own layout), mu / omega [C, P], CUDA float64 tensors.
+        -> (red [C, 1 + 2P] = (log posterior, d/d mu, d/d omega) per chain, dtheta [P, C, n_local]); both are this
+        object's buffers, valid until the next call, ordered on torch's current stream."""
+        torch = self._torch
+        stream = torch.cuda.current_stream().cuda_stream
+        self.problem.hier_logp_grad(self.C, self.n_local, theta, mu, omega, self.dtheta, self.red, status=self.status,
+                                    stream=stream)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.red, op=dist.ReduceOp.SUM, group=self.group)     # NCCL, ordered after the epilogue kernel
+        runtime.hier_finish(self.C, self.P, self.red, mu, omega, self.mu_prior_mean, self.mu_prior_sd, self.omega_prior,
+                            stream=stream)
+        return self.red, self.dtheta

@@ -47,6 +47,7 @@ ABI = {
     "pv_problem_set_schedule": (C.c_int, [C.c_void_p, C.c_int]),
     "pv_problem_set_layout": (C.c_int, [C.c_void_p, C.c_int]),
     "pv_problem_set_stiff_switch": (C.c_int, [C.c_void_p, C.c_int]),
+    "pv_problem_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "pv_problem_set_observables": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]),
     "pv_problem_set_data": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
     "pv_simulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -63,6 +64,8 @@ ABI = {
                                    C.c_void_p, C.c_void_p]),
     "pv_logp_grad_fim_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                         C.c_void_p]),
+    "pv_hier_logp_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 8),
+    "pv_hier_finish": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _dp, _dp, _dp, C.c_void_p]),
     "pv_logp_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pv_logp_grad_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pv_launch_count": (C.c_int64, []),
@@ -215,6 +218,10 @@ class Problem:
         """LAYOUT_AUTO / LAYOUT_LANE / LAYOUT_SPLIT of the Rosenbrock sensitivity kernels (``pv_problem_set_layout``)."""
         _check(self._lib.pv_problem_set_layout(self._h, int(layout)))
 
+    def set_tuning(self, max_ctas_per_sm: int = 0, host_chunk_rows: int = 0) -> None:
+        """Launch-configuration knobs (``pv_problem_set_tuning``); 0 = default."""
+        _check(self._lib.pv_problem_set_tuning(self._h, int(max_ctas_per_sm), int(host_chunk_rows)))
+
     def set_stiff_switch(self, switch_steps: int = 4000) -> None:
         _check(self._lib.pv_problem_set_stiff_switch(self._h, int(switch_steps)))
 
@@ -271,6 +278,13 @@ class Problem:
         _check(self._lib.pv_logp_grad(self._h, B, _ptr(P), _ptr(logp), _ptr(grad), seg_len, _ptr(logp_seg),
                                       _ptr(status), _ptr(steps), stream))
 
+    def hier_logp_grad(self, n_chains: int, n_local: int, theta, mu, omega, dtheta, red, status=None, steps=None,
+                       stream: int = 0) -> None:
+        """Device-resident hierarchical logp + gradient (``pv_hier_logp_grad``): CUDA tensors in, CUDA tensors out,
+        two launches on ``stream``, no synchronisation."""
+        _check(self._lib.pv_hier_logp_grad(self._h, int(n_chains), int(n_local), _ptr(theta), _ptr(mu), _ptr(omega),
+                                           _ptr(dtheta), _ptr(red), _ptr(status), _ptr(steps), stream))
+
     # ---- host-buffer calls (numpy) -----------------------------------------------------------
     def simulate_host(self, P: Optional[np.ndarray], B: int, Y: Optional[np.ndarray] = None,
                       status: Optional[np.ndarray] = None, steps: Optional[np.ndarray] = None,
@@ -298,11 +312,14 @@ class Problem:
         nf = _check(self._lib.pv_logp_grad_fim_host(self._h, B, _ptr(P), _ptr(lp), _ptr(g), _ptr(f), seg_len, _ptr(seg)))
         return lp, g, f, seg, nf
 
-    def logp_host(self, P: np.ndarray, seg_len: int = 0, grad: bool = False):
-        """-> (logp [B], grad [n_sens, B] or None, logp_seg [B/seg_len] or None, n_failed)."""
+    def logp_host(self, P: np.ndarray, seg_len: int = 0, grad: bool = False, out: Optional[np.ndarray] = None):
+        """-> (logp [B], grad [n_sens, B] or None, logp_seg [B/seg_len] or None, n_failed).  ``out``: caller's logp buffer
+        (e.g. ``pinned_empty(B)`` so the copy back runs at PCIe speed)."""
         P = np.ascontiguousarray(P, dtype=np.float64)
         B = P.shape[-1]
-        lp = np.empty(B)
+        if out is not None and (out.shape != (B,) or out.dtype != np.float64 or not out.flags.c_contiguous):
+            raise ValueError(f"out must be a contiguous float64 array of shape ({B},)")
+        lp = np.empty(B) if out is None else out
         seg = np.empty(B // seg_len) if seg_len else None
         if grad:
             g = np.empty((self.n_sens, B))
@@ -320,6 +337,13 @@ class SamplerOptions(C.Structure):
     """``pv_sampler_options`` (include/parvar_b200.h)."""
     _fields_ = [("decay_constant", C.c_double), ("target_acceptance_rate", C.c_double), ("reg_factor", C.c_double),
                 ("nu", C.c_double), ("eta", C.c_double), ("threshold_sample", C.c_int64), ("adapt_betas", C.c_int32)]
+
+
+def hier_finish(n_chains: int, n_cols: int, red, mu, omega, mu_prior_mean, mu_prior_sd, omega_prior, stream: int = 0) -> None:
+    """Hyper-priors added in place to the (all-reduced) buffer ``red`` [n_chains, 1 + 2 n_cols] (``pv_hier_finish``)."""
+    m, s, h = (np.ascontiguousarray(a, dtype=np.float64) for a in (mu_prior_mean, mu_prior_sd, omega_prior))
+    _check(load_library().pv_hier_finish(int(n_chains), int(n_cols), _ptr(red), _ptr(mu), _ptr(omega), m.ctypes.data_as(_dp),
+                                         s.ctypes.data_as(_dp), h.ctypes.data_as(_dp), stream))
 
 
 def launch_count() -> int:

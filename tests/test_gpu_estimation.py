@@ -89,6 +89,74 @@ def test_hierarchical_objective_vs_oracle(cuda_lib, rt, oracle):
         np.testing.assert_allclose(dth[c, i], g + d_theta[i], rtol=1e-6)
 
 
+@pytest.mark.parametrize("columns", [["k_abs", "CL"], ["CL", "k_abs"]])
+def test_hierarchical_objective_device_resident(cuda_lib, rt, oracle, columns):
+    """pv_hier_logp_grad + pv_hier_finish (CUDA tensors in and out, no host round trip) against the oracle and against the
+    host-algebra ``HierarchicalObjective``; columns in and against the compiled sensitivity order; repeated evaluations are
+    bit-identical (fixed-order reductions); theta <= 0 and a rank without individuals behave."""
+    import torch
+    po = pkg("optimization.petab_optimization")
+    t = np.linspace(0, 40, 10)
+    n_ind, C = 300, 5           # > 256: every thread of the epilogue CTA walks more than one individual
+    th_true = np.stack([lognormal_draws(1, n_ind), lognormal_draws(2, n_ind)], axis=1)
+    rs = np.random.RandomState(5)
+    y = np.stack([oracle.simple_pk_exact({"k_abs": a, "CL": c}, t) for a, c in th_true])
+    y = y * (1 + 0.05 * rs.normal(size=y.shape))
+    pb = rt.Problem("simple_pk")
+    pb.set_solver(rtol=1e-9, atol=1e-13)
+    pb.set_columns(columns)
+    pb.set_timepoints(t)
+    pb.set_observables(["y_gut", "y_cent", "y_peri"])
+    pb.set_data(np.stack([po.sufficient_statistics(y[i:i + 1], 0) for i in range(n_ind)], axis=-1), 0.05)
+    mu_prior, omega_prior = [(0.0, 1.0), (-0.3, 0.5)], [1.0, 0.7]
+    theta = np.stack([np.stack([lognormal_draws(10 + c, n_ind), lognormal_draws(20 + c, n_ind)], axis=1) for c in range(C)])
+    mu = rs.normal(size=(C, 2)) * 0.3
+    omega = 0.5 + rs.rand(C, 2)
+    H = po.HierarchicalObjective(pb, n_ind, mu_prior=mu_prior, omega_prior=omega_prior)
+    lp_h, dth_h, dmu_h, dom_h = H(theta, mu, omega)                      # host algebra (oracle-checked above)
+    D = po.HierarchicalObjectiveDevice(pb, C, n_ind, mu_prior=mu_prior, omega_prior=omega_prior)
+    th_d = torch.from_numpy(np.ascontiguousarray(theta.transpose(2, 0, 1))).cuda()
+    mu_d, om_d = torch.from_numpy(mu).cuda(), torch.from_numpy(omega).cuda()
+    red, dth = D(th_d, mu_d, om_d)
+    torch.cuda.synchronize()
+    red1, dth1 = red.cpu().numpy().copy(), dth.cpu().numpy().copy()
+    assert int(D.status.abs().sum()) == 0
+    np.testing.assert_allclose(red1[:, 0], lp_h, rtol=1e-12)
+    np.testing.assert_allclose(red1[:, 1:3], dmu_h, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(red1[:, 3:5], dom_h, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(dth1.transpose(1, 2, 0), dth_h, rtol=1e-12, atol=1e-12 * np.abs(dth_h).max())
+    # ... and directly against the oracle for one chain
+    c = 2
+    names = {n: j for j, n in enumerate(columns)}
+    ref = 0.0
+    for i in range(n_ind):
+        over = {n: theta[c, i, j] for n, j in names.items()}
+        ref += oracle.loglik_normal(oracle.simple_pk_exact(over, t), y[i], 0.05)
+    pop, d_theta, d_mu, d_sigma = oracle.population_lognormal_logpdf(theta[c], mu[c], omega[c])
+    m0, s0 = np.array([a for a, _ in mu_prior]), np.array([b for _, b in mu_prior])
+    ref += pop + oracle.log_prior_normal(mu[c], m0, s0)[0]
+    ref += np.sum(0.5 * np.log(2 / np.pi) - np.log(omega_prior) - 0.5 * (omega[c] / np.array(omega_prior)) ** 2)
+    assert red1[c, 0] == pytest.approx(ref, rel=1e-7)
+    np.testing.assert_allclose(red1[c, 1:3], d_mu + oracle.log_prior_normal(mu[c], m0, s0)[1], rtol=1e-9)
+    np.testing.assert_allclose(red1[c, 3:5], d_sigma - omega[c] / np.array(omega_prior) ** 2, rtol=1e-9)
+    # deterministic
+    red, dth = D(th_d, mu_d, om_d)
+    torch.cuda.synchronize()
+    assert np.array_equal(red.cpu().numpy(), red1) and np.array_equal(dth.cpu().numpy(), dth1)
+    # theta <= 0 poisons exactly its chain
+    bad = th_d.clone()
+    bad[0, 1, 7] = -0.5
+    red, _ = D(bad, mu_d, om_d)
+    torch.cuda.synchronize()
+    r = red.cpu().numpy()
+    assert np.isnan(r[1, 0]) and np.all(np.isfinite(np.delete(r[:, 0], 1)))
+    # a rank without individuals contributes zeros before the hyper-priors
+    E = po.HierarchicalObjectiveDevice(pb, C, n_ind, mu_prior=mu_prior, omega_prior=omega_prior, first_individual=n_ind, n_local=0)
+    pb.hier_logp_grad(C, 0, None, mu_d, om_d, None, E.red)
+    torch.cuda.synchronize()
+    assert np.all(E.red.cpu().numpy() == 0.0)
+
+
 def test_petab_directory_literal_and_intended(cuda_lib, rt, oracle, tmp_path):
     io = pkg("optimization.petab_io")
     po = pkg("optimization.petab_optimization")

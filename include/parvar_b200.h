@@ -41,7 +41,7 @@ enum {
 };
 
 /* per-trajectory status codes written to status[B] */
-enum { PV_TRAJ_OK = 0, PV_TRAJ_MAX_STEPS = 1, PV_TRAJ_STEP_TOO_SMALL = 2, PV_TRAJ_NONFINITE = 3 };
+enum { PV_TRAJ_OK = 0, PV_TRAJ_MAX_STEPS = 1, PV_TRAJ_STEP_TOO_SMALL = 2, PV_TRAJ_NONFINITE = 3, PV_TRAJ_STIFF = 4 };
 
 enum { PV_METHOD_AUTO = 0, PV_METHOD_DOPRI5 = 1, PV_METHOD_RODAS4 = 2 };
 enum { PV_NOISE_NORMAL = 0, PV_NOISE_LOGNORMAL = 1 };
@@ -105,6 +105,13 @@ int pv_problem_set_tuning(pv_problem* p, int max_ctas_per_sm, int64_t host_chunk
  * 1e8 that a tempered chain or a uniform start point visits - are re-run with RODAS4 in a second launch on the
  * same stream (the reference's CVODE is implicit throughout).  switch_steps >= max_steps disables the second pass. */
 int pv_problem_set_stiff_switch(pv_problem* p, int switch_steps);
+/* The explicit first pass of PV_METHOD_AUTO does not have to use up its budget to find out: after `after_steps`
+ * attempted steps (default 64) DOPRI5 estimates h*|lambda| from its last two stages at every accepted step (Hairer's
+ * stiffness test); 15 consecutive estimates beyond the stability bound 3.25 end the explicit attempt (status
+ * PV_TRAJ_STIFF internally) and the trajectory goes to the RODAS4 pass.  A sampler's tempered chains roam the PEtab
+ * bounds [0, 1e8]; without the test every such evaluation costs switch_steps explicit steps of pure latency.
+ * after_steps = INT32_MAX disables it.  An explicitly selected PV_METHOD_DOPRI5 never runs the test. */
+int pv_problem_set_stiffness_detection(pv_problem* p, int after_steps);
 
 /* `r.resetAll(); r.setValue(key, value)` for values shared by the whole batch (dosage dict,
  * petab_factory.py:229-233).  id = a theta id, or a state id / "[state id]" for an initial concentration. */

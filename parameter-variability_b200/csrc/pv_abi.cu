@@ -78,6 +78,7 @@ struct pv_problem {
     // METHOD_AUTO on a non-stiff model: trajectories that exhaust switch_steps explicit steps (stiff parameter
     // values) are re-run with RODAS4.  Scratch per launch slot: 0 = caller's stream, 1..3 = internal pipeline streams.
     int switch_steps = 4000;
+    int stiff_after = 64;          // DOPRI5 stiffness detection of the AUTO first pass starts after this many steps
     int32_t* d_scratch_status[4] = {nullptr, nullptr, nullptr, nullptr};
     int32_t* d_scratch_index[4] = {nullptr, nullptr, nullptr, nullptr};
     int* d_scratch_count[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -238,6 +239,13 @@ extern "C" int pv_problem_set_stiff_switch(pv_problem* p, int switch_steps) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
     if (switch_steps < 1) return fail(PV_E_ARG, "switch_steps must be >= 1");
     p->switch_steps = switch_steps;
+    return 0;
+}
+
+extern "C" int pv_problem_set_stiffness_detection(pv_problem* p, int after_steps) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (after_steps < 0) return fail(PV_E_ARG, "after_steps must be >= 0");
+    p->stiff_after = after_steps;
     return 0;
 }
 
@@ -552,9 +560,11 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     lp.refill_min = p->refill_min > 0 ? p->refill_min : (method == PV_METHOD_RODAS4 ? 32 : 6);
     // explicit first pass with a step budget, implicit second pass for what did not finish (stiff parameter values)
     const bool two_pass = p->method == PV_METHOD_AUTO && !p->tab->stiff && p->switch_steps < p->max_steps;
+    lp.stiff_after = 0x7fffffff;
     if (two_pass) {
         if (int rc = ensure_scratch(p, slot, B)) return rc;
         lp.max_steps = p->switch_steps;
+        lp.stiff_after = p->stiff_after;
         if (!lp.status) lp.status = p->d_scratch_status[slot];
     }
     size_t shmem = sizeof(double) * (lp.T + p->tab->n_theta + p->tab->n_states);
@@ -571,7 +581,7 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     if (two_pass) {
         int* cnt = p->d_scratch_count[slot];
         CUDA_OK(cudaMemsetAsync(cnt, 0, sizeof(int), s));
-        pv_compact_status_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(lp.status, B, PV_ERR_MAX_STEPS,
+        pv_compact_status_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(lp.status, B, (1u << PV_ERR_MAX_STEPS) | (1u << PV_ERR_STIFF),
                                                                            p->d_scratch_index[slot], cnt);
         g_launches.fetch_add(1);
         CUDA_OK(cudaGetLastError());

@@ -112,6 +112,10 @@ PV_COEF_SPACE double pv_dp5[32] = {
     /* 28 d4 */ -10690763975.0 / 1880347072.0, /* 29 d5 */ 701980252875.0 / 199316789632.0,
     /* 30 d6 */ -1453857185.0 / 822651844.0, /* 31 d7 */ 69997945.0 / 29380423.0};
 
+#ifndef PV_STIFF_REMAINING_STEPS
+#define PV_STIFF_REMAINING_STEPS 600.0
+#endif
+
 struct pv_step_stats {
     int accepted;
     int rejected;
@@ -122,6 +126,7 @@ enum pv_status_code : int {
     PV_ERR_MAX_STEPS = 1,    // step budget exhausted before t_end
     PV_ERR_STEP_TOO_SMALL = 2,
     PV_ERR_NONFINITE = 3,
+    PV_ERR_STIFF = 4,        // explicit integrator gave up: step size limited by stability (see pv_dopri5_lane::stiff_after)
 };
 
 // Flops of one attempted step besides the RHS evaluations: 21 a_ij + 6 b/e FMAs for the stages
@@ -150,6 +155,16 @@ struct pv_dopri5_lane {
     bool last_rejected;
     int jout, nstep;
     pv_step_stats st;
+    // Stiffness detection (Hairer, Norsett, Wanner II.4 / dopri5.f): after `stiff_after` attempted steps every accepted
+    // step estimates h * |lambda| ~ h * |f(t+h, y1) - f(t+h, g6)| / |y1 - g6| from the last two stages; 15 consecutive
+    // estimates above DOPRI5's stability bound 3.25 mean the step size is set by stability, not accuracy.  That alone
+    // is not a reason to stop: simple_pk's tail (t > 40 of [0, 100], solution at atol level) is stability limited at
+    // h ~ 1.3 and still only ~60 steps long.  The lane gives up (PV_ERR_STIFF, so the caller can hand the trajectory to
+    // the implicit integrator) only if, at the stability-limited step size, the rest of the interval would take more
+    // than PV_STIFF_REMAINING_STEPS steps - more than a whole RODAS4 run costs.
+    // INT_MAX = off (an explicitly chosen DOPRI5 integrates whatever it is given).
+    int stiff_after = 0x7fffffff;
+    int stiff_run;     // consecutive stiff estimates (high half) | consecutive non-stiff estimates (low half)
 
     // z0 -> y, outputs for grid points at t0, first derivative, initial step size
     template <class Out>
@@ -158,6 +173,7 @@ struct pv_dopri5_lane {
         st.accepted = 0;
         st.rejected = 0;
         nstep = 0;
+        stiff_run = 0;
         lfacold = -13.287712f;   // log2(1e-4)
         last_rejected = false;
         t = t0;
@@ -302,6 +318,22 @@ struct pv_dopri5_lane {
                     ++jout;
                     t_next = jout < T ? tgrid[jout] : 1e300;
                 } while (t_next <= tn);
+            }
+            if (nstep > stiff_after) {
+                double num = 0.0, den = 0.0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double g6 = fma(h, fma(pv_dp5[14], k5[i], fma(pv_dp5[13], k4[i], fma(pv_dp5[12], k3[i], fma(pv_dp5[11], k2[i], pv_dp5[10] * k1[i])))), y[i]);
+                    const double dy = yn[i] - g6, dk = k7[i] - k6[i];
+                    num = fma(dk, dk, num);
+                    den = fma(dy, dy, den);
+                }
+                if (den > 0.0 && h * h * num > 10.5625 * den) {          // (h lambda)^2 > 3.25^2
+                    stiff_run = (stiff_run & ~0xffff) + 0x10000;
+                    if (stiff_run >= 15 * 0x10000 && (tend - t) > PV_STIFF_REMAINING_STEPS * h) return PV_ERR_STIFF;
+                } else if (((++stiff_run) & 0xffff) >= 6) {
+                    stiff_run = 0;
+                }
             }
             // h_new = h / clamp(fac11 / facold^beta / 0.9, 0.1, 5)  ->  multiply by 2^-(log2 of the clamped factor)
             // (a step that follows a rejection must not grow: lower bound 0 instead of log2(1/5))

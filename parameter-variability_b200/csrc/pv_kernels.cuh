@@ -52,6 +52,7 @@ struct pv_launch_params {
     const int* n_items_dev;        // number of work items if it lives on the device (nullptr: B)
     double t0;                     // integration start (initial values hold at t0 <= tgrid[0])
     int n_cols, T, n_obs, n_data, noise_model, max_steps, refill_min;
+    int stiff_after;               // DOPRI5 stiffness detection starts after this many steps (INT_MAX = off)
 };
 
 // The batch-wide values (`setValue` calls shared by all rows) ride in the kernel parameters themselves: a launch
@@ -347,6 +348,7 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
                     }
                     sink.begin(b, qbase);
                     have = true;
+                    if constexpr (METHOD == 1) lane.stiff_after = p.stiff_after;
                     const int rc = lane.start(ks, z, p.t0, sh_t, p.T, p.rtol, p.atol, sink);
                     if (rc != PV_RUNNING) finish(rc);
                 }
@@ -376,11 +378,11 @@ __global__ void pv_segment_sum_kernel(const double* __restrict__ x, int64_t seg_
     if (lane == 0) out[seg] = acc;
 }
 
-// work list of the trajectories whose status == code (order irrelevant: results go to their own slots)
-__global__ void pv_compact_status_kernel(const int32_t* __restrict__ status, int64_t B, int code, int32_t* __restrict__ index,
+// work list of the trajectories whose status code is in code_mask (bit k = code k) (order irrelevant: results go to their own slots)
+__global__ void pv_compact_status_kernel(const int32_t* __restrict__ status, int64_t B, unsigned code_mask, int32_t* __restrict__ index,
                                          int* __restrict__ count) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool hit = i < B && status[i] == code;
+    const bool hit = i < B && ((code_mask >> (status[i] & 31)) & 1u);
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     if (!m) return;
     const int lane = threadIdx.x & 31;

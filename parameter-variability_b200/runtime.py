@@ -19,7 +19,7 @@ LIB_PATH = Path(__import__("os").environ.get("PARVAR_B200_LIB", PKG_DIR / "lib" 
 METHOD_AUTO, METHOD_DOPRI5, METHOD_RODAS4 = 0, 1, 2
 NOISE_NORMAL, NOISE_LOGNORMAL = 0, 1
 LAYOUT_AUTO, LAYOUT_LANE, LAYOUT_SPLIT = 0, 1, 2
-STATUS_TEXT = {0: "ok", 1: "max_steps", 2: "step_too_small", 3: "nonfinite"}
+STATUS_TEXT = {0: "ok", 1: "max_steps", 2: "step_too_small", 3: "nonfinite", 4: "stiff"}
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -48,6 +48,7 @@ ABI = {
     "pv_problem_set_layout": (C.c_int, [C.c_void_p, C.c_int]),
     "pv_problem_set_stiff_switch": (C.c_int, [C.c_void_p, C.c_int]),
     "pv_problem_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
+    "pv_problem_set_stiffness_detection": (C.c_int, [C.c_void_p, C.c_int]),
     "pv_problem_set_observables": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]),
     "pv_problem_set_data": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
     "pv_simulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -217,6 +218,9 @@ class Problem:
     def set_layout(self, layout: int = 0) -> None:
         """LAYOUT_AUTO / LAYOUT_LANE / LAYOUT_SPLIT of the Rosenbrock sensitivity kernels (``pv_problem_set_layout``)."""
         _check(self._lib.pv_problem_set_layout(self._h, int(layout)))
+
+    def set_stiffness_detection(self, after_steps: int = 64) -> None:
+        _check(self._lib.pv_problem_set_stiffness_detection(self._h, int(after_steps)))
 
     def set_tuning(self, max_ctas_per_sm: int = 0, host_chunk_rows: int = 0) -> None:
         """Launch-configuration knobs (``pv_problem_set_tuning``); 0 = default."""

@@ -40,9 +40,10 @@ def meta(model: str) -> dict:
 
 
 def simulate(model: str, overrides: dict, tgrid, rtol: float, atol: float, method: int = 1, sens: bool = False,
-             max_steps: int = 1_000_000):
-    """-> (rc, Y [T, NX] or [T, NX*(1+NS)], (accepted, rejected))."""
+             max_steps: int = 1_000_000, stiff_after: int = 0x7fffffff):
+    """-> (rc, Y [T, NX] or [T, NX*(1+NS)], (accepted, rejected)).  ``stiff_after``: DOPRI5 stiffness detection."""
     lib = load()
+    lib.hh_set_stiff_after(int(stiff_after))
     m = meta(model)
     th = np.array(m["theta_default"], float)
     y0o = np.full(m["NX"], np.nan)

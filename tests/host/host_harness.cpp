@@ -18,6 +18,9 @@ struct Collect {
     }
 };
 
+static int g_stiff_after = 0x7fffffff;   // DOPRI5 stiffness detection of the next hh_simulate call (hh_set_stiff_after)
+extern "C" void hh_set_stiff_after(int n) { g_stiff_after = n; }
+
 template <class M, bool SENS>
 static int run(int method, const double* theta, const double* y0_over, const double* tgrid, int T, double rtol,
                double atol, int max_steps, double* out, int* stats) {
@@ -38,9 +41,13 @@ static int run(int method, const double* theta, const double* y0_over, const dou
     Collect<Sys::N> col{out};
     pv_step_stats st;
     int rc;
-    if (method == 1)
-        rc = pv_dopri5_integrate<Sys>(ks, z, tgrid[0], tgrid, T, rtol, atol, max_steps, col, st);
-    else
+    if (method == 1) {
+        pv_dopri5_lane<Sys> lane;
+        lane.stiff_after = g_stiff_after;
+        rc = lane.start(ks, z, tgrid[0], tgrid, T, rtol, atol, col);
+        while (rc == PV_RUNNING) rc = lane.step(ks, tgrid, T, rtol, atol, max_steps, col);
+        st = lane.st;
+    } else
         rc = pv_rosenbrock_integrate<M, SENS>(ks, z, tgrid[0], tgrid, T, rtol, atol, max_steps, col, st);
     stats[0] = st.accepted;
     stats[1] = st.rejected;

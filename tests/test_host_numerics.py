@@ -92,3 +92,22 @@ def test_status_codes():
     assert rc == 1
     rc, Y, st = harness.simulate("simple_pk", {"k_abs": float("nan")}, t, 1e-7, 1e-10, DOPRI5)
     assert rc != 0
+
+
+def test_dopri5_stiffness_detection_hands_over_early_and_only_when_it_pays():
+    """PV_METHOD_AUTO's explicit first pass (pv_dopri5_lane::stiff_after): rate constants near the PEtab upper bound end
+    the explicit attempt after ~100 steps instead of the 4000-step budget; the benchmark's log-normal cloud - stability
+    limited in its flat tail, but cheap - is never handed over."""
+    t = np.linspace(0, 100, 50)
+    for k, cl in ((1e5, 1.0), (1.0, 1e6), (1e8, 1e8)):
+        rc0, _, st0 = harness.simulate("simple_pk", {"k_abs": k, "CL": cl}, t, 1e-7, 1e-10, max_steps=4000)
+        rc1, _, st1 = harness.simulate("simple_pk", {"k_abs": k, "CL": cl}, t, 1e-7, 1e-10, max_steps=4000, stiff_after=64)
+        assert rc0 == 1 and sum(st0) == 4000          # PV_ERR_MAX_STEPS after the whole budget
+        assert rc1 == 4 and sum(st1) < 200            # PV_ERR_STIFF
+    rs = np.random.RandomState(1234)
+    th = rs.lognormal(-0.3465735902799726, 0.8325546111576977, size=(2, 300))
+    for b in range(300):
+        over = {"k_abs": th[0, b], "CL": th[1, b]}
+        rc0, Y0, st0 = harness.simulate("simple_pk", over, t, 1e-7, 1e-10)
+        rc1, Y1, st1 = harness.simulate("simple_pk", over, t, 1e-7, 1e-10, stiff_after=64)
+        assert rc0 == 0 and rc1 == 0 and st0 == st1 and np.array_equal(Y0, Y1)

@@ -240,6 +240,35 @@ int pv_sampler_step(int64_t Q, int C, int dim, int64_t it, int64_t n_trace, cons
                     double* cov_hist, double* cov_scale, double* cov, double* n_acc, double* n_swap, double* n_swap_try,
                     double* trace_x, double* trace_neglogpost, double* trace_neglogprior);
 
+/* ---- the same sampler, device resident --------------------------------------------------------------------
+ * Chain state, proposal covariances, ladder and trace live in HBM; one iteration = proposal kernel -> the batched
+ * objective of `p` (n_chains * Q * n_groups trajectories, pv_logp) -> accept / adapt / swap / trace kernel, recorded
+ * once into a CUDA graph (use_graph != 0) and replayed per iteration on the sampler's own stream; nothing of an
+ * iteration touches the host.  Replaces, for Q problems at once, the loop behind `pypesto.sample.sample(...)`
+ * (petab_optimization.py:158-173).
+ *   p            configured problem: columns = the per-group parameters (n_cols), data = one data set per
+ *                (problem, group), n_data == Q * n_groups; x = [n_cols][n_groups] flattened, dim = n_cols * n_groups <= 16
+ *   prior_loc / prior_scale [Q][dim]  parameterScaleNormal priors on the lin scale, NaN loc = none (petab_factory.py:443-449)
+ *   x0 [Q][dim]  start of every chain of a problem; cov0 [dim][dim] or NULL (identity); ladder: near-exponential, T_max 5e4
+ *   rng_block    iterations per uploaded block of random numbers
+ * pv_sampler_advance queues n_iter <= rng_block iterations with the caller's random numbers, laid out
+ * xi [n_iter][Q][C][dim] ~ N(0,1), u_acc [n_iter][Q][C], u_swap [n_iter][Q][C-1] ~ U(0,1), and returns without waiting for
+ * them (it waits for the PREVIOUS block only, to reuse the staging buffers).  Every block but the last must be rng_block long.
+ * pv_sampler_result synchronises and copies out rows 0..iterations of the traces ([n_samples+1][Q][C][dim] iteration-major,
+ * as pv_sampler_step), the final ladder and the counters; any pointer may be NULL.
+ * While a sampler exists its problem must not be used for other launches (they share the problem's scratch buffers). */
+typedef struct pv_sampler pv_sampler;
+pv_sampler* pv_sampler_create(pv_problem* p, int64_t Q, int n_groups, int n_chains, int64_t n_samples,
+                              const pv_sampler_options* options, const double* lb, const double* ub, const double* prior_loc,
+                              const double* prior_scale, const double* x0, const double* cov0, int64_t rng_block,
+                              int use_graph);
+int pv_sampler_advance(pv_sampler* s, int64_t n_iter, const double* xi_host, const double* u_acc_host,
+                       const double* u_swap_host);
+int pv_sampler_result(pv_sampler* s, double* trace_x_host, double* trace_neglogpost_host, double* trace_neglogprior_host,
+                      double* betas_host, double* n_acc_host, double* n_swap_host, double* n_swap_try_host,
+                      int64_t* n_bad_cov);
+void pv_sampler_destroy(pv_sampler* s);
+
 /* ---- measurement helpers ------------------------------------------------------------------------------ */
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t pv_launch_count(void);

@@ -22,6 +22,7 @@
 #include "pv_kernels.cuh"
 #include "pv_rosenbrock_split.cuh"
 #include "pv_hier.cuh"
+#include "pv_sampler_device.cuh"
 #include "generated/simple_chain.cuh"
 #include "generated/simple_pk.cuh"
 #include "generated/icg_body_flat.cuh"
@@ -67,6 +68,8 @@ struct pv_problem {
     // lane-refill work counters: one per launch in flight (ring), zeroed in-stream before each launch
     unsigned long long* d_counters = nullptr;
     int counter_next = 0;
+    unsigned long long* own_counters = nullptr;   // set while a sampler captures its iteration graph: that graph's private slots
+    int own_counter_next = 0;
     int num_sms = 0;
     int refill_min = 0;   // 0 = per-integrator default (DOPRI5: 6, RODAS4: 32), see pv_problem_set_schedule
     int layout = PV_LAYOUT_AUTO;   // see pv_problem_set_layout
@@ -85,6 +88,7 @@ struct pv_problem {
     int64_t scratch_cap[4] = {0, 0, 0, 0};
 };
 #define PV_COUNTER_RING 1024
+#define PV_SAMPLER_COUNTERS 8
 
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int pv_abi_version(void) { return PV_ABI_VERSION; }
@@ -502,6 +506,15 @@ static int ensure_scratch(pv_problem* p, int slot, int64_t B) {
     return 0;
 }
 
+// lane-refill work counter of the next launch: a slot of the problem's ring, or - while a sampler records its iteration
+// graph, whose replays must not share a slot with launches made meanwhile - one of the graph's own slots
+static unsigned long long* next_counter(pv_problem* p) {
+    if (p->own_counters) return p->own_counters + (p->own_counter_next++ % PV_SAMPLER_COUNTERS);
+    unsigned long long* c = p->d_counters + p->counter_next;
+    p->counter_next = (p->counter_next + 1) % PV_COUNTER_RING;
+    return c;
+}
+
 static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y, double* S, double* logp,
                   double* grad, int32_t* status, int32_t* steps, cudaStream_t s, double* fim = nullptr, int slot = 0) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
@@ -549,8 +562,7 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     lp.noise_model = p->noise_model;
     lp.max_steps = p->max_steps;
     lp.t0 = p->t0;
-    lp.counter = p->d_counters + p->counter_next;
-    p->counter_next = (p->counter_next + 1) % PV_COUNTER_RING;
+    lp.counter = next_counter(p);
     CUDA_OK(cudaMemsetAsync(lp.counter, 0, sizeof(unsigned long long), s));
     int method = p->method;
     if (method == PV_METHOD_AUTO) method = p->tab->stiff ? PV_METHOD_RODAS4 : PV_METHOD_DOPRI5;
@@ -589,8 +601,7 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
         lp.refill_min = p->refill_min > 0 ? p->refill_min : 32;
         lp.index_map = p->d_scratch_index[slot];
         lp.n_items_dev = cnt;
-        lp.counter = p->d_counters + p->counter_next;
-        p->counter_next = (p->counter_next + 1) % PV_COUNTER_RING;
+        lp.counter = next_counter(p);
         CUDA_OK(cudaMemsetAsync(lp.counter, 0, sizeof(unsigned long long), s));
         e = cudaErrorInvalidValue;
         switch (p->model) {
@@ -897,6 +908,227 @@ extern "C" int pv_sampler_step(int64_t Q, int C, int dim, int64_t it, int64_t n_
     if (pv_sampler_step_impl(Q, C, dim, it, n_trace, o, x, llh, lpr, x_new, llh_new, lpr_new, inside, u_acc, u_swap, betas,
                              mean_hist, cov_hist, cov_scale, cov, n_acc, n_swap, n_swap_try, trace_x, trace_lp, trace_pr))
         return fail(PV_E_ARG, "pv_sampler_step: dim or number of temperatures too large");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device-resident sampler (pv_sampler_device.cuh)
+// ---------------------------------------------------------------------------------------------------------
+struct pv_sampler {
+    pv_problem* p = nullptr;
+    pv_sampler_dev d;
+    std::vector<void*> allocs;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaEvent_t ev_block = nullptr;      // the iterations of the last uploaded block of random numbers are done
+    double *h_xi = nullptr, *h_ua = nullptr, *h_us = nullptr;   // pinned staging of one block
+    double *d_xi = nullptr, *d_ua = nullptr, *d_us = nullptr;
+    int32_t* d_status = nullptr;
+    double* d_logp = nullptr;
+    long long it_host = 0;               // iterations queued so far (the next one to run is it_host + 1)
+    int step_threads = 0, step_blocks = 0;
+    size_t step_shmem = 0;
+};
+
+template <class T>
+static T* sampler_alloc(pv_sampler* s, size_t n, bool zero = true) {
+    void* ptr = nullptr;
+    if (cudaMalloc(&ptr, sizeof(T) * std::max<size_t>(n, 1)) != cudaSuccess) ptr = nullptr;
+    if (ptr && zero) cudaMemset(ptr, 0, sizeof(T) * std::max<size_t>(n, 1));
+    s->allocs.push_back(ptr);      // a failed allocation stays in the list as NULL: pv_sampler_create checks for it
+    return (T*)ptr;
+}
+
+// one iteration on the sampler's stream: proposal -> objective (one batched launch for all problems and temperatures) ->
+// accept / adapt / swap / trace
+static int sampler_enqueue_iteration(pv_sampler* s) {
+    const pv_sampler_dev& d = s->d;
+    const int64_t QC = d.Q * d.C;
+    pv_sampler_propose_kernel<<<(unsigned)((QC + 127) / 128), 128, 0, s->stream>>>(d);
+    g_launches.fetch_add(1);
+    CUDA_OK(cudaGetLastError());
+    const int64_t B = QC * d.G;
+    if (int rc = launch(s->p, PV_MODE_LOGP, B, d.P, nullptr, nullptr, s->d_logp, nullptr, s->d_status, nullptr, s->stream)) return rc;
+    if (int rc = segment_sum(s->d_logp, B, d.G, d.seg, s->stream)) return rc;
+    pv_sampler_step_kernel<<<s->step_blocks, s->step_threads, s->step_shmem, s->stream>>>(d);
+    g_launches.fetch_add(1);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" void pv_sampler_destroy(pv_sampler* s) {
+    if (!s) return;
+    if (s->p) cudaSetDevice(s->p->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->exec) cudaGraphExecDestroy(s->exec);
+    if (s->graph) cudaGraphDestroy(s->graph);
+    if (s->ev_block) cudaEventDestroy(s->ev_block);
+    for (void* a : s->allocs) cudaFree(a);
+    if (s->h_xi) cudaFreeHost(s->h_xi);
+    if (s->h_ua) cudaFreeHost(s->h_ua);
+    if (s->h_us) cudaFreeHost(s->h_us);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" pv_sampler* pv_sampler_create(pv_problem* p, int64_t Q, int n_groups, int n_chains, int64_t n_samples,
+                                         const pv_sampler_options* options, const double* lb, const double* ub,
+                                         const double* prior_loc, const double* prior_scale, const double* x0,
+                                         const double* cov0, int64_t rng_block, int use_graph) {
+    auto bad = [](const char* m) -> pv_sampler* {
+        fail(PV_E_ARG, std::string("pv_sampler_create: ") + m);
+        return nullptr;
+    };
+    if (!p || !options || !lb || !ub || !prior_loc || !prior_scale || !x0) return bad("NULL argument");
+    const int NP = (int)p->col_target.size(), G = n_groups, C = n_chains;
+    if (Q < 1 || G < 1 || C < 1 || C > 64 || n_samples < 1 || rng_block < 1) return bad("Q, n_groups, n_chains (<= 64), n_samples, rng_block must be >= 1");
+    const int dim = NP * G;
+    if (NP < 1 || dim > pv_sampler_math::MAXD) return bad("configure the per-group parameters as columns first (n_cols * n_groups <= 16)");
+    if (p->stats.empty() || p->n_data != Q * G) return bad("the problem must hold one data set per (problem, group): n_data == Q * n_groups");
+    if (cudaSetDevice(p->device) != cudaSuccess) return bad("cudaSetDevice failed");
+    auto* s = new pv_sampler();
+    s->p = p;
+    memset(&s->d, 0, sizeof(s->d));
+    pv_sampler_dev& d = s->d;
+    d.Q = Q; d.C = C; d.G = G; d.NP = NP; d.dim = dim; d.S = C > 1 ? C - 1 : 1;
+    d.n_trace = n_samples + 1;
+    d.rng_block = rng_block;
+    d.o = *options;
+    const int64_t QC = Q * C;
+    bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
+    s->own_stream = ok;
+    ok = ok && cudaEventCreateWithFlags(&s->ev_block, cudaEventDisableTiming) == cudaSuccess;
+    d.x = sampler_alloc<double>(s, QC * dim); d.llh = sampler_alloc<double>(s, QC); d.lpr = sampler_alloc<double>(s, QC);
+    d.betas = sampler_alloc<double>(s, QC); d.mean_hist = sampler_alloc<double>(s, QC * dim);
+    d.cov_hist = sampler_alloc<double>(s, QC * dim * dim); d.cov_scale = sampler_alloc<double>(s, QC);
+    d.cov = sampler_alloc<double>(s, QC * dim * dim); d.n_acc = sampler_alloc<double>(s, QC);
+    d.n_swap = sampler_alloc<double>(s, Q * d.S); d.n_swap_try = sampler_alloc<double>(s, Q * d.S);
+    d.x_new = sampler_alloc<double>(s, QC * dim); d.lpr_new = sampler_alloc<double>(s, QC);
+    d.inside = sampler_alloc<unsigned char>(s, QC);
+    d.P = sampler_alloc<double>(s, (size_t)NP * QC * G); d.seg = sampler_alloc<double>(s, QC);
+    double* d_lb = sampler_alloc<double>(s, dim); double* d_ub = sampler_alloc<double>(s, dim);
+    double* d_pl = sampler_alloc<double>(s, Q * dim); double* d_ps = sampler_alloc<double>(s, Q * dim);
+    s->d_xi = sampler_alloc<double>(s, (size_t)rng_block * QC * dim); s->d_ua = sampler_alloc<double>(s, (size_t)rng_block * QC);
+    s->d_us = sampler_alloc<double>(s, (size_t)rng_block * Q * d.S);
+    d.trace_x = sampler_alloc<double>(s, (size_t)d.n_trace * QC * dim, false);
+    d.trace_lp = sampler_alloc<double>(s, (size_t)d.n_trace * QC, false);
+    d.trace_pr = sampler_alloc<double>(s, (size_t)d.n_trace * QC, false);
+    d.it = sampler_alloc<long long>(s, 1); d.done = sampler_alloc<unsigned int>(s, 1);
+    d.n_bad_cov = sampler_alloc<unsigned long long>(s, 1);
+    s->d_status = sampler_alloc<int32_t>(s, QC * G); s->d_logp = sampler_alloc<double>(s, QC * G);
+    unsigned long long* counters = sampler_alloc<unsigned long long>(s, PV_SAMPLER_COUNTERS);
+    for (void* a : s->allocs) ok = ok && a != nullptr;
+    ok = ok && cudaHostAlloc(&s->h_xi, sizeof(double) * rng_block * QC * dim, cudaHostAllocDefault) == cudaSuccess &&
+         cudaHostAlloc(&s->h_ua, sizeof(double) * rng_block * QC, cudaHostAllocDefault) == cudaSuccess &&
+         cudaHostAlloc(&s->h_us, sizeof(double) * rng_block * Q * d.S, cudaHostAllocDefault) == cudaSuccess;
+    if (!ok) {
+        fail(PV_E_CUDA, std::string("pv_sampler_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+        pv_sampler_destroy(s);
+        return nullptr;
+    }
+    d.lb = d_lb; d.ub = d_ub; d.prior_loc = d_pl; d.prior_scale = d_ps;
+    d.xi = s->d_xi; d.u_acc = s->d_ua; d.u_swap = s->d_us;
+    // ---- initial state (optimization/sampler.py::sample): every chain of a problem starts at x0[q]; ladder; covariance --
+    std::vector<double> hx((size_t)QC * dim), hb(QC), hc((size_t)QC * dim * dim), ones(QC, 1.0);
+    for (int64_t q = 0; q < Q; ++q)
+        for (int c = 0; c < C; ++c) {
+            for (int i = 0; i < dim; ++i) hx[(q * C + c) * dim + i] = x0[q * dim + i];
+            // near-exponential temperature ladder: T_c = 1 + (c / (C - 1))^4 (5e4 - 1)
+            const double frac = C > 1 ? (double)c / (double)(C - 1) : 0.0;
+            hb[q * C + c] = 1.0 / (1.0 + frac * frac * frac * frac * (5e4 - 1.0));
+            double* cv = hc.data() + (q * C + c) * dim * dim;
+            for (int i = 0; i < dim; ++i)
+                for (int j = 0; j < dim; ++j) cv[i * dim + j] = cov0 ? cov0[i * dim + j] : (i == j ? 1.0 : 0.0);
+            pv_sampler_math::regularize(dim, cv, options->reg_factor);
+        }
+    auto up = [&](double* dst, const double* src, size_t n) { return cudaMemcpy(dst, src, sizeof(double) * n, cudaMemcpyHostToDevice) == cudaSuccess; };
+    ok = up(d.x, hx.data(), hx.size()) && up(d.mean_hist, hx.data(), hx.size()) && up(d.betas, hb.data(), hb.size()) &&
+         up(d.cov, hc.data(), hc.size()) && up(d.cov_hist, hc.data(), hc.size()) && up(d.cov_scale, ones.data(), ones.size()) &&
+         up(d_lb, lb, dim) && up(d_ub, ub, dim) && up(d_pl, prior_loc, (size_t)Q * dim) && up(d_ps, prior_scale, (size_t)Q * dim) &&
+         cudaStreamSynchronize(0) == cudaSuccess;
+    // step kernel geometry: all temperatures of a problem in one block
+    const int qpb = std::max(1, 128 / C);
+    s->step_threads = qpb * C;
+    s->step_blocks = (int)((Q + qpb - 1) / qpb);
+    s->step_shmem = (size_t)qpb * d.S;
+    // ---- iteration 0 = the objective at the start points (also warms every cache the capture below must not touch) ----
+    int rc = ok ? sampler_enqueue_iteration(s) : PV_E_CUDA;
+    if (!rc && cudaStreamSynchronize(s->stream) != cudaSuccess) rc = PV_E_CUDA;
+    if (!rc && use_graph) {
+        p->own_counters = counters;
+        p->own_counter_next = 0;
+        cudaError_t e = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            rc = sampler_enqueue_iteration(s);
+            e = cudaStreamEndCapture(s->stream, &s->graph);
+            if (e == cudaSuccess && !rc) e = cudaGraphInstantiate(&s->exec, s->graph, 0);
+        }
+        p->own_counters = nullptr;
+        if (e != cudaSuccess && !rc) {
+            fail(PV_E_CUDA, std::string("pv_sampler_create: graph capture: ") + cudaGetErrorString(e));
+            rc = PV_E_CUDA;
+        }
+    }
+    if (rc) {
+        if (ok && rc == PV_E_CUDA && g_last_error.empty()) fail(PV_E_CUDA, "pv_sampler_create: CUDA error");
+        pv_sampler_destroy(s);
+        return nullptr;
+    }
+    return s;
+}
+
+extern "C" int pv_sampler_advance(pv_sampler* s, int64_t n_iter, const double* xi_host, const double* u_acc_host,
+                                  const double* u_swap_host) {
+    if (!s || !xi_host || !u_acc_host || (s->d.C > 1 && !u_swap_host)) return fail(PV_E_ARG, "pv_sampler_advance: NULL argument");
+    const pv_sampler_dev& d = s->d;
+    if (n_iter < 1 || n_iter > d.rng_block) return fail(PV_E_ARG, "pv_sampler_advance: 1 <= n_iter <= rng_block required");
+    if (s->it_host % d.rng_block) return fail(PV_E_STATE, "pv_sampler_advance: only the last block may be shorter than rng_block");
+    if (s->it_host + n_iter > d.n_trace - 1) return fail(PV_E_ARG, "pv_sampler_advance: more iterations than n_samples");
+    CUDA_OK(cudaSetDevice(s->p->device));
+    // the staging buffers and the device block are free once the previous block's iterations have run
+    if (s->it_host > 0) CUDA_OK(cudaEventSynchronize(s->ev_block));
+    const int64_t QC = d.Q * d.C;
+    memcpy(s->h_xi, xi_host, sizeof(double) * n_iter * QC * d.dim);
+    memcpy(s->h_ua, u_acc_host, sizeof(double) * n_iter * QC);
+    if (d.C > 1) memcpy(s->h_us, u_swap_host, sizeof(double) * n_iter * d.Q * d.S);
+    CUDA_OK(cudaMemcpyAsync(s->d_xi, s->h_xi, sizeof(double) * n_iter * QC * d.dim, cudaMemcpyHostToDevice, s->stream));
+    CUDA_OK(cudaMemcpyAsync(s->d_ua, s->h_ua, sizeof(double) * n_iter * QC, cudaMemcpyHostToDevice, s->stream));
+    if (d.C > 1) CUDA_OK(cudaMemcpyAsync(s->d_us, s->h_us, sizeof(double) * n_iter * d.Q * d.S, cudaMemcpyHostToDevice, s->stream));
+    for (int64_t k = 0; k < n_iter; ++k) {
+        if (s->exec) {
+            CUDA_OK(cudaGraphLaunch(s->exec, s->stream));
+            g_launches.fetch_add(6);     // nodes of the recorded iteration: propose, 2 objective passes + compaction, segment sum, step
+        } else if (int rc = sampler_enqueue_iteration(s)) {
+            return rc;
+        }
+    }
+    CUDA_OK(cudaEventRecord(s->ev_block, s->stream));
+    s->it_host += n_iter;
+    return 0;
+}
+
+extern "C" int pv_sampler_result(pv_sampler* s, double* trace_x_host, double* trace_neglogpost_host, double* trace_neglogprior_host,
+                                 double* betas_host, double* n_acc_host, double* n_swap_host, double* n_swap_try_host,
+                                 int64_t* n_bad_cov) {
+    if (!s) return fail(PV_E_ARG, "pv_sampler_result: sampler is NULL");
+    const pv_sampler_dev& d = s->d;
+    CUDA_OK(cudaSetDevice(s->p->device));
+    CUDA_OK(cudaStreamSynchronize(s->stream));
+    const int64_t QC = d.Q * d.C;
+    const size_t rows = (size_t)(s->it_host + 1);
+    auto down = [&](void* dst, const void* src, size_t bytes) { return !dst || cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess; };
+    unsigned long long bad = 0;
+    long long it_dev = -1;
+    bool ok = down(trace_x_host, d.trace_x, sizeof(double) * rows * QC * d.dim) && down(trace_neglogpost_host, d.trace_lp, sizeof(double) * rows * QC) &&
+              down(trace_neglogprior_host, d.trace_pr, sizeof(double) * rows * QC) && down(betas_host, d.betas, sizeof(double) * QC) &&
+              down(n_acc_host, d.n_acc, sizeof(double) * QC) && down(n_swap_host, d.n_swap, sizeof(double) * d.Q * d.S) &&
+              down(n_swap_try_host, d.n_swap_try, sizeof(double) * d.Q * d.S) && down(&bad, d.n_bad_cov, sizeof(bad)) &&
+              down(&it_dev, d.it, sizeof(it_dev));
+    if (!ok) return fail(PV_E_CUDA, std::string("pv_sampler_result: ") + cudaGetErrorString(cudaGetLastError()));
+    if (it_dev != s->it_host + 1) return fail(PV_E_STATE, "pv_sampler_result: device iteration counter out of step with the host");
+    if (n_bad_cov) *n_bad_cov = (int64_t)bad;
     return 0;
 }
 

@@ -13,11 +13,17 @@
 #include <stdint.h>
 #include "../../include/parvar_b200.h"   // pv_sampler_options
 
-namespace pv_sampler {
+#if defined(__CUDACC__)
+#define PV_SAMPLER_HD __host__ __device__ inline
+#else
+#define PV_SAMPLER_HD inline
+#endif
+
+namespace pv_sampler_math {
 constexpr int MAXD = 16;
 
 // in-place Cholesky of the symmetric a [n][n] (row-major, lower triangle used); false if a pivot is not > 0
-inline bool cholesky(int n, const double* a, double* low) {
+PV_SAMPLER_HD bool cholesky(int n, const double* a, double* low) {
     for (int i = 0; i < n * n; ++i) low[i] = 0.0;
     for (int j = 0; j < n; ++j) {
         double d = a[j * n + j];
@@ -35,7 +41,7 @@ inline bool cholesky(int n, const double* a, double* low) {
 }
 
 // cyclic Jacobi eigen-decomposition of the symmetric a [n][n]: a = V diag(w) V^T (V row-major, columns = vectors)
-inline void jacobi_eigh(int n, double* a, double* w, double* V) {
+PV_SAMPLER_HD void jacobi_eigh(int n, double* a, double* w, double* V) {
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) V[i * n + j] = (i == j) ? 1.0 : 0.0;
     for (int sweep = 0; sweep < 60; ++sweep) {
@@ -72,7 +78,7 @@ inline void jacobi_eigh(int n, double* a, double* w, double* V) {
 
 // optimization/sampler.py::_regularize for one matrix: symmetrise; eigenvalues >= max(reg, 1e-12 lambda_max).
 // The cheap test first: cov - f I positive definite for f = max(reg, 1e-12 trace) >= that floor.
-inline void regularize(int n, double* cov, double reg) {
+PV_SAMPLER_HD void regularize(int n, double* cov, double reg) {
     double tr = 0.0;
     for (int i = 0; i < n; ++i) {
         tr += cov[i * n + i];
@@ -97,17 +103,17 @@ inline void regularize(int n, double* cov, double reg) {
             cov[i * n + j] = s;
         }
 }
-}  // namespace pv_sampler
+}  // namespace pv_sampler_math
 
 // x_new = x + chol(cov) xi;  inside = lb <= x_new <= ub;  x_eval = inside ? x_new : x  (what the objective is asked for)
 // returns the number of covariance matrices whose Cholesky factorisation failed (their proposal is x itself)
 static int64_t pv_sampler_propose_impl(int64_t Q, int C, int dim, const double* cov, const double* x, const double* xi,
                                        const double* lb, const double* ub, double* x_new, uint8_t* inside, double* x_eval) {
-    if (dim > pv_sampler::MAXD) return -1;
+    if (dim > pv_sampler_math::MAXD) return -1;
     int64_t bad = 0;
     for (int64_t qc = 0; qc < Q * C; ++qc) {
-        double low[pv_sampler::MAXD * pv_sampler::MAXD];
-        const bool ok = pv_sampler::cholesky(dim, cov + qc * dim * dim, low);
+        double low[pv_sampler_math::MAXD * pv_sampler_math::MAXD];
+        const bool ok = pv_sampler_math::cholesky(dim, cov + qc * dim * dim, low);
         bad += !ok;
         bool in = true;
         for (int i = 0; i < dim; ++i) {
@@ -132,7 +138,7 @@ static int pv_sampler_step_impl(int64_t Q, int C, int dim, int64_t it, int64_t n
                                 double* betas, double* mean_hist, double* cov_hist, double* cov_scale, double* cov,
                                 double* n_acc, double* n_swap, double* n_swap_try, double* trace_x, double* trace_lp,
                                 double* trace_pr) {
-    if (dim > pv_sampler::MAXD || C > 64) return -1;
+    if (dim > pv_sampler_math::MAXD || C > 64) return -1;
     const int S = C > 1 ? C - 1 : 1;
     const double ninf = -INFINITY;
     const double rate = pow((double)it, -o->decay_constant), scale_gain = 1.0 / pow((double)(it + 1), o->decay_constant);
@@ -151,7 +157,7 @@ static int pv_sampler_step_impl(int64_t Q, int C, int dim, int64_t it, int64_t n
             }
             n_acc[qc] += accept;
             if (it > o->threshold_sample) {   // Haario et al.
-                double dx[pv_sampler::MAXD];
+                double dx[pv_sampler_math::MAXD];
                 for (int i = 0; i < dim; ++i) {
                     mean_hist[qc * dim + i] = (1 - rate) * mean_hist[qc * dim + i] + rate * x[qc * dim + i];
                     dx[i] = x[qc * dim + i] - mean_hist[qc * dim + i];
@@ -162,7 +168,7 @@ static int pv_sampler_step_impl(int64_t Q, int C, int dim, int64_t it, int64_t n
                 cov_scale[qc] *= exp((exp(log_acc) - o->target_acceptance_rate) * scale_gain);
                 double* cv = cov + qc * dim * dim;
                 for (int i = 0; i < dim * dim; ++i) cv[i] = cov_scale[qc] * ch[i];
-                pv_sampler::regularize(dim, cv, o->reg_factor);
+                pv_sampler_math::regularize(dim, cv, o->reg_factor);
             }
         }
         // ---- swaps, hottest pair first -----------------------------------------------------------------------------

@@ -85,14 +85,19 @@ class GpuPetabSampler:
         self.optim_duration = time.perf_counter() - t0
         return self.optimize_result
 
-    def bayesian_sampler(self, n_samples: int = 5000, n_chains: int = 4, seed: int = 1234):
-        """Adaptive Metropolis inside adaptive parallel tempering, started at the best optimisation result (:158-194)."""
+    def bayesian_sampler(self, n_samples: int = 5000, n_chains: int = 4, seed: int = 1234, device_loop: bool = True):
+        """Adaptive Metropolis inside adaptive parallel tempering, started at the best optimisation result (:158-194).
+        ``device_loop``: the whole loop on the GPU (``sampler.sample_device``); False = host loop, one objective launch per
+        iteration (``sampler.sample``) - same random stream, same chains up to round-off."""
         if self.optimize_result is None:
             raise RuntimeError("run_optimization first (pyPESTO starts the chains at the best optimisation result)")
         x0 = self.optimize_result.x[:, 0, :]
         t0 = time.perf_counter()
-        self.sample_result = smp_mod.sample(self._eval_sample, x0, self.objective.lb, self.objective.ub,
-                                            n_samples=n_samples, n_chains=n_chains, seed=seed)
+        if device_loop:
+            self.sample_result = smp_mod.sample_device(self.objective, x0, n_samples=n_samples, n_chains=n_chains, seed=seed)
+        else:
+            self.sample_result = smp_mod.sample(self._eval_sample, x0, self.objective.lb, self.objective.ub,
+                                                n_samples=n_samples, n_chains=n_chains, seed=seed)
         smp_mod.effective_sample_size(self.sample_result)
         self.sampler_duration = time.perf_counter() - t0
         return self.sample_result

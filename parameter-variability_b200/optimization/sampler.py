@@ -226,6 +226,65 @@ def _sample_native(evaluate, x0, lb, ub, n_samples, n_chains, seed, cov0, decay_
                         acceptance_rate=n_acc / n_samples, swap_rate=n_swap / np.maximum(n_swap_try, 1), n_evals=n_evals)
 
 
+def sample_device(objective, x0: np.ndarray, n_samples: int = 5000, n_chains: int = 4, seed: int = 1234,
+                  cov0: Optional[np.ndarray] = None, decay_constant: float = 0.51, target_acceptance_rate: float = 0.234,
+                  reg_factor: float = 1e-6, threshold_sample: int = 1, nu: float = 1e3, eta: float = 100.0,
+                  adapt_betas: bool = True, rng_block: int = 250, use_graph: bool = True) -> SampleResult:
+    """The loop of ``sample`` resident on the GPU (``pv_sampler_create`` / ``pv_sampler_advance`` / ``pv_sampler_result``):
+    chain state, covariances, ladder and trace stay in HBM, one iteration is a recorded CUDA graph (proposal kernel ->
+    batched objective -> accept / adapt / swap kernel).  ``objective`` is a ``PetabObjectiveBatch`` (its problem, data,
+    priors and bounds are used directly).  Random numbers are drawn here, in the order the numpy loop draws them, and
+    uploaded in blocks of ``rng_block`` iterations while the previous block runs - so the device loop walks the same chains as
+    ``sample(..., native=False)`` up to round-off."""
+    import ctypes
+    from .. import runtime
+    lib = runtime.load_library()
+    rs = np.random.RandomState(seed)
+    x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=np.float64)))
+    Q, dim = x0.shape
+    C, S = int(n_chains), max(int(n_chains) - 1, 1)
+    if Q != objective.Q or dim != objective.dim:
+        raise ValueError(f"x0 must be [{objective.Q}, {objective.dim}]")
+    lb = np.ascontiguousarray(np.broadcast_to(np.asarray(objective.lb, dtype=np.float64), (dim,)))
+    ub = np.ascontiguousarray(np.broadcast_to(np.asarray(objective.ub, dtype=np.float64), (dim,)))
+    ploc = np.ascontiguousarray(objective.prior_loc, dtype=np.float64)
+    pscale = np.ascontiguousarray(np.where(np.isfinite(objective.prior_loc), objective.prior_scale, 1.0), dtype=np.float64)
+    opts = runtime.SamplerOptions(decay_constant, target_acceptance_rate, reg_factor, nu, eta, int(threshold_sample),
+                                  int(bool(adapt_betas)))
+    c0 = None if cov0 is None else np.ascontiguousarray(np.broadcast_to(np.asarray(cov0, dtype=np.float64), (dim, dim)))
+    ptr = lambda a: None if a is None else a.ctypes.data   # noqa: E731
+    K = int(min(rng_block, n_samples))
+    h = lib.pv_sampler_create(objective.problem._h, Q, objective.G, C, int(n_samples), ctypes.addressof(opts), ptr(lb), ptr(ub),
+                              ptr(ploc), ptr(pscale), ptr(x0), ptr(c0), K, int(bool(use_graph)))
+    if not h:
+        raise runtime.ParvarB200Error(f"pv_sampler_create failed: {runtime.last_error()}")
+    try:
+        done = 0
+        while done < n_samples:
+            n = min(K, n_samples - done)
+            xi, ua, us = np.empty((n, Q, C, dim)), np.empty((n, Q, C)), np.zeros((n, Q, S))
+            for k in range(n):                      # the numpy loop's draw order, iteration by iteration
+                xi[k] = rs.normal(size=(Q, C, dim))
+                ua[k] = rs.uniform(size=(Q, C))
+                for j in range(C - 1, 0, -1):
+                    us[k, :, j - 1] = rs.uniform(size=Q)
+            runtime._check(lib.pv_sampler_advance(h, n, ptr(xi), ptr(ua), ptr(us)))
+            done += n
+        n_tr = n_samples + 1
+        trace_x, trace_lp, trace_pr = np.empty((n_tr, Q, C, dim)), np.empty((n_tr, Q, C)), np.empty((n_tr, Q, C))
+        betas, n_acc, n_swap, n_swap_try = np.empty((Q, C)), np.empty((Q, C)), np.empty((Q, S)), np.empty((Q, S))
+        n_bad = ctypes.c_int64(0)
+        runtime._check(lib.pv_sampler_result(h, ptr(trace_x), ptr(trace_lp), ptr(trace_pr), ptr(betas), ptr(n_acc), ptr(n_swap),
+                                             ptr(n_swap_try), ctypes.addressof(n_bad)))
+    finally:
+        lib.pv_sampler_destroy(h)
+    objective.n_evals += Q * C * n_tr
+    return SampleResult(trace_x=np.ascontiguousarray(trace_x.transpose(1, 2, 0, 3)),
+                        trace_neglogpost=np.ascontiguousarray(trace_lp.transpose(1, 2, 0)),
+                        trace_neglogprior=np.ascontiguousarray(trace_pr.transpose(1, 2, 0)), betas=betas,
+                        acceptance_rate=n_acc / n_samples, swap_rate=n_swap / np.maximum(n_swap_try, 1), n_evals=Q * C * n_tr)
+
+
 # ---- diagnostics (pyPESTO ``effective_sample_size``: Geweke burn-in + Sokal autocorrelation time) ----------------------
 def autocorrelation_time_sokal(chain: np.ndarray) -> float:
     """Integrated autocorrelation time of a 1-D chain with Sokal's adaptive window (as pyPESTO's ``autocorrelation_sokal``)."""

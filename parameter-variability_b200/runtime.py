@@ -72,6 +72,10 @@ ABI = {
     "pv_launch_count": (C.c_int64, []),
     "pv_sampler_propose": (C.c_int64, [C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 8),
     "pv_sampler_step": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 21),
+    "pv_sampler_create": (C.c_void_p, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 7 + [C.c_int64, C.c_int]),
+    "pv_sampler_advance": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pv_sampler_result": (C.c_int, [C.c_void_p] * 9),
+    "pv_sampler_destroy": (None, [C.c_void_p]),
     "pv_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "pv_fma_peak_tflops": (C.c_double, [C.c_int, C.c_int, C.c_int]),
     "pv_host_alloc": (C.c_void_p, [C.c_size_t]),

@@ -221,6 +221,48 @@ def test_sampler_posterior_matches_laplace(cuda_lib, rt, oracle):
     assert sr.effective_sample_size[0] > 50
 
 
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_device_resident_sampler_walks_the_host_loops_chains(cuda_lib, rt, oracle, use_graph):
+    """``sampler.sample_device`` (pv_sampler_create / advance / result: the whole adaptive-Metropolis + parallel-tempering loop
+    on the GPU, one recorded CUDA graph per iteration) against the host loop (``sampler.sample``: one objective launch per
+    iteration, bookkeeping on the host) on the same PetabObjectiveBatch and the same random stream: identical accept /
+    swap decisions, chains equal up to round-off.  Wide bounds [0, 1e8]: the hot chains visit stiff parameter values
+    (RODAS4 re-run inside the recorded iteration) and leave the box (rejected proposals); several blocks of random numbers,
+    the last one short."""
+    po = pkg("optimization.petab_optimization")
+    smp = pkg("optimization.sampler")
+    t = np.linspace(0, 30, 12)
+    truths = {"MALE": (0.8, 1.1), "FEMALE": (1.3, 0.6)}
+    problems = [_pk_groups(oracle, t, truths, n, cv, s) for n, cv, s in ((3, 0.05, 1), (10, 0.2, 2), (1, 0.0, 3), (5, 0.1, 4), (2, 0.5, 5))]
+    priors = [{"k_abs_MALE": (0.5, 1.0), "CL_FEMALE": (0.5, 2.0)}, {}, {"CL_MALE": (1.0, 0.3)},
+              {"k_abs_MALE": (0.5, 1.0), "k_abs_FEMALE": (1.0, 1.0), "CL_MALE": (1.0, 1.0), "CL_FEMALE": (0.5, 1.0)}, {}]
+    batch = po.PetabObjectiveBatch("simple_pk", ["k_abs", "CL"], problems, t, OBS, sigma=0.1, priors=priors)
+    x0 = np.tile(np.array([0.8, 1.3, 1.1, 0.6]), (len(problems), 1)) * (1 + 0.05 * np.arange(len(problems)))[:, None]
+    n = 230
+
+    def evaluate(X):
+        o = batch.evaluate(X, order=0)
+        return o["llh"], o["lprior"]
+
+    for chains in (4, 1):
+        host = smp.sample(evaluate, x0, batch.lb, batch.ub, n_samples=n, n_chains=chains, seed=7)
+        n0 = rt.launch_count()
+        dev = smp.sample_device(batch, x0, n_samples=n, n_chains=chains, seed=7, rng_block=100, use_graph=use_graph)
+        assert rt.launch_count() - n0 >= 4 * n          # the iterations did run through this library's kernels
+        np.testing.assert_array_equal(dev.acceptance_rate, host.acceptance_rate)
+        np.testing.assert_array_equal(dev.swap_rate, host.swap_rate)
+        np.testing.assert_allclose(dev.trace_x, host.trace_x, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(dev.trace_neglogpost, host.trace_neglogpost, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(dev.trace_neglogprior, host.trace_neglogprior, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(dev.betas, host.betas, rtol=1e-10)
+        assert dev.trace_x.shape == (len(problems), chains, n + 1, 4)
+        assert 0.02 < dev.acceptance_rate[:, 0].mean() < 0.95
+        if chains == 4:
+            assert dev.trace_x[:, -1].max() > 100.0       # the hottest chain did roam far outside the posterior's bulk
+    # the problem is usable again after the sampler is gone
+    assert np.all(np.isfinite(batch.evaluate(x0[:, None, :], order=0)["llh"]))
+
+
 def test_optimize_experiments_writes_reference_results_tsv(cuda_lib, rt, oracle, tmp_path):
     io = pkg("optimization.petab_io")
     drv = pkg("optimization.driver")

@@ -98,8 +98,10 @@ class GpuPetabSampler:
         else:
             self.sample_result = smp_mod.sample(self._eval_sample, x0, self.objective.lb, self.objective.ub,
                                                 n_samples=n_samples, n_chains=n_chains, seed=seed)
+        t1 = time.perf_counter()
         smp_mod.effective_sample_size(self.sample_result)
         self.sampler_duration = time.perf_counter() - t0
+        self.ess_duration = time.perf_counter() - t1
         return self.sample_result
 
     # ---- results (columns of results_df, :254-269) ---------------------------------------------------------------------------

@@ -82,6 +82,7 @@ class SampleResult:
     n_evals: int
     burn_in: Optional[np.ndarray] = None
     effective_sample_size: Optional[np.ndarray] = None
+    timing: Optional[dict] = None  # device loop: seconds spent drawing random numbers / queueing + waiting / copying out
 
 
 def sample(evaluate: Callable[[np.ndarray], tuple[np.ndarray, np.ndarray]], x0: np.ndarray, lb: np.ndarray, ub: np.ndarray,
@@ -258,31 +259,40 @@ def sample_device(objective, x0: np.ndarray, n_samples: int = 5000, n_chains: in
                               ptr(ploc), ptr(pscale), ptr(x0), ptr(c0), K, int(bool(use_graph)))
     if not h:
         raise runtime.ParvarB200Error(f"pv_sampler_create failed: {runtime.last_error()}")
+    import time
+    tm = {"rng_s": 0.0, "advance_s": 0.0, "result_s": 0.0}
     try:
         done = 0
         while done < n_samples:
             n = min(K, n_samples - done)
+            t_a = time.perf_counter()
             xi, ua, us = np.empty((n, Q, C, dim)), np.empty((n, Q, C)), np.zeros((n, Q, S))
             for k in range(n):                      # the numpy loop's draw order, iteration by iteration
                 xi[k] = rs.normal(size=(Q, C, dim))
                 ua[k] = rs.uniform(size=(Q, C))
                 for j in range(C - 1, 0, -1):
                     us[k, :, j - 1] = rs.uniform(size=Q)
+            t_b = time.perf_counter()
             runtime._check(lib.pv_sampler_advance(h, n, ptr(xi), ptr(ua), ptr(us)))
+            tm["rng_s"] += t_b - t_a
+            tm["advance_s"] += time.perf_counter() - t_b
             done += n
+        t_a = time.perf_counter()
         n_tr = n_samples + 1
         trace_x, trace_lp, trace_pr = np.empty((n_tr, Q, C, dim)), np.empty((n_tr, Q, C)), np.empty((n_tr, Q, C))
         betas, n_acc, n_swap, n_swap_try = np.empty((Q, C)), np.empty((Q, C)), np.empty((Q, S)), np.empty((Q, S))
         n_bad = ctypes.c_int64(0)
         runtime._check(lib.pv_sampler_result(h, ptr(trace_x), ptr(trace_lp), ptr(trace_pr), ptr(betas), ptr(n_acc), ptr(n_swap),
                                              ptr(n_swap_try), ctypes.addressof(n_bad)))
+        tm["result_s"] = time.perf_counter() - t_a
     finally:
         lib.pv_sampler_destroy(h)
     objective.n_evals += Q * C * n_tr
     return SampleResult(trace_x=np.ascontiguousarray(trace_x.transpose(1, 2, 0, 3)),
                         trace_neglogpost=np.ascontiguousarray(trace_lp.transpose(1, 2, 0)),
                         trace_neglogprior=np.ascontiguousarray(trace_pr.transpose(1, 2, 0)), betas=betas,
-                        acceptance_rate=n_acc / n_samples, swap_rate=n_swap / np.maximum(n_swap_try, 1), n_evals=Q * C * n_tr)
+                        acceptance_rate=n_acc / n_samples, swap_rate=n_swap / np.maximum(n_swap_try, 1), n_evals=Q * C * n_tr,
+                        timing=tm)
 
 
 # ---- diagnostics (pyPESTO ``effective_sample_size``: Geweke burn-in + Sokal autocorrelation time) ----------------------

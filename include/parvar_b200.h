@@ -258,12 +258,24 @@ int pv_sampler_step(int64_t Q, int C, int dim, int64_t it, int64_t n_trace, cons
  * as pv_sampler_step), the final ladder and the counters; any pointer may be NULL.
  * While a sampler exists its problem must not be used for other launches (they share the problem's scratch buffers). */
 typedef struct pv_sampler pv_sampler;
+/* numpy's legacy stream (np.random.RandomState) as exported by get_state(): MT19937 key, position, cached deviate */
+typedef struct pv_mt19937_state {
+    uint32_t key[624];
+    int32_t pos, has_gauss;
+    double gauss;
+} pv_mt19937_state;
 pv_sampler* pv_sampler_create(pv_problem* p, int64_t Q, int n_groups, int n_chains, int64_t n_samples,
                               const pv_sampler_options* options, const double* lb, const double* ub, const double* prior_loc,
                               const double* prior_scale, const double* x0, const double* cov0, int64_t rng_block,
                               int use_graph);
 int pv_sampler_advance(pv_sampler* s, int64_t n_iter, const double* xi_host, const double* u_acc_host,
                        const double* u_swap_host);
+/* pv_sampler_advance with the random numbers drawn by the library itself from numpy's legacy stream (state in / out), in
+ * the order optimization/sampler.py draws them, straight into the pinned staging buffers: same chain, no interpreter time.
+ * pv_rng_sampler_block is the generator alone (host arrays laid out as pv_sampler_advance takes them). */
+int pv_sampler_advance_mt(pv_sampler* s, int64_t n_iter, pv_mt19937_state* rng);
+int pv_rng_sampler_block(pv_mt19937_state* rng, int64_t n_iter, int64_t Q, int n_chains, int dim, double* xi_host,
+                         double* u_acc_host, double* u_swap_host);
 int pv_sampler_result(pv_sampler* s, double* trace_x_host, double* trace_neglogpost_host, double* trace_neglogprior_host,
                       double* betas_host, double* n_acc_host, double* n_swap_host, double* n_swap_try_host,
                       int64_t* n_bad_cov);

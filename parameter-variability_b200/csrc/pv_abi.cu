@@ -23,6 +23,7 @@
 #include "pv_rosenbrock_split.cuh"
 #include "pv_hier.cuh"
 #include "pv_sampler_device.cuh"
+#include "pv_rng_host.cuh"
 #include "generated/simple_chain.cuh"
 #include "generated/simple_pk.cuh"
 #include "generated/icg_body_flat.cuh"
@@ -922,8 +923,9 @@ struct pv_sampler {
     bool own_stream = false;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    cudaEvent_t ev_block = nullptr;      // the iterations of the last uploaded block of random numbers are done
-    double *h_xi = nullptr, *h_ua = nullptr, *h_us = nullptr;   // pinned staging of one block
+    cudaEvent_t ev_block[2] = {nullptr, nullptr};   // the iterations of the block staged in that half are done
+    double *h_xi = nullptr, *h_ua = nullptr, *h_us = nullptr;   // pinned staging, two blocks each
+    int64_t blocks_queued = 0;
     double *d_xi = nullptr, *d_ua = nullptr, *d_us = nullptr;
     int32_t* d_status = nullptr;
     double* d_logp = nullptr;
@@ -964,7 +966,8 @@ extern "C" void pv_sampler_destroy(pv_sampler* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->exec) cudaGraphExecDestroy(s->exec);
     if (s->graph) cudaGraphDestroy(s->graph);
-    if (s->ev_block) cudaEventDestroy(s->ev_block);
+    for (auto& e : s->ev_block)
+        if (e) cudaEventDestroy(e);
     for (void* a : s->allocs) cudaFree(a);
     if (s->h_xi) cudaFreeHost(s->h_xi);
     if (s->h_ua) cudaFreeHost(s->h_ua);
@@ -999,7 +1002,7 @@ extern "C" pv_sampler* pv_sampler_create(pv_problem* p, int64_t Q, int n_groups,
     const int64_t QC = Q * C;
     bool ok = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) == cudaSuccess;
     s->own_stream = ok;
-    ok = ok && cudaEventCreateWithFlags(&s->ev_block, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& e : s->ev_block) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     d.x = sampler_alloc<double>(s, QC * dim); d.llh = sampler_alloc<double>(s, QC); d.lpr = sampler_alloc<double>(s, QC);
     d.betas = sampler_alloc<double>(s, QC); d.mean_hist = sampler_alloc<double>(s, QC * dim);
     d.cov_hist = sampler_alloc<double>(s, QC * dim * dim); d.cov_scale = sampler_alloc<double>(s, QC);
@@ -1020,9 +1023,9 @@ extern "C" pv_sampler* pv_sampler_create(pv_problem* p, int64_t Q, int n_groups,
     s->d_status = sampler_alloc<int32_t>(s, QC * G); s->d_logp = sampler_alloc<double>(s, QC * G);
     unsigned long long* counters = sampler_alloc<unsigned long long>(s, PV_SAMPLER_COUNTERS);
     for (void* a : s->allocs) ok = ok && a != nullptr;
-    ok = ok && cudaHostAlloc(&s->h_xi, sizeof(double) * rng_block * QC * dim, cudaHostAllocDefault) == cudaSuccess &&
-         cudaHostAlloc(&s->h_ua, sizeof(double) * rng_block * QC, cudaHostAllocDefault) == cudaSuccess &&
-         cudaHostAlloc(&s->h_us, sizeof(double) * rng_block * Q * d.S, cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&s->h_xi, sizeof(double) * 2 * rng_block * QC * dim, cudaHostAllocDefault) == cudaSuccess &&
+         cudaHostAlloc(&s->h_ua, sizeof(double) * 2 * rng_block * QC, cudaHostAllocDefault) == cudaSuccess &&
+         cudaHostAlloc(&s->h_us, sizeof(double) * 2 * rng_block * Q * d.S, cudaHostAllocDefault) == cudaSuccess;
     if (!ok) {
         fail(PV_E_CUDA, std::string("pv_sampler_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
         pv_sampler_destroy(s);
@@ -1079,23 +1082,33 @@ extern "C" pv_sampler* pv_sampler_create(pv_problem* p, int64_t Q, int n_groups,
     return s;
 }
 
-extern "C" int pv_sampler_advance(pv_sampler* s, int64_t n_iter, const double* xi_host, const double* u_acc_host,
-                                  const double* u_swap_host) {
-    if (!s || !xi_host || !u_acc_host || (s->d.C > 1 && !u_swap_host)) return fail(PV_E_ARG, "pv_sampler_advance: NULL argument");
+// queue n_iter iterations; the random numbers of the block are either copied from the caller's arrays or drawn here
+static int sampler_advance_impl(pv_sampler* s, int64_t n_iter, const double* xi_host, const double* u_acc_host,
+                                const double* u_swap_host, pv_mt19937_state* rng) {
     const pv_sampler_dev& d = s->d;
     if (n_iter < 1 || n_iter > d.rng_block) return fail(PV_E_ARG, "pv_sampler_advance: 1 <= n_iter <= rng_block required");
     if (s->it_host % d.rng_block) return fail(PV_E_STATE, "pv_sampler_advance: only the last block may be shorter than rng_block");
     if (s->it_host + n_iter > d.n_trace - 1) return fail(PV_E_ARG, "pv_sampler_advance: more iterations than n_samples");
     CUDA_OK(cudaSetDevice(s->p->device));
-    // the staging buffers and the device block are free once the previous block's iterations have run
-    if (s->it_host > 0) CUDA_OK(cudaEventSynchronize(s->ev_block));
     const int64_t QC = d.Q * d.C;
-    memcpy(s->h_xi, xi_host, sizeof(double) * n_iter * QC * d.dim);
-    memcpy(s->h_ua, u_acc_host, sizeof(double) * n_iter * QC);
-    if (d.C > 1) memcpy(s->h_us, u_swap_host, sizeof(double) * n_iter * d.Q * d.S);
-    CUDA_OK(cudaMemcpyAsync(s->d_xi, s->h_xi, sizeof(double) * n_iter * QC * d.dim, cudaMemcpyHostToDevice, s->stream));
-    CUDA_OK(cudaMemcpyAsync(s->d_ua, s->h_ua, sizeof(double) * n_iter * QC, cudaMemcpyHostToDevice, s->stream));
-    if (d.C > 1) CUDA_OK(cudaMemcpyAsync(s->d_us, s->h_us, sizeof(double) * n_iter * d.Q * d.S, cudaMemcpyHostToDevice, s->stream));
+    // double-buffered staging: block k is drawn / copied into half k % 2 while block k - 1 runs; half k % 2 was last read by
+    // the upload of block k - 2, which has completed once block k - 2's event has (recorded after its iterations)
+    const int half = (int)((s->it_host / d.rng_block) & 1);
+    if (s->blocks_queued >= 2) CUDA_OK(cudaEventSynchronize(s->ev_block[half]));
+    double* h_xi = s->h_xi + (size_t)half * d.rng_block * QC * d.dim;
+    double* h_ua = s->h_ua + (size_t)half * d.rng_block * QC;
+    double* h_us = s->h_us + (size_t)half * d.rng_block * d.Q * d.S;
+    if (rng) {
+        pv_rng::fill_sampler_block(rng, n_iter, d.Q, d.C, d.dim, h_xi, h_ua, h_us);
+    } else {
+        memcpy(h_xi, xi_host, sizeof(double) * n_iter * QC * d.dim);
+        memcpy(h_ua, u_acc_host, sizeof(double) * n_iter * QC);
+        if (d.C > 1) memcpy(h_us, u_swap_host, sizeof(double) * n_iter * d.Q * d.S);
+    }
+    // the device block is single: its upload is ordered behind the previous block's iterations on the stream
+    CUDA_OK(cudaMemcpyAsync(s->d_xi, h_xi, sizeof(double) * n_iter * QC * d.dim, cudaMemcpyHostToDevice, s->stream));
+    CUDA_OK(cudaMemcpyAsync(s->d_ua, h_ua, sizeof(double) * n_iter * QC, cudaMemcpyHostToDevice, s->stream));
+    if (d.C > 1) CUDA_OK(cudaMemcpyAsync(s->d_us, h_us, sizeof(double) * n_iter * d.Q * d.S, cudaMemcpyHostToDevice, s->stream));
     for (int64_t k = 0; k < n_iter; ++k) {
         if (s->exec) {
             CUDA_OK(cudaGraphLaunch(s->exec, s->stream));
@@ -1104,8 +1117,30 @@ extern "C" int pv_sampler_advance(pv_sampler* s, int64_t n_iter, const double* x
             return rc;
         }
     }
-    CUDA_OK(cudaEventRecord(s->ev_block, s->stream));
+    CUDA_OK(cudaEventRecord(s->ev_block[half], s->stream));
     s->it_host += n_iter;
+    s->blocks_queued += 1;
+    return 0;
+}
+
+extern "C" int pv_sampler_advance(pv_sampler* s, int64_t n_iter, const double* xi_host, const double* u_acc_host,
+                                  const double* u_swap_host) {
+    if (!s || !xi_host || !u_acc_host || (s->d.C > 1 && !u_swap_host)) return fail(PV_E_ARG, "pv_sampler_advance: NULL argument");
+    return sampler_advance_impl(s, n_iter, xi_host, u_acc_host, u_swap_host, nullptr);
+}
+
+extern "C" int pv_sampler_advance_mt(pv_sampler* s, int64_t n_iter, pv_mt19937_state* rng) {
+    if (!s || !rng) return fail(PV_E_ARG, "pv_sampler_advance_mt: NULL argument");
+    if (rng->pos < 0 || rng->pos > 624) return fail(PV_E_ARG, "pv_sampler_advance_mt: bad generator state");
+    return sampler_advance_impl(s, n_iter, nullptr, nullptr, nullptr, rng);
+}
+
+extern "C" int pv_rng_sampler_block(pv_mt19937_state* rng, int64_t n_iter, int64_t Q, int n_chains, int dim, double* xi_host,
+                                    double* u_acc_host, double* u_swap_host) {
+    if (!rng || n_iter < 0 || Q < 1 || n_chains < 1 || dim < 1 || !xi_host || !u_acc_host || !u_swap_host)
+        return fail(PV_E_ARG, "pv_rng_sampler_block: bad arguments");
+    if (rng->pos < 0 || rng->pos > 624) return fail(PV_E_ARG, "pv_rng_sampler_block: bad generator state");
+    pv_rng::fill_sampler_block(rng, n_iter, Q, n_chains, dim, xi_host, u_acc_host, u_swap_host);
     return 0;
 }
 

@@ -230,13 +230,16 @@ def _sample_native(evaluate, x0, lb, ub, n_samples, n_chains, seed, cov0, decay_
 def sample_device(objective, x0: np.ndarray, n_samples: int = 5000, n_chains: int = 4, seed: int = 1234,
                   cov0: Optional[np.ndarray] = None, decay_constant: float = 0.51, target_acceptance_rate: float = 0.234,
                   reg_factor: float = 1e-6, threshold_sample: int = 1, nu: float = 1e3, eta: float = 100.0,
-                  adapt_betas: bool = True, rng_block: int = 250, use_graph: bool = True) -> SampleResult:
+                  adapt_betas: bool = True, rng_block: int = 250, use_graph: bool = True,
+                  library_rng: bool = True) -> SampleResult:
     """The loop of ``sample`` resident on the GPU (``pv_sampler_create`` / ``pv_sampler_advance`` / ``pv_sampler_result``):
     chain state, covariances, ladder and trace stay in HBM, one iteration is a recorded CUDA graph (proposal kernel ->
     batched objective -> accept / adapt / swap kernel).  ``objective`` is a ``PetabObjectiveBatch`` (its problem, data,
     priors and bounds are used directly).  Random numbers are drawn here, in the order the numpy loop draws them, and
     uploaded in blocks of ``rng_block`` iterations while the previous block runs - so the device loop walks the same chains as
-    ``sample(..., native=False)`` up to round-off."""
+    ``sample(..., native=False)`` up to round-off.  ``library_rng``: the blocks are drawn by the library's restatement of
+    numpy's legacy stream (``pv_sampler_advance_mt``: same numbers, compiled code, interpreter lock released) instead of
+    by numpy calls here."""
     import ctypes
     from .. import runtime
     lib = runtime.load_library()
@@ -263,6 +266,13 @@ def sample_device(objective, x0: np.ndarray, n_samples: int = 5000, n_chains: in
     tm = {"rng_s": 0.0, "advance_s": 0.0, "result_s": 0.0}
     try:
         done = 0
+        mt = runtime.MT19937State.from_random_state(rs) if library_rng else None
+        while mt is not None and done < n_samples:
+            n = min(K, n_samples - done)
+            t_a = time.perf_counter()
+            runtime._check(lib.pv_sampler_advance_mt(h, n, ctypes.addressof(mt)))
+            tm["advance_s"] += time.perf_counter() - t_a
+            done += n
         while done < n_samples:
             n = min(K, n_samples - done)
             t_a = time.perf_counter()
@@ -329,18 +339,37 @@ def geweke_burn_in(chain: np.ndarray, zscore: float = 2.0) -> int:
     return int(0.5 * n)
 
 
+def _sokal_tau_batch(chains: np.ndarray) -> np.ndarray:
+    """``autocorrelation_time_sokal`` for a batch of chains [n_chains, n] at once (one FFT call, the window search on
+    cumulative sums): tau(m) = 1 + 2 sum_{k<=m} rho_k, first m with m >= 6 tau(m)."""
+    n = chains.shape[1]
+    xc = chains - chains.mean(axis=1, keepdims=True)
+    flat = np.all(np.isclose(xc, 0.0), axis=1)
+    nfft = 1 << int(np.ceil(np.log2(2 * n)))
+    f = np.fft.rfft(xc, nfft, axis=1)
+    ac = np.fft.irfft(f * np.conjugate(f), axis=1)[:, :n].real
+    ac0 = np.where(ac[:, :1] == 0.0, 1.0, ac[:, :1])
+    ac = ac / ac0
+    tau_m = 1.0 + 2.0 * np.cumsum(ac[:, 1:], axis=1)                 # tau after window m = 1 .. n-1
+    m = np.arange(1, n)
+    hit = m[None, :] >= 6.0 * tau_m
+    first = np.where(hit.any(axis=1), hit.argmax(axis=1), n - 2)
+    tau = np.maximum(tau_m[np.arange(len(chains)), first], 1.0)
+    return np.where(flat, float(n), tau)
+
+
 def effective_sample_size(result: SampleResult) -> np.ndarray:
-    """ESS of the cold chain of every problem: (n - burn_in) / (1 + max_p tau_p)  (pyPESTO's definition)."""
+    """ESS of the cold chain of every problem: (n - burn_in) / (1 + max_p tau_p)  (pyPESTO's definition).  Problems that
+    share a burn-in length are processed together (``_sokal_tau_batch``)."""
     Q = result.trace_x.shape[0]
     ess = np.zeros(Q)
-    burn = np.zeros(Q, dtype=int)
-    for q in range(Q):
-        chain = result.trace_x[q, 0]
-        b = geweke_burn_in(chain)
-        burn[q] = b
-        rest = chain[b:]
-        tau = max(autocorrelation_time_sokal(rest[:, p]) for p in range(rest.shape[1]))
-        ess[q] = len(rest) / (1.0 + tau)
+    burn = np.array([geweke_burn_in(result.trace_x[q, 0]) for q in range(Q)], dtype=int)
+    for b in np.unique(burn):
+        qs = np.nonzero(burn == b)[0]
+        rest = result.trace_x[qs, 0, b:, :]                             # [nq, n - b, dim]
+        nq, n, dim = rest.shape
+        tau = _sokal_tau_batch(rest.transpose(0, 2, 1).reshape(nq * dim, n)).reshape(nq, dim).max(axis=1)
+        ess[qs] = n / (1.0 + tau)
     result.burn_in, result.effective_sample_size = burn, ess
     return ess
 

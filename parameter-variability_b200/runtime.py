@@ -74,6 +74,8 @@ ABI = {
     "pv_sampler_step": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 21),
     "pv_sampler_create": (C.c_void_p, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 7 + [C.c_int64, C.c_int]),
     "pv_sampler_advance": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pv_sampler_advance_mt": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "pv_rng_sampler_block": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pv_sampler_result": (C.c_int, [C.c_void_p] * 9),
     "pv_sampler_destroy": (None, [C.c_void_p]),
     "pv_last_kernel_ms": (C.c_double, [C.c_void_p]),
@@ -352,6 +354,24 @@ def hier_finish(n_chains: int, n_cols: int, red, mu, omega, mu_prior_mean, mu_pr
     m, s, h = (np.ascontiguousarray(a, dtype=np.float64) for a in (mu_prior_mean, mu_prior_sd, omega_prior))
     _check(load_library().pv_hier_finish(int(n_chains), int(n_cols), _ptr(red), _ptr(mu), _ptr(omega), m.ctypes.data_as(_dp),
                                          s.ctypes.data_as(_dp), h.ctypes.data_as(_dp), stream))
+
+
+class MT19937State(C.Structure):
+    """``pv_mt19937_state``: numpy's legacy stream as ``RandomState.get_state()`` exports it."""
+    _fields_ = [("key", C.c_uint32 * 624), ("pos", C.c_int32), ("has_gauss", C.c_int32), ("gauss", C.c_double)]
+
+    @classmethod
+    def from_random_state(cls, rs: "np.random.RandomState") -> "MT19937State":
+        name, key, pos, has_gauss, gauss = rs.get_state()
+        if name != "MT19937":
+            raise ValueError("a legacy MT19937 RandomState is required")
+        st = cls()
+        C.memmove(st.key, np.ascontiguousarray(key, dtype=np.uint32).ctypes.data, 624 * 4)
+        st.pos, st.has_gauss, st.gauss = int(pos), int(has_gauss), float(gauss)
+        return st
+
+    def to_random_state(self, rs: "np.random.RandomState") -> None:
+        rs.set_state(("MT19937", np.frombuffer(self.key, dtype=np.uint32).copy(), int(self.pos), int(self.has_gauss), float(self.gauss)))
 
 
 def launch_count() -> int:

@@ -332,3 +332,48 @@ def test_covariance_regularisation_and_sampler_abi_errors():
     assert "dim" in rt.last_error()
     assert lib.pv_sampler_propose(Q, C, dim, None, p(x), p(xi), p(lb), p(ub), p(x_new), p(inside), p(x_eval)) < 0
     assert "pv_sampler_propose" in rt.last_error()
+
+
+def test_library_rng_is_numpys_legacy_stream():
+    """pv_rng_sampler_block / pv_sampler_advance_mt draw the sampler's blocks of random numbers in compiled code: bit for bit
+    the numbers numpy's RandomState yields in the numpy loop's draw order (normal / uniform interleaved, cached second
+    deviate of the polar method included), and the exported state continues the stream."""
+    import ctypes
+    rt = pkg("runtime")
+    lib = rt.load_library()
+    for n, Q, C, dim, seed in ((37, 5, 4, 3, 7), (10, 3, 1, 2, 1234), (60, 50, 4, 4, 99)):
+        rs = np.random.RandomState(seed)
+        rs.normal(size=3)                                   # odd count: a cached deviate is pending at hand-over
+        st = rt.MT19937State.from_random_state(rs)
+        S = max(C - 1, 1)
+        xi, ua, us = np.empty((n, Q, C, dim)), np.empty((n, Q, C)), np.zeros((n, Q, S))
+        for k in range(n):
+            xi[k] = rs.normal(size=(Q, C, dim))
+            ua[k] = rs.uniform(size=(Q, C))
+            for j in range(C - 1, 0, -1):
+                us[k, :, j - 1] = rs.uniform(size=Q)
+        xi2, ua2, us2 = np.empty_like(xi), np.empty_like(ua), np.empty_like(us)
+        assert lib.pv_rng_sampler_block(ctypes.addressof(st), n, Q, C, dim, xi2.ctypes.data, ua2.ctypes.data, us2.ctypes.data) == 0
+        assert np.array_equal(xi, xi2) and np.array_equal(ua, ua2) and np.array_equal(us, us2)
+        rs2 = np.random.RandomState(0)
+        st.to_random_state(rs2)
+        assert rs2.normal() == rs.normal() and rs2.uniform() == rs.uniform()
+    assert lib.pv_rng_sampler_block(None, 1, 1, 1, 1, xi2.ctypes.data, ua2.ctypes.data, us2.ctypes.data) < 0
+
+
+def test_batched_effective_sample_size_equals_the_per_chain_statement():
+    smp = pkg("optimization.sampler")
+    rs = np.random.RandomState(0)
+    tr = np.zeros((6, 2, 2001, 2))
+    for q in range(6):
+        for i in range(1, 2001):
+            tr[q, :, i] = (0.5 + 0.08 * q) * tr[q, :, i - 1] + rs.normal(size=(2, 2))
+    tr[5, 0, :, 1] = 3.0                                       # a constant component: tau = n
+    res = smp.SampleResult(tr, None, None, None, None, None, 0)
+    ess = smp.effective_sample_size(res)
+    for q in range(6):
+        ch = tr[q, 0]
+        b = smp.geweke_burn_in(ch)
+        rest = ch[b:]
+        tau = max(smp.autocorrelation_time_sokal(rest[:, p]) for p in range(2))
+        assert res.burn_in[q] == b and ess[q] == pytest.approx(len(rest) / (1.0 + tau), rel=1e-12)

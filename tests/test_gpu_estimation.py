@@ -247,7 +247,9 @@ def test_device_resident_sampler_walks_the_host_loops_chains(cuda_lib, rt, oracl
     for chains in (4, 1):
         host = smp.sample(evaluate, x0, batch.lb, batch.ub, n_samples=n, n_chains=chains, seed=7)
         n0 = rt.launch_count()
-        dev = smp.sample_device(batch, x0, n_samples=n, n_chains=chains, seed=7, rng_block=100, use_graph=use_graph)
+        # library_rng: the blocks of random numbers drawn by the library (numpy's legacy stream restated) / by numpy here
+        dev = smp.sample_device(batch, x0, n_samples=n, n_chains=chains, seed=7, rng_block=100, use_graph=use_graph,
+                                library_rng=use_graph)
         assert rt.launch_count() - n0 >= 4 * n          # the iterations did run through this library's kernels
         np.testing.assert_array_equal(dev.acceptance_rate, host.acceptance_rate)
         np.testing.assert_array_equal(dev.swap_rate, host.swap_rate)

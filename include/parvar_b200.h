@@ -80,6 +80,12 @@ int pv_problem_set_solver(pv_problem* p, int method, double rtol, double atol, i
  * measured per-integrator default (DOPRI5: 6, RODAS4: 32) */
 int pv_problem_set_schedule(pv_problem* p, int refill_min);
 
+/* Locality schedule (divergence control): the trajectories of a launch are bucketed on the device by their parameter
+ * values (first two columns) so that the lanes of a warp integrate neighbouring points of parameter space and therefore
+ * step, cross the output grid and finish together.  Only the order in which trajectories are picked up changes; results
+ * are bit-identical.  mode 0 = auto (launches of >= 4096 trajectories with per-trajectory columns), 1 = off, 2 = on. */
+int pv_problem_set_locality(pv_problem* p, int mode);
+
 /* Data layout of the Rosenbrock sensitivity kernels (logp + gradient, + Fisher information) of the large models
  * (augmented system of more than 16 components; of the built-in models: icg_body_flat):
  *   PV_LAYOUT_LANE   one trajectory per lane (all blocks of the augmented system in one thread)

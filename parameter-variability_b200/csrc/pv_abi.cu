@@ -22,6 +22,7 @@
 #include "pv_kernels.cuh"
 #include "pv_rosenbrock_split.cuh"
 #include "pv_hier.cuh"
+#include "pv_schedule.cuh"
 #include "pv_sampler_device.cuh"
 #include "pv_rng_host.cuh"
 #include "generated/simple_chain.cuh"
@@ -82,6 +83,10 @@ struct pv_problem {
     // METHOD_AUTO on a non-stiff model: trajectories that exhaust switch_steps explicit steps (stiff parameter
     // values) are re-run with RODAS4.  Scratch per launch slot: 0 = caller's stream, 1..3 = internal pipeline streams.
     int switch_steps = 4000;
+    int locality = 0;              // pv_problem_set_locality: 0 = auto (sorted launches from 4096 trajectories), 1 = off, 2 = on
+    int32_t* d_sched_index[4] = {nullptr, nullptr, nullptr, nullptr};     // per launch slot, like the stiff re-run scratch
+    unsigned int* d_sched_bins[4] = {nullptr, nullptr, nullptr, nullptr};  // [PV_SCHED_BINS] bins + 2 x int64 sums behind them
+    int64_t sched_cap[4] = {0, 0, 0, 0};
     int stiff_after = 64;          // DOPRI5 stiffness detection of the AUTO first pass starts after this many steps
     int32_t* d_scratch_status[4] = {nullptr, nullptr, nullptr, nullptr};
     int32_t* d_scratch_index[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -178,6 +183,8 @@ extern "C" void pv_problem_destroy(pv_problem* p) {
         cudaFree(p->d_scratch_status[i]);
         cudaFree(p->d_scratch_index[i]);
         cudaFree(p->d_scratch_count[i]);
+        cudaFree(p->d_sched_index[i]);
+        cudaFree(p->d_sched_bins[i]);
     }
     for (int i = 0; i < 3; ++i) {
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
@@ -244,6 +251,13 @@ extern "C" int pv_problem_set_stiff_switch(pv_problem* p, int switch_steps) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
     if (switch_steps < 1) return fail(PV_E_ARG, "switch_steps must be >= 1");
     p->switch_steps = switch_steps;
+    return 0;
+}
+
+extern "C" int pv_problem_set_locality(pv_problem* p, int mode) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (mode < 0 || mode > 2) return fail(PV_E_ARG, "mode must be 0 (auto), 1 (off) or 2 (on)");
+    p->locality = mode;
     return 0;
 }
 
@@ -516,6 +530,35 @@ static unsigned long long* next_counter(pv_problem* p) {
     return c;
 }
 
+// locality schedule of one launch (pv_schedule.cuh): fills the slot's index map on stream s
+static int locality_schedule(pv_problem* p, int slot, int64_t B, const double* P, cudaStream_t s, const int32_t** index_out) {
+    if (p->sched_cap[slot] < B) {
+        cudaFree(p->d_sched_index[slot]);
+        p->d_sched_index[slot] = nullptr;
+        p->sched_cap[slot] = 0;
+        CUDA_OK(cudaMalloc(&p->d_sched_index[slot], sizeof(int32_t) * B));
+        if (!p->d_sched_bins[slot]) CUDA_OK(cudaMalloc(&p->d_sched_bins[slot], sizeof(unsigned int) * PV_SCHED_BINS + 2 * sizeof(long long)));
+        p->sched_cap[slot] = B;
+    }
+    pv_sched_params sp;
+    sp.P = P;
+    sp.B = B;
+    sp.n_key_cols = std::min<int>((int)p->col_target.size(), 2);
+    sp.bins = p->d_sched_bins[slot];
+    sp.sums = (long long*)(p->d_sched_bins[slot] + PV_SCHED_BINS);
+    sp.index = p->d_sched_index[slot];
+    CUDA_OK(cudaMemsetAsync(sp.bins, 0, sizeof(unsigned int) * PV_SCHED_BINS + 2 * sizeof(long long), s));
+    const unsigned blocks = (unsigned)std::min<int64_t>((B + 255) / 256, (int64_t)p->num_sms * 8);
+    pv_sched_mean_kernel<<<blocks, 256, 0, s>>>(sp);
+    pv_sched_hist_kernel<<<blocks, 256, 0, s>>>(sp);
+    pv_sched_scan_kernel<<<1, 1024, 0, s>>>(sp.bins);
+    pv_sched_scatter_kernel<<<blocks, 256, 0, s>>>(sp);
+    g_launches.fetch_add(4);
+    CUDA_OK(cudaGetLastError());
+    *index_out = sp.index;
+    return 0;
+}
+
 static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y, double* S, double* logp,
                   double* grad, int32_t* status, int32_t* steps, cudaStream_t s, double* fim = nullptr, int slot = 0) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
@@ -580,6 +623,8 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
         lp.stiff_after = p->stiff_after;
         if (!lp.status) lp.status = p->d_scratch_status[slot];
     }
+    if (!p->col_target.empty() && (p->locality == 2 || (p->locality == 0 && B >= 4096)))
+        if (int rc = locality_schedule(p, slot, B, P, s, &lp.index_map)) return rc;
     size_t shmem = sizeof(double) * (lp.T + p->tab->n_theta + p->tab->n_states);
     if (need_logp && lp.n_data == 1) shmem += sizeof(double) * PV_QSTRIDE * lp.T * lp.n_obs;
     if (shmem > 200 * 1024) return fail(PV_E_ARG, "time grid / data too large for shared memory");

@@ -18,6 +18,8 @@ import torch  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--refill", type=int, default=0)
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--locality", type=int, default=0, help="0 auto, 1 off, 2 on (pv_problem_set_locality)")
+ap.add_argument("--mode", default="traj_logp", choices=["traj_logp", "logp", "traj"])
 args = ap.parse_args()
 rt = importlib.import_module("parameter-variability_b200.runtime")
 B, T = 1_000_000, 50
@@ -35,14 +37,16 @@ d = np.ones((T, 3))
 pb.set_data(np.stack([d, d, d])[..., None], 1.0)
 if args.refill:
     pb.set_schedule(args.refill)
+pb.set_locality(args.locality)
+run = {"traj_logp": lambda: pb.simulate_logp(P, Y, lp), "logp": lambda: pb.logp(P, lp), "traj": lambda: pb.simulate(P, Y)}[args.mode]
 for _ in range(3):
-    pb.simulate_logp(P, Y, lp)
+    run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(args.reps):
-    pb.simulate_logp(P, Y, lp)
+    run()
 e1.record()
 torch.cuda.synchronize()
-print(f"{os.environ.get('PARVAR_B200_LIB') or 'default'} refill={args.refill or 'default'}: "
+print(f"{os.environ.get('PARVAR_B200_LIB') or 'default'} refill={args.refill or 'default'} locality={args.locality} mode={args.mode}: "
       f"{e0.elapsed_time(e1) / args.reps:.3f} ms  logp_sum={float(lp.sum()):.6f}", flush=True)

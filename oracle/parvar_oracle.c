@@ -20,7 +20,7 @@
  *     error control in the weighted RMS norm with atol + rtol*|y| weights, polynomial dense output;
  *   - the Gaussian log-likelihood of the PEtab problem the reference writes (petab_factory.py:388-417).
  * It is checked against oracle/parvar_oracle.py (closed forms, scipy LSODA/Radau/BDF) in
- * tests/test_oracle_c.py, and is the bench's cpu_baseline ("port", all host cores via OpenMP).
+ * tests/test_golden.py (C restatement vs the Python oracle and the golden vectors), and is the bench's cpu_baseline ("port", all host cores via OpenMP).
  */
 #include <math.h>
 #include <stdlib.h>

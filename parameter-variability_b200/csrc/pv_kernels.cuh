@@ -276,13 +276,15 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
     auto finish = [&](int rc) {
         const int64_t b = sink.b;
         if constexpr (LOGP) {
-            p.logp[b] = (rc == 0) ? sink.lp : __longlong_as_double(0x7ff8000000000000LL);
+            // a trajectory that did not finish has no likelihood: NaN in logp, gradient and Fisher information alike
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            p.logp[b] = (rc == 0) ? sink.lp : nan;
             if constexpr (SENS) {
 #pragma unroll
-                for (int s = 0; s < M::NS; ++s) p.grad[(int64_t)s * p.B + b] = sink.g[s];
+                for (int s = 0; s < M::NS; ++s) p.grad[(int64_t)s * p.B + b] = (rc == 0) ? sink.g[s] : nan;
                 if constexpr ((MODE & PV_MODE_FIM) != 0) {
 #pragma unroll
-                    for (int q = 0; q < M::NS * (M::NS + 1) / 2; ++q) p.fim[(int64_t)q * p.B + b] = sink.fim[q];
+                    for (int q = 0; q < M::NS * (M::NS + 1) / 2; ++q) p.fim[(int64_t)q * p.B + b] = (rc == 0) ? sink.fim[q] : nan;
                 }
             }
         }

@@ -484,13 +484,16 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
                     p.steps[p.B + b] = n_rej;
                 }
             } else {
-                p.grad[(int64_t)(warp - 1) * p.B + b] = g;
+                // (the controller state, rc included, is replicated in every warp) a trajectory that did not finish has no
+                // likelihood: NaN in logp, gradient and Fisher information alike
+                const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                p.grad[(int64_t)(warp - 1) * p.B + b] = (rc == 0) ? g : nan;
                 if constexpr (FIM) {
                     // upper triangle, row-major: row k = warp - 1 starts at k NS - k (k - 1) / 2
                     const int k = warp - 1, q0 = k * NS - k * (k - 1) / 2;
 #pragma unroll
                     for (int r2 = 0; r2 < NS; ++r2)
-                        if (r2 >= k) p.fim[(int64_t)(q0 + r2 - k) * p.B + b] = fim[r2];
+                        if (r2 >= k) p.fim[(int64_t)(q0 + r2 - k) * p.B + b] = (rc == 0) ? fim[r2] : nan;
                 }
             }
         }

@@ -20,7 +20,7 @@ import pandas as pd
 
 from . import optimizer as opt_mod
 from . import sampler as smp_mod
-from .petab_io import load_petab_problem, read_petab_tables
+from .petab_io import load_petab_problem, parse_petab_problem, read_petab_tables
 from .petab_optimization import GroupData, PetabObjectiveBatch
 
 DEFAULT_SETTINGS = dict(          # petab_optimization.py:294-306
@@ -130,18 +130,21 @@ class GpuPetabSampler:
 
 
 def _batch_from_yaml(yaml_paths: Sequence[Path], mode: str, dosage, device: int) -> PetabObjectiveBatch:
-    objs = [load_petab_problem(p, mode=mode, dosage=dosage, device=device) for p in yaml_paths[:1]]
-    first = objs[0]
-    problems, priors = [], []
-    for p in yaml_paths:
-        o = first if p == yaml_paths[0] else load_petab_problem(p, mode=mode, dosage=dosage, device=device)
-        if (o.model, o.parameters, o.observables) != (first.model, first.parameters, first.observables) or \
-                not np.array_equal(o.timepoints, first.timepoints):
-            raise ValueError("experiments batched together must share model, parameters, observables and time grid")
-        problems.append(o.groups)
-        priors.append({n: (l, s) for n, l, s in zip(o.x_names, o.prior_loc, o.prior_scale) if np.isfinite(l)})
-    batch = PetabObjectiveBatch(first.model, first.parameters, problems, first.timepoints, first.observables,
-                                sigma=1.0, priors=priors, mode=mode, dosage=dosage, device=device)
+    """One batched objective for PEtab directories that share model, parameters, observables, time grid, noise formula,
+    bounds and (literal mode) condition-table initial values; measurements and priors are per problem.  The tables are
+    parsed without creating GPU objects; ONE ``Problem`` is built for the whole batch."""
+    parsed = [parse_petab_problem(p) for p in yaml_paths]
+    first = parsed[0]
+    for p, o in zip(yaml_paths, parsed):
+        same = (o.model, o.parameters, o.species) == (first.model, first.parameters, first.species) and \
+            np.array_equal(o.timepoints, first.timepoints) and np.array_equal(o.sigma, first.sigma) and \
+            np.array_equal(o.lb, first.lb) and np.array_equal(o.ub, first.ub) and o.literal_values == first.literal_values
+        if not same:
+            raise ValueError(f"{p}: experiments batched together must share model, parameters, observables, time grid, noise "
+                             "formula, bounds and condition-table initial values")
+    batch = PetabObjectiveBatch(first.model, first.parameters, [o.groups for o in parsed], first.timepoints, first.species,
+                                sigma=first.sigma, priors=[o.priors for o in parsed], mode=mode, dosage=dosage, device=device,
+                                initial_values=first.literal_values if mode == "literal" else None)
     batch.lb, batch.ub = first.lb, first.ub
     return batch
 

@@ -61,14 +61,25 @@ def read_petab_tables(yaml_path: str | Path) -> PetabTables:
     )
 
 
-def load_petab_problem(yaml_path: str | Path, mode: str = "literal", dosage: Optional[dict[str, float]] = None,
-                       device: int = 0, **objective_kwargs) -> PetabObjective:
-    """Build the GPU objective for one reference experiment directory.
+@dataclass
+class ParsedPetab:
+    """What the tables of one reference experiment directory say (no GPU object involved)."""
+    model: str
+    parameters: list            # model parameters mapped to estimated "<par>_<cond>" ids, condition-table column order
+    groups: list                # GroupData per condition
+    timepoints: np.ndarray
+    species: list               # observableFormula per observable = the observed species
+    sigma: np.ndarray           # noiseFormula per observable
+    priors: dict                # x_name -> (loc, scale)
+    literal_values: dict        # species columns of the condition table (quirk Q4: observed species -> 0.0, no dose)
+    x_names: list
+    lb: np.ndarray
+    ub: np.ndarray
+    x_nominal: np.ndarray
 
-    ``mode="literal"`` applies the condition table as written - which sets every observed species' initial
-    value to 0.0 and carries no dose (quirk Q4) - exactly what AMICI would simulate for these files;
-    ``mode="intended"`` ignores those species overrides and applies ``dosage`` instead.
-    """
+
+def parse_petab_problem(yaml_path: str | Path) -> ParsedPetab:
+    """Read and check the tables ``create_petab_example`` writes (petab_factory.py:320-517)."""
     from ..experiments.petab_factory import resolve_model
     tb = read_petab_tables(yaml_path)
     model = resolve_model(tb.model_path)
@@ -91,7 +102,7 @@ def load_petab_problem(yaml_path: str | Path, mode: str = "literal", dosage: Opt
     # condition columns mapping a model parameter to an estimated parameter id "<par>_<cond>"
     model_pars = [c for c in cond.columns if c not in ("conditionId", "conditionName")
                   and all(str(v) in set(est["parameterId"]) for v in cond[c])]
-    x_expected = [f"{p}_{c}" for p in model_pars for c in cond_ids]
+    x_names = [f"{p}_{c}" for p in model_pars for c in cond_ids]
     for p in model_pars:
         for c, v in zip(cond_ids, cond[p]):
             if str(v) != f"{p}_{c}":
@@ -130,33 +141,50 @@ def load_petab_problem(yaml_path: str | Path, mode: str = "literal", dosage: Opt
                 loc, scale = (float(v) for v in str(pp).split(";"))
                 priors[pid] = (loc, scale)
 
-    objective = PetabObjective(model, model_pars, groups, times, species, sigma=sigma, priors=priors, mode="intended",
-                               dosage=dosage if mode == "intended" else None, device=device, **objective_kwargs)
-    if mode == "literal":
-        # apply the species columns of the condition table (identical for every condition in the reference's files)
-        for col in cond.columns:
-            if col in ("conditionId", "conditionName") or col in model_pars:
-                continue
-            vals = set(float(v) for v in cond[col])
-            if len(vals) != 1:
-                raise NotImplementedError(f"condition-specific initial value for {col}")
-            objective.problem.set_value(col, vals.pop())
-    elif mode != "intended":
-        raise ValueError("mode must be 'literal' or 'intended'")
-    assert objective.x_names == x_expected
+    # the species columns of the condition table (identical for every condition in the reference's files)
+    literal_values = {}
+    for col in cond.columns:
+        if col in ("conditionId", "conditionName") or col in model_pars:
+            continue
+        vals = set(float(v) for v in cond[col])
+        if len(vals) != 1:
+            raise NotImplementedError(f"condition-specific initial value for {col}")
+        literal_values[col] = vals.pop()
     lb = {pid: float(v) for pid, v in zip(par["parameterId"], par["lowerBound"])}
     ub = {pid: float(v) for pid, v in zip(par["parameterId"], par["upperBound"])}
-    objective.lb = np.array([lb[n] for n in objective.x_names])
-    objective.ub = np.array([ub[n] for n in objective.x_names])
-    objective.x_nominal = np.array([float(par.set_index("parameterId").loc[n, "nominalValue"]) for n in objective.x_names])
+    nominal = par.set_index("parameterId")["nominalValue"]
+    return ParsedPetab(model=model, parameters=model_pars, groups=groups, timepoints=times, species=species, sigma=sigma,
+                       priors=priors, literal_values=literal_values, x_names=x_names,
+                       lb=np.array([lb[n] for n in x_names]), ub=np.array([ub[n] for n in x_names]),
+                       x_nominal=np.array([float(nominal.loc[n]) for n in x_names]))
+
+
+def load_petab_problem(yaml_path: str | Path, mode: str = "literal", dosage: Optional[dict[str, float]] = None,
+                       device: int = 0, **objective_kwargs) -> PetabObjective:
+    """Build the GPU objective for one reference experiment directory.
+
+    ``mode="literal"`` applies the condition table as written - which sets every observed species' initial
+    value to 0.0 and carries no dose (quirk Q4) - exactly what AMICI would simulate for these files;
+    ``mode="intended"`` ignores those species overrides and applies ``dosage`` instead.
+    """
+    if mode not in ("literal", "intended"):
+        raise ValueError("mode must be 'literal' or 'intended'")
+    pp = parse_petab_problem(yaml_path)
+    objective = PetabObjective(pp.model, pp.parameters, pp.groups, pp.timepoints, pp.species, sigma=pp.sigma, priors=pp.priors,
+                               mode="intended", dosage=dosage if mode == "intended" else None, device=device, **objective_kwargs)
+    if mode == "literal":
+        for col, v in pp.literal_values.items():
+            objective.problem.set_value(col, v)
+    assert objective.x_names == pp.x_names
+    objective.lb, objective.ub, objective.x_nominal = pp.lb, pp.ub, pp.x_nominal
     return objective
 
 
 def write_petab_like_reference(directory: Path, model_path: Path, groups: list[GroupData], timepoints, species: list[str],
                                parameters: list[str], priors: dict[str, tuple[float, float]]) -> Path:
     """Write the four tables + yaml in the layout and column set of ``create_petab_example`` (:320-517).
-    Test helper (the reference's writer needs xarray / roadrunner, which this image lacks); kept next to the reader
-    so the two are maintained together."""
+    The product's PEtab writer (``experiments/workflow.py`` uses it; byte-identical to the reference's five files,
+    tests/test_golden.py); kept next to the reader so the two are maintained together."""
     directory = Path(directory)
     petab = directory / "petab"
     petab.mkdir(parents=True, exist_ok=True)

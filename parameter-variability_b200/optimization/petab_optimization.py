@@ -71,7 +71,7 @@ class PetabObjective:
                  priors: Optional[dict[str, tuple[float, float]]] = None, noise_model: int = runtime.NOISE_NORMAL,
                  mode: str = "intended", dosage: Optional[dict[str, float]] = None, device: int = 0,
                  rtol: float = 1e-8, atol: float = 1e-11, method: int = runtime.METHOD_AUTO,
-                 prior_constant: bool = True, max_steps: int = 10000):
+                 prior_constant: bool = True, max_steps: int = 10000, t0: float = 0.0):
         if mode not in ("intended", "literal"):
             raise ValueError("mode must be 'intended' or 'literal'")
         self.model = model
@@ -104,7 +104,8 @@ class PetabObjective:
             for k, v in dosage.items():
                 pb.set_value(k, v)
         pb.set_columns(self.parameters)
-        pb.set_timepoints(self.timepoints)
+        # PEtab / AMICI: the initial values hold at t = 0 even when the first measurement is later
+        pb.set_timepoints(self.timepoints, t0=min(float(t0), float(self.timepoints[0])))
         pb.set_observables(self.observables)
         stats = np.stack([sufficient_statistics(g.y, noise_model) for g in self.groups], axis=-1)  # [3,T,K,G]
         pb.set_data(stats, sigma, noise_model)
@@ -140,8 +141,10 @@ class PetabObjective:
                 logp = logp - 0.5 * np.sum(LOG_2PI + 2.0 * np.log(self.prior_scale[self._has_prior]))
             if grad:
                 dx[:, self._has_prior] -= z / self.prior_scale[self._has_prior]
-        if n_failed:
-            bad = ~np.isfinite(lp_x)
+        # a failed integration (NaN from the kernel) and a non-finite likelihood of a finished one (log-normal noise with
+        # f <= 0) are both failed evaluations: fval = inf, grad = nan - whatever n_failed says
+        bad = ~np.isfinite(lp_x)
+        if bad.any():
             logp[bad] = -np.inf
             if grad:
                 dx[bad] = np.nan
@@ -197,7 +200,8 @@ class PetabObjectiveBatch:
                  priors: Optional[Sequence[dict[str, tuple[float, float]]]] = None,
                  noise_model: int = runtime.NOISE_NORMAL, mode: str = "intended",
                  dosage: Optional[dict[str, float]] = None, device: int = 0, rtol: float = 1e-8, atol: float = 1e-11,
-                 method: int = runtime.METHOD_AUTO, t0: float = 0.0, max_steps: int = 10000):
+                 method: int = runtime.METHOD_AUTO, t0: float = 0.0, max_steps: int = 10000,
+                 initial_values: Optional[dict[str, float]] = None):
         self.model = model
         self.parameters = list(parameters)
         self.Q = len(problems)
@@ -223,8 +227,10 @@ class PetabObjectiveBatch:
         pb = runtime.Problem(model, device=device)
         pb.set_solver(method=method, rtol=rtol, atol=atol, max_steps=max_steps)      # AMICI's default budget, see PetabObjective
         if mode == "literal":
-            for o in self.observables:
-                pb.set_value(o, 0.0)
+            # the condition table's species columns when given (read from the files), else what the reference always
+            # writes: every observed species 0.0 (quirk Q4)
+            for k, v in (initial_values if initial_values is not None else {o: 0.0 for o in self.observables}).items():
+                pb.set_value(k, v)
         elif mode == "intended":
             for k, v in (dosage or {}).items():
                 pb.set_value(k, v)

@@ -243,6 +243,18 @@ def test_petab_reader_and_writer_against_reference_written_directory(tmp_path, m
     np.testing.assert_array_equal(obj.lb, np.zeros(4))
     np.testing.assert_array_equal(obj.ub, np.full(4, 1e8))
     np.testing.assert_array_equal(obj.x_nominal, np.ones(4))
+    # the same tables parsed without any GPU object (what the batched driver uses), and handed on to the batch objective
+    pp = io.parse_petab_problem(xp / "petab.yaml")
+    assert (pp.model, pp.parameters, pp.species, pp.x_names) == ("simple_pk", ["k_abs", "CL"], species, obj.x_names)
+    assert pp.priors == priors and pp.literal_values == {"y_cent": 0.0, "y_gut": 0.0, "y_peri": 0.0}
+    np.testing.assert_array_equal(pp.sigma, [1.0, 1.0, 1.0])
+    drv = pkg("optimization.driver")
+    got = {}
+    monkeypatch.setattr(drv, "PetabObjectiveBatch", lambda *a, **kw: got.update(a=a, kw=kw) or type("B", (), {})())
+    drv._batch_from_yaml([xp / "petab.yaml", xp / "petab.yaml"], "literal", None, 0)
+    assert got["a"][0] == "simple_pk" and len(got["a"][2]) == 2 and got["kw"]["initial_values"] == pp.literal_values
+    np.testing.assert_array_equal(got["kw"]["sigma"], pp.sigma)
+    assert got["kw"]["priors"] == [priors, priors]
 
     mine = tmp_path / "mine"
     groups = [io.GroupData("MALE", data["MALE"]), io.GroupData("FEMALE", data["FEMALE"])]

@@ -746,3 +746,35 @@ def test_sweep_extremes_timepoints_and_samples(cuda_lib, rt, oracle):
         pb.set_data(opt.sufficient_statistics(data, rt.NOISE_NORMAL)[..., None], 1.0)
         lp, g, _, nf = pb.logp_host(np.array([[1.0], [1.0]]), grad=True)
         assert nf == 0 and lp[0] == pytest.approx(oracle.loglik_normal(clean, data, 1.0), rel=1e-6)
+
+
+def test_objective_integrates_from_t0_and_poisons_failed_evaluations(cuda_lib, rt, oracle):
+    """PEtab / AMICI semantics: the initial values hold at t = 0 even when the first measurement is later (PetabObjective
+    like PetabObjectiveBatch); a trajectory that does not finish yields fval = inf and a NaN gradient (never a finite
+    partial sum), with and without the Fisher information."""
+    opt = pkg("optimization.petab_optimization")
+    t = np.linspace(0, 30, 16)[3:]                       # measurements start at t = 6
+    cols = [oracle.SIMPLE_PK.states.index(o) for o in ("y_cent", "y_peri")]
+    truth = oracle.simple_pk_exact({}, t)[:, cols]
+    y = _noisy_data(truth, 0.05, 11)[None]
+    groups = [opt.GroupData("MALE", y), opt.GroupData("FEMALE", y * 1.1)]
+    obj = opt.PetabObjective("simple_pk", ["k_abs", "CL"], groups, t, ["y_cent", "y_peri"], sigma=0.05, rtol=1e-9, atol=1e-13)
+    x = np.array([0.9, 1.2, 1.1, 0.7])
+    fval, g = obj(x, (0, 1))
+    ref, ref_g = 0.0, np.zeros(4)
+    for gi, gr in enumerate(groups):
+        over = {"k_abs": x[gi], "CL": x[2 + gi]}
+        f = oracle.simple_pk_exact(over, t)[:, cols]          # exact solution started at t = 0
+        s = oracle.simple_pk_exact_sens(over, t)[:, cols, :]
+        ref -= oracle.loglik_normal(f, gr.y[0], 0.05)
+        gg = oracle.loglik_normal_grad(f, s, gr.y[0], 0.05)
+        ref_g[gi], ref_g[2 + gi] = -gg[0], -gg[1]
+    assert fval == pytest.approx(ref, rel=1e-6)
+    np.testing.assert_allclose(g, ref_g, rtol=1e-6, atol=1e-6 * np.abs(ref_g).max())
+    # failed evaluation: a step budget no trajectory can meet
+    bad = opt.PetabObjective("simple_pk", ["k_abs", "CL"], groups, t, ["y_cent", "y_peri"], sigma=0.05, max_steps=5,
+                             method=rt.METHOD_DOPRI5)
+    fv, gb = bad(x, (0, 1))
+    assert fv == np.inf and np.all(np.isnan(gb))
+    lp, gr_, fim, _, nf = bad.problem.logp_fim_host(np.array([[0.9, 1.2], [1.1, 0.7]]))
+    assert nf == 2 and np.all(np.isnan(lp)) and np.all(np.isnan(gr_)) and np.all(np.isnan(fim))

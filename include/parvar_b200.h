@@ -82,9 +82,16 @@ int pv_problem_set_schedule(pv_problem* p, int refill_min);
 
 /* Locality schedule (divergence control): the trajectories of a launch are bucketed on the device by their parameter
  * values (first two columns) so that the lanes of a warp integrate neighbouring points of parameter space and therefore
- * step, cross the output grid and finish together.  Only the order in which trajectories are picked up changes; results
- * are bit-identical.  mode 0 = auto (launches of >= 4096 trajectories with per-trajectory columns), 1 = off, 2 = on. */
+ * step, cross the output grid and finish together (stable radix sort on the device: the order is a pure function of
+ * the inputs).  Only the order in which trajectories are picked up changes; results are bit-identical.  mode 0 = auto (launches of >= 4096 trajectories with per-trajectory columns), 1 = off, 2 = on. */
 int pv_problem_set_locality(pv_problem* p, int mode);
+
+/* Lockstep warps (DOPRI5 kernels): the 32 lanes of a warp - 32 consecutive work items, neighbours in parameter space under
+ * the locality schedule - advance with ONE step size chosen from the largest error norm among them (warp-level
+ * agreement), so t, h, accept / reject and the grid crossings are warp-uniform: no divergence, no refill.  Every lane
+ * still meets its own tolerance; a lane's digits beyond the tolerance now depend on its neighbours (a given batch
+ * reproduces itself bit for bit: the work order is deterministic).  mode 0 = auto, 1 = off, 2 = on. */
+int pv_problem_set_lockstep(pv_problem* p, int mode);
 
 /* Data layout of the Rosenbrock sensitivity kernels (logp + gradient, + Fisher information) of the large models
  * (augmented system of more than 16 components; of the built-in models: icg_body_flat):

@@ -84,8 +84,8 @@ struct pv_problem {
     // values) are re-run with RODAS4.  Scratch per launch slot: 0 = caller's stream, 1..3 = internal pipeline streams.
     int switch_steps = 4000;
     int locality = 0;              // pv_problem_set_locality: 0 = auto (sorted launches from 4096 trajectories), 1 = off, 2 = on
-    int32_t* d_sched_index[4] = {nullptr, nullptr, nullptr, nullptr};     // per launch slot, like the stiff re-run scratch
-    unsigned int* d_sched_bins[4] = {nullptr, nullptr, nullptr, nullptr};  // [PV_SCHED_BINS] bins + 2 x int64 sums behind them
+    int32_t* d_sched_index[4] = {nullptr, nullptr, nullptr, nullptr};     // locality-schedule scratch per launch slot (pv_schedule.cuh)
+    int lockstep = 0;              // pv_problem_set_lockstep: 0 = auto, 1 = off, 2 = on
     int64_t sched_cap[4] = {0, 0, 0, 0};
     int stiff_after = 64;          // DOPRI5 stiffness detection of the AUTO first pass starts after this many steps
     int32_t* d_scratch_status[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -95,6 +95,9 @@ struct pv_problem {
 };
 #define PV_COUNTER_RING 1024
 #define PV_SAMPLER_COUNTERS 8
+#ifndef PV_LOCKSTEP_AUTO
+#define PV_LOCKSTEP_AUTO 0     // measured default of pv_problem_set_lockstep(0) for sorted launches
+#endif
 
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int pv_abi_version(void) { return PV_ABI_VERSION; }
@@ -184,7 +187,6 @@ extern "C" void pv_problem_destroy(pv_problem* p) {
         cudaFree(p->d_scratch_index[i]);
         cudaFree(p->d_scratch_count[i]);
         cudaFree(p->d_sched_index[i]);
-        cudaFree(p->d_sched_bins[i]);
     }
     for (int i = 0; i < 3; ++i) {
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
@@ -258,6 +260,13 @@ extern "C" int pv_problem_set_locality(pv_problem* p, int mode) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
     if (mode < 0 || mode > 2) return fail(PV_E_ARG, "mode must be 0 (auto), 1 (off) or 2 (on)");
     p->locality = mode;
+    return 0;
+}
+
+extern "C" int pv_problem_set_lockstep(pv_problem* p, int mode) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (mode < 0 || mode > 2) return fail(PV_E_ARG, "mode must be 0 (auto), 1 (off) or 2 (on)");
+    p->lockstep = mode;
     return 0;
 }
 
@@ -440,7 +449,7 @@ static int resident_ctas(const void* kern, int threads, size_t shmem, cudaError_
 }
 
 struct pv_launch_ctx {
-    int num_sms, layout, max_ctas_per_sm;
+    int num_sms, layout, max_ctas_per_sm, lockstep;
     const double* theta;   // host [NTH]
     const double* y0;      // host [NX]
 };
@@ -471,6 +480,9 @@ static cudaError_t launch_persistent(KernelT kern, const pv_launch_params& lp, c
 
 template <class M, int METHOD, int MODE, bool OBSID>
 static cudaError_t launch_one(const pv_launch_params& lp, const pv_launch_ctx& cx, size_t shmem, cudaStream_t s) {
+    if constexpr (METHOD == 1) {
+        if (cx.lockstep) return launch_persistent<M>(pv_batch_lockstep_kernel<M, MODE, OBSID>, lp, cx, PV_BLOCK, PV_BLOCK, shmem, s);
+    }
     return launch_persistent<M>(pv_batch_kernel<M, METHOD, MODE, OBSID>, lp, cx, PV_BLOCK, PV_BLOCK, shmem, s);
 }
 
@@ -532,30 +544,45 @@ static unsigned long long* next_counter(pv_problem* p) {
 
 // locality schedule of one launch (pv_schedule.cuh): fills the slot's index map on stream s
 static int locality_schedule(pv_problem* p, int slot, int64_t B, const double* P, cudaStream_t s, const int32_t** index_out) {
+    const size_t per = ((size_t)B + 63) / 64 * 64;    // elements per array, 256-byte multiples
     if (p->sched_cap[slot] < B) {
         cudaFree(p->d_sched_index[slot]);
         p->d_sched_index[slot] = nullptr;
         p->sched_cap[slot] = 0;
-        CUDA_OK(cudaMalloc(&p->d_sched_index[slot], sizeof(int32_t) * B));
-        if (!p->d_sched_bins[slot]) CUDA_OK(cudaMalloc(&p->d_sched_bins[slot], sizeof(unsigned int) * PV_SCHED_BINS + 2 * sizeof(long long)));
+        // idx_a | idx_b | key_a | key_b | counts [256][PV_SCHED_MAX_TILES] | sums [2]
+        CUDA_OK(cudaMalloc(&p->d_sched_index[slot], 4 * per * sizeof(int32_t) + sizeof(uint32_t) * 256 * PV_SCHED_MAX_TILES +
+                                                       2 * sizeof(long long)));
         p->sched_cap[slot] = B;
     }
+    const size_t cap = ((size_t)p->sched_cap[slot] + 63) / 64 * 64;
     pv_sched_params sp;
     sp.P = P;
     sp.B = B;
     sp.n_key_cols = std::min<int>((int)p->col_target.size(), 2);
-    sp.bins = p->d_sched_bins[slot];
-    sp.sums = (long long*)(p->d_sched_bins[slot] + PV_SCHED_BINS);
-    sp.index = p->d_sched_index[slot];
-    CUDA_OK(cudaMemsetAsync(sp.bins, 0, sizeof(unsigned int) * PV_SCHED_BINS + 2 * sizeof(long long), s));
+    sp.idx_a = p->d_sched_index[slot];
+    sp.idx_b = sp.idx_a + cap;
+    sp.key_a = (uint32_t*)(sp.idx_b + cap);
+    sp.key_b = sp.key_a + cap;
+    sp.counts = sp.key_b + cap;
+    sp.sums = (long long*)(sp.counts + 256 * PV_SCHED_MAX_TILES);
+    sp.n_tiles = (int)std::min<int64_t>(PV_SCHED_MAX_TILES, std::max<int64_t>(1, (B + 255) / 256));
+    sp.tile = (B + sp.n_tiles - 1) / sp.n_tiles;
+    sp.n_tiles = (int)((B + sp.tile - 1) / sp.tile);
+    CUDA_OK(cudaMemsetAsync(sp.sums, 0, 2 * sizeof(long long), s));
     const unsigned blocks = (unsigned)std::min<int64_t>((B + 255) / 256, (int64_t)p->num_sms * 8);
+    const unsigned tile_blocks = (unsigned)((sp.n_tiles + 3) / 4);
     pv_sched_mean_kernel<<<blocks, 256, 0, s>>>(sp);
-    pv_sched_hist_kernel<<<blocks, 256, 0, s>>>(sp);
-    pv_sched_scan_kernel<<<1, 1024, 0, s>>>(sp.bins);
-    pv_sched_scatter_kernel<<<blocks, 256, 0, s>>>(sp);
-    g_launches.fetch_add(4);
+    pv_sched_key_kernel<<<blocks, 256, 0, s>>>(sp);
+    // pass 1: low digit a -> b; pass 2: high digit b -> a
+    pv_sched_hist_kernel<<<tile_blocks, 128, 0, s>>>(sp, sp.key_a, 0);
+    pv_sched_scan_kernel<<<1, 1024, 0, s>>>(sp.counts, 256 * sp.n_tiles);
+    pv_sched_scatter_kernel<<<tile_blocks, 128, 0, s>>>(sp, sp.key_a, sp.idx_a, sp.key_b, sp.idx_b, 0);
+    pv_sched_hist_kernel<<<tile_blocks, 128, 0, s>>>(sp, sp.key_b, 8);
+    pv_sched_scan_kernel<<<1, 1024, 0, s>>>(sp.counts, 256 * sp.n_tiles);
+    pv_sched_scatter_kernel<<<tile_blocks, 128, 0, s>>>(sp, sp.key_b, sp.idx_b, sp.key_a, sp.idx_a, 8);
+    g_launches.fetch_add(8);
     CUDA_OK(cudaGetLastError());
-    *index_out = sp.index;
+    *index_out = sp.idx_a;
     return 0;
 }
 
@@ -630,7 +657,11 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     if (shmem > 200 * 1024) return fail(PV_E_ARG, "time grid / data too large for shared memory");
     bool obsid = lp.n_obs == p->tab->n_states;
     for (int k = 0; k < lp.n_obs && obsid; ++k) obsid = (lp.obs_idx[k] == k);
-    const pv_launch_ctx cx{p->num_sms, p->layout, p->max_ctas_per_sm, p->theta_base.data(), p->y0_base.data()};
+    // lockstep warps (one common step size per warp) pay when the lanes integrate similar trajectories: with the locality
+    // schedule.  The stiff re-run pass (RODAS4 on a handful of rows) is not affected.
+    const bool sorted = lp.index_map != nullptr;
+    const int lockstep = p->lockstep == 2 || (p->lockstep == 0 && sorted && PV_LOCKSTEP_AUTO) ? 1 : 0;
+    const pv_launch_ctx cx{p->num_sms, p->layout, p->max_ctas_per_sm, lockstep, p->theta_base.data(), p->y0_base.data()};
     cudaError_t e = cudaErrorInvalidValue;
     switch (p->model) {
         PV_MODEL_DISPATCH(e = launch_model, (method, mode, obsid, lp, cx, shmem, s))

@@ -116,6 +116,30 @@ PV_COEF_SPACE double pv_dp5[32] = {
 #define PV_STIFF_REMAINING_STEPS 600.0
 #endif
 
+// ---- warp agreement (lockstep schedule) ---------------------------------------------------------------------
+// max over the warp of a non-negative float (one REDUX on the bit pattern: for x >= 0 the IEEE order is the integer order)
+PV_HD float pv_warp_max_nonneg(float x) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(x)));
+#else
+    return x;
+#endif
+}
+PV_HD double pv_warp_min(double x) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x = fmin(x, __shfl_xor_sync(0xffffffffu, x, off));
+#endif
+    return x;
+}
+PV_HD bool pv_warp_any(bool x) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(0xffffffffu, x);
+#else
+    return x;
+#endif
+}
+
 struct pv_step_stats {
     int accepted;
     int rejected;
@@ -165,6 +189,14 @@ struct pv_dopri5_lane {
     // INT_MAX = off (an explicitly chosen DOPRI5 integrates whatever it is given).
     int stiff_after = 0x7fffffff;
     int stiff_run;     // consecutive stiff estimates (high half) | consecutive non-stiff estimates (low half)
+    // Lockstep schedule (step<true>): the 32 lanes of a warp advance with ONE step size - the controller sees the largest
+    // error norm of the warp - so t, h, accept / reject and the grid crossings are warp-uniform: no divergence anywhere,
+    // the per-grid-point code runs with all lanes or not at all.  Every lane still meets its own tolerance (its error is
+    // <= the warp's).  Pays when the lanes integrate similar trajectories (locality schedule, pv_schedule.cuh).
+    // A lane whose own error estimate stays non-finite is taken out of the agreement (`dead`) instead of dragging its
+    // neighbours' step size to zero.
+    int nonfinite_run = 0;
+    bool dead = false;
 
     // z0 -> y, outputs for grid points at t0, first derivative, initial step size
     template <class Out>
@@ -174,6 +206,8 @@ struct pv_dopri5_lane {
         st.rejected = 0;
         nstep = 0;
         stiff_run = 0;
+        nonfinite_run = 0;
+        dead = false;
         lfacold = -13.287712f;   // log2(1e-4)
         last_rejected = false;
         t = t0;
@@ -226,6 +260,18 @@ struct pv_dopri5_lane {
     template <class Out>
     PV_HD int step(const typename Sys::Consts& ks, const double* tgrid, int T, double rtol, double atol,
                    int max_steps, Out& out) {
+        return step_impl<false>(ks, tgrid, T, rtol, atol, max_steps, out);
+    }
+    // one attempted step of the whole warp (all 32 lanes must call it together)
+    template <class Out>
+    PV_HD int step_lockstep(const typename Sys::Consts& ks, const double* tgrid, int T, double rtol, double atol,
+                            int max_steps, Out& out) {
+        return step_impl<true>(ks, tgrid, T, rtol, atol, max_steps, out);
+    }
+
+    template <bool LS, class Out>
+    PV_HD int step_impl(const typename Sys::Consts& ks, const double* tgrid, int T, double rtol, double atol,
+                        int max_steps, Out& out) {
         if (nstep >= max_steps) return PV_ERR_MAX_STEPS;
         ++nstep;
         bool last = false;
@@ -283,7 +329,13 @@ struct pv_dopri5_lane {
         }
         float err2 = (float)(err2d * (1.0 / N));
         // a non-finite stage value makes e, hence err2, NaN or inf: treated as a failed step (give up once h is tiny)
-        if (!(err2 <= 3.0e38f)) {
+        if constexpr (LS) {
+            const bool bad = !(err2 <= 3.0e38f);
+            nonfinite_run = bad ? nonfinite_run + 1 : 0;
+            dead = dead || nonfinite_run >= 8;
+            err2 = pv_warp_max_nonneg(dead ? 0.0f : (bad ? 1e10f : err2));
+            if (err2 >= 1e10f && fabs(h) < 1e-12) return PV_ERR_NONFINITE;
+        } else if (!(err2 <= 3.0e38f)) {
             err2 = 1e10f;
             if (fabs(h) < 1e-12) return PV_ERR_NONFINITE;
         }
@@ -328,7 +380,9 @@ struct pv_dopri5_lane {
                     num = fma(dk, dk, num);
                     den = fma(dy, dy, den);
                 }
-                if (den > 0.0 && h * h * num > 10.5625 * den) {          // (h lambda)^2 > 3.25^2
+                bool stiff_now = den > 0.0 && h * h * num > 10.5625 * den;     // (h lambda)^2 > 3.25^2
+                if constexpr (LS) stiff_now = pv_warp_any(stiff_now && !dead);
+                if (stiff_now) {
                     stiff_run = (stiff_run & ~0xffff) + 0x10000;
                     if (stiff_run >= 15 * 0x10000 && (tend - t) > PV_STIFF_REMAINING_STEPS * h) return PV_ERR_STIFF;
                 } else if (((++stiff_run) & 0xffff) >= 6) {

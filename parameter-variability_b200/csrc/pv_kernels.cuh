@@ -367,6 +367,111 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
     }
 }
 
+// ---- the lockstep kernel -------------------------------------------------------------------------------------
+// One warp = 32 CONSECUTIVE work items (neighbours in parameter space when the launch carries the locality schedule's
+// index map) integrated with one common step size (pv_dopri5_lane::step_lockstep).  Everything that makes
+// pv_batch_kernel's warps diverge is warp-uniform here: t, h, accept / reject, the grid crossings, start and end of a
+// trajectory - so there is no refill machinery, the per-grid-point code runs with all 32 lanes, and a warp executes
+// (steps of its most demanding lane) instead of (sum over iterations of whichever lanes are busy).  A lane's result now
+// depends on its 31 neighbours' step sizes - within the tolerances, but not bit-identical across batch compositions; the
+// work-item order of a launch is deterministic (pv_schedule.cuh sorts every bucket), so a given batch reproduces itself.
+template <class M, int MODE, bool OBSID>
+__global__ void __launch_bounds__(PV_BLOCK, pv_kernel_traits<M, 1, MODE>::MIN_BLOCKS)
+pv_batch_lockstep_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
+    constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
+    constexpr bool LOGP = (MODE & PV_MODE_LOGP) != 0;
+    using Sys = pv_system<M, SENS>;
+    using Lane = pv_dopri5_lane<Sys>;
+    extern __shared__ __align__(16) double sh[];
+    const bool stats_shared = LOGP && p.n_data == 1;
+    double* sh_stats = sh;
+    double* sh_t = sh + (stats_shared ? PV_QSTRIDE * p.T * p.n_obs : 0);
+    double* sh_theta = sh_t + p.T;
+    double* sh_y0 = sh_theta + M::NTH;
+    for (int i = threadIdx.x; i < p.T; i += blockDim.x) sh_t[i] = p.tgrid[i];
+    for (int i = threadIdx.x; i < M::NTH; i += blockDim.x) sh_theta[i] = p.theta_base[i];
+    for (int i = threadIdx.x; i < M::NX; i += blockDim.x) sh_y0[i] = p.y0_base[i];
+    if (stats_shared)
+        for (int i = threadIdx.x; i < PV_QSTRIDE * p.T * p.n_obs; i += blockDim.x) sh_stats[i] = p.stats[i];
+    __syncthreads();
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane_id = threadIdx.x & 31;
+    const int64_t n_items = p.n_items_dev ? (int64_t)*p.n_items_dev : p.B;
+    const double* qbase = stats_shared ? sh_stats : p.stats;
+    typename Sys::Consts ks;
+    Lane lane;
+    lane.stiff_after = p.stiff_after;
+    pv_sink<M, MODE, OBSID> sink{p, 0, nullptr, nullptr, nullptr, {}, 0.0, {}, {}};
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane_id == 0) base = atomicAdd(p.counter, 32ull);
+        base = __shfl_sync(FULL, base, 0);
+        if ((int64_t)base >= n_items) break;
+        // lanes past the end of the work list integrate a copy of the last item (identical values to identical addresses)
+        const int64_t item = min((int64_t)base + lane_id, n_items - 1);
+        const int64_t b = p.index_map ? (int64_t)p.index_map[item] : item;
+        double pc[PV_MAX_COLS];
+#pragma unroll
+        for (int j = 0; j < PV_MAX_COLS; ++j) pc[j] = (j < p.n_cols) ? __ldg(p.P + (int64_t)j * p.B + b) : 0.0;
+        double z[Sys::N];
+        double th[M::NTH];
+#pragma unroll
+        for (int i = 0; i < M::NTH; ++i) {
+            double v = sh_theta[i];
+#pragma unroll
+            for (int j = 0; j < PV_MAX_COLS; ++j) v = (j < p.n_cols && p.col_target[j] == i) ? pc[j] : v;
+            th[i] = v;
+        }
+        double y0[M::NX];
+        M::hoist(th, ks.c, y0, sink.obs);
+        bool over[M::NX];
+#pragma unroll
+        for (int i = 0; i < M::NX; ++i) {
+            double v = sh_y0[i];
+            over[i] = (v == v);
+            v = over[i] ? v : y0[i];
+#pragma unroll
+            for (int j = 0; j < PV_MAX_COLS; ++j)
+                if (j < p.n_cols && p.col_target[j] == M::NTH + i) {
+                    v = pc[j];
+                    over[i] = true;
+                }
+            z[i] = v;
+        }
+        if constexpr (SENS) {
+            double dy0[M::NSD][M::NX];
+            M::hoist_sens(th, ks.dc, dy0);
+#pragma unroll
+            for (int s = 0; s < M::NS; ++s)
+#pragma unroll
+                for (int i = 0; i < M::NX; ++i) z[M::NX * (1 + s) + i] = over[i] ? 0.0 : dy0[s][i];
+        }
+        sink.begin(b, qbase);
+        int rc = lane.start(ks, z, p.t0, sh_t, p.T, p.rtol, p.atol, sink);     // uniform: same t0 and grid for every lane
+        lane.h = pv_warp_min(lane.h == lane.h ? lane.h : 1e300);                // one step size; a NaN estimate does not veto
+        while (rc == PV_RUNNING) rc = lane.step_lockstep(ks, sh_t, p.T, p.rtol, p.atol, p.max_steps, sink);
+        if (lane.dead) rc = PV_ERR_NONFINITE;
+        if constexpr (LOGP) {
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            p.logp[b] = (rc == 0) ? sink.lp : nan;
+            if constexpr (SENS) {
+#pragma unroll
+                for (int s = 0; s < M::NS; ++s) p.grad[(int64_t)s * p.B + b] = (rc == 0) ? sink.g[s] : nan;
+                if constexpr ((MODE & PV_MODE_FIM) != 0) {
+#pragma unroll
+                    for (int q = 0; q < M::NS * (M::NS + 1) / 2; ++q) p.fim[(int64_t)q * p.B + b] = (rc == 0) ? sink.fim[q] : nan;
+                }
+            }
+        }
+        if (p.status) p.status[b] = rc;
+        if (p.steps) {
+            p.steps[b] = lane.st.accepted;
+            p.steps[p.B + b] = lane.st.rejected;
+        }
+    }
+}
+
 // ---- deterministic segment sum: one warp per segment, fixed association order --------------------------------
 __global__ void pv_segment_sum_kernel(const double* __restrict__ x, int64_t seg_len, int64_t n_seg,
                                       double* __restrict__ out) {

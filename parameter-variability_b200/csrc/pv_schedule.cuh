@@ -1,28 +1,34 @@
-// Locality schedule (divergence control): before a batch launch the trajectories are bucketed by their parameter values
+// Locality schedule (divergence control): before a batch launch the trajectories are ordered by their parameter values
 // so that the 32 lanes of a warp integrate NEIGHBOURING points of parameter space.  Neighbours take nearly the same step
 // sequence, so a warp's lanes accept / reject together, cross the output grid in the same iterations (the per-grid-point
-// code then runs with most lanes active instead of ~7 of 32) and finish together.  Results cannot change: the order in
-// which trajectories are picked up is all that differs (every trajectory is integrated by one lane from its own inputs
-// and written to its own rows).
+// code then runs with most lanes active instead of ~7 of 32) and finish together; the lockstep kernel
+// (pv_batch_lockstep_kernel) goes one step further and gives them one common step size.
 //
 // Key: per column the top bits of the IEEE pattern of the value (monotone in the value for positive numbers:
 // 2^(52 - PV_SCHED_SHIFT) levels per octave), centred on the batch mean, clamped to 8 bits; the first two columns are
-// Morton-interleaved into a 16-bit bucket number.  Counting sort: histogram -> exclusive scan -> scatter.  Four small
-// launches, ~0.05 ms for 10^6 trajectories; the order inside a bucket is whatever the atomics produce.
+// Morton-interleaved into a 16-bit key.  Sort: hand-written STABLE least-significant-digit radix sort, two passes of 8
+// bits (per-warp tile histogram -> exclusive scan -> stable per-warp scatter ranked with __match_any_sync), so the work
+// order of a launch is a pure function of its inputs: a given batch always forms the same warps.  ~0.05 ms for 10^6
+// trajectories.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define PV_SCHED_BINS 65536
 #define PV_SCHED_SHIFT 47          // 5 mantissa bits: 32 levels per octave, 8 octaves around the batch mean
+#define PV_SCHED_MAX_TILES 2048    // warps of the sort kernels = contiguous tiles of the input
 
 struct pv_sched_params {
     const double* P;               // [n_cols][B]
     int64_t B;
     int n_key_cols;                // 1 or 2
     long long* sums;               // [2] sum of the raw keys per column
-    unsigned int* bins;            // [PV_SCHED_BINS + 1] histogram, then bucket cursors
-    int32_t* index;                // [B] work item -> trajectory
+    uint32_t* key_a;               // [B] 16-bit sort keys (ping)
+    uint32_t* key_b;               // [B] (pong)
+    int32_t* idx_a;                // [B] (ping)
+    int32_t* idx_b;                // [B] (pong) ; the final order lands in idx_a again after two passes
+    uint32_t* counts;              // [256][n_tiles] digit-major tile histograms, scanned in place
+    int n_tiles;
+    int64_t tile;                  // elements per tile
 };
 
 __device__ __forceinline__ long long pv_sched_raw_key(double v) {
@@ -40,60 +46,98 @@ __global__ void pv_sched_mean_kernel(const pv_sched_params p) {
         s0 += __shfl_xor_sync(0xffffffffu, s0, off);
         s1 += __shfl_xor_sync(0xffffffffu, s1, off);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0) {     // integer sums: the result does not depend on the order of the atomics
         atomicAdd((unsigned long long*)&p.sums[0], (unsigned long long)s0);
         if (p.n_key_cols > 1) atomicAdd((unsigned long long*)&p.sums[1], (unsigned long long)s1);
     }
 }
 
-__device__ __forceinline__ unsigned pv_sched_bucket(const pv_sched_params& p, int64_t i, long long c0, long long c1) {
-    long long k0 = pv_sched_raw_key(p.P[i]) - c0 + 128;
-    k0 = k0 < 0 ? 0 : (k0 > 255 ? 255 : k0);
-    if (p.n_key_cols == 1) return (unsigned)k0 << 8;
-    long long k1 = pv_sched_raw_key(p.P[p.B + i]) - c1 + 128;
-    k1 = k1 < 0 ? 0 : (k1 > 255 ? 255 : k1);
-    // Morton interleave of two 8-bit numbers
-    unsigned x = (unsigned)k0, y = (unsigned)k1;
-    x = (x | (x << 4)) & 0x0f0fu; x = (x | (x << 2)) & 0x3333u; x = (x | (x << 1)) & 0x5555u;
-    y = (y | (y << 4)) & 0x0f0fu; y = (y | (y << 2)) & 0x3333u; y = (y | (y << 1)) & 0x5555u;
-    return x | (y << 1);
-}
-
-__global__ void pv_sched_hist_kernel(const pv_sched_params p) {
+__global__ void pv_sched_key_kernel(const pv_sched_params p) {
     const long long c0 = p.sums[0] / p.B, c1 = p.sums[1] / p.B;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.B; i += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(&p.bins[pv_sched_bucket(p, i, c0, c1)], 1u);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.B; i += (int64_t)gridDim.x * blockDim.x) {
+        long long k0 = pv_sched_raw_key(p.P[i]) - c0 + 128;
+        k0 = k0 < 0 ? 0 : (k0 > 255 ? 255 : k0);
+        unsigned key = (unsigned)k0 << 8;
+        if (p.n_key_cols > 1) {
+            long long k1 = pv_sched_raw_key(p.P[p.B + i]) - c1 + 128;
+            k1 = k1 < 0 ? 0 : (k1 > 255 ? 255 : k1);
+            unsigned x = (unsigned)k0, y = (unsigned)k1;   // Morton interleave of two 8-bit numbers
+            x = (x | (x << 4)) & 0x0f0fu; x = (x | (x << 2)) & 0x3333u; x = (x | (x << 1)) & 0x5555u;
+            y = (y | (y << 4)) & 0x0f0fu; y = (y | (y << 2)) & 0x3333u; y = (y | (y << 1)) & 0x5555u;
+            key = x | (y << 1);
+        }
+        p.key_a[i] = key;
+        p.idx_a[i] = (int32_t)i;
+    }
 }
 
-// exclusive scan of the histogram in place, one block of 1024 threads (64 bins each)
-__global__ void __launch_bounds__(1024) pv_sched_scan_kernel(unsigned int* bins) {
-    constexpr int PER = PV_SCHED_BINS / 1024;
-    __shared__ unsigned int part[1024];
-    unsigned int local[PER];
-    unsigned int sum = 0;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        local[k] = bins[threadIdx.x * PER + k];
-        sum += local[k];
+// one warp per tile: histogram of the 8-bit digit at `shift`
+__global__ void __launch_bounds__(128) pv_sched_hist_kernel(const pv_sched_params p, const uint32_t* __restrict__ keys, int shift) {
+    __shared__ uint32_t cnt[4][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_id = blockIdx.x * 4 + w;
+    for (int d = lane; d < 256; d += 32) cnt[w][d] = 0;
+    __syncwarp();
+    if (tile_id < p.n_tiles) {
+        const int64_t lo = (int64_t)tile_id * p.tile, hi = min(lo + p.tile, p.B);
+        for (int64_t i = lo + lane; i < hi; i += 32) atomicAdd(&cnt[w][(keys[i] >> shift) & 255u], 1u);
+        __syncwarp();
+        for (int d = lane; d < 256; d += 32) p.counts[(int64_t)d * p.n_tiles + tile_id] = cnt[w][d];
     }
+}
+
+// exclusive scan of counts[256 * n_tiles] in place, one block of 1024 threads
+__global__ void __launch_bounds__(1024) pv_sched_scan_kernel(uint32_t* counts, int n) {
+    __shared__ uint32_t part[1024];
+    const int per = (n + 1023) / 1024;
+    const int lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
+    uint32_t sum = 0;
+    for (int k = lo; k < hi; ++k) sum += counts[k];
     part[threadIdx.x] = sum;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) {
-        const unsigned int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+        const uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
         __syncthreads();
         part[threadIdx.x] += v;
         __syncthreads();
     }
-    unsigned int run = part[threadIdx.x] - sum;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        bins[threadIdx.x * PER + k] = run;
-        run += local[k];
+    uint32_t run = part[threadIdx.x] - sum;
+    for (int k = lo; k < hi; ++k) {
+        const uint32_t c = counts[k];
+        counts[k] = run;
+        run += c;
     }
 }
 
-__global__ void pv_sched_scatter_kernel(const pv_sched_params p) {
-    const long long c0 = p.sums[0] / p.B, c1 = p.sums[1] / p.B;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.B; i += (int64_t)gridDim.x * blockDim.x)
-        p.index[atomicAdd(&p.bins[pv_sched_bucket(p, i, c0, c1)], 1u)] = (int32_t)i;
+// one warp per tile: stable scatter (elements of a tile in input order; equal digits keep their order)
+__global__ void __launch_bounds__(128) pv_sched_scatter_kernel(const pv_sched_params p, const uint32_t* __restrict__ keys_in,
+                                                               const int32_t* __restrict__ idx_in, uint32_t* __restrict__ keys_out,
+                                                               int32_t* __restrict__ idx_out, int shift) {
+    __shared__ uint32_t run[4][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_id = blockIdx.x * 4 + w;
+    if (tile_id >= p.n_tiles) return;
+    for (int d = lane; d < 256; d += 32) run[w][d] = p.counts[(int64_t)d * p.n_tiles + tile_id];
+    __syncwarp();
+    const int64_t lo = (int64_t)tile_id * p.tile, hi = min(lo + p.tile, p.B);
+    for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+        const int64_t i = i0 + lane;
+        const bool have = i < hi;
+        const uint32_t key = have ? keys_in[i] : 0u;
+        const uint32_t d = have ? ((key >> shift) & 255u) : 256u + lane;     // idle lanes match nobody
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t off = 0;
+        if (have && lane == leader) {
+            off = run[w][d];
+            run[w][d] = off + __popc(peers);
+        }
+        off = __shfl_sync(0xffffffffu, off, leader);
+        if (have) {
+            keys_out[off + rank] = key;
+            idx_out[off + rank] = idx_in[i];
+        }
+        __syncwarp();
+    }
 }

@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--refill", type=int, default=0)
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--locality", type=int, default=0, help="0 auto, 1 off, 2 on (pv_problem_set_locality)")
+ap.add_argument("--lockstep", type=int, default=0, help="0 auto, 1 off, 2 on (pv_problem_set_lockstep)")
 ap.add_argument("--mode", default="traj_logp", choices=["traj_logp", "logp", "traj"])
 args = ap.parse_args()
 rt = importlib.import_module("parameter-variability_b200.runtime")
@@ -38,7 +39,10 @@ pb.set_data(np.stack([d, d, d])[..., None], 1.0)
 if args.refill:
     pb.set_schedule(args.refill)
 pb.set_locality(args.locality)
-run = {"traj_logp": lambda: pb.simulate_logp(P, Y, lp), "logp": lambda: pb.logp(P, lp), "traj": lambda: pb.simulate(P, Y)}[args.mode]
+pb.set_lockstep(args.lockstep)
+st = torch.zeros((2, B), dtype=torch.int32, device="cuda")
+status = torch.zeros(B, dtype=torch.int32, device="cuda")
+run = {"traj_logp": lambda: pb.simulate_logp(P, Y, lp, status=status, steps=st), "logp": lambda: pb.logp(P, lp), "traj": lambda: pb.simulate(P, Y)}[args.mode]
 for _ in range(3):
     run()
 torch.cuda.synchronize()
@@ -48,5 +52,5 @@ for _ in range(args.reps):
     run()
 e1.record()
 torch.cuda.synchronize()
-print(f"{os.environ.get('PARVAR_B200_LIB') or 'default'} refill={args.refill or 'default'} locality={args.locality} mode={args.mode}: "
-      f"{e0.elapsed_time(e1) / args.reps:.3f} ms  logp_sum={float(lp.sum()):.6f}", flush=True)
+print(f"{os.environ.get('PARVAR_B200_LIB') or 'default'} refill={args.refill or 'default'} locality={args.locality} lockstep={args.lockstep} mode={args.mode}: "
+      f"{e0.elapsed_time(e1) / args.reps:.3f} ms  logp_sum={float(lp.sum()):.6f} steps/traj={float(st.sum()) / B:.1f} failed={int((status != 0).sum())}", flush=True)

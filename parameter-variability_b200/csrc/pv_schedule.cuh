@@ -15,7 +15,7 @@
 #include <stdint.h>
 
 #define PV_SCHED_SHIFT 47          // 5 mantissa bits: 32 levels per octave, 8 octaves around the batch mean
-#define PV_SCHED_MAX_TILES 2048    // warps of the sort kernels = contiguous tiles of the input
+#define PV_SCHED_MAX_TILES 512     // warps of the sort kernels = contiguous tiles of the input
 
 struct pv_sched_params {
     const double* P;               // [n_cols][B]
@@ -86,26 +86,41 @@ __global__ void __launch_bounds__(128) pv_sched_hist_kernel(const pv_sched_param
     }
 }
 
-// exclusive scan of counts[256 * n_tiles] in place, one block of 1024 threads
+// exclusive scan of counts[n] in place, one block of 32 warps: every warp owns a contiguous segment and walks it with
+// coalesced 32-wide loads (a thread-per-segment walk was 0.9 ms of uncoalesced traffic for 5 * 10^5 entries)
 __global__ void __launch_bounds__(1024) pv_sched_scan_kernel(uint32_t* counts, int n) {
-    __shared__ uint32_t part[1024];
-    const int per = (n + 1023) / 1024;
-    const int lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
+    __shared__ uint32_t warp_base[32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = ((n + 31) / 32 + 31) / 32 * 32;          // entries per warp, a multiple of 32
+    const int lo = min(w * seg, n), hi = min(lo + seg, n);
     uint32_t sum = 0;
-    for (int k = lo; k < hi; ++k) sum += counts[k];
-    part[threadIdx.x] = sum;
+    for (int k = lo + lane; k < hi; k += 32) sum += counts[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (lane == 0) warp_base[w] = sum;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        const uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    if (w == 0) {
+        uint32_t v = warp_base[lane], incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += u;
+        }
+        warp_base[lane] = incl - v;
     }
-    uint32_t run = part[threadIdx.x] - sum;
-    for (int k = lo; k < hi; ++k) {
-        const uint32_t c = counts[k];
-        counts[k] = run;
-        run += c;
+    __syncthreads();
+    uint32_t run = warp_base[w];
+    for (int k0 = lo; k0 < hi; k0 += 32) {
+        const int k = k0 + lane;
+        const uint32_t c = k < hi ? counts[k] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += u;
+        }
+        if (k < hi) counts[k] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 

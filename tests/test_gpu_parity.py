@@ -778,3 +778,50 @@ def test_objective_integrates_from_t0_and_poisons_failed_evaluations(cuda_lib, r
     assert fv == np.inf and np.all(np.isnan(gb))
     lp, gr_, fim, _, nf = bad.problem.logp_fim_host(np.array([[0.9, 1.2], [1.1, 0.7]]))
     assert nf == 2 and np.all(np.isnan(lp)) and np.all(np.isnan(gr_)) and np.all(np.isnan(fim))
+
+
+@pytest.mark.parametrize("B", [4099, 50000])
+def test_locality_schedule_and_lockstep_warps(cuda_lib, rt, oracle, B):
+    """pv_problem_set_locality: the device-side stable radix sort only changes the order in which trajectories are picked
+    up - trajectories, logp and step counts are bit-identical with and without it (which also proves the index map is a
+    permutation: a missing row would keep its poison value), for ragged batch sizes, duplicate, non-positive and NaN
+    parameter values.  pv_problem_set_lockstep: one step size per warp - results inside the parity band against the exact
+    solution, identical from run to run (deterministic work order), and a NaN row fails alone."""
+    torch = _torch()
+    T = 50
+    t = np.linspace(0, 100, T)
+    th = np.stack([lognormal_draws(71, B), lognormal_draws(72, B)])
+    th[:, 100:140] = th[:, 100:101]                      # duplicates
+    th[0, 7] = np.nan                                    # a row that cannot be integrated
+    th[1, 11] = 0.0                                      # CL = 0: legal, key of a non-positive value
+    pb = _problem(rt, "simple_pk", ["k_abs", "CL"], t, ["y_gut", "y_cent", "y_peri"], method=rt.METHOD_DOPRI5)
+    truth = oracle.simple_pk_exact({}, t)
+    pb.set_data(np.stack([np.ones_like(truth), truth, truth * truth])[..., None], 1.0)
+    P = torch.from_numpy(th).cuda()
+
+    def run(locality, lockstep):
+        pb.set_locality(locality)
+        pb.set_lockstep(lockstep)
+        Y = torch.full((B, T, 3), -7.0, dtype=torch.float64, device="cuda")
+        lp = torch.full((B,), -7.0, dtype=torch.float64, device="cuda")
+        st = torch.full((B,), -7, dtype=torch.int32, device="cuda")
+        steps = torch.full((2, B), -7, dtype=torch.int32, device="cuda")
+        pb.simulate_logp(P, Y, lp, status=st, steps=steps)
+        torch.cuda.synchronize()
+        return Y.cpu().numpy(), lp.cpu().numpy(), st.cpu().numpy(), steps.cpu().numpy()
+
+    Y0, lp0, st0, n0 = run(1, 1)
+    Y1, lp1, st1, n1 = run(2, 1)
+    ok = st0 == 0
+    assert st0[7] != 0 and ok.sum() == B - 1
+    assert np.array_equal(st0, st1) and np.array_equal(n0, n1)
+    assert np.array_equal(Y0[ok], Y1[ok]) and np.array_equal(lp0[ok], lp1[ok])
+    Y2, lp2, st2, n2 = run(2, 2)
+    Y3, lp3, st3, n3 = run(2, 2)
+    assert np.array_equal(st2, st0)                       # the NaN row fails alone, its 31 warp neighbours finish
+    assert np.array_equal(Y2[ok], Y3[ok]) and np.array_equal(lp2[ok], lp3[ok]) and np.array_equal(n2, n3)
+    for b in list(range(0, B, max(B // 40, 1))) + [11, 100, 139, B - 1]:
+        ref = oracle.simple_pk_exact({"k_abs": th[0, b], "CL": th[1, b]}, t)
+        assert parity_violation(Y2[b], ref) <= 1.0 and parity_violation(Y0[b], ref) <= 1.0
+    np.testing.assert_allclose(lp2[ok], lp0[ok], rtol=1e-6)
+    assert n2[:, ok].sum() < 1.15 * n0[:, ok].sum()       # neighbours in parameter space: a common step size costs few steps

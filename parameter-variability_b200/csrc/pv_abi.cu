@@ -481,7 +481,11 @@ static cudaError_t launch_persistent(KernelT kern, const pv_launch_params& lp, c
 template <class M, int METHOD, int MODE, bool OBSID>
 static cudaError_t launch_one(const pv_launch_params& lp, const pv_launch_ctx& cx, size_t shmem, cudaStream_t s) {
     if constexpr (METHOD == 1) {
-        if (cx.lockstep) return launch_persistent<M>(pv_batch_lockstep_kernel<M, MODE, OBSID>, lp, cx, PV_BLOCK, PV_BLOCK, shmem, s);
+        if (cx.lockstep) {
+            if ((MODE & PV_MODE_LOGP) && lp.n_data == 1)
+                return launch_persistent<M>(pv_batch_lockstep_kernel<M, MODE, OBSID, (MODE & PV_MODE_LOGP) != 0>, lp, cx, PV_BLOCK, PV_BLOCK, shmem, s);
+            return launch_persistent<M>(pv_batch_lockstep_kernel<M, MODE, OBSID, false>, lp, cx, PV_BLOCK, PV_BLOCK, shmem, s);
+        }
     }
     return launch_persistent<M>(pv_batch_kernel<M, METHOD, MODE, OBSID>, lp, cx, PV_BLOCK, PV_BLOCK, shmem, s);
 }

@@ -189,14 +189,6 @@ struct pv_dopri5_lane {
     // INT_MAX = off (an explicitly chosen DOPRI5 integrates whatever it is given).
     int stiff_after = 0x7fffffff;
     int stiff_run;     // consecutive stiff estimates (high half) | consecutive non-stiff estimates (low half)
-    // Lockstep schedule (step<true>): the 32 lanes of a warp advance with ONE step size - the controller sees the largest
-    // error norm of the warp - so t, h, accept / reject and the grid crossings are warp-uniform: no divergence anywhere,
-    // the per-grid-point code runs with all lanes or not at all.  Every lane still meets its own tolerance (its error is
-    // <= the warp's).  Pays when the lanes integrate similar trajectories (locality schedule, pv_schedule.cuh).
-    // A lane whose own error estimate stays non-finite is taken out of the agreement (`dead`) instead of dragging its
-    // neighbours' step size to zero.
-    int nonfinite_run = 0;
-    bool dead = false;
 
     // z0 -> y, outputs for grid points at t0, first derivative, initial step size
     template <class Out>
@@ -206,8 +198,6 @@ struct pv_dopri5_lane {
         st.rejected = 0;
         nstep = 0;
         stiff_run = 0;
-        nonfinite_run = 0;
-        dead = false;
         lfacold = -13.287712f;   // log2(1e-4)
         last_rejected = false;
         t = t0;
@@ -260,18 +250,6 @@ struct pv_dopri5_lane {
     template <class Out>
     PV_HD int step(const typename Sys::Consts& ks, const double* tgrid, int T, double rtol, double atol,
                    int max_steps, Out& out) {
-        return step_impl<false>(ks, tgrid, T, rtol, atol, max_steps, out);
-    }
-    // one attempted step of the whole warp (all 32 lanes must call it together)
-    template <class Out>
-    PV_HD int step_lockstep(const typename Sys::Consts& ks, const double* tgrid, int T, double rtol, double atol,
-                            int max_steps, Out& out) {
-        return step_impl<true>(ks, tgrid, T, rtol, atol, max_steps, out);
-    }
-
-    template <bool LS, class Out>
-    PV_HD int step_impl(const typename Sys::Consts& ks, const double* tgrid, int T, double rtol, double atol,
-                        int max_steps, Out& out) {
         if (nstep >= max_steps) return PV_ERR_MAX_STEPS;
         ++nstep;
         bool last = false;
@@ -329,13 +307,7 @@ struct pv_dopri5_lane {
         }
         float err2 = (float)(err2d * (1.0 / N));
         // a non-finite stage value makes e, hence err2, NaN or inf: treated as a failed step (give up once h is tiny)
-        if constexpr (LS) {
-            const bool bad = !(err2 <= 3.0e38f);
-            nonfinite_run = bad ? nonfinite_run + 1 : 0;
-            dead = dead || nonfinite_run >= 8;
-            err2 = pv_warp_max_nonneg(dead ? 0.0f : (bad ? 1e10f : err2));
-            if (err2 >= 1e10f && fabs(h) < 1e-12) return PV_ERR_NONFINITE;
-        } else if (!(err2 <= 3.0e38f)) {
+        if (!(err2 <= 3.0e38f)) {
             err2 = 1e10f;
             if (fabs(h) < 1e-12) return PV_ERR_NONFINITE;
         }
@@ -380,9 +352,7 @@ struct pv_dopri5_lane {
                     num = fma(dk, dk, num);
                     den = fma(dy, dy, den);
                 }
-                bool stiff_now = den > 0.0 && h * h * num > 10.5625 * den;     // (h lambda)^2 > 3.25^2
-                if constexpr (LS) stiff_now = pv_warp_any(stiff_now && !dead);
-                if (stiff_now) {
+                if (den > 0.0 && h * h * num > 10.5625 * den) {          // (h lambda)^2 > 3.25^2
                     stiff_run = (stiff_run & ~0xffff) + 0x10000;
                     if (stiff_run >= 15 * 0x10000 && (tend - t) > PV_STIFF_REMAINING_STEPS * h) return PV_ERR_STIFF;
                 } else if (((++stiff_run) & 0xffff) >= 6) {

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include "pv_common.cuh"
 #include "pv_dopri5.cuh"
+#include "pv_dopri5_warp.cuh"
 #include "pv_rosenbrock.cuh"
 
 #define PV_MAX_COLS 8
@@ -79,7 +80,10 @@ PV_D double pv_pick(const double (&a)[N], int block, int idx) {
 // selection chains, the indexed constant loads and the k-loop overhead disappear (the common case of the
 // cheap non-stiff models, where the per-output code is a sizeable share of a step).
 #define PV_QSTRIDE 4   // doubles per likelihood coefficient record (q0, q1, q2, pad): two 16-byte loads
-template <class M, int MODE, bool OBSID>
+// QSH = true: the coefficient records are known to sit in shared memory; they are read with ld.shared through a 32-bit
+// address (the generic-address loads of the default path may alias the trajectory stores as far as the compiler knows,
+// which pins them behind the stores and puts their latency on the critical path of every grid point).
+template <class M, int MODE, bool OBSID, bool QSH = false>
 struct pv_sink {
     static constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
     static constexpr bool TRAJ = (MODE & PV_MODE_TRAJ) != 0;
@@ -93,6 +97,7 @@ struct pv_sink {
     double* srow;             // &S[b][j][0][0]
     const double* qrow;       // &q[d][j][0][0]: coefficients of the trajectory's data set d = b % n_data, either in the
                               // block's shared-memory copy (n_data == 1) or in global memory (generic address)
+    unsigned qaddr = 0;       // the same as a shared-memory address (QSH)
     double obs[M::NX];
     double lp;
     double g[M::NSD];
@@ -107,7 +112,15 @@ struct pv_sink {
             yrow = p.Y + off;
             if constexpr (SENS) srow = p.S + off * M::NS;
         }
-        if constexpr (LOGP) qrow = qbase + (int64_t)(b_ % p.n_data) * (p.T * n_obs * PV_QSTRIDE);
+        if constexpr (LOGP) {
+            if constexpr (QSH) {
+#if defined(__CUDA_ARCH__)
+                qaddr = (unsigned)__cvta_generic_to_shared(qbase);      // n_data == 1: every trajectory reads the one record set
+#endif
+            } else {
+                qrow = qbase + (int64_t)(b_ % p.n_data) * (p.T * n_obs * PV_QSTRIDE);
+            }
+        }
         lp = 0.0;
 #pragma unroll
         for (int s = 0; s < M::NSD; ++s) g[s] = 0.0;
@@ -130,9 +143,20 @@ struct pv_sink {
         }
         if constexpr (LOGP) {
             // lp term = q0 + v (q1 + q2 v), v = f (normal) or log f (log-normal); n = 0 entries have q = 0
-            const double2 q01 = *reinterpret_cast<const double2*>(qrow + k * PV_QSTRIDE);
-            const double q2 = qrow[k * PV_QSTRIDE + 2];
-            const double q0 = q01.x, q1 = q01.y;
+            double q0, q1, q2;
+            if constexpr (QSH) {
+#if defined(__CUDA_ARCH__)
+                asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q0), "=d"(q1) : "r"(qaddr + k * (PV_QSTRIDE * 8)));
+                asm("ld.shared.f64 %0, [%1];" : "=d"(q2) : "r"(qaddr + k * (PV_QSTRIDE * 8) + 16));
+#else
+                q0 = q1 = q2 = 0.0;
+#endif
+            } else {
+                const double2 q01 = *reinterpret_cast<const double2*>(qrow + k * PV_QSTRIDE);
+                q2 = qrow[k * PV_QSTRIDE + 2];
+                q0 = q01.x;
+                q1 = q01.y;
+            }
             if constexpr (!LOGNORMAL) {
                 lp += fma(f, fma(q2, f, q1), q0);
                 if constexpr (SENS) {
@@ -212,7 +236,12 @@ struct pv_sink {
             yrow += n_obs;
             if constexpr (SENS) srow += n_obs * M::NS;
         }
-        if constexpr (LOGP) qrow += n_obs * PV_QSTRIDE;
+        if constexpr (LOGP) {
+            if constexpr (QSH)
+                qaddr += n_obs * (PV_QSTRIDE * 8);
+            else
+                qrow += n_obs * PV_QSTRIDE;
+        }
     }
 };
 
@@ -268,7 +297,7 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
     const int64_t n_items = p.n_items_dev ? (int64_t)*p.n_items_dev : p.B;
     typename Sys::Consts ks;
     Lane lane;
-    pv_sink<M, MODE, OBSID> sink{p, 0, nullptr, nullptr, nullptr, {}, 0.0, {}, {}};
+    pv_sink<M, MODE, OBSID> sink{p, 0, nullptr, nullptr, nullptr, 0u, {}, 0.0, {}, {}};
     const double* qbase = stats_shared ? sh_stats : p.stats;
     bool have = false;        // this lane is integrating trajectory sink.b
     bool exhausted = false;   // the work counter ran past B
@@ -375,15 +404,18 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
 // (steps of its most demanding lane) instead of (sum over iterations of whichever lanes are busy).  A lane's result now
 // depends on its 31 neighbours' step sizes - within the tolerances, but not bit-identical across batch compositions; the
 // work-item order of a launch is deterministic (pv_schedule.cuh sorts every bucket), so a given batch reproduces itself.
-template <class M, int MODE, bool OBSID>
-__global__ void __launch_bounds__(PV_BLOCK, pv_kernel_traits<M, 1, MODE>::MIN_BLOCKS)
+#ifndef PV_MINB_LOCKSTEP
+#define PV_MINB_LOCKSTEP PV_MINB_SMALL
+#endif
+template <class M, int MODE, bool OBSID, bool QSH>
+__global__ void __launch_bounds__(PV_BLOCK, (pv_system<M, (MODE & PV_MODE_SENS) != 0>::N <= 4) ? PV_MINB_LOCKSTEP : 1)
 pv_batch_lockstep_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
     constexpr bool SENS = (MODE & PV_MODE_SENS) != 0;
     constexpr bool LOGP = (MODE & PV_MODE_LOGP) != 0;
     using Sys = pv_system<M, SENS>;
-    using Lane = pv_dopri5_lane<Sys>;
+    using Lane = pv_dopri5_warp<Sys>;
     extern __shared__ __align__(16) double sh[];
-    const bool stats_shared = LOGP && p.n_data == 1;
+    constexpr bool stats_shared = LOGP && QSH;     // QSH <=> n_data == 1 (the host dispatches on it)
     double* sh_stats = sh;
     double* sh_t = sh + (stats_shared ? PV_QSTRIDE * p.T * p.n_obs : 0);
     double* sh_theta = sh_t + p.T;
@@ -402,7 +434,7 @@ pv_batch_lockstep_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
     typename Sys::Consts ks;
     Lane lane;
     lane.stiff_after = p.stiff_after;
-    pv_sink<M, MODE, OBSID> sink{p, 0, nullptr, nullptr, nullptr, {}, 0.0, {}, {}};
+    pv_sink<M, MODE, OBSID, stats_shared> sink{p, 0, nullptr, nullptr, nullptr, 0u, {}, 0.0, {}, {}};
     for (;;) {
         unsigned long long base = 0;
         if (lane_id == 0) base = atomicAdd(p.counter, 32ull);
@@ -449,8 +481,9 @@ pv_batch_lockstep_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
         }
         sink.begin(b, qbase);
         int rc = lane.start(ks, z, p.t0, sh_t, p.T, p.rtol, p.atol, sink);     // uniform: same t0 and grid for every lane
-        lane.h = pv_warp_min(lane.h == lane.h ? lane.h : 1e300);                // one step size; a NaN estimate does not veto
-        while (rc == PV_RUNNING) rc = lane.step_lockstep(ks, sh_t, p.T, p.rtol, p.atol, p.max_steps, sink);
+        while (rc == PV_RUNNING)           // an accepted step flips lane.cur: a warp-uniform jump to the other copy of the step
+            rc = lane.cur ? lane.template step<1>(ks, sh_t, p.T, p.rtol, p.atol, p.max_steps, sink)
+                          : lane.template step<0>(ks, sh_t, p.T, p.rtol, p.atol, p.max_steps, sink);
         if (lane.dead) rc = PV_ERR_NONFINITE;
         if constexpr (LOGP) {
             const double nan = __longlong_as_double(0x7ff8000000000000LL);

@@ -83,7 +83,11 @@ struct pv_dopri5_warp {
         const double dm = fmax(d1, d2);
         const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / dm, 0.2);
         h = fmin(fmin(100.0 * h0, h1), tend - t);
-        h = pv_warp_min(h == h ? h : 1e300);      // a lane with a NaN estimate does not veto (it will be `dead` soon)
+        // a lane whose estimate is not a number (NaN parameters) does not vote: it will be `dead` within 8 steps, and fmin /
+        // fmax would have turned its NaNs into the lower clamp 1e-12
+        const bool sane = (d0 == d0) && (d1 == d1) && (d2 == d2) && (h == h);
+        h = pv_warp_min(sane ? h : 1e300);
+        h = fmin(h, tend - t);
         return PV_RUNNING;
     }
 

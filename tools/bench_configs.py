@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--only", default="")
     ap.add_argument("--layout", type=int, default=0, help="pv_problem_set_layout for the Rosenbrock sensitivity kernels: 0 auto, 1 lane, 2 split")
+    ap.add_argument("--locality", type=int, default=0, help="pv_problem_set_locality: 0 auto, 1 off, 2 on")
+    ap.add_argument("--lockstep", type=int, default=0, help="pv_problem_set_lockstep: 0 auto, 1 off, 2 on")
     ap.add_argument("--sizes", default="1000,16000", help="individuals per chain for the icg cases")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
@@ -45,6 +47,7 @@ def main():
     import parvar_oracle as oracle
     rt = importlib.import_module(PKG + ".runtime")
     opt = importlib.import_module(PKG + ".optimization.petab_optimization")
+    bc = importlib.import_module(PKG + ".bench_cases")
     peak64 = rt.fma_peak_tflops(0, True)
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -56,6 +59,7 @@ def main():
                 "flops_per_step": pb.flops(step_key), "achieved_tflops": flops / (ms * 1e-3) / 1e12,
                 "fp64_peak_tflops": peak64, "frac_of_fp64_peak": flops / (ms * 1e-3) / 1e12 / peak64}
         line.update(extra or {})
+        line.update({"locality": args.locality, "lockstep": args.lockstep})
         print(json.dumps(line), flush=True)
 
     # ---- C3: simple_pk, 8 chains x 1000 individuals, logp + grad (forward sensitivities), T = 20 ----------------
@@ -73,6 +77,8 @@ def main():
         pb.set_timepoints(t)
         pb.set_observables(["y_gut", "y_cent", "y_peri"])
         pb.set_data(stats, 0.05)
+        pb.set_locality(args.locality)
+        pb.set_lockstep(args.lockstep)
         B = n_chains * n_ind
         th = np.concatenate([np.random.RandomState(1234 + c).lognormal(MU, SG, size=(2, n_ind)) for c in range(n_chains)], axis=1)
         P = torch.from_numpy(th).cuda()
@@ -108,7 +114,9 @@ def main():
             y = truth[None] * (1 + 0.05 * rs.normal(size=(n_ind,) + truth.shape))
             stats = np.stack([opt.sufficient_statistics(y[i:i + 1], 0) for i in range(n_ind)], axis=-1)
             pb = rt.Problem("icg_body_flat")
-            pb.set_solver(rtol=1e-7, atol=1e-11)
+            pb.set_solver(rtol=bc.C4.rtol, atol=bc.C4.atol)
+            pb.set_locality(args.locality)
+            pb.set_lockstep(args.lockstep)
             pb.set_value("IVDOSE_icg", 10.0)
             pb.set_columns(["BW", "LI__ICGIM_Vmax"])
             pb.set_timepoints(t)
@@ -122,7 +130,7 @@ def main():
             seg = torch.empty(n_chains, dtype=torch.float64, device="cuda")
             steps = torch.zeros((2, B), dtype=torch.int32, device="cuda")
             ms = time_launches(lambda: pb.simulate(P, Y, steps=steps, stream=stream), max(args.reps // 4, 3))
-            emit(f"icg_body_flat forward RODAS4, {B} trajectories (T=20, rtol 1e-7)", ms, B, pb, steps, "step_rodas4", "dense_rodas4", T)
+            emit(f"icg_body_flat forward RODAS4, {B} trajectories (T=20, rtol {bc.C4.rtol:g})", ms, B, pb, steps, "step_rodas4", "dense_rodas4", T)
             ms = time_launches(lambda: pb.logp(P, lp, steps=steps, stream=stream), max(args.reps // 4, 3))
             emit(f"icg_body_flat logp RODAS4, {B} trajectories", ms, B, pb, steps, "step_rodas4", "dense_rodas4", T)
             ms = time_launches(lambda: pb.logp_grad(P, lp, g, seg_len=n_ind, logp_seg=seg, steps=steps, stream=stream),

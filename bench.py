@@ -308,7 +308,7 @@ def extra_measurements(rt, torch, pb, P, logp, status, steps, stream, B, T, th_h
                             "trajectories_per_s": B / (ms * 1e-3), "ms_per_step": ms,
                             "e2e_trajectories_per_s": B / dt, "e2e_ms_per_step": dt * 1e3, "e2e_api": "pv_logp_host",
                             "h2d_bytes_per_step": int(16 * B), "d2h_bytes_per_step": int(8 * B),
-                            "e2e_matches_device": bool(np.array_equal(lp_h[:1000], logp[:1000].cpu().numpy()))}
+                            "e2e_matches_device": bool(np.array_equal(lp_h[:1000], logp[:1000].cpu().numpy()))}      # same batch, same warps: bit-identical
     # C1: one parameter set (defaults), the reference's own CPU-runnable case: latency of one call through the host API
     c1 = {}
     for Tn in (21, 50):
@@ -464,7 +464,9 @@ def main() -> None:
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(t_e.item())
-    e2e_ok = bool(np.allclose(lp_pin[:1000], logp[:1000].cpu().numpy(), rtol=0, atol=0))
+    # the host pipeline integrates 32 768-row chunks, the device call the whole batch: different warps under the lockstep
+    # schedule, so the two agree within the integration tolerance, not bit for bit
+    e2e_ok = bool(np.allclose(lp_pin[:1000], logp[:1000].cpu().numpy(), rtol=1e-9, atol=0))
 
     lg = logp_grad_leg(rt, torch, dist, rank, world, local)
     extra = extra_measurements(rt, torch, pb, P, logp, status, steps, stream, B, T, th_host) if rank == 0 else {}

@@ -96,7 +96,7 @@ struct pv_problem {
 #define PV_COUNTER_RING 1024
 #define PV_SAMPLER_COUNTERS 8
 #ifndef PV_LOCKSTEP_AUTO
-#define PV_LOCKSTEP_AUTO 0     // measured default of pv_problem_set_lockstep(0) for sorted launches
+#define PV_LOCKSTEP_AUTO 1     // measured default of pv_problem_set_lockstep(0) for sorted launches (tools/bench_configs.py)
 #endif
 
 // ---------------------------------------------------------------------------------------------------------

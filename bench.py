@@ -159,7 +159,8 @@ def workload_config(n_gpus: int) -> dict:
     return {"workload": "C2: simple_pk batched forward simulation + Gaussian logp, "
                         f"{B_PER_GPU} log-normal (k_abs, CL) draws x {T_POINTS} timepoints x 3 observables per GPU",
             "trajectories_per_gpu": B_PER_GPU, "timepoints": T_POINTS, "observables": OBS,
-            "integrator": "METHOD_AUTO: DOPRI5 adaptive with dense output; rows that exhaust 4000 explicit steps are re-run with RODAS4 (none in this cloud)", "rtol": RTOL, "atol": ATOL,
+            "integrator": "METHOD_AUTO: DOPRI5 adaptive with dense output, stiffness detection; stiff rows are re-run with RODAS4 (none in this cloud)",
+            "schedule": "device-side locality sort of the draws (stable radix sort, inside the timed region) + lockstep warps (one step size per warp)", "rtol": RTOL, "atol": ATOL,
             "l2": "outputs (1.2 GB per step) exceed the 126 MB L2, so every step streams to HBM",
             "sharding": f"independent draws, {n_gpus} rank(s), no data-path collective"}
 
@@ -408,9 +409,18 @@ def main() -> None:
     n_failed = int((status != 0).sum())
     if n_failed:
         raise SystemExit(f"{n_failed} trajectories failed to integrate")
+    executed = int(steps.sum())               # steps the launch executes (lockstep warps: every lane takes its warp's steps)
+    # ALGORITHMIC steps = what each trajectory needs on its own (per-lane adaptive stepping): counted once with the
+    # lockstep schedule switched off; the roofline's flops use this figure, not the (slightly larger) executed one
+    pb.set_lockstep(1)
+    pb.simulate_logp(P, Y, logp, status=status, steps=steps, stream=stream)
+    torch.cuda.synchronize()
+    pb.set_lockstep(0)
     attempted = int(steps.sum())
     accepted = int(steps[0].sum())
     steps_max = int(steps.sum(dim=0).max())
+    pb.simulate_logp(P, Y, logp, status=status, steps=steps, stream=stream)     # back to the default schedule
+    torch.cuda.synchronize()
     fl_step = pb.flops("step_dopri5")
     fl_dense = pb.flops("dense_dopri5")
     fl_hoist = pb.flops("hoist")
@@ -506,10 +516,13 @@ def main() -> None:
                                          f"bytes per launch = {bytes_per_launch}",
                          "peak_source": "measured in this run: pv_fma_peak_tflops (register-resident DFMA chains)",
                          "fp32_fma_peak_tflops": peak32,
-                         "kernel": "pv_batch_kernel<pv_model_simple_pk, DOPRI5, TRAJ|LOGP>",
+                         "kernel": "pv_batch_lockstep_kernel<pv_model_simple_pk, TRAJ|LOGP>",
                          "kernel_ms": kernel_ms, "flops_per_launch": flops_per_launch,
                          "flops_per_attempted_step": fl_step,
                          "attempted_steps_per_trajectory": attempted / B, "accepted_steps_per_trajectory": accepted / B,
+                         "executed_steps_per_trajectory": executed / B,
+                         "flops_note": "algorithmic flops = steps of per-trajectory adaptive stepping x generator flop counts; the default "
+                                       "schedule (locality sort + lockstep warps) executes executed_steps_per_trajectory",
                          "max_steps_in_batch": steps_max,
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "peak_source": hbm_src, "bytes_per_launch": bytes_per_launch}},

@@ -119,7 +119,7 @@ int pv_problem_set_tuning(pv_problem* p, int max_ctas_per_sm, int64_t host_chunk
  * same stream (the reference's CVODE is implicit throughout).  switch_steps >= max_steps disables the second pass. */
 int pv_problem_set_stiff_switch(pv_problem* p, int switch_steps);
 /* The explicit first pass of PV_METHOD_AUTO does not have to use up its budget to find out: after `after_steps`
- * attempted steps (default 64) DOPRI5 estimates h*|lambda| from its last two stages at every accepted step (Hairer's
+ * attempted steps (default 128) DOPRI5 estimates h*|lambda| from its last two stages at every 4th step (Hairer's
  * stiffness test); 15 consecutive estimates beyond the stability bound 3.25 end the explicit attempt (status
  * PV_TRAJ_STIFF internally) and the trajectory goes to the RODAS4 pass.  A sampler's tempered chains roam the PEtab
  * bounds [0, 1e8]; without the test every such evaluation costs switch_steps explicit steps of pure latency.

@@ -87,7 +87,7 @@ struct pv_problem {
     int32_t* d_sched_index[4] = {nullptr, nullptr, nullptr, nullptr};     // locality-schedule scratch per launch slot (pv_schedule.cuh)
     int lockstep = 0;              // pv_problem_set_lockstep: 0 = auto, 1 = off, 2 = on
     int64_t sched_cap[4] = {0, 0, 0, 0};
-    int stiff_after = 64;          // DOPRI5 stiffness detection of the AUTO first pass starts after this many steps
+    int stiff_after = 128;         // DOPRI5 stiffness detection of the AUTO first pass starts after this many steps
     int32_t* d_scratch_status[4] = {nullptr, nullptr, nullptr, nullptr};
     int32_t* d_scratch_index[4] = {nullptr, nullptr, nullptr, nullptr};
     int* d_scratch_count[4] = {nullptr, nullptr, nullptr, nullptr};

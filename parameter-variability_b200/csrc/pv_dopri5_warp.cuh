@@ -175,7 +175,7 @@ struct pv_dopri5_warp {
                     t_next1 = jout + 1 < T ? tgrid[jout + 1] : 1e300;      // needed one output from now
                 } while (t_next <= tn);
             }
-            if (nstep > stiff_after) {
+            if (nstep > stiff_after && (nstep & 3) == 0) {      // every 4th step: the test costs ~30 flops + a vote
                 double num = 0.0, den = 0.0;
 #pragma unroll
                 for (int i = 0; i < N; ++i) {

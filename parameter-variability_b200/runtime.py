@@ -235,7 +235,7 @@ class Problem:
         """Lockstep warps of the DOPRI5 kernels: 0 = auto, 1 = off, 2 = on (``pv_problem_set_lockstep``)."""
         _check(self._lib.pv_problem_set_lockstep(self._h, int(mode)))
 
-    def set_stiffness_detection(self, after_steps: int = 64) -> None:
+    def set_stiffness_detection(self, after_steps: int = 128) -> None:
         _check(self._lib.pv_problem_set_stiffness_detection(self._h, int(after_steps)))
 
     def set_tuning(self, max_ctas_per_sm: int = 0, host_chunk_rows: int = 0) -> None:

@@ -553,8 +553,8 @@ static int locality_schedule(pv_problem* p, int slot, int64_t B, const double* P
         cudaFree(p->d_sched_index[slot]);
         p->d_sched_index[slot] = nullptr;
         p->sched_cap[slot] = 0;
-        // idx_a | idx_b | key_a | key_b | counts [256][PV_SCHED_MAX_TILES] | sums [2]
-        CUDA_OK(cudaMalloc(&p->d_sched_index[slot], 4 * per * sizeof(int32_t) + sizeof(uint32_t) * 256 * PV_SCHED_MAX_TILES +
+        // idx_a | idx_b | key_a | key_b | counts [256][PV_SCHED_MAX_TILES] | digit_total [256] | digit_base [256] | sums [2]
+        CUDA_OK(cudaMalloc(&p->d_sched_index[slot], 4 * per * sizeof(int32_t) + sizeof(uint32_t) * (256 * PV_SCHED_MAX_TILES + 512) +
                                                        2 * sizeof(long long)));
         p->sched_cap[slot] = B;
     }
@@ -568,8 +568,10 @@ static int locality_schedule(pv_problem* p, int slot, int64_t B, const double* P
     sp.key_a = (uint32_t*)(sp.idx_b + cap);
     sp.key_b = sp.key_a + cap;
     sp.counts = sp.key_b + cap;
-    sp.sums = (long long*)(sp.counts + 256 * PV_SCHED_MAX_TILES);
-    sp.n_tiles = (int)std::min<int64_t>(PV_SCHED_MAX_TILES, std::max<int64_t>(1, (B + 255) / 256));
+    sp.digit_total = sp.counts + 256 * PV_SCHED_MAX_TILES;
+    sp.digit_base = sp.digit_total + 256;
+    sp.sums = (long long*)(sp.digit_base + 256);
+    sp.n_tiles = (int)std::min<int64_t>(PV_SCHED_MAX_TILES, std::max<int64_t>(1, (B + 127) / 128));
     sp.tile = (B + sp.n_tiles - 1) / sp.n_tiles;
     sp.n_tiles = (int)((B + sp.tile - 1) / sp.tile);
     CUDA_OK(cudaMemsetAsync(sp.sums, 0, 2 * sizeof(long long), s));
@@ -579,12 +581,14 @@ static int locality_schedule(pv_problem* p, int slot, int64_t B, const double* P
     pv_sched_key_kernel<<<blocks, 256, 0, s>>>(sp);
     // pass 1: low digit a -> b; pass 2: high digit b -> a
     pv_sched_hist_kernel<<<tile_blocks, 128, 0, s>>>(sp, sp.key_a, 0);
-    pv_sched_scan_kernel<<<1, 1024, 0, s>>>(sp.counts, 256 * sp.n_tiles);
+    pv_sched_rowscan_kernel<<<256, 256, 0, s>>>(sp.counts, sp.n_tiles, sp.digit_total);
+    pv_sched_digitscan_kernel<<<1, 32, 0, s>>>(sp.digit_total, sp.digit_base);
     pv_sched_scatter_kernel<<<tile_blocks, 128, 0, s>>>(sp, sp.key_a, sp.idx_a, sp.key_b, sp.idx_b, 0);
     pv_sched_hist_kernel<<<tile_blocks, 128, 0, s>>>(sp, sp.key_b, 8);
-    pv_sched_scan_kernel<<<1, 1024, 0, s>>>(sp.counts, 256 * sp.n_tiles);
+    pv_sched_rowscan_kernel<<<256, 256, 0, s>>>(sp.counts, sp.n_tiles, sp.digit_total);
+    pv_sched_digitscan_kernel<<<1, 32, 0, s>>>(sp.digit_total, sp.digit_base);
     pv_sched_scatter_kernel<<<tile_blocks, 128, 0, s>>>(sp, sp.key_b, sp.idx_b, sp.key_a, sp.idx_a, 8);
-    g_launches.fetch_add(8);
+    g_launches.fetch_add(10);
     CUDA_OK(cudaGetLastError());
     *index_out = sp.idx_a;
     return 0;

@@ -113,7 +113,7 @@ PV_COEF_SPACE double pv_dp5[32] = {
     /* 30 d6 */ -1453857185.0 / 822651844.0, /* 31 d7 */ 69997945.0 / 29380423.0};
 
 #ifndef PV_STIFF_REMAINING_STEPS
-#define PV_STIFF_REMAINING_STEPS 600.0
+#define PV_STIFF_REMAINING_STEPS 2500.0
 #endif
 
 // ---- warp agreement (lockstep schedule) ---------------------------------------------------------------------
@@ -185,7 +185,9 @@ struct pv_dopri5_lane {
     // is not a reason to stop: simple_pk's tail (t > 40 of [0, 100], solution at atol level) is stability limited at
     // h ~ 1.3 and still only ~60 steps long.  The lane gives up (PV_ERR_STIFF, so the caller can hand the trajectory to
     // the implicit integrator) only if, at the stability-limited step size, the rest of the interval would take more
-    // than PV_STIFF_REMAINING_STEPS steps - more than a whole RODAS4 run costs.
+    // than PV_STIFF_REMAINING_STEPS steps - more than a whole RODAS4 run (300 - 400 steps at ~3x the cost each) plus the
+    // latency of the extra pass costs: a few hundred rows re-run alone took 0.6 ms on top of a 3.2 ms launch when the
+    // benchmark cloud's k_abs ~ 50 rows (1600 explicit steps) were handed over at a threshold of 600.
     // INT_MAX = off (an explicitly chosen DOPRI5 integrates whatever it is given).
     int stiff_after = 0x7fffffff;
     int stiff_run;     // consecutive stiff estimates (high half) | consecutive non-stiff estimates (low half)

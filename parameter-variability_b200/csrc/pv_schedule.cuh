@@ -7,7 +7,7 @@
 // Key: per column the top bits of the IEEE pattern of the value (monotone in the value for positive numbers:
 // 2^(52 - PV_SCHED_SHIFT) levels per octave), centred on the batch mean, clamped to 8 bits; the first two columns are
 // Morton-interleaved into a 16-bit key.  Sort: hand-written STABLE least-significant-digit radix sort, two passes of 8
-// bits (per-warp tile histogram -> exclusive scan -> stable per-warp scatter ranked with __match_any_sync), so the work
+// bits (per-warp tile histogram -> two-level exclusive scan -> stable per-warp scatter ranked with __match_any_sync), so the work
 // order of a launch is a pure function of its inputs: a given batch always forms the same warps.  ~0.05 ms for 10^6
 // trajectories.
 #pragma once
@@ -15,7 +15,7 @@
 #include <stdint.h>
 
 #define PV_SCHED_SHIFT 47          // 5 mantissa bits: 32 levels per octave, 8 octaves around the batch mean
-#define PV_SCHED_MAX_TILES 512     // warps of the sort kernels = contiguous tiles of the input
+#define PV_SCHED_MAX_TILES 2048    // warps of the sort kernels = contiguous tiles of the input
 
 struct pv_sched_params {
     const double* P;               // [n_cols][B]
@@ -26,7 +26,9 @@ struct pv_sched_params {
     uint32_t* key_b;               // [B] (pong)
     int32_t* idx_a;                // [B] (ping)
     int32_t* idx_b;                // [B] (pong) ; the final order lands in idx_a again after two passes
-    uint32_t* counts;              // [256][n_tiles] digit-major tile histograms, scanned in place
+    uint32_t* counts;              // [256][n_tiles] digit-major tile histograms, scanned in place (per digit row)
+    uint32_t* digit_total;         // [256] row totals
+    uint32_t* digit_base;          // [256] exclusive scan of the totals
     int n_tiles;
     int64_t tile;                  // elements per tile
 };
@@ -46,9 +48,16 @@ __global__ void pv_sched_mean_kernel(const pv_sched_params p) {
         s0 += __shfl_xor_sync(0xffffffffu, s0, off);
         s1 += __shfl_xor_sync(0xffffffffu, s1, off);
     }
-    if ((threadIdx.x & 31) == 0) {     // integer sums: the result does not depend on the order of the atomics
-        atomicAdd((unsigned long long*)&p.sums[0], (unsigned long long)s0);
-        if (p.n_key_cols > 1) atomicAdd((unsigned long long*)&p.sums[1], (unsigned long long)s1);
+    __shared__ long long part[2][8];
+    if ((threadIdx.x & 31) == 0) {
+        part[0][threadIdx.x >> 5] = s0;
+        part[1][threadIdx.x >> 5] = s1;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 && threadIdx.x < p.n_key_cols) {     // integer sums: the result does not depend on the order of the atomics
+        long long tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[threadIdx.x][w];
+        atomicAdd((unsigned long long*)&p.sums[threadIdx.x], (unsigned long long)tot);
     }
 }
 
@@ -86,40 +95,49 @@ __global__ void __launch_bounds__(128) pv_sched_hist_kernel(const pv_sched_param
     }
 }
 
-// exclusive scan of counts[n] in place, one block of 32 warps: every warp owns a contiguous segment and walks it with
-// coalesced 32-wide loads (a thread-per-segment walk was 0.9 ms of uncoalesced traffic for 5 * 10^5 entries)
-__global__ void __launch_bounds__(1024) pv_sched_scan_kernel(uint32_t* counts, int n) {
-    __shared__ uint32_t warp_base[32];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seg = ((n + 31) / 32 + 31) / 32 * 32;          // entries per warp, a multiple of 32
-    const int lo = min(w * seg, n), hi = min(lo + seg, n);
-    uint32_t sum = 0;
-    for (int k = lo + lane; k < hi; k += 32) sum += counts[k];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-    if (lane == 0) warp_base[w] = sum;
+// exclusive scan of the digit-major histogram in two parallel levels: (1) one block per digit scans that digit's row of
+// tile counts in place and leaves the row total in digit_total[d]; (2) one warp scans the 256 totals into digit_base[d].
+// The scatter adds the two.  (A single-block scan of the whole array was latency bound: 46 us per pass.)
+__global__ void __launch_bounds__(256) pv_sched_rowscan_kernel(uint32_t* counts, int n_tiles, uint32_t* digit_total) {
+    __shared__ uint32_t warp_sum[8];
+    __shared__ uint32_t carry_sh;
+    uint32_t* row = counts + (int64_t)blockIdx.x * n_tiles;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_sh = 0;
     __syncthreads();
-    if (w == 0) {
-        uint32_t v = warp_base[lane], incl = v;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += u;
-        }
-        warp_base[lane] = incl - v;
-    }
-    __syncthreads();
-    uint32_t run = warp_base[w];
-    for (int k0 = lo; k0 < hi; k0 += 32) {
-        const int k = k0 + lane;
-        const uint32_t c = k < hi ? counts[k] : 0u;
+    for (int k0 = 0; k0 < n_tiles; k0 += 256) {
+        const int k = k0 + threadIdx.x;
+        const uint32_t c = k < n_tiles ? row[k] : 0u;
         uint32_t incl = c;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
             if (lane >= off) incl += u;
         }
-        if (k < hi) counts[k] = run + incl - c;
+        if (lane == 31) warp_sum[w] = incl;
+        __syncthreads();
+        uint32_t base = carry_sh;
+        for (int v = 0; v < w; ++v) base += warp_sum[v];
+        if (k < n_tiles) row[k] = base + incl - c;
+        __syncthreads();
+        if (threadIdx.x == 255) carry_sh = base + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) digit_total[blockIdx.x] = carry_sh;
+}
+
+__global__ void __launch_bounds__(32) pv_sched_digitscan_kernel(const uint32_t* digit_total, uint32_t* digit_base) {
+    const int lane = threadIdx.x;
+    uint32_t run = 0;
+    for (int k0 = 0; k0 < 256; k0 += 32) {
+        const uint32_t c = digit_total[k0 + lane];
+        uint32_t incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += u;
+        }
+        digit_base[k0 + lane] = run + incl - c;
         run += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
@@ -132,7 +150,7 @@ __global__ void __launch_bounds__(128) pv_sched_scatter_kernel(const pv_sched_pa
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_id = blockIdx.x * 4 + w;
     if (tile_id >= p.n_tiles) return;
-    for (int d = lane; d < 256; d += 32) run[w][d] = p.counts[(int64_t)d * p.n_tiles + tile_id];
+    for (int d = lane; d < 256; d += 32) run[w][d] = p.digit_base[d] + p.counts[(int64_t)d * p.n_tiles + tile_id];
     __syncwarp();
     const int64_t lo = (int64_t)tile_id * p.tile, hi = min(lo + p.tile, p.B);
     for (int64_t i0 = lo; i0 < hi; i0 += 32) {

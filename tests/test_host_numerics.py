@@ -103,7 +103,7 @@ def test_dopri5_stiffness_detection_hands_over_early_and_only_when_it_pays():
         rc0, _, st0 = harness.simulate("simple_pk", {"k_abs": k, "CL": cl}, t, 1e-7, 1e-10, max_steps=4000)
         rc1, _, st1 = harness.simulate("simple_pk", {"k_abs": k, "CL": cl}, t, 1e-7, 1e-10, max_steps=4000, stiff_after=64)
         assert rc0 == 1 and sum(st0) == 4000          # PV_ERR_MAX_STEPS after the whole budget
-        assert rc1 == 4 and sum(st1) < 400            # PV_ERR_STIFF
+        assert rc1 == 4 and sum(st1) < 600            # PV_ERR_STIFF
     rs = np.random.RandomState(1234)
     th = rs.lognormal(-0.3465735902799726, 0.8325546111576977, size=(2, 300))
     for b in range(300):

@@ -93,6 +93,12 @@ int pv_problem_set_locality(pv_problem* p, int mode);
  * reproduces itself bit for bit: the work order is deterministic).  mode 0 = auto, 1 = off, 2 = on. */
 int pv_problem_set_lockstep(pv_problem* p, int mode);
 
+/* DOPRI5 logp + gradient of SMALL batches: one trajectory per group of 1 + n_sens neighbouring lanes (state block and
+ * sensitivity blocks on different lanes of a lockstep warp, stage state exchanged by shuffles): the dependent chain of
+ * a step shrinks by ~(1 + n_sens), which is what bounds a launch that is a single wave (BASELINE config 3: 8 x 1000).
+ * mode 0 = auto (launches that fit one wave), 1 = off, 2 = on. */
+int pv_problem_set_group_lanes(pv_problem* p, int mode);
+
 /* Data layout of the Rosenbrock sensitivity kernels (logp + gradient, + Fisher information) of the large models
  * (augmented system of more than 16 components; of the built-in models: icg_body_flat):
  *   PV_LAYOUT_LANE   one trajectory per lane (all blocks of the augmented system in one thread)

@@ -394,6 +394,35 @@ def emit_model(hs: HoistedSystem, struct_name: str | None = None) -> EmittedMode
     blk_rhs_max = max(blk_rhs_flops, default=0)
     blk_term_max = max(blk_term_flops, default=0)
 
+    # ---- role-uniform block function for the block-per-lane DOPRI5 kernel: out = J(y) v + (df/dc)(y) w ---------------
+    # every lane of a trajectory's group runs the SAME code on its own block vector v and its own dense coefficient
+    # direction w (sensitivity block k: v = s_k, w = d c / d theta_k); dc_dense builds w for a run-time k
+    wsyms = [sp.Symbol(f"w_{m}") for m in range(NC)]
+    symmap_u = dict(symmap)
+    for j in range(NX):
+        symmap_u[vsyms[j]] = f"v[{j}]"
+    for m in range(NC):
+        symmap_u[wsyms[m]] = f"w[{m}]"
+    uni_exprs = []
+    for i in range(NX):
+        e = sp.Integer(0)
+        for j in range(NX):
+            if (i, j) in hs.jac:
+                e += hs.jac[(i, j)] * vsyms[j]
+        for m in range(NC):
+            if (i, m) in hs.dfdc:
+                e += hs.dfdc[(i, m)] * wsyms[m]
+        uni_exprs.append((f"out[{i}]", e))
+    uni_code, uni_flops = _emit_block(uni_exprs, symmap_u, "u", fast_rcp=True)
+    # f(y) = (df/dc)(y) c exactly when every f_i is linear and homogeneous in the hoisted coefficients
+    zero_c = {cm: 0 for cm in hs.c_syms}
+    lin_in_c = all(sp.simplify(fi.xreplace(zero_c)) == 0 and
+                   all(sp.diff(fi, cm, cn) == 0 for cm in hs.c_syms for cn in hs.c_syms if cm in fi.free_symbols and cn in fi.free_symbols)
+                   for fi in hs.f)
+    dense_lines = [f"    w[{m}] = 0.0;" for m in range(NC)]
+    for (k_, m_), n_ in sorted(dc_index.items(), key=lambda kv: kv[1]):
+        dense_lines.append(f"    w[{m_}] = (k == {k_}) ? dc[{n_}] : w[{m_}];")
+
     unused = "(void)t; (void)y; (void)c;"
     NSd = max(NS, 1)
     header = f"""// GENERATED by parameter-variability_b200/codegen (emit.py) from SBML model '{name}'. Do not edit.
@@ -425,6 +454,8 @@ struct {struct_name} {{
     static constexpr int FLOPS_SENS_TERM = {st_flops};
     static constexpr int FLOPS_DFDP = {fp_flops};
     static constexpr int FLOPS_JV = {jv_flops};
+    static constexpr int FLOPS_JV_DFDC = {uni_flops};
+    static constexpr bool RHS_LINEAR_IN_C = {'true' if lin_in_c else 'false'};  // rhs(y) == (df/dc)(y) c
 
     PV_HD static void hoist(const double (&th)[NTH], double (&c)[NC], double (&y0)[NX], double (&obs)[NX]) {{
 {hoist_code}
@@ -493,6 +524,20 @@ struct {struct_name} {{
 {st_code}
     }}
 
+    // ---- role-uniform block right-hand side (block-per-lane DOPRI5 kernel): every lane of a trajectory's group runs this
+    // one function on its own block vector v and its own coefficient direction w: out = J(y) v + (df/dc)(y) w.
+    // Sensitivity block k: v = s_k, w = d c / d theta_k (dc_dense); the state lane selects rhs(y) instead. ----
+    PV_HD static void jv_plus_dfdc(double t, const double (&y)[NX], const double (&v)[NX], const double (&c)[NC],
+                                   const double (&w)[NC], double (&out)[NX]) {{
+        {unused} (void)v; (void)w; (void)out;
+{uni_code}
+    }}
+    // w = d c / d theta_k as a dense [NC] vector for a run-time k (zeros where c_m does not depend on theta_k)
+    PV_HD static void dc_dense(int k, const double (&dc)[NDC], double (&w)[NC]) {{
+        (void)k; (void)dc;
+{chr(10).join(dense_lines)}
+    }}
+
     // ---- one sensitivity block at a time (block-per-warp Rosenbrock kernel): s, v, out are the block's own vectors;
     // c and dc may live in registers or in shared memory (any indexable container) ----
     static constexpr int FLOPS_SENS_RHS_BLOCK = {blk_rhs_max};    // max over K
@@ -545,7 +590,7 @@ struct {struct_name} {{
         "dead_rules": ode.dead_rules,
         "flops": {"rhs": rhs_flops, "rhs_sens": rs_flops, "jac": jac_flops, "lu": lu_flops,
                   "solve": sol_flops, "hoist": hoist_flops, "hoist_sens": hs_flops,
-                  "sens_stage_term": st_flops, "dfdp": fp_flops, "jac_vec": jv_flops},
+                  "sens_stage_term": st_flops, "dfdp": fp_flops, "jac_vec": jv_flops, "jv_plus_dfdc": uni_flops},
     }
     return EmittedModel(name=name, struct_name=struct_name, header=header, meta=meta)
 

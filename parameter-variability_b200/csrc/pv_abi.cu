@@ -86,6 +86,7 @@ struct pv_problem {
     int locality = 0;              // pv_problem_set_locality: 0 = auto (sorted launches from 4096 trajectories), 1 = off, 2 = on
     int32_t* d_sched_index[4] = {nullptr, nullptr, nullptr, nullptr};     // locality-schedule scratch per launch slot (pv_schedule.cuh)
     int lockstep = 0;              // pv_problem_set_lockstep: 0 = auto, 1 = off, 2 = on
+    int roles = 0;                 // pv_problem_set_group_lanes: 0 = auto, 1 = off, 2 = on
     int64_t sched_cap[4] = {0, 0, 0, 0};
     int stiff_after = 128;         // DOPRI5 stiffness detection of the AUTO first pass starts after this many steps
     int32_t* d_scratch_status[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -270,6 +271,13 @@ extern "C" int pv_problem_set_lockstep(pv_problem* p, int mode) {
     return 0;
 }
 
+extern "C" int pv_problem_set_group_lanes(pv_problem* p, int mode) {
+    if (!p) return fail(PV_E_ARG, "problem is NULL");
+    if (mode < 0 || mode > 2) return fail(PV_E_ARG, "mode must be 0 (auto), 1 (off) or 2 (on)");
+    p->roles = mode;
+    return 0;
+}
+
 extern "C" int pv_problem_set_stiffness_detection(pv_problem* p, int after_steps) {
     if (!p) return fail(PV_E_ARG, "problem is NULL");
     if (after_steps < 0) return fail(PV_E_ARG, "after_steps must be >= 0");
@@ -449,7 +457,7 @@ static int resident_ctas(const void* kern, int threads, size_t shmem, cudaError_
 }
 
 struct pv_launch_ctx {
-    int num_sms, layout, max_ctas_per_sm, lockstep;
+    int num_sms, layout, max_ctas_per_sm, lockstep, roles;
     const double* theta;   // host [NTH]
     const double* y0;      // host [NX]
 };
@@ -507,6 +515,17 @@ static cudaError_t launch_model(int method, int mode, bool obsid, const pv_launc
             return mode == PV_MODE_LOGP_GRAD
                        ? launch_persistent<M>(pv_rodas4_split_kernel<M, PV_MODE_LOGP_GRAD>, lp, cx, threads, 32, sh, s)
                        : launch_persistent<M>(pv_rodas4_split_kernel<M, PV_MODE_LOGP_GRAD_FIM>, lp, cx, threads, 32, sh, s);
+        }
+    }
+    // small batches of DOPRI5 logp + gradient: one trajectory per GROUP of 1 + NS lanes (pv_dopri5_roles.cuh) while the
+    // launch fits one wave of that kernel - beyond it the lane-per-trajectory kernels' throughput wins
+    if constexpr (M::NS >= 1) {
+        constexpr int TPW = 32 / (1 + M::NS);
+        const int64_t one_wave = (int64_t)cx.num_sms * 4 * (PV_BLOCK / 32) * TPW;
+        if (method == 1 && mode == PV_MODE_LOGP_GRAD && (cx.roles == 2 || (cx.roles == 0 && lp.B <= one_wave))) {
+            const int64_t per_cta = (PV_BLOCK / 32) * TPW;
+            if (lp.n_data == 1) return launch_persistent<M>(pv_batch_roles_kernel<M, true>, lp, cx, PV_BLOCK, per_cta, shmem, s);
+            return launch_persistent<M>(pv_batch_roles_kernel<M, false>, lp, cx, PV_BLOCK, per_cta, shmem, s);
         }
     }
     // the all-states-in-order specialisation is compiled for the explicit integrator only (cheap steps, where the
@@ -669,7 +688,7 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
     // schedule.  The stiff re-run pass (RODAS4 on a handful of rows) is not affected.
     const bool sorted = lp.index_map != nullptr;
     const int lockstep = p->lockstep == 2 || (p->lockstep == 0 && sorted && PV_LOCKSTEP_AUTO) ? 1 : 0;
-    const pv_launch_ctx cx{p->num_sms, p->layout, p->max_ctas_per_sm, lockstep, p->theta_base.data(), p->y0_base.data()};
+    const pv_launch_ctx cx{p->num_sms, p->layout, p->max_ctas_per_sm, lockstep, p->roles, p->theta_base.data(), p->y0_base.data()};
     cudaError_t e = cudaErrorInvalidValue;
     switch (p->model) {
         PV_MODEL_DISPATCH(e = launch_model, (method, mode, obsid, lp, cx, shmem, s))

@@ -14,6 +14,12 @@
 #define PV_D inline
 #endif
 
+// compile-time integer as a value (generic lambdas instantiated per register set)
+template <int I>
+struct pv_int_tag {
+    static constexpr int value = I;
+};
+
 PV_HD float pv_fdiv_fast(float a, float b) {
 #if defined(__CUDA_ARCH__)
     return __fdividef(a, b);     // MUFU.RCP + FMUL: the controller needs two digits, not IEEE division

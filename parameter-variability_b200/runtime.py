@@ -51,6 +51,7 @@ ABI = {
     "pv_problem_set_stiffness_detection": (C.c_int, [C.c_void_p, C.c_int]),
     "pv_problem_set_locality": (C.c_int, [C.c_void_p, C.c_int]),
     "pv_problem_set_lockstep": (C.c_int, [C.c_void_p, C.c_int]),
+    "pv_problem_set_group_lanes": (C.c_int, [C.c_void_p, C.c_int]),
     "pv_problem_set_observables": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p)]),
     "pv_problem_set_data": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
     "pv_simulate": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -234,6 +235,10 @@ class Problem:
     def set_lockstep(self, mode: int = 0) -> None:
         """Lockstep warps of the DOPRI5 kernels: 0 = auto, 1 = off, 2 = on (``pv_problem_set_lockstep``)."""
         _check(self._lib.pv_problem_set_lockstep(self._h, int(mode)))
+
+    def set_group_lanes(self, mode: int = 0) -> None:
+        """One trajectory per group of 1 + n_sens lanes for small DOPRI5 logp + gradient launches: 0 = auto, 1 = off, 2 = on."""
+        _check(self._lib.pv_problem_set_group_lanes(self._h, int(mode)))
 
     def set_stiffness_detection(self, after_steps: int = 128) -> None:
         _check(self._lib.pv_problem_set_stiffness_detection(self._h, int(after_steps)))

@@ -826,3 +826,58 @@ def test_locality_schedule_and_lockstep_warps(cuda_lib, rt, oracle, B):
     np.testing.assert_allclose(lp2[ok], lp0[ok], rtol=1e-6)
     # neighbours in parameter space: a common step size costs few extra steps (the denser the batch, the fewer)
     assert n2[:, ok].sum() < (1.15 if B >= 50000 else 1.6) * n0[:, ok].sum()
+
+
+@pytest.mark.parametrize("noise", ["normal", "lognormal"])
+@pytest.mark.parametrize("model", ["simple_pk", "simple_chain"])
+def test_group_lanes_kernel_matches_lane_kernel_and_oracle(cuda_lib, rt, oracle, model, noise):
+    """pv_problem_set_group_lanes: the small-batch DOPRI5 logp + gradient kernel that spreads a trajectory over 1 + n_sens
+    lanes (pv_dopri5_roles.cuh) against the one-trajectory-per-lane kernel and the exact solution: ragged batch (not a
+    multiple of the trajectories per warp), per-trajectory data sets and a pooled one, both noise models, a NaN row that
+    fails alone, sensitivity columns in a non-compiled order."""
+    opt = pkg("optimization.petab_optimization")
+    nm = rt.NOISE_NORMAL if noise == "normal" else rt.NOISE_LOGNORMAL
+    B = 203
+    if model == "simple_pk":
+        cols, obs = ["CL", "k_abs"], ["y_cent", "y_peri"]
+        t = np.linspace(0, 30, 13)[1:]
+        th = np.stack([lognormal_draws(91, B), lognormal_draws(92, B)])
+        exact = lambda b: (oracle.simple_pk_exact({"CL": th[0, b], "k_abs": th[1, b]}, t)[:, [1, 2]],           # noqa: E731
+                           oracle.simple_pk_exact_sens({"CL": th[0, b], "k_abs": th[1, b]}, t, sens=("CL", "k_abs"))[:, [1, 2], :])
+        truth = oracle.simple_pk_exact({}, t)[:, [1, 2]]
+    else:
+        cols, obs = ["k1"], ["S1", "S2"]
+        t = np.linspace(0, 8, 9)[1:]
+        th = lognormal_draws(93, B)[None, :]
+        exact = lambda b: (oracle.simple_chain_exact(th[0, b], t), oracle.simple_chain_exact_sens(th[0, b], t)[..., None])  # noqa: E731
+        truth = oracle.simple_chain_exact(1.0, t)
+    th[0, 17] = np.nan
+    rs = np.random.RandomState(3)
+    for n_data in (1, 7):
+        data = np.abs(truth[None] * (1 + 0.05 * rs.normal(size=(n_data,) + truth.shape))) + 1e-9
+        stats = np.stack([opt.sufficient_statistics(data[i:i + 1], nm) for i in range(n_data)], axis=-1)
+        sigma = 0.2 if nm == rt.NOISE_LOGNORMAL else 0.05
+        pb = _problem(rt, model, cols, t, obs, rtol=1e-9, atol=1e-14, method=rt.METHOD_DOPRI5)
+        pb.set_timepoints(t, t0=0.0)
+        pb.set_data(stats, sigma, nm)
+        out = {}
+        for mode in (1, 2):
+            pb.set_group_lanes(mode)
+            n0 = rt.launch_count()
+            lp, g, _, nf = pb.logp_host(th, grad=True)
+            assert nf == 1 and rt.launch_count() > n0
+            out[mode] = (lp, g)
+        ok = np.arange(B) != 17
+        assert np.isnan(out[2][0][17]) and np.all(np.isnan(out[2][1][:, 17])) and np.all(np.isfinite(out[2][0][ok]))
+        np.testing.assert_allclose(out[2][0][ok], out[1][0][ok], rtol=1e-8)
+        np.testing.assert_allclose(out[2][1][:, ok], out[1][1][:, ok], rtol=1e-6, atol=1e-7 * np.abs(out[1][1][:, ok]).max())
+        rows = [pb.sens_ids.index(c) for c in cols]
+        for b in (0, 9, 10, 11, 200, 202):
+            f, s = exact(b)
+            d = data[b % n_data]
+            if nm == rt.NOISE_NORMAL:
+                ref_lp, ref_g = oracle.loglik_normal(f, d, sigma), oracle.loglik_normal_grad(f, s, d, sigma)
+            else:
+                ref_lp, ref_g = oracle.loglik_lognormal(f, d, sigma), oracle.loglik_lognormal_grad(f, s, d, sigma)
+            assert out[2][0][b] == pytest.approx(ref_lp, rel=1e-6)
+            np.testing.assert_allclose(out[2][1][rows, b], ref_g, rtol=1e-6, atol=1e-6 * np.abs(ref_g).max())

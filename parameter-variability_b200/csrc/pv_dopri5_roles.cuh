@@ -323,7 +323,8 @@ pv_batch_roles_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
         };
         while (rc == PV_RUNNING) rc = cur ? step(pv_int_tag<1>{}) : step(pv_int_tag<0>{});
         // a trajectory is dead if any lane of its group is
-        if (__shfl_sync(FULL, (int)dead, src) || group_sum(dead ? 1.0 : 0.0) > 0.0) rc = PV_ERR_NONFINITE;
+        const double n_dead = group_sum(dead ? 1.0 : 0.0);      // (every lane takes part in the shuffles: no short-circuit)
+        if (n_dead > 0.0) rc = PV_ERR_NONFINITE;
 
         // ---- results ---------------------------------------------------------------------------------------------------
         const double nan = __longlong_as_double(0x7ff8000000000000LL);

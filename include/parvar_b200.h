@@ -83,7 +83,7 @@ int pv_problem_set_schedule(pv_problem* p, int refill_min);
 /* Locality schedule (divergence control): the trajectories of a launch are bucketed on the device by their parameter
  * values (first two columns) so that the lanes of a warp integrate neighbouring points of parameter space and therefore
  * step, cross the output grid and finish together (stable radix sort on the device: the order is a pure function of
- * the inputs).  Only the order in which trajectories are picked up changes; results are bit-identical.  mode 0 = auto (launches of >= 4096 trajectories with per-trajectory columns), 1 = off, 2 = on. */
+ * the inputs).  Only the order in which trajectories are picked up changes; results are bit-identical.  mode 0 = auto (launches of >= 32 768 trajectories with per-trajectory columns), 1 = off, 2 = on. */
 int pv_problem_set_locality(pv_problem* p, int mode);
 
 /* Lockstep warps (DOPRI5 kernels): the 32 lanes of a warp - 32 consecutive work items, neighbours in parameter space under

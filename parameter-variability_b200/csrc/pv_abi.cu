@@ -25,10 +25,12 @@
 #include "pv_schedule.cuh"
 #include "pv_sampler_device.cuh"
 #include "pv_rng_host.cuh"
-#include "generated/simple_chain.cuh"
-#include "generated/simple_pk.cuh"
-#include "generated/icg_body_flat.cuh"
-#include "generated/model_tables.inc"
+// the models compiled into this library: the three registry models by default; a run-time build of another SBML file
+// (codegen.compile_model: generate -> nvcc -> cached .so) points PV_MODELS_INC at its own list
+#ifndef PV_MODELS_INC
+#define PV_MODELS_INC "generated/models.inc"
+#endif
+#include PV_MODELS_INC
 
 static thread_local std::string g_last_error;
 static std::atomic<int64_t> g_launches{0};

@@ -116,9 +116,11 @@ def _builtin_fingerprints() -> dict[str, str]:
     return _FINGERPRINTS
 
 
-def resolve_model(model_path: Path | str) -> str:
+def resolve_model(model_path: Path | str, sens: Optional[list[str]] = None, compile_unknown: bool = True) -> str:
     """Map an SBML file (the reference's annotated file or the math-only copy) to the compiled
-    model it describes, by the fingerprint of its ODE system - not by file name."""
+    model it describes, by the fingerprint of its ODE system - not by file name.  A file outside the registry - or a
+    registry model asked for another sensitivity-parameter set ``sens`` - is generated, compiled (nvcc) and cached as its
+    own library on first use, like the reference's roadrunner JIT / AMICI model build (:183-190; run_optimization.py:43-46)."""
     from .. import codegen
     model_path = Path(model_path)
     if not model_path.exists():
@@ -126,13 +128,19 @@ def resolve_model(model_path: Path | str) -> str:
     sb = codegen.read_sbml(model_path)
     ode = codegen.build_ode_system(sb)
     ode.name = model_path.stem
-    for name, sens in codegen.BUILTIN.items():
-        fp = codegen.model_fingerprint(ode, sens)
-        if _builtin_fingerprints().get(fp) == name:
+    for name, builtin_sens in codegen.BUILTIN.items():
+        fp = codegen.model_fingerprint(ode, builtin_sens)
+        if _builtin_fingerprints().get(fp) == name and (sens is None or set(sens) <= set(builtin_sens)):
             return name
-    raise runtime.ParvarB200Error(
-        f"{model_path}: this ODE system is not compiled into libparvar_b200.so "
-        f"(compiled: {sorted(set(_builtin_fingerprints().values()))}); add it to codegen.BUILTIN and rebuild")
+    if not compile_unknown:
+        raise runtime.ParvarB200Error(
+            f"{model_path}: this ODE system is not compiled into libparvar_b200.so "
+            f"(compiled: {sorted(set(_builtin_fingerprints().values()))})")
+    name, lib_path = codegen.compile_model(model_path, sens or [])
+    name = f"{name}@{lib_path.stem.rsplit('_', 1)[-1]}"      # registry key: model + fingerprint (several builds may coexist)
+    if name not in runtime._model_libs:
+        runtime.load_model_library(name, lib_path)
+    return name
 
 
 class ODESampleSimulator:
@@ -146,6 +154,8 @@ class ODESampleSimulator:
 
     def __init__(self, model_path: Path, abs_tol: float = 1e-10, rel_tol: float = 1e-7, device: int = 0,
                  method: int = runtime.METHOD_AUTO, max_steps: int = 20000):
+        # any SBML file, as the reference's RoadRunner(str(model_path)) (:185): a registry model by fingerprint, anything
+        # else generated + compiled + cached on first use
         self.model_name = resolve_model(model_path)
         self.problem = runtime.Problem(self.model_name, device=device)
         # 20000 = roadrunner's CVODE default `maximum_num_steps`; rows that need more raise like the reference does

@@ -48,6 +48,18 @@ def sufficient_statistics(y: np.ndarray, noise_model: int) -> np.ndarray:
     return np.stack([ok.sum(axis=0).astype(np.float64), v0.sum(axis=0), (v0 * v0).sum(axis=0)])
 
 
+def model_with_sensitivities(model: str, parameters: Sequence[str]) -> str:
+    """The compiled model to use for gradients with respect to ``parameters``: the registry build when they are among its
+    sensitivity parameters, otherwise a run-time build of the same SBML file with exactly this set (generated, compiled
+    and cached on first use - AMICI likewise builds its model for whatever the PEtab table estimates,
+    petab_optimization.py:43-45)."""
+    from .. import MODELS, codegen
+    if model not in codegen.BUILTIN or set(parameters) <= set(codegen.BUILTIN[model]):
+        return model
+    from ..experiments.petab_factory import resolve_model
+    return resolve_model(MODELS[model], sens=list(parameters))
+
+
 class PetabObjective:
     """Negative log posterior of a parvar PEtab problem, evaluated on the GPU.
 
@@ -93,7 +105,7 @@ class PetabObjective:
             self.prior_loc[i], self.prior_scale[i] = loc, scale
         self._has_prior = np.isfinite(self.prior_loc)
 
-        pb = runtime.Problem(model, device=device)
+        pb = runtime.Problem(model_with_sensitivities(model, self.parameters), device=device)
         # max_steps = 10000 is AMICI's default step budget: a parameter vector that needs more (start points and tempered
         # chains roam the PEtab bounds [0, 1e8]) is a failed evaluation (fval = inf), not a minutes-long integration
         pb.set_solver(method=method, rtol=rtol, atol=atol, max_steps=max_steps)
@@ -224,7 +236,7 @@ class PetabObjectiveBatch:
                 self.prior_loc[q, i], self.prior_scale[q, i] = loc, scale
         self.has_prior = np.isfinite(self.prior_loc)
 
-        pb = runtime.Problem(model, device=device)
+        pb = runtime.Problem(model_with_sensitivities(model, self.parameters), device=device)
         pb.set_solver(method=method, rtol=rtol, atol=atol, max_steps=max_steps)      # AMICI's default budget, see PetabObjective
         if mode == "literal":
             # the condition table's species columns when given (read from the files), else what the reference always

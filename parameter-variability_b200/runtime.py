@@ -94,6 +94,26 @@ class ParvarB200Error(RuntimeError):
     pass
 
 
+_model_libs: dict[str, C.CDLL] = {}      # run-time compiled models (codegen.compile_model): model name -> its library
+
+
+def load_model_library(name: str, path: Path) -> C.CDLL:
+    """dlopen a library built by ``codegen.compile_model`` (same ABI, one model) and register it under the model's name:
+    ``Problem(name)`` then finds it."""
+    path = Path(path)
+    if not path.exists():
+        raise ParvarB200Error(f"{path} is missing")
+    lib = C.CDLL(str(path))
+    for sym, (res, args) in ABI.items():
+        fn = getattr(lib, sym)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pv_abi_version() != 1:
+        raise ParvarB200Error("ABI version mismatch")
+    _model_libs[name] = lib
+    return lib
+
+
 def load_library(path: Optional[Path] = None) -> C.CDLL:
     """dlopen the in-tree library and type every exported symbol."""
     global _lib
@@ -117,7 +137,8 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
 
 
 def last_error() -> str:
-    return (load_library().pv_last_error() or b"").decode()
+    msgs = [(lib.pv_last_error() or b"").decode() for lib in [load_library(), *_model_libs.values()]]
+    return next((m for m in reversed(msgs) if m), "")
 
 
 def _check(rc: int) -> int:
@@ -176,8 +197,10 @@ class Problem:
     """One loaded model + its simulation settings (a ``pv_problem``)."""
 
     def __init__(self, model: str, device: int = 0):
-        self._lib = load_library()
-        self._h = self._lib.pv_problem_create(model.encode(), int(device))
+        # a model compiled at run time lives in its own library (load_model_library); the registry models in the main one
+        self._lib = _model_libs.get(model) or load_library()
+        # "name@fingerprint" = a run-time compiled model: inside its library it is just "name"
+        self._h = self._lib.pv_problem_create(model.split("@")[0].encode(), int(device))
         if not self._h:
             raise ParvarB200Error(f"cannot create problem for model {model!r}: {last_error()}")
         self.model = model

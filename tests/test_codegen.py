@@ -123,3 +123,59 @@ def test_no_ieee_division_inside_a_step():
             assert "/" not in body, (name, fn)
     icg = (gen / "icg_body_flat.cuh").read_text()
     assert icg.count("pv_rcp_newton") >= 12 + 4          # 12 pivots + the Michaelis-Menten denominators
+
+
+def perturbed_simple_pk(tmp_path):
+    """simple_pk with an extra, saturable elimination from the peripheral compartment (two new parameters): an ODE system
+    that is in no registry - and not linear in its coefficients, unlike the three shipped models' explicit ones."""
+    P = pkg()
+    xml = P.MODELS["simple_pk"].read_text()
+    xml = xml.replace('<parameter id="Q" value="1" constant="true" />',
+                      '<parameter id="Q" value="1" constant="true" />\n   <parameter id="k_el" value="0.3" constant="true" />\n'
+                      '   <parameter id="Km" value="0.05" constant="true" />')
+    reaction = '''   <reaction id="ELIMINATION" reversible="false">
+    <listOfReactants>
+     <speciesReference species="y_peri" stoichiometry="1" constant="true" />
+    </listOfReactants>
+    <kineticLaw>
+     <math:math>
+      <math:apply>
+       <math:divide />
+       <math:apply><math:times /><math:ci>k_el</math:ci><math:ci>y_peri</math:ci></math:apply>
+       <math:apply><math:plus /><math:ci>Km</math:ci><math:ci>y_peri</math:ci></math:apply>
+      </math:apply>
+     </math:math>
+    </kineticLaw>
+   </reaction>
+  </listOfReactions>'''
+    xml = xml.replace("  </listOfReactions>", reaction).replace('<model id="simple_pk">', '<model id="pk_saturable">')
+    path = tmp_path / "pk_saturable.xml"
+    path.write_text(xml)
+    return path
+
+
+def test_runtime_compile_of_an_unregistered_model(tmp_path):
+    """codegen.compile_model: an SBML file outside the registry becomes its own build of the library (same C ABI, one
+    model, the requested sensitivity set), cached by fingerprint - the reference's roadrunner JIT / AMICI model build
+    (petab_factory.py:183-190, run_optimization.py:43-46).  No GPU needed to build, load and inspect it."""
+    cg = pkg("codegen")
+    rt = pkg("runtime")
+    pf = pkg("experiments.petab_factory")
+    path = perturbed_simple_pk(tmp_path)
+    with pytest.raises(rt.ParvarB200Error, match="not compiled"):
+        pf.resolve_model(path, compile_unknown=False)
+    name, lib_path = cg.compile_model(path, sens=["k_abs", "k_el"], cache_dir=tmp_path / "cache")
+    assert name == "pk_saturable" and lib_path.exists()
+    again = cg.compile_model(path, sens=["k_abs", "k_el"], cache_dir=tmp_path / "cache")
+    assert again == (name, lib_path)                                   # cached: same fingerprint, no second build
+    other = cg.compile_model(path, sens=["CL"], cache_dir=tmp_path / "cache")[1]
+    assert other != lib_path                                           # another sensitivity set = another build
+    lib = rt.load_model_library("pk_saturable@test", lib_path)
+    assert lib.pv_model_count() == 1 and lib.pv_model_name(0) == b"pk_saturable"
+    meta = json.loads(lib_path.with_suffix(".json").read_text())
+    assert meta["states"] == ["y_gut", "y_cent", "y_peri"] and {"k_el", "Km"} <= set(meta["theta"])
+    assert meta["sens"] == ["k_abs", "k_el"]
+    header = cg.generate_model(path, ["k_abs", "k_el"]).header
+    assert "RHS_LINEAR_IN_C = false" in header                         # Km sits inside a denominator
+    if lib.pv_device_count() <= 0:                                     # still no CPU fallback in a run-time build
+        assert not lib.pv_problem_create(b"pk_saturable", 0) and b"no CUDA device" in lib.pv_last_error()

@@ -884,3 +884,65 @@ def test_group_lanes_kernel_matches_lane_kernel_and_oracle(cuda_lib, rt, oracle,
                 ref_lp, ref_g = oracle.loglik_lognormal(f, d, sigma), oracle.loglik_lognormal_grad(f, s, d, sigma)
             assert out[2][0][b] == pytest.approx(ref_lp, rel=1e-6)
             np.testing.assert_allclose(out[2][1][rows, b], ref_g, rtol=1e-6, atol=1e-6 * np.abs(ref_g).max())
+
+
+def test_unregistered_sbml_model_and_other_sensitivity_sets_end_to_end(cuda_lib, rt, oracle, tmp_path):
+    """Run-time model compile (petab_factory.py:183-190: the reference loads ANY SBML file): a perturbed copy of
+    simple_pk.xml - extra saturable elimination, two new parameters - goes SBML -> generated CUDA -> nvcc -> cached library
+    -> batched simulation, checked against scipy on the same ODE; its gradient with respect to a sensitivity set chosen at
+    run time against finite differences of that oracle.  And a registry model asked for a parameter that is NOT among its
+    compiled sensitivity parameters (simple_pk, Q) is rebuilt for that set instead of raising."""
+    import pandas as pd
+    from scipy.integrate import solve_ivp
+    from test_codegen import perturbed_simple_pk
+    pf = pkg("experiments.petab_factory")
+    ex = pkg("experiments.experiment")
+    opt = pkg("optimization.petab_optimization")
+    path = perturbed_simple_pk(tmp_path)
+    t = np.linspace(0, 30, 16)
+
+    def solve(k_abs, k_el, CL=1.0, Q=1.0, Km=0.05):
+        def f(_, y):
+            return [-k_abs * y[0], k_abs * y[0] - (CL + Q) * y[1] + Q * y[2], Q * y[1] - Q * y[2] - k_el * y[2] / (Km + y[2])]
+        return solve_ivp(f, (0, 30), [1.0, 0.0, 0.0], method="LSODA", t_eval=t, rtol=1e-12, atol=1e-14).y.T
+
+    # ---- B1: the simulator mirror on the unknown file ----------------------------------------------------------------
+    sim = pf.ODESampleSimulator(path)
+    assert sim.model_name.startswith("pk_saturable@") and "k_el" in sim.ids and "[y_peri]" in sim.ids
+    n = 9
+    pars = pd.DataFrame({"k_abs": lognormal_draws(5, n), "k_el": lognormal_draws(6, n, 0.3, 0.1)})
+    st = pf.SimulationSettings(start=0.0, end=30.0, steps=15, dosage=None, noise=ex.Noise(add_noise=False, cv=0.0),
+                               observables=[ex.Observable(id=o) for o in ("y_gut", "y_cent", "y_peri")])
+    ds = sim.simulate_samples(pars, st)
+    got = np.stack([ds[f"[{o}]"].values for o in ("y_gut", "y_cent", "y_peri")], axis=2)
+    for i in range(n):
+        assert parity_violation(got[i], solve(pars["k_abs"][i], pars["k_el"][i])) <= 1.0
+    # ---- B2: gradient with respect to (k_abs, k_el), a set chosen now -------------------------------------------------
+    name = pf.resolve_model(path, sens=["k_abs", "k_el"])
+    pb = _problem(rt, name, ["k_abs", "k_el"], t, ["y_cent", "y_peri"], rtol=1e-9, atol=1e-13, method=rt.METHOD_DOPRI5)
+    assert pb.sens_ids == ["k_abs", "k_el"]
+    data = _noisy_data(solve(1.0, 0.3)[:, 1:], 0.05, 4)[None]
+    sigma = 0.02
+    pb.set_data(opt.sufficient_statistics(data, rt.NOISE_NORMAL)[..., None], sigma, rt.NOISE_NORMAL)
+    th = np.stack([pars["k_abs"].to_numpy(), pars["k_el"].to_numpy()])
+    for mode in (1, 2):                                   # lane kernel / group-lanes kernel (rhs not linear in c: select path)
+        pb.set_group_lanes(mode)
+        lp, g, _, nf = pb.logp_host(th, grad=True)
+        assert nf == 0
+        for i in (0, 4, 8):
+            ka, ke = th[:, i]
+            ll = lambda a, e: oracle.loglik_normal(solve(a, e)[:, 1:], data[0], sigma)     # noqa: E731
+            assert lp[i] == pytest.approx(ll(ka, ke), rel=1e-6)
+            fd = np.array([(ll(ka * (1 + 1e-5), ke) - ll(ka * (1 - 1e-5), ke)) / (2e-5 * ka),
+                           (ll(ka, ke * (1 + 1e-5)) - ll(ka, ke * (1 - 1e-5))) / (2e-5 * ke)])
+            np.testing.assert_allclose(g[:, i], fd, rtol=2e-4, atol=2e-4 * np.abs(fd).max())
+    # ---- a registry model, another sensitivity set ---------------------------------------------------------------------
+    cols = [oracle.SIMPLE_PK.states.index(o) for o in ("y_cent", "y_peri")]
+    y = _noisy_data(oracle.simple_pk_exact({}, t)[:, cols], 0.05, 8)[None]
+    obj = opt.PetabObjective("simple_pk", ["Q"], [opt.GroupData("MALE", y)], t, ["y_cent", "y_peri"], sigma=0.05, rtol=1e-9, atol=1e-13)
+    assert obj.problem.sens_ids == ["Q"] and obj.problem.model.startswith("simple_pk@")
+    fval, grad = obj(np.array([1.3]), (0, 1))
+    f = oracle.simple_pk_exact({"Q": 1.3}, t)[:, cols]
+    s = oracle.simple_pk_exact_sens({"Q": 1.3}, t, sens=("Q",))[:, cols, :]
+    assert fval == pytest.approx(-oracle.loglik_normal(f, y[0], 0.05), rel=1e-6)
+    np.testing.assert_allclose(grad, -oracle.loglik_normal_grad(f, s, y[0], 0.05), rtol=1e-6)

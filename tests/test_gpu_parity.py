@@ -872,8 +872,10 @@ def test_group_lanes_kernel_matches_lane_kernel_and_oracle(cuda_lib, rt, oracle,
             out[mode] = (lp, g)
         ok = np.arange(B) != 17
         assert np.isnan(out[2][0][17]) and np.all(np.isnan(out[2][1][:, 17])) and np.all(np.isfinite(out[2][0][ok]))
-        np.testing.assert_allclose(out[2][0][ok], out[1][0][ok], rtol=1e-8)
-        np.testing.assert_allclose(out[2][1][:, ok], out[1][1][:, ok], rtol=1e-6, atol=1e-7 * np.abs(out[1][1][:, ok]).max())
+        # two step sequences of the same method at rtol 1e-9; the log-normal likelihood multiplies the relative error of f by
+        # residual / sigma^2 (a few hundred here)
+        np.testing.assert_allclose(out[2][0][ok], out[1][0][ok], rtol=1e-8 if nm == rt.NOISE_NORMAL else 1e-6)
+        np.testing.assert_allclose(out[2][1][:, ok], out[1][1][:, ok], rtol=1e-6, atol=1e-6 * np.abs(out[1][1][:, ok]).max())
         rows = [pb.sens_ids.index(c) for c in cols]
         for b in (0, 9, 10, 11, 200, 202):
             f, s = exact(b)

@@ -852,7 +852,7 @@ def test_group_lanes_kernel_matches_lane_kernel_and_oracle(cuda_lib, rt, oracle,
         cols, obs = ["k1"], ["S1", "S2"]
         t = np.linspace(0, 8, 9)[1:]
         th = lognormal_draws(93, B, 1.0, 1.0 if noise == "normal" else 0.3)[None, :]
-        exact = lambda b: (oracle.simple_chain_exact(th[0, b], t), oracle.simple_chain_exact_sens(th[0, b], t)[..., None])  # noqa: E731
+        exact = lambda b: (oracle.simple_chain_exact(th[0, b], t), oracle.simple_chain_exact_sens(th[0, b], t))  # noqa: E731
         truth = oracle.simple_chain_exact(1.0, t)
     th[0, 17] = np.nan
     rs = np.random.RandomState(3)

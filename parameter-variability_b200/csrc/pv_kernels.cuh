@@ -440,8 +440,12 @@ pv_batch_lockstep_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
         if (lane_id == 0) base = atomicAdd(p.counter, 32ull);
         base = __shfl_sync(FULL, base, 0);
         if ((int64_t)base >= n_items) break;
+        // Tiles are handed out from the END of the work list: under the locality schedule that is the high-key end (largest
+        // rate constants = most steps), so the longest tiles start first and the launch does not end on a 1700-step tile
+        // that was picked up last (longest-processing-time-first).
         // lanes past the end of the work list integrate a copy of the last item (identical values to identical addresses)
-        const int64_t item = min((int64_t)base + lane_id, n_items - 1);
+        const int64_t tile0 = (n_items - 1) / 32 * 32 - (int64_t)base;
+        const int64_t item = min(tile0 + lane_id, n_items - 1);
         const int64_t b = p.index_map ? (int64_t)p.index_map[item] : item;
         double pc[PV_MAX_COLS];
 #pragma unroll

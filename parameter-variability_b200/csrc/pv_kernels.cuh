@@ -335,8 +335,11 @@ pv_batch_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
             if (lane_id == leader) base = atomicAdd(p.counter, (unsigned long long)__popc(need));
             base = __shfl_sync(FULL, base, leader);
             if ((need >> lane_id) & 1u) {
-                const int64_t item = (int64_t)base + __popc(need & ((1u << lane_id) - 1u));
-                if (item >= n_items) {
+                const int64_t taken = (int64_t)base + __popc(need & ((1u << lane_id) - 1u));
+                // handed out from the END of the work list: the high-key end under the locality schedule, where the
+                // longest trajectories are - they start first instead of forming the launch's tail
+                const int64_t item = n_items - 1 - taken;
+                if (taken >= n_items) {
                     exhausted = true;
                 } else {
                     const int64_t b = p.index_map ? (int64_t)p.index_map[item] : item;

@@ -111,8 +111,9 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
         __syncthreads();   // previous batch completely finished (s_item, shared arrays)
         if (threadIdx.x == 0) s_item = (long long)atomicAdd(p.counter, 32ull);
         __syncthreads();
-        const int64_t item0 = s_item;
-        if (item0 >= n_items) break;
+        if (s_item >= n_items) break;
+        // batches are handed out from the END of the work list (the high-key end under the locality schedule: longest first)
+        const int64_t item0 = (n_items - 1) / 32 * 32 - s_item;
         const int64_t item = item0 + lane;
         const bool valid = item < n_items;
         const int64_t b = valid ? (p.index_map ? (int64_t)p.index_map[item] : item) : 0;

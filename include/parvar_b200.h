@@ -300,6 +300,25 @@ int pv_sampler_result(pv_sampler* s, double* trace_x_host, double* trace_neglogp
                       int64_t* n_bad_cov);
 void pv_sampler_destroy(pv_sampler* s);
 
+/* ---- batched multistart optimiser, device resident -------------------------------------------------------------
+ * Damped Gauss-Newton / Levenberg-Marquardt on the Fisher information + prior precision with box projection (the model
+ * fides minimises with FIM Hessian; optimization/optimizer.py states the loop in numpy) for Q problems x n_starts
+ * starts at once; replaces `pypesto.optimize.minimize(..., FidesOptimizer, n_starts = 100)` run per problem
+ * (petab_optimization.py:99-156).  One iteration = step kernel -> pv_logp_grad_fim over n_starts * Q * n_groups
+ * trajectories -> accept / damping / convergence kernel; the host only polls the number of active starts every
+ * poll_every iterations.  Problem set-up as for pv_sampler_create (columns must be compiled sensitivity parameters);
+ * x0 [Q][n_starts][dim] (clipped to the box), priors [Q][dim] (NaN loc = none).
+ * pv_optimizer_run returns the number of starts still active (0 = all converged or stalled), < 0 on error.
+ * pv_optimizer_result: x, g [Q][n_starts][dim], f [Q][n_starts] = negative log posterior, in start order (unsorted). */
+typedef struct pv_optimizer pv_optimizer;
+pv_optimizer* pv_optimizer_create(pv_problem* p, int64_t Q, int n_groups, int n_starts, const double* lb, const double* ub,
+                                  const double* prior_loc, const double* prior_scale, const double* x0, double fatol,
+                                  double frtol, double gtol);
+int pv_optimizer_run(pv_optimizer* o, int max_iter, int poll_every, int* iterations_done);
+int pv_optimizer_result(pv_optimizer* o, double* x_host, double* f_host, double* g_host, int32_t* n_iter_host,
+                        uint8_t* converged_host, int64_t* n_evals);
+void pv_optimizer_destroy(pv_optimizer* o);
+
 /* ---- measurement helpers ------------------------------------------------------------------------------ */
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t pv_launch_count(void);

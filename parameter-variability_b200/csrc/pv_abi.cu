@@ -25,6 +25,7 @@
 #include "pv_schedule.cuh"
 #include "pv_sampler_device.cuh"
 #include "pv_rng_host.cuh"
+#include "pv_optimizer_device.cuh"
 // the models compiled into this library: the three registry models by default; a run-time build of another SBML file
 // (codegen.compile_model: generate -> nvcc -> cached .so) points PV_MODELS_INC at its own list
 #ifndef PV_MODELS_INC
@@ -1271,6 +1272,161 @@ extern "C" int pv_sampler_result(pv_sampler* s, double* trace_x_host, double* tr
     if (!ok) return fail(PV_E_CUDA, std::string("pv_sampler_result: ") + cudaGetErrorString(cudaGetLastError()));
     if (it_dev != s->it_host + 1) return fail(PV_E_STATE, "pv_sampler_result: device iteration counter out of step with the host");
     if (n_bad_cov) *n_bad_cov = (int64_t)bad;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device-resident multistart optimiser (pv_optimizer_device.cuh)
+// ---------------------------------------------------------------------------------------------------------
+struct pv_optimizer {
+    pv_problem* p = nullptr;
+    pv_opt_dev d;
+    std::vector<void*> allocs;
+    cudaStream_t stream = nullptr;
+    double *d_logp = nullptr, *d_grad = nullptr, *d_fim = nullptr;
+    int32_t* d_status = nullptr;
+    int iterations = 0;
+};
+
+template <class T>
+static T* optimizer_alloc(pv_optimizer* o, size_t n) {
+    void* ptr = nullptr;
+    if (cudaMalloc(&ptr, sizeof(T) * std::max<size_t>(n, 1)) != cudaSuccess) ptr = nullptr;
+    if (ptr) cudaMemset(ptr, 0, sizeof(T) * std::max<size_t>(n, 1));
+    o->allocs.push_back(ptr);
+    return (T*)ptr;
+}
+
+static int optimizer_enqueue(pv_optimizer* o, int init) {
+    const pv_opt_dev& d = o->d;
+    const int64_t QS = d.Q * d.S, B = QS * d.G;
+    const unsigned blocks = (unsigned)((QS + 127) / 128);
+    pv_opt_propose_kernel<<<blocks, 128, 0, o->stream>>>(d, init);
+    g_launches.fetch_add(1);
+    CUDA_OK(cudaGetLastError());
+    if (int rc = launch(o->p, PV_MODE_LOGP_GRAD_FIM, B, d.P, nullptr, nullptr, o->d_logp, o->d_grad, o->d_status, nullptr, o->stream, o->d_fim)) return rc;
+    CUDA_OK(cudaMemsetAsync(d.n_active, 0, sizeof(int), o->stream));
+    pv_opt_update_kernel<<<blocks, 128, 0, o->stream>>>(d, init);
+    g_launches.fetch_add(1);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" void pv_optimizer_destroy(pv_optimizer* o) {
+    if (!o) return;
+    if (o->p) cudaSetDevice(o->p->device);
+    if (o->stream) {
+        cudaStreamSynchronize(o->stream);
+        cudaStreamDestroy(o->stream);
+    }
+    for (void* a : o->allocs) cudaFree(a);
+    delete o;
+}
+
+extern "C" pv_optimizer* pv_optimizer_create(pv_problem* p, int64_t Q, int n_groups, int n_starts, const double* lb, const double* ub,
+                                             const double* prior_loc, const double* prior_scale, const double* x0, double fatol,
+                                             double frtol, double gtol) {
+    auto bad = [](const char* m) -> pv_optimizer* {
+        fail(PV_E_ARG, std::string("pv_optimizer_create: ") + m);
+        return nullptr;
+    };
+    if (!p || !lb || !ub || !prior_loc || !prior_scale || !x0) return bad("NULL argument");
+    const int NP = (int)p->col_target.size(), G = n_groups, S = n_starts;
+    if (Q < 1 || G < 1 || S < 1) return bad("Q, n_groups, n_starts must be >= 1");
+    const int dim = NP * G;
+    if (NP < 1 || NP > 8 || dim > PV_OPT_MAXD) return bad("configure the per-group parameters as columns first (n_cols <= 8, n_cols * n_groups <= 16)");
+    if (p->stats.empty() || p->n_data != Q * G) return bad("the problem must hold one data set per (problem, group): n_data == Q * n_groups");
+    if (cudaSetDevice(p->device) != cudaSuccess) return bad("cudaSetDevice failed");
+    auto* o = new pv_optimizer();
+    o->p = p;
+    memset(&o->d, 0, sizeof(o->d));
+    pv_opt_dev& d = o->d;
+    d.Q = Q; d.S = S; d.G = G; d.NP = NP; d.dim = dim; d.NS = p->tab->n_sens;
+    d.fatol = fatol; d.frtol = frtol; d.gtol = gtol;
+    for (int j = 0; j < NP; ++j) {
+        int row = -1;
+        for (int k = 0; k < p->tab->n_sens; ++k)
+            if (p->tab->sens_index[k] == p->col_target[j]) row = k;
+        if (row < 0) {
+            delete o;
+            fail(PV_E_MODEL, "pv_optimizer_create: a column is not a compiled sensitivity parameter of the model");
+            return nullptr;
+        }
+        d.sens_row[j] = row;
+    }
+    const int64_t QS = Q * S, B = QS * G;
+    const int ns = d.NS;
+    bool ok = cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) == cudaSuccess;
+    d.x = optimizer_alloc<double>(o, QS * dim); d.f = optimizer_alloc<double>(o, QS); d.g = optimizer_alloc<double>(o, QS * dim);
+    d.H = optimizer_alloc<double>(o, QS * dim * dim); d.lam = optimizer_alloc<double>(o, QS);
+    d.active = optimizer_alloc<unsigned char>(o, QS); d.converged = optimizer_alloc<unsigned char>(o, QS);
+    d.n_iter = optimizer_alloc<int>(o, QS);
+    d.x_try = optimizer_alloc<double>(o, QS * dim); d.p = optimizer_alloc<double>(o, QS * dim); d.pred = optimizer_alloc<double>(o, QS);
+    d.P = optimizer_alloc<double>(o, (size_t)NP * B);
+    o->d_logp = optimizer_alloc<double>(o, B); o->d_grad = optimizer_alloc<double>(o, (size_t)ns * B);
+    o->d_fim = optimizer_alloc<double>(o, (size_t)(ns * (ns + 1) / 2) * B); o->d_status = optimizer_alloc<int32_t>(o, B);
+    double* d_lb = optimizer_alloc<double>(o, dim); double* d_ub = optimizer_alloc<double>(o, dim);
+    double* d_pl = optimizer_alloc<double>(o, Q * dim); double* d_ps = optimizer_alloc<double>(o, Q * dim);
+    d.n_evals = optimizer_alloc<unsigned long long>(o, 1); d.n_active = optimizer_alloc<int>(o, 1);
+    for (void* a : o->allocs) ok = ok && a != nullptr;
+    if (!ok) {
+        fail(PV_E_CUDA, std::string("pv_optimizer_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+        pv_optimizer_destroy(o);
+        return nullptr;
+    }
+    d.logp = o->d_logp; d.grad = o->d_grad; d.fim = o->d_fim;
+    d.lb = d_lb; d.ub = d_ub; d.prior_loc = d_pl; d.prior_scale = d_ps;
+    std::vector<double> hx((size_t)QS * dim);
+    for (int64_t k = 0; k < QS; ++k)
+        for (int i = 0; i < dim; ++i) hx[k * dim + i] = std::min(std::max(x0[k * dim + i], lb[i]), ub[i]);
+    auto up = [&](double* dst, const double* src, size_t n) { return cudaMemcpy(dst, src, sizeof(double) * n, cudaMemcpyHostToDevice) == cudaSuccess; };
+    ok = up(d.x, hx.data(), hx.size()) && up(d_lb, lb, dim) && up(d_ub, ub, dim) && up(d_pl, prior_loc, (size_t)Q * dim) &&
+         up(d_ps, prior_scale, (size_t)Q * dim) && cudaStreamSynchronize(0) == cudaSuccess;
+    int rc = ok ? optimizer_enqueue(o, 1) : PV_E_CUDA;          // objective at the start points
+    if (!rc && cudaStreamSynchronize(o->stream) != cudaSuccess) rc = PV_E_CUDA;
+    if (rc) {
+        if (rc == PV_E_CUDA) fail(PV_E_CUDA, std::string("pv_optimizer_create: ") + cudaGetErrorString(cudaGetLastError()));
+        pv_optimizer_destroy(o);
+        return nullptr;
+    }
+    return o;
+}
+
+extern "C" int pv_optimizer_run(pv_optimizer* o, int max_iter, int poll_every, int* iterations_done) {
+    if (!o || max_iter < 0 || poll_every < 1) return fail(PV_E_ARG, "pv_optimizer_run: bad arguments");
+    CUDA_OK(cudaSetDevice(o->p->device));
+    int n_active = 0;
+    CUDA_OK(cudaMemcpyAsync(&n_active, o->d.n_active, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+    CUDA_OK(cudaStreamSynchronize(o->stream));
+    int it = 0;
+    while (it < max_iter && n_active > 0) {
+        const int burst = std::min(poll_every, max_iter - it);
+        for (int k = 0; k < burst; ++k)
+            if (int rc = optimizer_enqueue(o, 0)) return rc;
+        it += burst;
+        // iterations past the point where the last start finished change nothing (every thread is masked by `active`)
+        CUDA_OK(cudaMemcpyAsync(&n_active, o->d.n_active, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+        CUDA_OK(cudaStreamSynchronize(o->stream));
+    }
+    o->iterations += it;
+    if (iterations_done) *iterations_done = o->iterations;
+    return n_active;
+}
+
+extern "C" int pv_optimizer_result(pv_optimizer* o, double* x_host, double* f_host, double* g_host, int32_t* n_iter_host,
+                                   uint8_t* converged_host, int64_t* n_evals) {
+    if (!o) return fail(PV_E_ARG, "pv_optimizer_result: optimizer is NULL");
+    const pv_opt_dev& d = o->d;
+    CUDA_OK(cudaSetDevice(o->p->device));
+    CUDA_OK(cudaStreamSynchronize(o->stream));
+    const int64_t QS = d.Q * d.S;
+    unsigned long long ne = 0;
+    auto down = [&](void* dst, const void* src, size_t bytes) { return !dst || cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess; };
+    const bool ok = down(x_host, d.x, sizeof(double) * QS * d.dim) && down(f_host, d.f, sizeof(double) * QS) &&
+                    down(g_host, d.g, sizeof(double) * QS * d.dim) && down(n_iter_host, d.n_iter, sizeof(int) * QS) &&
+                    down(converged_host, d.converged, QS) && down(&ne, d.n_evals, sizeof(ne));
+    if (!ok) return fail(PV_E_CUDA, std::string("pv_optimizer_result: ") + cudaGetErrorString(cudaGetLastError()));
+    if (n_evals) *n_evals = (int64_t)ne;
     return 0;
 }
 

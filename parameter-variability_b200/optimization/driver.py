@@ -74,14 +74,17 @@ class GpuPetabSampler:
 
     # ---- stages ------------------------------------------------------------------------------------------------------------
     def run_optimization(self, maxiter: float = 1e4, fatol: float = 1e-12, frtol: float = 1e-12, n_starts: int = 100,
-                         seed: int = 1234, **_):
+                         seed: int = 1234, device_loop: bool = True, **_):
         """Multistart optimisation (:99-156).  Start points are uniform in the bounds like the reference
         (``pypesto.startpoint.uniform`` on [0, 1e8], :120-121) unless a ``start_box`` was given."""
         lb, ub = self.objective.lb, self.objective.ub
         slb, sub = self.start_box if self.start_box is not None else (lb, ub)
         x0 = opt_mod.uniform_startpoints(n_starts, np.asarray(slb, float), np.asarray(sub, float), Q=self.objective.Q, seed=seed)
         t0 = time.perf_counter()
-        self.optimize_result = opt_mod.minimize(self._eval_opt, x0, lb, ub, maxiter=int(min(maxiter, 1e4)), fatol=fatol, frtol=frtol)
+        if device_loop:       # the whole loop on the GPU; False = numpy loop, one objective launch per iteration
+            self.optimize_result = opt_mod.minimize_device(self.objective, x0, maxiter=int(min(maxiter, 1e4)), fatol=fatol, frtol=frtol)
+        else:
+            self.optimize_result = opt_mod.minimize(self._eval_opt, x0, lb, ub, maxiter=int(min(maxiter, 1e4)), fatol=fatol, frtol=frtol)
         self.optim_duration = time.perf_counter() - t0
         return self.optimize_result
 

@@ -86,3 +86,41 @@ def minimize(evaluate: Callable[[np.ndarray], dict], x0: np.ndarray, lb: np.ndar
     take = lambda a: np.take_along_axis(a, order[(...,) + (None,) * (a.ndim - 2)], axis=1)  # noqa: E731
     return OptimizeResult(x=take(x), fval=take(f), grad=take(g), n_iter=take(n_iter), converged=take(converged),
                           x0=take(np.clip(np.asarray(x0, dtype=np.float64), lb, ub)), n_evals=n_evals)
+
+
+def minimize_device(objective, x0: np.ndarray, maxiter: int = 200, fatol: float = 1e-12, frtol: float = 1e-12, gtol: float = 1e-8,
+                    poll_every: int = 4) -> OptimizeResult:
+    """``minimize`` with the whole loop on the GPU (``pv_optimizer_create`` / ``run`` / ``result``): iterate, gradient, FIM,
+    damping and convergence flags of every start of every problem stay in HBM; one iteration is step kernel -> batched
+    objective with Fisher information -> update kernel.  ``objective`` is a ``PetabObjectiveBatch`` (problem, priors and
+    bounds are taken from it).  Same steps, same accept and stopping rules as the numpy statement above."""
+    import ctypes
+    from .. import runtime
+    lib = runtime.load_library() if objective.problem._lib is None else objective.problem._lib
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    Q, S, dim = x0.shape
+    if Q != objective.Q or dim != objective.dim:
+        raise ValueError(f"x0 must be [{objective.Q}, S, {objective.dim}]")
+    lb = np.ascontiguousarray(np.broadcast_to(np.asarray(objective.lb, dtype=np.float64), (dim,)))
+    ub = np.ascontiguousarray(np.broadcast_to(np.asarray(objective.ub, dtype=np.float64), (dim,)))
+    ploc = np.ascontiguousarray(objective.prior_loc, dtype=np.float64)
+    pscale = np.ascontiguousarray(np.where(np.isfinite(objective.prior_loc), objective.prior_scale, 1.0), dtype=np.float64)
+    ptr = lambda a: a.ctypes.data   # noqa: E731
+    h = lib.pv_optimizer_create(objective.problem._h, Q, objective.G, S, ptr(lb), ptr(ub), ptr(ploc), ptr(pscale), ptr(x0),
+                                float(fatol), float(frtol), float(gtol))
+    if not h:
+        raise runtime.ParvarB200Error(f"pv_optimizer_create failed: {runtime.last_error()}")
+    try:
+        done = ctypes.c_int(0)
+        runtime._check(lib.pv_optimizer_run(h, int(maxiter), int(poll_every), ctypes.addressof(done)))
+        x, f, g = np.empty((Q, S, dim)), np.empty((Q, S)), np.empty((Q, S, dim))
+        n_iter, conv = np.empty((Q, S), dtype=np.int32), np.empty((Q, S), dtype=np.uint8)
+        ne = ctypes.c_int64(0)
+        runtime._check(lib.pv_optimizer_result(h, ptr(x), ptr(f), ptr(g), ptr(n_iter), ptr(conv), ctypes.addressof(ne)))
+    finally:
+        lib.pv_optimizer_destroy(h)
+    objective.n_evals += int(ne.value)
+    order = np.argsort(np.where(np.isfinite(f), f, np.inf), axis=1, kind="stable")
+    take = lambda a: np.take_along_axis(a, order[(...,) + (None,) * (a.ndim - 2)], axis=1)  # noqa: E731
+    return OptimizeResult(x=take(x), fval=take(f), grad=take(g), n_iter=take(n_iter.astype(int)), converged=take(conv.astype(bool)),
+                          x0=take(np.clip(x0, lb, ub)), n_evals=int(ne.value))

@@ -81,6 +81,10 @@ ABI = {
     "pv_rng_sampler_block": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pv_sampler_result": (C.c_int, [C.c_void_p] * 9),
     "pv_sampler_destroy": (None, [C.c_void_p]),
+    "pv_optimizer_create": (C.c_void_p, [C.c_void_p, C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_double] * 3),
+    "pv_optimizer_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "pv_optimizer_result": (C.c_int, [C.c_void_p] * 7),
+    "pv_optimizer_destroy": (None, [C.c_void_p]),
     "pv_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "pv_fma_peak_tflops": (C.c_double, [C.c_int, C.c_int, C.c_int]),
     "pv_host_alloc": (C.c_void_p, [C.c_size_t]),

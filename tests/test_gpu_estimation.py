@@ -192,6 +192,42 @@ def test_multistart_optimizer_recovers_parameters(cuda_lib, rt, oracle):
     assert (res.converged[:, 0]).all()
 
 
+def test_device_resident_optimizer_takes_the_host_loops_steps(cuda_lib, rt, oracle):
+    """``optimizer.minimize_device`` (pv_optimizer_create / run / result: the multistart trust-region loop on the GPU) against
+    ``optimizer.minimize`` (numpy loop, one objective launch per iteration) from the same start points: per start the same
+    number of iterations and the same convergence flag, final iterates and objective values equal up to round-off; priors,
+    bounds that bind, starts in stiff corners of the box [0, 1e8] (failed / re-run evaluations) included."""
+    po = pkg("optimization.petab_optimization")
+    om = pkg("optimization.optimizer")
+    drv = pkg("optimization.driver")
+    t = np.linspace(0, 30, 16)
+    truths = [{"MALE": (0.8, 1.1), "FEMALE": (1.3, 0.6)}, {"MALE": (2.0, 0.4), "FEMALE": (0.5, 1.8)}, {"MALE": (1.0, 1.0), "FEMALE": (1.0, 1.0)}]
+    problems = [_pk_groups(oracle, t, tr, 3, 0.05, 1 + k) for k, tr in enumerate(truths)]
+    priors = [{"k_abs_MALE": (0.5, 1.0), "CL_FEMALE": (0.5, 2.0)}, {}, {"k_abs_MALE": (1.0, 0.1), "k_abs_FEMALE": (1.0, 0.1), "CL_MALE": (1.0, 0.1), "CL_FEMALE": (1.0, 0.1)}]
+    batch = po.PetabObjectiveBatch("simple_pk", ["k_abs", "CL"], problems, t, OBS, sigma=0.05, priors=priors, rtol=1e-9, atol=1e-13)
+    batch.lb = np.array([0.0, 0.0, 0.7, 0.0])                   # a lower bound above problem 1's optimum for CL_MALE: it binds
+    S = 20
+    x0 = om.uniform_startpoints(S, np.full(4, 0.05), np.full(4, 5.0), Q=3, seed=3)
+    x0[:, -2:] = om.uniform_startpoints(2, np.zeros(4), np.full(4, 1e8), Q=3, seed=4)      # two starts per problem anywhere in [0, 1e8]
+    d = drv.GpuPetabSampler(batch)
+    host = om.minimize(d._eval_opt, x0, batch.lb, batch.ub, maxiter=60)
+    n0 = rt.launch_count()
+    dev = om.minimize_device(batch, x0, maxiter=60)
+    assert rt.launch_count() - n0 >= 3 * int(dev.n_iter.max())
+    # both results are sorted by objective value; undo that through the (unique) start points
+    for q in range(3):
+        hi = {tuple(np.round(a, 12)): k for k, a in enumerate(host.x0[q])}
+        perm = [hi[tuple(np.round(a, 12))] for a in dev.x0[q]]
+        np.testing.assert_array_equal(dev.n_iter[q], host.n_iter[q][perm])
+        np.testing.assert_array_equal(dev.converged[q], host.converged[q][perm])
+        np.testing.assert_allclose(dev.fval[q], host.fval[q][perm], rtol=1e-9)
+        np.testing.assert_allclose(dev.x[q], host.x[q][perm], rtol=1e-7, atol=1e-9)
+    assert dev.n_evals == host.n_evals
+    assert dev.converged[:, 0].all() and dev.x[1, 0, 2] == pytest.approx(0.7)       # the binding bound
+    want = np.array([truths[0]["MALE"][0], truths[0]["FEMALE"][0], truths[0]["MALE"][1], truths[0]["FEMALE"][1]])
+    np.testing.assert_allclose(dev.x[0, 0], want, rtol=0.2)
+
+
 def test_sampler_posterior_matches_laplace(cuda_lib, rt, oracle):
     """simple_chain, one well-identified parameter per group: the sampled posterior must agree with the Laplace
     approximation (mean = optimum, sd = FIM^-1/2) that the optimiser's own quantities give."""

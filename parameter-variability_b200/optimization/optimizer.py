@@ -109,14 +109,14 @@ def minimize_device(objective, x0: np.ndarray, maxiter: int = 200, fatol: float 
     h = lib.pv_optimizer_create(objective.problem._h, Q, objective.G, S, ptr(lb), ptr(ub), ptr(ploc), ptr(pscale), ptr(x0),
                                 float(fatol), float(frtol), float(gtol))
     if not h:
-        raise runtime.ParvarB200Error(f"pv_optimizer_create failed: {runtime.last_error()}")
+        raise runtime.ParvarB200Error(f"pv_optimizer_create failed: {runtime.last_error(lib)}")
     try:
         done = ctypes.c_int(0)
-        runtime._check(lib.pv_optimizer_run(h, int(maxiter), int(poll_every), ctypes.addressof(done)))
+        runtime._check(lib.pv_optimizer_run(h, int(maxiter), int(poll_every), ctypes.addressof(done)), lib)
         x, f, g = np.empty((Q, S, dim)), np.empty((Q, S)), np.empty((Q, S, dim))
         n_iter, conv = np.empty((Q, S), dtype=np.int32), np.empty((Q, S), dtype=np.uint8)
         ne = ctypes.c_int64(0)
-        runtime._check(lib.pv_optimizer_result(h, ptr(x), ptr(f), ptr(g), ptr(n_iter), ptr(conv), ctypes.addressof(ne)))
+        runtime._check(lib.pv_optimizer_result(h, ptr(x), ptr(f), ptr(g), ptr(n_iter), ptr(conv), ctypes.addressof(ne)), lib)
     finally:
         lib.pv_optimizer_destroy(h)
     objective.n_evals += int(ne.value)

@@ -213,14 +213,14 @@ def _sample_native(evaluate, x0, lb, ub, n_samples, n_chains, seed, cov0, decay_
     for it in range(1, n_samples + 1):
         xi = rs.normal(size=(Q, C, dim))
         if lib.pv_sampler_propose(Q, C, dim, p_cov, p_x, ptr(xi), *a_propose) < 0:
-            raise runtime.ParvarB200Error(runtime.last_error())
+            raise runtime.ParvarB200Error(runtime.last_error(lib))
         llh_new, lpr_new = (np.ascontiguousarray(a, dtype=np.float64) for a in evaluate(x_eval))
         n_evals += Q * C
         u_acc = rs.uniform(size=(Q, C))
         for k in range(C - 1, 0, -1):
             u_swap[:, k - 1] = rs.uniform(size=Q)
         if lib.pv_sampler_step(Q, C, dim, it, n_tr, p_opts, *a_state, ptr(llh_new), ptr(lpr_new), p_inside, ptr(u_acc), *a_rest):
-            raise runtime.ParvarB200Error(runtime.last_error())
+            raise runtime.ParvarB200Error(runtime.last_error(lib))
     return SampleResult(trace_x=np.ascontiguousarray(trace_x.transpose(1, 2, 0, 3)),
                         trace_neglogpost=np.ascontiguousarray(trace_lp.transpose(1, 2, 0)),
                         trace_neglogprior=np.ascontiguousarray(trace_pr.transpose(1, 2, 0)), betas=betas,
@@ -242,7 +242,7 @@ def sample_device(objective, x0: np.ndarray, n_samples: int = 5000, n_chains: in
     by numpy calls here."""
     import ctypes
     from .. import runtime
-    lib = runtime.load_library()
+    lib = objective.problem._lib or runtime.load_library()     # a run-time compiled model's own library owns its handle
     rs = np.random.RandomState(seed)
     x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=np.float64)))
     Q, dim = x0.shape
@@ -261,7 +261,7 @@ def sample_device(objective, x0: np.ndarray, n_samples: int = 5000, n_chains: in
     h = lib.pv_sampler_create(objective.problem._h, Q, objective.G, C, int(n_samples), ctypes.addressof(opts), ptr(lb), ptr(ub),
                               ptr(ploc), ptr(pscale), ptr(x0), ptr(c0), K, int(bool(use_graph)))
     if not h:
-        raise runtime.ParvarB200Error(f"pv_sampler_create failed: {runtime.last_error()}")
+        raise runtime.ParvarB200Error(f"pv_sampler_create failed: {runtime.last_error(lib)}")
     import time
     tm = {"rng_s": 0.0, "advance_s": 0.0, "result_s": 0.0}
     try:
@@ -270,7 +270,7 @@ def sample_device(objective, x0: np.ndarray, n_samples: int = 5000, n_chains: in
         while mt is not None and done < n_samples:
             n = min(K, n_samples - done)
             t_a = time.perf_counter()
-            runtime._check(lib.pv_sampler_advance_mt(h, n, ctypes.addressof(mt)))
+            runtime._check(lib.pv_sampler_advance_mt(h, n, ctypes.addressof(mt)), lib)
             tm["advance_s"] += time.perf_counter() - t_a
             done += n
         while done < n_samples:
@@ -283,7 +283,7 @@ def sample_device(objective, x0: np.ndarray, n_samples: int = 5000, n_chains: in
                 for j in range(C - 1, 0, -1):
                     us[k, :, j - 1] = rs.uniform(size=Q)
             t_b = time.perf_counter()
-            runtime._check(lib.pv_sampler_advance(h, n, ptr(xi), ptr(ua), ptr(us)))
+            runtime._check(lib.pv_sampler_advance(h, n, ptr(xi), ptr(ua), ptr(us)), lib)
             tm["rng_s"] += t_b - t_a
             tm["advance_s"] += time.perf_counter() - t_b
             done += n
@@ -293,7 +293,7 @@ def sample_device(objective, x0: np.ndarray, n_samples: int = 5000, n_chains: in
         betas, n_acc, n_swap, n_swap_try = np.empty((Q, C)), np.empty((Q, C)), np.empty((Q, S)), np.empty((Q, S))
         n_bad = ctypes.c_int64(0)
         runtime._check(lib.pv_sampler_result(h, ptr(trace_x), ptr(trace_lp), ptr(trace_pr), ptr(betas), ptr(n_acc), ptr(n_swap),
-                                             ptr(n_swap_try), ctypes.addressof(n_bad)))
+                                             ptr(n_swap_try), ctypes.addressof(n_bad)), lib)
         tm["result_s"] = time.perf_counter() - t_a
     finally:
         lib.pv_sampler_destroy(h)

@@ -140,14 +140,17 @@ def load_library(path: Optional[Path] = None) -> C.CDLL:
     return lib
 
 
-def last_error() -> str:
-    msgs = [(lib.pv_last_error() or b"").decode() for lib in [load_library(), *_model_libs.values()]]
-    return next((m for m in reversed(msgs) if m), "")
+def last_error(lib: Optional[C.CDLL] = None) -> str:
+    """Message of the last failed call of this thread in `lib` (every library keeps its own); without `lib` the
+    base library's, then the run-time compiled model libraries'."""
+    libs = [lib] if lib is not None else [load_library(), *_model_libs.values()]
+    msgs = [(l.pv_last_error() or b"").decode() for l in libs]
+    return next((m for m in msgs if m), "")
 
 
-def _check(rc: int) -> int:
+def _check(rc: int, lib: Optional[C.CDLL] = None) -> int:
     if rc < 0:
-        raise ParvarB200Error(f"parvar_b200 error {rc}: {last_error()}")
+        raise ParvarB200Error(f"parvar_b200 error {rc}: {last_error(lib)}")
     return rc
 
 
@@ -206,11 +209,11 @@ class Problem:
         # "name@fingerprint" = a run-time compiled model: inside its library it is just "name"
         self._h = self._lib.pv_problem_create(model.split("@")[0].encode(), int(device))
         if not self._h:
-            raise ParvarB200Error(f"cannot create problem for model {model!r}: {last_error()}")
+            raise ParvarB200Error(f"cannot create problem for model {model!r}: {last_error(self._lib)}")
         self.model = model
         self.device = int(device)
         nx, nth, ns = C.c_int(), C.c_int(), C.c_int()
-        _check(self._lib.pv_problem_dims(self._h, C.byref(nx), C.byref(nth), C.byref(ns)))
+        _check(self._lib.pv_problem_dims(self._h, C.byref(nx), C.byref(nth), C.byref(ns)), self._lib)
         self.n_states, self.n_theta, self.n_sens = nx.value, nth.value, ns.value
         self.state_ids = [self._lib.pv_problem_state_id(self._h, i).decode() for i in range(self.n_states)]
         self.theta_ids = [self._lib.pv_problem_theta_id(self._h, i).decode() for i in range(self.n_theta)]
@@ -235,59 +238,59 @@ class Problem:
     # ---- configuration -------------------------------------------------------------------
     def set_solver(self, method: int = METHOD_AUTO, rtol: float = 1e-7, atol: float = 1e-10,
                    max_steps: int = 1_000_000) -> None:
-        _check(self._lib.pv_problem_set_solver(self._h, method, rtol, atol, max_steps))
+        _check(self._lib.pv_problem_set_solver(self._h, method, rtol, atol, max_steps), self._lib)
 
     def set_value(self, sid: str, value: float) -> None:
-        _check(self._lib.pv_problem_set_value(self._h, sid.encode(), float(value)))
+        _check(self._lib.pv_problem_set_value(self._h, sid.encode(), float(value)), self._lib)
 
     def reset_values(self) -> None:
-        _check(self._lib.pv_problem_reset_values(self._h))
+        _check(self._lib.pv_problem_reset_values(self._h), self._lib)
 
     def set_columns(self, ids: Sequence[str]) -> None:
         ids = list(ids)
-        _check(self._lib.pv_problem_set_columns(self._h, len(ids), _cstr_array(ids) if ids else None))
+        _check(self._lib.pv_problem_set_columns(self._h, len(ids), _cstr_array(ids) if ids else None), self._lib)
         self.columns = ids
 
     def set_schedule(self, refill_min: int = 0) -> None:
-        _check(self._lib.pv_problem_set_schedule(self._h, int(refill_min)))
+        _check(self._lib.pv_problem_set_schedule(self._h, int(refill_min)), self._lib)
 
     def set_layout(self, layout: int = 0) -> None:
         """LAYOUT_AUTO / LAYOUT_LANE / LAYOUT_SPLIT of the Rosenbrock sensitivity kernels (``pv_problem_set_layout``)."""
-        _check(self._lib.pv_problem_set_layout(self._h, int(layout)))
+        _check(self._lib.pv_problem_set_layout(self._h, int(layout)), self._lib)
 
     def set_locality(self, mode: int = 0) -> None:
         """Locality schedule of the batch launches: 0 = auto, 1 = off, 2 = on (``pv_problem_set_locality``)."""
-        _check(self._lib.pv_problem_set_locality(self._h, int(mode)))
+        _check(self._lib.pv_problem_set_locality(self._h, int(mode)), self._lib)
 
     def set_lockstep(self, mode: int = 0) -> None:
         """Lockstep warps of the DOPRI5 kernels: 0 = auto, 1 = off, 2 = on (``pv_problem_set_lockstep``)."""
-        _check(self._lib.pv_problem_set_lockstep(self._h, int(mode)))
+        _check(self._lib.pv_problem_set_lockstep(self._h, int(mode)), self._lib)
 
     def set_group_lanes(self, mode: int = 0) -> None:
         """One trajectory per group of 1 + n_sens lanes for small DOPRI5 logp + gradient launches: 0 = auto, 1 = off, 2 = on."""
-        _check(self._lib.pv_problem_set_group_lanes(self._h, int(mode)))
+        _check(self._lib.pv_problem_set_group_lanes(self._h, int(mode)), self._lib)
 
     def set_stiffness_detection(self, after_steps: int = 128) -> None:
-        _check(self._lib.pv_problem_set_stiffness_detection(self._h, int(after_steps)))
+        _check(self._lib.pv_problem_set_stiffness_detection(self._h, int(after_steps)), self._lib)
 
     def set_tuning(self, max_ctas_per_sm: int = 0, host_chunk_rows: int = 0) -> None:
         """Launch-configuration knobs (``pv_problem_set_tuning``); 0 = default."""
-        _check(self._lib.pv_problem_set_tuning(self._h, int(max_ctas_per_sm), int(host_chunk_rows)))
+        _check(self._lib.pv_problem_set_tuning(self._h, int(max_ctas_per_sm), int(host_chunk_rows)), self._lib)
 
     def set_stiff_switch(self, switch_steps: int = 4000) -> None:
-        _check(self._lib.pv_problem_set_stiff_switch(self._h, int(switch_steps)))
+        _check(self._lib.pv_problem_set_stiff_switch(self._h, int(switch_steps)), self._lib)
 
     def set_timepoints(self, t: Sequence[float], t0: Optional[float] = None) -> None:
         """Output grid; ``t0`` (default: the first grid point) is where the initial values hold."""
         t = np.ascontiguousarray(t, dtype=np.float64)
         t0 = float(t[0]) if t0 is None else float(t0)
-        _check(self._lib.pv_problem_set_timepoints(self._h, t0, len(t), t.ctypes.data_as(_dp)))
+        _check(self._lib.pv_problem_set_timepoints(self._h, t0, len(t), t.ctypes.data_as(_dp)), self._lib)
         self.timepoints = t.copy()
         self.n_data = 0
 
     def set_observables(self, ids: Sequence[str]) -> None:
         ids = list(ids)
-        _check(self._lib.pv_problem_set_observables(self._h, len(ids), _cstr_array(ids)))
+        _check(self._lib.pv_problem_set_observables(self._h, len(ids), _cstr_array(ids)), self._lib)
         self.observables = [s.strip("[]") for s in ids]
         self.n_data = 0
 
@@ -299,43 +302,43 @@ class Problem:
             raise ValueError(f"stats must have shape (3, {T}, {K}, n_data), got {stats.shape}")
         sigma = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (K,)))
         _check(self._lib.pv_problem_set_data(self._h, noise_model, stats.shape[3], stats.ctypes.data_as(_dp),
-                                             sigma.ctypes.data_as(_dp)))
+                                             sigma.ctypes.data_as(_dp)), self._lib)
         self.n_data = stats.shape[3]
 
     def flops(self, what: str) -> int:
-        return _check(self._lib.pv_problem_flops(self._h, what.encode()))
+        return _check(self._lib.pv_problem_flops(self._h, what.encode()), self._lib)
 
     # ---- device-pointer calls (torch CUDA tensors) --------------------------------------------
     def simulate(self, P, Y=None, status=None, steps=None, stream: int = 0, B: Optional[int] = None) -> None:
         B = int(B if B is not None else (P.shape[-1] if P is not None else 0))
-        _check(self._lib.pv_simulate(self._h, B, _ptr(P), _ptr(Y), _ptr(status), _ptr(steps), stream))
+        _check(self._lib.pv_simulate(self._h, B, _ptr(P), _ptr(Y), _ptr(status), _ptr(steps), stream), self._lib)
 
     def simulate_logp(self, P, Y, logp, status=None, steps=None, stream: int = 0, B: Optional[int] = None) -> None:
         B = int(B if B is not None else P.shape[-1])
-        _check(self._lib.pv_simulate_logp(self._h, B, _ptr(P), _ptr(Y), _ptr(logp), _ptr(status), _ptr(steps), stream))
+        _check(self._lib.pv_simulate_logp(self._h, B, _ptr(P), _ptr(Y), _ptr(logp), _ptr(status), _ptr(steps), stream), self._lib)
 
     def simulate_sens(self, P, Y, S, status=None, steps=None, stream: int = 0, B: Optional[int] = None) -> None:
         B = int(B if B is not None else P.shape[-1])
-        _check(self._lib.pv_simulate_sens(self._h, B, _ptr(P), _ptr(Y), _ptr(S), _ptr(status), _ptr(steps), stream))
+        _check(self._lib.pv_simulate_sens(self._h, B, _ptr(P), _ptr(Y), _ptr(S), _ptr(status), _ptr(steps), stream), self._lib)
 
     def logp(self, P, logp, seg_len: int = 0, logp_seg=None, status=None, steps=None, stream: int = 0,
              B: Optional[int] = None) -> None:
         B = int(B if B is not None else P.shape[-1])
         _check(self._lib.pv_logp(self._h, B, _ptr(P), _ptr(logp), seg_len, _ptr(logp_seg), _ptr(status),
-                                 _ptr(steps), stream))
+                                 _ptr(steps), stream), self._lib)
 
     def logp_grad(self, P, logp, grad, seg_len: int = 0, logp_seg=None, status=None, steps=None,
                   stream: int = 0, B: Optional[int] = None) -> None:
         B = int(B if B is not None else P.shape[-1])
         _check(self._lib.pv_logp_grad(self._h, B, _ptr(P), _ptr(logp), _ptr(grad), seg_len, _ptr(logp_seg),
-                                      _ptr(status), _ptr(steps), stream))
+                                      _ptr(status), _ptr(steps), stream), self._lib)
 
     def hier_logp_grad(self, n_chains: int, n_local: int, theta, mu, omega, dtheta, red, status=None, steps=None,
                        stream: int = 0) -> None:
         """Device-resident hierarchical logp + gradient (``pv_hier_logp_grad``): CUDA tensors in, CUDA tensors out,
         two launches on ``stream``, no synchronisation."""
         _check(self._lib.pv_hier_logp_grad(self._h, int(n_chains), int(n_local), _ptr(theta), _ptr(mu), _ptr(omega),
-                                           _ptr(dtheta), _ptr(red), _ptr(status), _ptr(steps), stream))
+                                           _ptr(dtheta), _ptr(red), _ptr(status), _ptr(steps), stream), self._lib)
 
     # ---- host-buffer calls (numpy) -----------------------------------------------------------
     def simulate_host(self, P: Optional[np.ndarray], B: int, Y: Optional[np.ndarray] = None,
@@ -351,7 +354,7 @@ class Problem:
             Y = np.empty((B, T, K), dtype=np.float64)
         elif Y.shape != (B, T, K) or not Y.flags.c_contiguous:
             raise ValueError(f"Y must be a C-contiguous array of shape ({B}, {T}, {K})")
-        n_failed = _check(self._lib.pv_simulate_host(self._h, B, _ptr(P), _ptr(Y), _ptr(logp), _ptr(status), _ptr(steps)))
+        n_failed = _check(self._lib.pv_simulate_host(self._h, B, _ptr(P), _ptr(Y), _ptr(logp), _ptr(status), _ptr(steps)), self._lib)
         return Y, n_failed
 
     def logp_fim_host(self, P: np.ndarray, seg_len: int = 0):
@@ -361,7 +364,7 @@ class Problem:
         lp, g = np.empty(B), np.empty((self.n_sens, B))
         f = np.empty((self.n_sens * (self.n_sens + 1) // 2, B))
         seg = np.empty(B // seg_len) if seg_len else None
-        nf = _check(self._lib.pv_logp_grad_fim_host(self._h, B, _ptr(P), _ptr(lp), _ptr(g), _ptr(f), seg_len, _ptr(seg)))
+        nf = _check(self._lib.pv_logp_grad_fim_host(self._h, B, _ptr(P), _ptr(lp), _ptr(g), _ptr(f), seg_len, _ptr(seg)), self._lib)
         return lp, g, f, seg, nf
 
     def logp_host(self, P: np.ndarray, seg_len: int = 0, grad: bool = False, out: Optional[np.ndarray] = None):
@@ -375,9 +378,9 @@ class Problem:
         seg = np.empty(B // seg_len) if seg_len else None
         if grad:
             g = np.empty((self.n_sens, B))
-            nf = _check(self._lib.pv_logp_grad_host(self._h, B, _ptr(P), _ptr(lp), _ptr(g), seg_len, _ptr(seg)))
+            nf = _check(self._lib.pv_logp_grad_host(self._h, B, _ptr(P), _ptr(lp), _ptr(g), seg_len, _ptr(seg)), self._lib)
             return lp, g, seg, nf
-        nf = _check(self._lib.pv_logp_host(self._h, B, _ptr(P), _ptr(lp), seg_len, _ptr(seg)))
+        nf = _check(self._lib.pv_logp_host(self._h, B, _ptr(P), _ptr(lp), seg_len, _ptr(seg)), self._lib)
         return lp, None, seg, nf
 
     @property

@@ -493,6 +493,7 @@ template <class M, int METHOD, int MODE, bool OBSID>
 static cudaError_t launch_one(const pv_launch_params& lp, const pv_launch_ctx& cx, size_t shmem, cudaStream_t s) {
     if constexpr (METHOD == 1) {
         if (cx.lockstep) {
+            shmem += pv_lockstep_stage_bytes<MODE>;
             if ((MODE & PV_MODE_LOGP) && lp.n_data == 1)
                 return launch_persistent<M>(pv_batch_lockstep_kernel<M, MODE, OBSID, (MODE & PV_MODE_LOGP) != 0>, lp, cx, PV_BLOCK, PV_BLOCK, shmem, s);
             return launch_persistent<M>(pv_batch_lockstep_kernel<M, MODE, OBSID, false>, lp, cx, PV_BLOCK, PV_BLOCK, shmem, s);

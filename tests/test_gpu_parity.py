@@ -828,6 +828,62 @@ def test_locality_schedule_and_lockstep_warps(cuda_lib, rt, oracle, B):
     assert n2[:, ok].sum() < (1.15 if B >= 50000 else 1.6) * n0[:, ok].sum()
 
 
+@pytest.mark.parametrize("case", ["pk_all_T50", "pk_two_obs_T13", "pk_one_obs_T31", "chain_T9", "pk_reordered_T3"])
+def test_lockstep_staged_trajectory_store(cuda_lib, rt, oracle, case):
+    """The lockstep kernel stores trajectories through a per-warp shared-memory staging block (pv_sink STAGE: 24 doubles
+    per row between flushes, the warp writes them out row-contiguously).  Every element of Y must be written exactly
+    where the per-lane kernel writes it: full and partial flushes (T * n_obs not a multiple of 24), the compile-time
+    all-states path and the run-time observable selection (n_obs = 1, 2, reordered), a grid whose first point is t0, a
+    ragged last tile, with and without the locality schedule's index map, TRAJ and TRAJ|LOGP launches."""
+    torch = _torch()
+    model, cols, obs, T, sel = {
+        "pk_all_T50": ("simple_pk", ["k_abs", "CL"], ["y_gut", "y_cent", "y_peri"], 50, [0, 1, 2]),
+        "pk_two_obs_T13": ("simple_pk", ["k_abs", "CL"], ["y_cent", "y_peri"], 13, [1, 2]),
+        "pk_one_obs_T31": ("simple_pk", ["k_abs", "CL"], ["y_peri"], 31, [2]),
+        "chain_T9": ("simple_chain", ["k1"], ["S1", "S2"], 9, [0, 1]),
+        "pk_reordered_T3": ("simple_pk", ["k_abs", "CL"], ["y_peri", "y_gut", "y_cent"], 3, [2, 0, 1]),
+    }[case]
+    B = 1000 + 13
+    t = np.linspace(0, 40, T)
+    th = np.stack([lognormal_draws(300 + i, B, 1.0, 0.5) for i in range(len(cols))])
+    pb = _problem(rt, model, cols, t, obs, method=rt.METHOD_DOPRI5)
+    P = torch.from_numpy(th).cuda()
+
+    def run(locality, lockstep, with_logp):
+        pb.set_locality(locality)
+        pb.set_lockstep(lockstep)
+        guard = 64
+        buf = torch.full((B * T * len(obs) + 2 * guard,), -7.0, dtype=torch.float64, device="cuda")
+        Y = buf[guard:guard + B * T * len(obs)].view(B, T, len(obs))
+        st = torch.full((B,), -7, dtype=torch.int32, device="cuda")
+        if with_logp:
+            lp = torch.empty((B,), dtype=torch.float64, device="cuda")
+            pb.simulate_logp(P, Y, lp, status=st)
+        else:
+            pb.simulate(P, Y, status=st)
+        torch.cuda.synchronize()
+        assert int((st != 0).sum()) == 0
+        g = buf.cpu().numpy()
+        assert np.all(g[:guard] == -7.0) and np.all(g[-guard:] == -7.0)      # nothing outside the rows
+        return Y.cpu().numpy()
+
+    Y_lane = run(1, 1, False)                                                  # per-lane kernel, direct stores
+    if model == "simple_pk":
+        ref = np.stack([oracle.simple_pk_exact({"k_abs": th[0, b], "CL": th[1, b]}, t)[:, sel] for b in range(B)])
+    else:
+        ref = np.stack([oracle.simple_chain_exact(th[0, b], t)[:, sel] for b in range(B)])
+    assert parity_violation(Y_lane, ref) <= 1.0
+    data = ref[0]
+    pb.set_data(np.stack([np.ones_like(data), data, data * data])[..., None], 1.0)
+    for locality in (1, 2):
+        Y_a = run(locality, 2, False)
+        Y_b = run(locality, 2, True)
+        assert not np.any(Y_a == -7.0)                                         # every element written
+        assert parity_violation(Y_a, ref) <= 1.0
+        assert np.array_equal(Y_a, Y_b)                                        # TRAJ and TRAJ|LOGP: the same trajectories
+        assert parity_violation(Y_a, Y_lane, rtol=1e-6, atol=1e-9) <= 1.0
+
+
 @pytest.mark.parametrize("noise", ["normal", "lognormal"])
 @pytest.mark.parametrize("model", ["simple_pk", "simple_chain"])
 def test_group_lanes_kernel_matches_lane_kernel_and_oracle(cuda_lib, rt, oracle, model, noise):

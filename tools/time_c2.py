@@ -53,4 +53,5 @@ for _ in range(args.reps):
 e1.record()
 torch.cuda.synchronize()
 print(f"{os.environ.get('PARVAR_B200_LIB') or 'default'} refill={args.refill or 'default'} locality={args.locality} lockstep={args.lockstep} mode={args.mode}: "
-      f"{e0.elapsed_time(e1) / args.reps:.3f} ms  logp_sum={float(lp.sum()):.6f} steps/traj={float(st.sum()) / B:.1f} failed={int((status != 0).sum())}", flush=True)
+      f"{e0.elapsed_time(e1) / args.reps:.3f} ms  logp_sum={float(lp.sum()):.6f} steps/traj={float(st.sum()) / B:.1f} failed={int((status != 0).sum())} "
+      f"Y_bits_checksum={int(Y.view(torch.int64).sum()) if args.mode != 'logp' else 0}", flush=True)

@@ -93,9 +93,10 @@ int pv_problem_set_locality(pv_problem* p, int mode);
  * reproduces itself bit for bit: the work order is deterministic).  mode 0 = auto, 1 = off, 2 = on. */
 int pv_problem_set_lockstep(pv_problem* p, int mode);
 
-/* DOPRI5 logp + gradient of SMALL batches: one trajectory per group of 1 + n_sens neighbouring lanes (state block and
- * sensitivity blocks on different lanes of a lockstep warp, stage state exchanged by shuffles): the dependent chain of
- * a step shrinks by ~(1 + n_sens), which is what bounds a launch that is a single wave (BASELINE config 3: 8 x 1000).
+/* DOPRI5 logp + gradient of SMALL batches: one trajectory per group of n_sens neighbouring lanes of a lockstep warp
+ * (lane k integrates the state block plus sensitivity block k; only the error norm crosses lanes), launched as one-warp
+ * CTAs so that a single-wave launch (BASELINE config 3: 8 x 1000) puts one warp on every scheduler: such a launch lasts
+ * as long as its longest trajectory's dependent chain, and this shortens the chain per step.
  * mode 0 = auto (launches that fit one wave), 1 = off, 2 = on. */
 int pv_problem_set_group_lanes(pv_problem* p, int mode);
 

@@ -521,15 +521,15 @@ static cudaError_t launch_model(int method, int mode, bool obsid, const pv_launc
                        : launch_persistent<M>(pv_rodas4_split_kernel<M, PV_MODE_LOGP_GRAD_FIM>, lp, cx, threads, 32, sh, s);
         }
     }
-    // small batches of DOPRI5 logp + gradient: one trajectory per GROUP of 1 + NS lanes (pv_dopri5_roles.cuh) while the
+    // small batches of DOPRI5 logp + gradient: one trajectory per GROUP of NS lanes (pv_dopri5_pairs.cuh) while the
     // launch fits one wave of that kernel - beyond it the lane-per-trajectory kernels' throughput wins
     if constexpr (M::NS >= 1) {
-        constexpr int TPW = 32 / (1 + M::NS);
-        const int64_t one_wave = (int64_t)cx.num_sms * 4 * (PV_BLOCK / 32) * TPW;
+        // one trajectory per group of NS lanes, one-warp CTAs (pv_dopri5_pairs.cuh); "one wave" = 4 warps per scheduler
+        constexpr int TPW = 32 / M::NS;
+        const int64_t one_wave = (int64_t)cx.num_sms * 16 * TPW;
         if (method == 1 && mode == PV_MODE_LOGP_GRAD && (cx.roles == 2 || (cx.roles == 0 && lp.B <= one_wave))) {
-            const int64_t per_cta = (PV_BLOCK / 32) * TPW;
-            if (lp.n_data == 1) return launch_persistent<M>(pv_batch_roles_kernel<M, true>, lp, cx, PV_BLOCK, per_cta, shmem, s);
-            return launch_persistent<M>(pv_batch_roles_kernel<M, false>, lp, cx, PV_BLOCK, per_cta, shmem, s);
+            if (lp.n_data == 1) return launch_persistent<M>(pv_batch_pairs_kernel<M, true>, lp, cx, PV_PAIRS_BLOCK, TPW, shmem, s);
+            return launch_persistent<M>(pv_batch_pairs_kernel<M, false>, lp, cx, PV_PAIRS_BLOCK, TPW, shmem, s);
         }
     }
     // the all-states-in-order specialisation is compiled for the explicit integrator only (cheap steps, where the

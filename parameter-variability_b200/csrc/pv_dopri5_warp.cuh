@@ -12,11 +12,40 @@
 // Every lane still meets its own tolerance (its error <= the warp's).  Same method, tableau, controller, dense output and
 // stiffness test as pv_dopri5_lane; replaces the reference's per-row CVODE call (petab_factory.py:242-246) likewise.
 #pragma once
+#include <type_traits>
 #include "pv_dopri5.cuh"
+
+// A system may spread ONE trajectory over Sys::GROUP neighbouring lanes (pv_dopri5_pairs.cuh): every lane of the group
+// carries the first Sys::ERR_SHARED components (the state block), the rest are the lane's own; the trajectory's error norm is
+// the mean square over its Sys::ERR_N distinct components.
+template <class Sys, class = void>
+struct pv_group_of {
+    static constexpr int G = 0;      // not grouped: one trajectory per lane
+    static constexpr int ERR_N = Sys::N;
+};
+template <class Sys>
+struct pv_group_of<Sys, std::void_t<decltype(Sys::GROUP)>> {
+    static constexpr int G = Sys::GROUP;
+    static constexpr int ERR_N = Sys::ERR_N;
+};
 
 template <class Sys>
 struct pv_dopri5_warp {
     static constexpr int N = Sys::N;
+    static constexpr int G = pv_group_of<Sys>::G;
+    int group_src = 0;           // first lane of this lane's group (grouped systems)
+    // sum over the lanes of this lane's group
+    PV_D double group_sum(double x) const {
+#if defined(__CUDA_ARCH__)
+        if constexpr (G > 1) {
+            double tot = 0.0;
+#pragma unroll
+            for (int r = 0; r < G; ++r) tot += __shfl_sync(0xffffffffu, x, group_src + r);
+            return tot;
+        }
+#endif
+        return x;
+    }
     double t, h, tend;
     double t_next, t_next1;      // tgrid[jout], tgrid[jout + 1] (1e300 past the end): the second is loaded one output ahead
     double y[2][N], k1[2][N];    // [cur] = state and its derivative at t; [1 - cur] receives y_new / k7 of the step
@@ -132,16 +161,27 @@ struct pv_dopri5_warp {
         Sys::rhs(t + h, YN, ks, K7);
 
         // error estimate: fp32 norm of an fp64 difference, then the warp's maximum
-        double err2d = 0.0;
+        double err2d = 0.0, err2own = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const double e = h * fma(pv_dp5[25], K7[i],
                                      fma(pv_dp5[24], k6[i], fma(pv_dp5[23], k5[i], fma(pv_dp5[22], k4[i], fma(pv_dp5[21], k3[i], pv_dp5[20] * K1[i])))));
             const double sc = atol + rtol * fmax(fabs(Y[i]), fabs(YN[i]));
             const double r = e * pv_rcp_approx(sc);
-            err2d = fma(r, r, err2d);
+            if constexpr (G > 0) {
+                if (i < Sys::ERR_SHARED)
+                    err2d = fma(r, r, err2d);
+                else
+                    err2own = fma(r, r, err2own);
+            } else {
+                err2d = fma(r, r, err2d);
+            }
         }
-        float err2 = (float)(err2d * (1.0 / N));
+        float err2;
+        if constexpr (G > 0)
+            err2 = (float)((err2d + group_sum(err2own)) * (1.0 / pv_group_of<Sys>::ERR_N));
+        else
+            err2 = (float)(err2d * (1.0 / N));
         const bool bad = !(err2 <= 3.0e38f);
         nonfinite_run = bad ? nonfinite_run + 1 : 0;
         dead = dead || nonfinite_run >= 8;

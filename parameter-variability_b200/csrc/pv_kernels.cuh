@@ -601,7 +601,7 @@ pv_batch_lockstep_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
     }
 }
 
-#include "pv_dopri5_roles.cuh"
+#include "pv_dopri5_pairs.cuh"
 
 // ---- deterministic segment sum: one warp per segment, fixed association order --------------------------------
 __global__ void pv_segment_sum_kernel(const double* __restrict__ x, int64_t seg_len, int64_t n_seg,

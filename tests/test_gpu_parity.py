@@ -887,8 +887,8 @@ def test_lockstep_staged_trajectory_store(cuda_lib, rt, oracle, case):
 @pytest.mark.parametrize("noise", ["normal", "lognormal"])
 @pytest.mark.parametrize("model", ["simple_pk", "simple_chain"])
 def test_group_lanes_kernel_matches_lane_kernel_and_oracle(cuda_lib, rt, oracle, model, noise):
-    """pv_problem_set_group_lanes: the small-batch DOPRI5 logp + gradient kernel that spreads a trajectory over 1 + n_sens
-    lanes (pv_dopri5_roles.cuh) against the one-trajectory-per-lane kernel and the exact solution: ragged batch (not a
+    """pv_problem_set_group_lanes: the small-batch DOPRI5 logp + gradient kernel that spreads a trajectory over n_sens
+    lanes (pv_dopri5_pairs.cuh) against the one-trajectory-per-lane kernel and the exact solution: ragged batch (not a
     multiple of the trajectories per warp), per-trajectory data sets and a pooled one, both noise models, a NaN row that
     fails alone, sensitivity columns in a non-compiled order."""
     opt = pkg("optimization.petab_optimization")

@@ -492,7 +492,7 @@ def main() -> None:
             hbm_peak = float(json.loads(peaks_file.read_text())["hbm_gbs"])
             hbm_src = "measured (MEASURED_PEAKS.json)"
         traffic = None
-        tf = ROOT / "profiles" / "r01_dominant_kernel_traffic.json"
+        tf = ROOT / "profiles" / "r02_dominant_kernel_traffic.json"
         if tf.exists() and B == B_PER_GPU:
             traffic = json.loads(tf.read_text())["traffic_bytes_per_launch"]     # from the committed ncu --set full capture
         kernel_ms = ms / args.steps
@@ -517,7 +517,11 @@ def main() -> None:
                          "peak_source": "measured in this run: pv_fma_peak_tflops (register-resident DFMA chains)",
                          "fp32_fma_peak_tflops": peak32,
                          "kernel": "pv_batch_lockstep_kernel<pv_model_simple_pk, TRAJ|LOGP>",
-                         "kernel_ms": kernel_ms, "flops_per_launch": flops_per_launch,
+                         "kernel_ms": kernel_ms,
+                         "kernel_ms_note": "timed region / steps, i.e. the whole step: the lockstep kernel is 96.9 % of it in the ncu "
+                                           "launch list (profiles/r02_bench_launch_list_staged.csv: 2.47 of 2.55 ms; the rest is the "
+                                           "locality sort's seven kernels and METHOD_AUTO's compaction + empty RODAS4 pass)",
+                         "flops_per_launch": flops_per_launch,
                          "flops_per_attempted_step": fl_step,
                          "attempted_steps_per_trajectory": attempted / B, "accepted_steps_per_trajectory": accepted / B,
                          "executed_steps_per_trajectory": executed / B,

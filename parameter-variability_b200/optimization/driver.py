@@ -124,6 +124,37 @@ class GpuPetabSampler:
                         "values": v, "hdi_low": lo, "hdi_high": hi}
         return res
 
+    def results_table(self, settings: dict, pool_tempered_chains: bool = True) -> pd.DataFrame:
+        """``results_df`` of ALL problems of the batch in one frame, without the ``values`` column: the same statistics
+        (mean / std / median / 94 % HDI over the pooled chains, ESS) computed for every (problem, parameter) at once - one
+        sort per batch instead of two per parameter and one small DataFrame per problem (at 2160 problems the per-problem
+        frames were half of the study's estimation time, and they hold the interpreter lock).  Rows in ``results_df`` order."""
+        tr = self.sample_result.trace_x                       # [Q, C, n+1, dim]
+        vals = tr if pool_tempered_chains else tr[:, :1]
+        Q, _, _, dim = vals.shape
+        v = np.ascontiguousarray(np.moveaxis(vals, 3, 1)).reshape(Q, dim, -1)      # [Q, dim, C (n+1)]
+        n = v.shape[2]
+        mean, std = v.mean(axis=2), v.std(axis=2)
+        v.sort(axis=2)                                        # in place: v is this function's copy
+        median = 0.5 * (v[:, :, (n - 1) // 2] + v[:, :, n // 2])
+        k = int(np.floor(0.94 * n))                           # smp_mod.hdi's default probability
+        if k < 1 or k >= n:
+            lo, hi = v[:, :, 0], v[:, :, -1]
+        else:
+            i = np.argmin(v[:, :, k:] - v[:, :, : n - k], axis=2)[..., None]
+            lo = np.take_along_axis(v, i, axis=2)[..., 0]
+            hi = np.take_along_axis(v, i + k, axis=2)[..., 0]
+        names = list(self.objective.x_names)
+        ess = np.asarray(self.sample_result.effective_sample_size, dtype=np.float64)
+        return pd.DataFrame({
+            "id": np.repeat(np.asarray(self.uids, dtype=object), dim),
+            "group": [get_group_from_pid(pid) for pid in names] * Q,
+            "parameter": [get_parameter_from_pid(pid) for pid in names] * Q,
+            "pid": names * Q,
+            "mean": mean.ravel(), "std": std.ravel(), "median": median.ravel(), "ess": np.repeat(ess, dim),
+            "n_samples": settings["n_samples"], "optim_duration": self.optim_duration, "sampler_duration": self.sampler_duration,
+            "hdi_low": lo.ravel(), "hdi_high": hi.ravel()})
+
     def results_df(self, q: int, settings: dict, pool_tempered_chains: bool = True) -> pd.DataFrame:
         rows = []
         for pid, stats in self.results_dict(q, settings, pool_tempered_chains).items():

@@ -377,3 +377,33 @@ def test_batched_effective_sample_size_equals_the_per_chain_statement():
         rest = ch[b:]
         tau = max(smp.autocorrelation_time_sokal(rest[:, p]) for p in range(2))
         assert res.burn_in[q] == b and ess[q] == pytest.approx(len(rest) / (1.0 + tau), rel=1e-12)
+
+
+def test_results_table_matches_the_per_problem_frames():
+    """GpuPetabSampler.results_table (all problems of a batch at once, one sort) against results_df problem by problem:
+    same rows, same order, same columns but ``values``; order statistics (median, HDI bounds) identical, moments to
+    round-off; also with the beta = 1 chain only and an even pooled sample count."""
+    import types
+    import pandas as pd
+    drv = pkg("optimization.driver")
+    rs = np.random.RandomState(5)
+    for Q, C, n, pooled in ((7, 4, 301, True), (3, 3, 50, False), (2, 1, 4, True)):
+        names = ["CL_MALE", "CL_FEMALE", "k_abs_MALE"]
+        d = drv.GpuPetabSampler.__new__(drv.GpuPetabSampler)
+        d.objective = types.SimpleNamespace(x_names=names, Q=Q, dim=len(names))
+        d.uids = [f"xp{q:05d}" for q in range(Q)]
+        d.optim_duration, d.sampler_duration = 1.5, 2.5
+        d.sample_result = types.SimpleNamespace(trace_x=rs.lognormal(size=(Q, C, n, len(names))),
+                                                effective_sample_size=rs.uniform(1, 100, size=Q))
+        settings = {"n_samples": n - 1}
+        tab = d.results_table(settings, pool_tempered_chains=pooled)
+        ref = pd.concat([d.results_df(q, settings, pool_tempered_chains=pooled).drop(columns=["values"]) for q in range(Q)],
+                        ignore_index=True)
+        assert list(tab.columns) == list(ref.columns) and len(tab) == len(ref)
+        for c in tab.columns:
+            if tab[c].dtype.kind == "f":
+                np.testing.assert_allclose(tab[c].to_numpy(), ref[c].to_numpy(), rtol=1e-13, atol=0, err_msg=c)
+            else:
+                assert (tab[c].to_numpy() == ref[c].to_numpy()).all(), c
+        for c in ("median", "hdi_low", "hdi_high"):
+            assert (tab[c].to_numpy() == ref[c].to_numpy()).all(), c

@@ -261,6 +261,22 @@ def logp_grad_leg(rt, torch, dist, rank: int, world: int, local: int) -> dict:
                 ms_h = _timed(torch, dist, world, host_eval, reps)
                 r["e2e"] = {"ms_per_batched_eval": ms_h, "logp_grad_evals_per_s": C / (ms_h * 1e-3),
                             "h2d_bytes_per_eval": int(th.numel() * 8), "d2h_bytes_per_eval": int((H.red.numel() + H.dtheta.numel()) * 8)}
+            if label == "weak":
+                # the consumer the north star names: a gradient-based sampler calling this evaluation at every step, with its own
+                # state on the GPU too (optimization/hmc.py::hmc_device: drift kernel -> evaluation -> kick kernel per leapfrog step)
+                hm = importlib.import_module(PKG + ".optimization.hmc")
+                x0 = np.concatenate([np.log(theta).reshape(C, -1), np.array([[m for m, _ in pop]] * C),
+                                     np.log(np.array([[s_ for _, s_ in pop]] * C))], axis=1)
+                hm.hmc_device(H, x0, n_samples=2, n_warmup=2, n_leapfrog=4, step_size=1e-3, seed=1, keep_theta=False)
+                if world > 1:
+                    dist.barrier()
+                t_h = time.perf_counter()
+                res = hm.hmc_device(H, x0, n_samples=10, n_warmup=10, n_leapfrog=10, step_size=1e-3, seed=1, keep_theta=False)
+                dt_h = time.perf_counter() - t_h
+                r["hmc_device"] = {"leapfrog_steps": int(res.n_grad_evals), "ms_per_leapfrog_step": 1e3 * dt_h / res.n_grad_evals,
+                                   "leapfrog_steps_per_s": res.n_grad_evals / dt_h, "mean_accept": float(np.mean(res.accept_rate)),
+                                   "what": "20 HMC iterations x ~10 leapfrog steps of all 8 chains, sampler state device resident, "
+                                           "wall clock of the whole call (random-number upload and result download included)"}
             if label == "strong_8x1000" and world > 1:
                 # every rank also evaluates ALL individuals alone: the sharded sums must agree with the unsharded ones
                 pb.set_data(np.stack([po.sufficient_statistics(y[i:i + 1], 0) for i in range(n_ind)], axis=-1), case.sigma)

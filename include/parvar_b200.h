@@ -232,6 +232,46 @@ int pv_hier_finish(int n_chains, int n_cols, double* red_dev, const double* mu_d
                    const double* mu_prior_mean_host, const double* mu_prior_sd_host, const double* omega_prior_host,
                    void* stream);
 
+/* ---- Hamiltonian Monte Carlo on the hierarchical posterior, device resident ------------------------------------
+ * The consumer the north star names for the logp + gradient op ("the MCMC / NUTS sampler calls at every step"): static-length
+ * HMC with jitter, dual-averaging step size, one-window diagonal mass adaptation - optimization/hmc.py states the loop in numpy -
+ * with position, momentum, gradient, adaptation state and the kept samples in HBM.  Positive quantities are sampled on the
+ * log scale: x_c = (log theta_ci [n_par], mu_c [n_par], log omega_c [n_par]), Jacobian included.  One leapfrog step =
+ *     pv_hmc_drift -> pv_hier_logp_grad(theta, mu_q, omega -> dtheta, red) [-> caller's all-reduce of red] -> pv_hier_finish
+ *     -> pv_hmc_kick
+ * and one iteration = pv_hmc_begin, L leapfrog steps, [caller's all-reduce of energy], pv_hmc_accept - all queued on one
+ * stream, no host synchronisation.  Every pointer is device memory (fp64 unless noted); arrays of the shape of theta are
+ * [n_par][n_chains * n_local] as pv_hier_logp_grad takes them, hyper arrays [n_chains][2 n_par] = (mu, log omega).
+ * The reference has no gradient-based sampler (pyPESTO's adaptive Metropolis, petab_optimization.py:158-173). */
+typedef struct pv_hmc_state {
+    int32_t n_chains, n_par, own_hyper, reserved;   /* own_hyper: 1 on the ONE rank that accounts for the hyper-parameters' energy terms */
+    int64_t n_local, n_total, first;                /* individuals of a chain on this rank / over all ranks / this rank's first */
+    double *lth, *mu, *lom, *g_lth, *g_hyp, *lp;    /* state of the chains: position, gradient of the log density, log density [n_chains] */
+    double *lth_q, *mu_q, *lom_q, *g_lth_q, *g_hyp_q;   /* trial point of the running trajectory */
+    double *p_lth, *p_hyp;                          /* momenta */
+    double *im_lth, *im_hyp;                        /* diagonal inverse mass */
+    double *eps;                                    /* [n_chains] step size */
+    double *theta, *omega, *dtheta, *red;           /* objective buffers: inputs exp(lth_q), exp(lom_q) [n_chains][n_par]; outputs */
+    double *energy;                                 /* [n_chains][4]: kinetic energy at start / end, Jacobian term, spare (this rank's partials) */
+    int32_t *ok;                                    /* [n_chains] 1 while every evaluation of the trajectory was finite */
+    double *da;                                     /* [n_chains][4] dual averaging: mu, log_eps_bar, h_bar, spare */
+    double *w_mean_lth, *w_m2_lth, *w_mean_hyp, *w_m2_hyp;   /* Welford moments for the mass matrix */
+    double *samples_lth, *samples_hyp, *samples_lp; /* [n_samples][shape of lth] (may be NULL), [n_samples][n_chains][2 n_par] (may be NULL), [n_samples][n_chains] */
+    double *acc_sum;                                /* [n_chains] sum of the acceptance probabilities of the kept iterations */
+    int32_t *n_div;                                 /* [n_chains] divergent kept iterations */
+} pv_hmc_state;
+/* momenta = z / sqrt(inverse mass) from this iteration's standard normals z_dev [n_chains][n_total * n_par + 2 n_par] (numpy
+ * order of optimization/hmc.py: individual-major theta block, then mu, then log omega), kinetic energy, trial point <- state */
+int pv_hmc_begin(const pv_hmc_state* s, const double* z_dev, void* stream);
+/* half kick + drift by scale * eps (scale = 0: evaluate the start point), objective inputs */
+int pv_hmc_drift(const pv_hmc_state* s, double scale, void* stream);
+/* transformed gradient from (dtheta, red), half kick; last != 0: end-of-trajectory energy partials */
+int pv_hmc_kick(const pv_hmc_state* s, double scale, int last, void* stream);
+/* mode 0: adopt the trial point (start); 1: warm-up iteration it (dual averaging; Welford update number w_n > 0; mass matrix and
+ * final step size at it == n_warmup - 1); 2: sampling iteration (kept sample it - n_warmup).  u_dev [n_chains] ~ U(0,1). */
+int pv_hmc_accept(const pv_hmc_state* s, int mode, int64_t it, int64_t n_warmup, const double* u_dev, double target_accept,
+                  double max_energy_error, int adapt_mass, int64_t w_n, void* stream);
+
 /* page-locked host memory for the *_host calls (cudaHostAlloc / cudaFreeHost); NULL on failure */
 void* pv_host_alloc(size_t bytes);
 void pv_host_free(void* ptr);

@@ -22,6 +22,7 @@
 #include "pv_kernels.cuh"
 #include "pv_rosenbrock_split.cuh"
 #include "pv_hier.cuh"
+#include "pv_hmc.cuh"
 #include "pv_schedule.cuh"
 #include "pv_sampler_device.cuh"
 #include "pv_rng_host.cuh"
@@ -836,6 +837,55 @@ extern "C" int pv_hier_finish(int n_chains, int n_par, double* red_dev, const do
         pr.h[q] = omega_prior_host[q];
     }
     pv_hier_finish_kernel<<<(n_chains + 63) / 64, 64, 0, (cudaStream_t)stream>>>(n_chains, n_par, red_dev, mu_dev, omega_dev, pr);
+    g_launches.fetch_add(1);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Hamiltonian Monte Carlo on the hierarchical posterior, device resident (pv_hmc.cuh)
+// ---------------------------------------------------------------------------------------------------------
+static int hmc_check(const pv_hmc_state* s) {
+    if (!s) return fail(PV_E_ARG, "pv_hmc: state is NULL");
+    if (s->n_chains <= 0 || s->n_par < 1 || s->n_par > PV_HIER_MAX_P || s->n_local < 0 || s->n_total < s->n_local || s->first < 0 ||
+        s->first + s->n_local > s->n_total)
+        return fail(PV_E_ARG, "pv_hmc: n_chains > 0, 1 <= n_par <= 8, 0 <= first, first + n_local <= n_total required");
+    const void* need[] = {s->lth, s->mu, s->lom, s->g_lth, s->g_hyp, s->lp, s->lth_q, s->mu_q, s->lom_q, s->g_lth_q, s->g_hyp_q,
+                          s->p_lth, s->p_hyp, s->im_lth, s->im_hyp, s->eps, s->theta, s->omega, s->dtheta, s->red, s->energy,
+                          s->ok, s->da, s->w_mean_lth, s->w_m2_lth, s->w_mean_hyp, s->w_m2_hyp, s->samples_lp, s->acc_sum, s->n_div};
+    for (const void* q : need)
+        if (!q) return fail(PV_E_ARG, "pv_hmc: NULL buffer in the state (only samples_lth / samples_hyp may be NULL)");
+    return 0;
+}
+extern "C" int pv_hmc_begin(const pv_hmc_state* s, const double* z_dev, void* stream) {
+    if (int rc = hmc_check(s)) return rc;
+    if (!z_dev) return fail(PV_E_ARG, "pv_hmc_begin: z is NULL");
+    pv_hmc_begin_kernel<<<s->n_chains, PV_HMC_THREADS, 0, (cudaStream_t)stream>>>(*s, z_dev);
+    g_launches.fetch_add(1);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" int pv_hmc_drift(const pv_hmc_state* s, double scale, void* stream) {
+    if (int rc = hmc_check(s)) return rc;
+    pv_hmc_drift_kernel<<<s->n_chains, PV_HMC_THREADS, 0, (cudaStream_t)stream>>>(*s, scale);
+    g_launches.fetch_add(1);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" int pv_hmc_kick(const pv_hmc_state* s, double scale, int last, void* stream) {
+    if (int rc = hmc_check(s)) return rc;
+    pv_hmc_kick_kernel<<<s->n_chains, PV_HMC_THREADS, 0, (cudaStream_t)stream>>>(*s, scale, last);
+    g_launches.fetch_add(1);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" int pv_hmc_accept(const pv_hmc_state* s, int mode, int64_t it, int64_t n_warmup, const double* u_dev, double target_accept,
+                             double max_energy_error, int adapt_mass, int64_t w_n, void* stream) {
+    if (int rc = hmc_check(s)) return rc;
+    if (mode < 0 || mode > 2 || (mode != 0 && !u_dev) || (mode == 2 && it < n_warmup) || it < 0)
+        return fail(PV_E_ARG, "pv_hmc_accept: mode 0..2, u for modes 1 / 2, it >= n_warmup for mode 2 required");
+    pv_hmc_accept_kernel<<<s->n_chains, PV_HMC_THREADS, 0, (cudaStream_t)stream>>>(*s, mode, it, n_warmup, u_dev, target_accept,
+                                                                                   max_energy_error, adapt_mass, w_n);
     g_launches.fetch_add(1);
     CUDA_OK(cudaGetLastError());
     return 0;

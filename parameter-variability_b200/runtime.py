@@ -70,6 +70,11 @@ ABI = {
                                         C.c_void_p]),
     "pv_hier_logp_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 8),
     "pv_hier_finish": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _dp, _dp, _dp, C.c_void_p]),
+    "pv_hmc_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pv_hmc_drift": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+    "pv_hmc_kick": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p]),
+    "pv_hmc_accept": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int64,
+                                C.c_void_p]),
     "pv_logp_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pv_logp_grad_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pv_launch_count": (C.c_int64, []),
@@ -399,6 +404,15 @@ def hier_finish(n_chains: int, n_cols: int, red, mu, omega, mu_prior_mean, mu_pr
     m, s, h = (np.ascontiguousarray(a, dtype=np.float64) for a in (mu_prior_mean, mu_prior_sd, omega_prior))
     _check(load_library().pv_hier_finish(int(n_chains), int(n_cols), _ptr(red), _ptr(mu), _ptr(omega), m.ctypes.data_as(_dp),
                                          s.ctypes.data_as(_dp), h.ctypes.data_as(_dp), stream))
+
+
+class HMCState(C.Structure):
+    """``pv_hmc_state`` (include/parvar_b200.h): sizes and the device addresses of every buffer of the device-resident HMC."""
+    POINTERS = ["lth", "mu", "lom", "g_lth", "g_hyp", "lp", "lth_q", "mu_q", "lom_q", "g_lth_q", "g_hyp_q", "p_lth", "p_hyp",
+                "im_lth", "im_hyp", "eps", "theta", "omega", "dtheta", "red", "energy", "ok", "da", "w_mean_lth", "w_m2_lth",
+                "w_mean_hyp", "w_m2_hyp", "samples_lth", "samples_hyp", "samples_lp", "acc_sum", "n_div"]
+    _fields_ = [("n_chains", C.c_int32), ("n_par", C.c_int32), ("own_hyper", C.c_int32), ("reserved", C.c_int32),
+                ("n_local", C.c_int64), ("n_total", C.c_int64), ("first", C.c_int64)] + [(n, C.c_void_p) for n in POINTERS]
 
 
 class MT19937State(C.Structure):

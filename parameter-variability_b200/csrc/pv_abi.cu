@@ -493,7 +493,8 @@ static cudaError_t launch_persistent(KernelT kern, const pv_launch_params& lp, c
 template <class M, int METHOD, int MODE, bool OBSID>
 static cudaError_t launch_one(const pv_launch_params& lp, const pv_launch_ctx& cx, size_t shmem, cudaStream_t s) {
     if constexpr (METHOD == 1) {
-        if (cx.lockstep) {
+        // (a time grid / data set so large that the staging block no longer fits keeps the per-lane kernel)
+        if (cx.lockstep && shmem + pv_lockstep_stage_bytes<MODE> <= (size_t)PV_MAX_DYN_SMEM) {
             shmem += pv_lockstep_stage_bytes<MODE>;
             if ((MODE & PV_MODE_LOGP) && lp.n_data == 1)
                 return launch_persistent<M>(pv_batch_lockstep_kernel<M, MODE, OBSID, (MODE & PV_MODE_LOGP) != 0>, lp, cx, PV_BLOCK, PV_BLOCK, shmem, s);
@@ -688,7 +689,7 @@ static int launch(pv_problem* p, int mode, int64_t B, const double* P, double* Y
         if (int rc = locality_schedule(p, slot, B, P, s, &lp.index_map)) return rc;
     size_t shmem = sizeof(double) * (lp.T + p->tab->n_theta + p->tab->n_states);
     if (need_logp && lp.n_data == 1) shmem += sizeof(double) * PV_QSTRIDE * lp.T * lp.n_obs;
-    if (shmem > 200 * 1024) return fail(PV_E_ARG, "time grid / data too large for shared memory");
+    if (shmem > (size_t)PV_MAX_DYN_SMEM) return fail(PV_E_ARG, "time grid / data too large for shared memory");
     bool obsid = lp.n_obs == p->tab->n_states;
     for (int k = 0; k < lp.n_obs && obsid; ++k) obsid = (lp.obs_idx[k] == k);
     // lockstep warps (one common step size per warp) pay when the lanes integrate similar trajectories: with the locality

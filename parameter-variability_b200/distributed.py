@@ -23,6 +23,21 @@ def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
+def assign_longest_first(costs: dict, world: int) -> dict:
+    """Whole work units (e.g. the time grids of the C5 sweep) to ranks: most expensive first, each to the least loaded
+    rank (ties: the lowest rank; equally expensive units in key order).  A pure function of ``costs``: every rank computes the same
+    assignment without communicating.  Returns {unit: rank}."""
+    if world <= 0:
+        raise ValueError(f"bad world {world}")
+    load = [0.0] * world
+    owner = {}
+    for unit in sorted(costs, key=lambda k: (-float(costs[k]), k)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[unit] = r
+        load[r] += float(costs[unit])
+    return owner
+
+
 class ShardedLikelihood:
     """log-likelihood of ``n_chains`` parameter sets over ``n_individuals`` individuals sharded across ranks.
 

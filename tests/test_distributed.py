@@ -89,3 +89,23 @@ def test_world1_needs_no_process_group():
     th = np.repeat(np.array([[0.5, 1.5], [1.0, 2.0]]), 5, axis=1)
     lp, g, shared = sl(th, shared_grad_rows=(0,))
     assert lp.shape == (2,) and g.shape == (2, 10) and shared.shape == (2, 1)
+
+
+def test_assign_longest_first_is_a_balanced_partition():
+    """The C5 sweep hands whole time grids to ranks (tools/run_study.py): every unit exactly once, the same answer on
+    every rank, the most expensive units on different ranks, loads within one unit of each other."""
+    d = pkg("distributed")
+    grids = [2, 3, 4, 5, 10, 20, 40, 80, 160]
+    costs = {g: 1.0 + g / 160.0 for g in grids}
+    for world in (1, 2, 4, 8, 9, 12):
+        owner = d.assign_longest_first(costs, world)
+        assert owner == d.assign_longest_first(dict(reversed(list(costs.items()))), world)      # input order does not matter
+        assert sorted(owner) == grids and all(0 <= r < world for r in owner.values())
+        load = [sum(costs[g] for g in grids if owner[g] == r) for r in range(world)]
+        used = [x for x in load if x > 0]
+        assert len(used) == min(world, len(grids))
+        assert max(used) - min(used) <= max(costs.values()) + 1e-12
+        top = sorted(grids, key=lambda g: -costs[g])[:min(world, len(grids))]
+        assert len({owner[g] for g in top}) == len(top)
+    with pytest.raises(ValueError):
+        d.assign_longest_first(costs, 0)

@@ -272,6 +272,50 @@ int pv_hmc_kick(const pv_hmc_state* s, double scale, int last, void* stream);
 int pv_hmc_accept(const pv_hmc_state* s, int mode, int64_t it, int64_t n_warmup, const double* u_dev, double target_accept,
                   double max_energy_error, int adapt_mass, int64_t w_n, void* stream);
 
+/* ---- No-U-Turn sampler on the hierarchical posterior, device resident ---------------------------------------------
+ * BASELINE config 3 names NUTS as the consumer of logp + gradient.  Multinomial NUTS (generalised U-turn criterion, iterative
+ * tree building with O(depth) momentum checkpoints, dual averaging, one-window diagonal mass adaptation) as
+ * optimization/nuts.py states it in numpy, with every tree vector in HBM and one CTA per chain; all chains advance in lock
+ * step, one leapfrog step of every growing chain =
+ *     pv_nuts_drift -> pv_hier_logp_grad(theta, mu_q, omega -> dtheta, red) -> pv_hier_finish -> pv_nuts_leaf.
+ * The host reads ic[PV_NUTS_GROWING] after a leaf and ic[PV_NUTS_DONE] after a merge (n_chains ints) and draws the uniforms
+ * (they travel in the kernel parameters).  Coordinates of a chain, in the order of the flat vectors: log theta_ci
+ * (individual-major, n_par each), mu_c [n_par], log omega_c [n_par]; dim = n_ind * n_par + 2 n_par.  One rank (no sharding of
+ * the individuals).  No analogue in the reference (pyPESTO's adaptive Metropolis, petab_optimization.py:158-173). */
+#define PV_NUTS_MAX_CHAINS 64
+enum pv_nuts_vec { PV_NUTS_X, PV_NUTS_G, PV_NUTS_XL, PV_NUTS_RL, PV_NUTS_GL, PV_NUTS_XR, PV_NUTS_RR, PV_NUTS_GR, PV_NUTS_XP,
+                   PV_NUTS_GP, PV_NUTS_RSUM, PV_NUTS_XE, PV_NUTS_RE, PV_NUTS_GE, PV_NUTS_SRSUM, PV_NUTS_SX, PV_NUTS_SG,
+                   PV_NUTS_XN, PV_NUTS_RN, PV_NUTS_GN, PV_NUTS_IM, PV_NUTS_WMEAN, PV_NUTS_WM2, PV_NUTS_NVEC };
+enum pv_nuts_scalar { PV_NUTS_LP, PV_NUTS_H0, PV_NUTS_LPP, PV_NUTS_LOGW, PV_NUTS_SLOGW, PV_NUTS_SLP, PV_NUTS_SUMACC, PV_NUTS_EPS,
+                      PV_NUTS_DA_MU, PV_NUTS_DA_LEB, PV_NUTS_DA_HBAR, PV_NUTS_ACCSUM, PV_NUTS_NSC };
+enum pv_nuts_int { PV_NUTS_DEPTH, PV_NUTS_DONE, PV_NUTS_DIVERGED, PV_NUTS_NLEAF, PV_NUTS_RIGHT, PV_NUTS_LEAF, PV_NUTS_STURN,
+                   PV_NUTS_SDIV, PV_NUTS_GROWING, PV_NUTS_NDIV, PV_NUTS_NIC };
+typedef struct pv_nuts_state {
+    int32_t n_chains, n_par, max_depth, reserved;
+    int64_t n_ind, n_samples;
+    double *vec;            /* [PV_NUTS_NVEC][n_chains][dim] tree vectors, state, inverse mass, Welford moments */
+    double *ck;             /* [2][max_depth + 1][n_chains][dim] momentum / momentum-sum checkpoints */
+    double *sc;             /* [PV_NUTS_NSC][n_chains] */
+    int32_t *ic;            /* [PV_NUTS_NIC][n_chains] */
+    double *theta, *mu_q, *omega, *dtheta, *red;   /* objective buffers as for pv_hier_logp_grad / pv_hier_finish */
+    double *samples;        /* [n_chains][n_samples][dim] */
+    double *samples_lp;     /* [n_chains][n_samples] */
+    int32_t *samples_depth; /* [n_chains][n_samples] */
+} pv_nuts_state;
+typedef struct pv_nuts_uniforms {
+    double u[PV_NUTS_MAX_CHAINS];   /* one U(0,1) per chain */
+} pv_nuts_uniforms;
+/* z_dev [n_chains][dim] standard normals of this iteration */
+int pv_nuts_begin(const pv_nuts_state* s, const double* z_dev, void* stream);
+int pv_nuts_start(const pv_nuts_state* s, const pv_nuts_uniforms* u_direction, void* stream);
+int pv_nuts_drift(const pv_nuts_state* s, void* stream);
+int pv_nuts_leaf(const pv_nuts_state* s, const pv_nuts_uniforms* u_take, double max_energy_error, void* stream);
+int pv_nuts_merge(const pv_nuts_state* s, const pv_nuts_uniforms* u_swap, void* stream);
+/* mode 0: adopt the evaluation of the start point (after drift with every chain not growing, the objective and leaf);
+ * 1: warm-up iteration it (Welford update number w_n > 0; mass matrix and final step size at it == n_warmup - 1); 2: sampling */
+int pv_nuts_finish(const pv_nuts_state* s, int mode, int64_t it, int64_t n_warmup, double target_accept, int adapt_mass,
+                   int64_t w_n, void* stream);
+
 /* page-locked host memory for the *_host calls (cudaHostAlloc / cudaFreeHost); NULL on failure */
 void* pv_host_alloc(size_t bytes);
 void pv_host_free(void* ptr);

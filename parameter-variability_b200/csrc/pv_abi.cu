@@ -23,6 +23,7 @@
 #include "pv_rosenbrock_split.cuh"
 #include "pv_hier.cuh"
 #include "pv_hmc.cuh"
+#include "pv_nuts.cuh"
 #include "pv_schedule.cuh"
 #include "pv_sampler_device.cuh"
 #include "pv_rng_host.cuh"
@@ -891,6 +892,58 @@ extern "C" int pv_hmc_accept(const pv_hmc_state* s, int mode, int64_t it, int64_
     CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// No-U-Turn sampler on the hierarchical posterior, device resident (pv_nuts.cuh)
+// ---------------------------------------------------------------------------------------------------------
+static int nuts_check(const pv_nuts_state* s) {
+    if (!s) return fail(PV_E_ARG, "pv_nuts: state is NULL");
+    if (s->n_chains <= 0 || s->n_chains > PV_NUTS_MAX_CHAINS || s->n_par < 1 || s->n_par > PV_HIER_MAX_P || s->n_ind < 0 ||
+        s->max_depth < 1 || s->max_depth > 20 || s->n_samples < 0)
+        return fail(PV_E_ARG, "pv_nuts: 1 <= n_chains <= 64, 1 <= n_par <= 8, 1 <= max_depth <= 20 required");
+    const void* need[] = {s->vec, s->ck, s->sc, s->ic, s->theta, s->mu_q, s->omega, s->dtheta, s->red, s->samples, s->samples_lp,
+                          s->samples_depth};
+    for (const void* q : need)
+        if (!q) return fail(PV_E_ARG, "pv_nuts: NULL buffer in the state");
+    return 0;
+}
+#define PV_NUTS_LAUNCH(kernel, ...)                                                                  \
+    kernel<<<s->n_chains, PV_NUTS_THREADS, 0, (cudaStream_t)stream>>>(*s, ##__VA_ARGS__);            \
+    g_launches.fetch_add(1);                                                                         \
+    CUDA_OK(cudaGetLastError());                                                                     \
+    return 0;
+extern "C" int pv_nuts_begin(const pv_nuts_state* s, const double* z_dev, void* stream) {
+    if (int rc = nuts_check(s)) return rc;
+    if (!z_dev) return fail(PV_E_ARG, "pv_nuts_begin: z is NULL");
+    PV_NUTS_LAUNCH(pv_nuts_begin_kernel, z_dev)
+}
+extern "C" int pv_nuts_start(const pv_nuts_state* s, const pv_nuts_uniforms* u, void* stream) {
+    if (int rc = nuts_check(s)) return rc;
+    if (!u) return fail(PV_E_ARG, "pv_nuts_start: uniforms are NULL");
+    PV_NUTS_LAUNCH(pv_nuts_start_kernel, *u)
+}
+extern "C" int pv_nuts_drift(const pv_nuts_state* s, void* stream) {
+    if (int rc = nuts_check(s)) return rc;
+    PV_NUTS_LAUNCH(pv_nuts_drift_kernel)
+}
+extern "C" int pv_nuts_leaf(const pv_nuts_state* s, const pv_nuts_uniforms* u, double max_energy_error, void* stream) {
+    if (int rc = nuts_check(s)) return rc;
+    if (!u) return fail(PV_E_ARG, "pv_nuts_leaf: uniforms are NULL");
+    PV_NUTS_LAUNCH(pv_nuts_leaf_kernel, *u, max_energy_error)
+}
+extern "C" int pv_nuts_merge(const pv_nuts_state* s, const pv_nuts_uniforms* u, void* stream) {
+    if (int rc = nuts_check(s)) return rc;
+    if (!u) return fail(PV_E_ARG, "pv_nuts_merge: uniforms are NULL");
+    PV_NUTS_LAUNCH(pv_nuts_merge_kernel, *u)
+}
+extern "C" int pv_nuts_finish(const pv_nuts_state* s, int mode, int64_t it, int64_t n_warmup, double target_accept, int adapt_mass,
+                              int64_t w_n, void* stream) {
+    if (int rc = nuts_check(s)) return rc;
+    if (mode < 0 || mode > 2 || it < 0 || (mode == 2 && (it < n_warmup || it - n_warmup >= s->n_samples)))
+        return fail(PV_E_ARG, "pv_nuts_finish: mode 0..2, n_warmup <= it < n_warmup + n_samples for mode 2 required");
+    PV_NUTS_LAUNCH(pv_nuts_finish_kernel, mode, it, n_warmup, target_accept, adapt_mass, w_n)
+}
+#undef PV_NUTS_LAUNCH
 
 // ---------------------------------------------------------------------------------------------------------
 // host-buffer pipelines

@@ -166,7 +166,7 @@ struct pv_dopri5_warp {
         for (int i = 0; i < N; ++i) {
             const double e = h * fma(pv_dp5[25], K7[i],
                                      fma(pv_dp5[24], k6[i], fma(pv_dp5[23], k5[i], fma(pv_dp5[22], k4[i], fma(pv_dp5[21], k3[i], pv_dp5[20] * K1[i])))));
-            const double sc = atol + rtol * fmax(fabs(Y[i]), fabs(YN[i]));
+            const double sc = atol + rtol * pv_absmax(Y[i], YN[i]);
             const double r = e * pv_rcp_approx(sc);
             if constexpr (G > 0) {
                 if (i < Sys::ERR_SHARED)

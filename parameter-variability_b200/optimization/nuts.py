@@ -214,3 +214,95 @@ def nuts(logp_and_grad: Callable[[np.ndarray], tuple[np.ndarray, np.ndarray]], x
             div_count += diverged
     return NUTSResult(samples=samples, logp=lps, accept_rate=acc_sum / max(n_samples, 1), step_size=eps, inv_mass=inv_mass,
                       tree_depth=depths, divergences=div_count, n_grad_evals=n_evals)
+
+
+def nuts_device(H, x0: np.ndarray, n_samples: int = 500, n_warmup: int = 500, step_size: float = 0.1, target_accept: float = 0.8,
+                max_depth: int = 8, seed: int = 1234, adapt_mass: bool = True, max_energy_error: float = 1000.0) -> NUTSResult:
+    """``nuts`` on the hierarchical posterior with the tree on the GPU (``csrc/pv_nuts.cuh``, entry points ``pv_nuts_begin /
+    _start / _drift / _leaf / _merge / _finish``).  ``H`` is a ``HierarchicalObjectiveDevice`` on ONE rank; ``x0`` [C, dim] in the
+    order log theta_ci (individual-major), mu_c, log omega_c - the parameterisation of ``tests/test_gpu_estimation.py``.
+    Every tree vector, the checkpoints, the adaptation state and the kept samples live in HBM; one leapfrog step of every
+    growing chain is drift kernel -> sensitivity kernel + epilogue -> hyper-prior kernel -> leaf kernel.  The host mirrors the
+    numpy loop's control flow: it reads C flags after each leaf (is any chain still growing) and each doubling (is every chain
+    done) and draws the random numbers in the numpy loop's order - with the same seed both walk the same chains up to round-off."""
+    import ctypes
+    import torch
+    from .. import runtime
+    if H.world != 1:
+        raise ValueError("nuts_device: the individuals must not be sharded (the U-turn tests are dot products over all coordinates)")
+    pb = H.problem
+    lib = pb._lib or runtime.load_library()
+    C, L, P = H.C, H.n_local, H.P
+    dim = L * P + 2 * P
+    if C > runtime.NUTS_MAX_CHAINS:
+        raise ValueError(f"at most {runtime.NUTS_MAX_CHAINS} chains")
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    if x0.shape != (C, dim):
+        raise ValueError(f"x0 must be [{C}, {dim}]")
+    dev = H.red.device
+    rs = np.random.RandomState(seed)
+    V, S, I = ({n: k for k, n in enumerate(names)} for names in (runtime.NUTS_VEC, runtime.NUTS_SC, runtime.NUTS_IC))
+    vec = torch.zeros((len(V), C, dim), dtype=torch.float64, device=dev)
+    ck = torch.zeros((2, max_depth + 1, C, dim), dtype=torch.float64, device=dev)
+    sc = torch.zeros((len(S), C), dtype=torch.float64, device=dev)
+    ic = torch.zeros((len(I), C), dtype=torch.int32, device=dev)
+    vec[V["X"]] = torch.from_numpy(x0).to(dev)
+    vec[V["IM"]] = 1.0
+    sc[S["EPS"]] = float(step_size)
+    sc[S["DA_MU"]] = float(np.log(10.0 * step_size))
+    theta = torch.zeros((P, C, L), dtype=torch.float64, device=dev)
+    mu_q = torch.zeros((C, P), dtype=torch.float64, device=dev)
+    omega = torch.ones((C, P), dtype=torch.float64, device=dev)
+    n_keep = max(int(n_samples), 1)
+    samples = torch.zeros((C, n_keep, dim), dtype=torch.float64, device=dev)
+    samples_lp = torch.zeros((C, n_keep), dtype=torch.float64, device=dev)
+    samples_depth = torch.zeros((C, n_keep), dtype=torch.int32, device=dev)
+    st = runtime.NUTSState()
+    st.n_chains, st.n_par, st.max_depth, st.n_ind, st.n_samples = C, P, int(max_depth), L, n_keep
+    for name, t in (("vec", vec), ("ck", ck), ("sc", sc), ("ic", ic), ("theta", theta), ("mu_q", mu_q), ("omega", omega),
+                    ("dtheta", H.dtheta), ("red", H.red), ("samples", samples), ("samples_lp", samples_lp),
+                    ("samples_depth", samples_depth)):
+        setattr(st, name, t.data_ptr())
+    sp = ctypes.addressof(st)
+    stream = torch.cuda.current_stream().cuda_stream
+    chk = lambda rc: runtime._check(rc, lib)                                               # noqa: E731
+    uni = runtime.NUTSUniforms()
+    up = ctypes.addressof(uni)
+
+    def uniforms(values):
+        uni.u[:C] = [float(x) for x in values]
+        return up
+
+    def leapfrog(u_take):
+        chk(lib.pv_nuts_drift(sp, stream))
+        H(theta, mu_q, omega)
+        chk(lib.pv_nuts_leaf(sp, uniforms(u_take), float(max_energy_error), stream))
+
+    leapfrog(np.zeros(C))                                    # no chain is growing: evaluates the start point
+    n_evals = 1
+    chk(lib.pv_nuts_finish(sp, 0, 0, int(n_warmup), float(target_accept), int(adapt_mass), 0, stream))
+    w_n = 0
+    for it in range(int(n_warmup) + int(n_samples)):
+        warm = it < n_warmup
+        z = torch.from_numpy(rs.normal(size=(C, dim))).to(dev)
+        chk(lib.pv_nuts_begin(sp, z.data_ptr(), stream))
+        done = np.zeros(C, dtype=bool)
+        while not np.all(done):
+            chk(lib.pv_nuts_start(sp, uniforms(rs.uniform(size=C)), stream))
+            growing = ~done
+            while np.any(growing):
+                leapfrog(rs.uniform(size=C))
+                n_evals += 1
+                growing = ic[I["GROWING"]].cpu().numpy() != 0
+            chk(lib.pv_nuts_merge(sp, uniforms(rs.uniform(size=C)), stream))
+            done = ic[I["DONE"]].cpu().numpy() != 0
+        wn = 0
+        if warm and adapt_mass and it >= n_warmup // 2:
+            w_n += 1
+            wn = w_n
+        chk(lib.pv_nuts_finish(sp, 1 if warm else 2, it, int(n_warmup), float(target_accept), int(adapt_mass), wn, stream))
+    torch.cuda.current_stream().synchronize()
+    return NUTSResult(samples=samples.cpu().numpy()[:, :n_samples], logp=samples_lp.cpu().numpy()[:, :n_samples],
+                      accept_rate=sc[S["ACCSUM"]].cpu().numpy() / max(n_samples, 1), step_size=sc[S["EPS"]].cpu().numpy(),
+                      inv_mass=vec[V["IM"]].cpu().numpy(), tree_depth=samples_depth.cpu().numpy()[:, :n_samples].astype(int),
+                      divergences=ic[I["NDIV"]].cpu().numpy().astype(int), n_grad_evals=n_evals)

@@ -70,6 +70,12 @@ ABI = {
                                         C.c_void_p]),
     "pv_hier_logp_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 8),
     "pv_hier_finish": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _dp, _dp, _dp, C.c_void_p]),
+    "pv_nuts_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pv_nuts_start": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pv_nuts_drift": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pv_nuts_leaf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
+    "pv_nuts_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pv_nuts_finish": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_int64, C.c_void_p]),
     "pv_hmc_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pv_hmc_drift": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
     "pv_hmc_kick": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p]),
@@ -413,6 +419,26 @@ class HMCState(C.Structure):
                 "w_mean_hyp", "w_m2_hyp", "samples_lth", "samples_hyp", "samples_lp", "acc_sum", "n_div"]
     _fields_ = [("n_chains", C.c_int32), ("n_par", C.c_int32), ("own_hyper", C.c_int32), ("reserved", C.c_int32),
                 ("n_local", C.c_int64), ("n_total", C.c_int64), ("first", C.c_int64)] + [(n, C.c_void_p) for n in POINTERS]
+
+
+NUTS_MAX_CHAINS = 64
+# slots of pv_nuts_state.vec / .sc / .ic (the enums of include/parvar_b200.h, in order)
+NUTS_VEC = ["X", "G", "XL", "RL", "GL", "XR", "RR", "GR", "XP", "GP", "RSUM", "XE", "RE", "GE", "SRSUM", "SX", "SG", "XN", "RN", "GN",
+            "IM", "WMEAN", "WM2"]
+NUTS_SC = ["LP", "H0", "LPP", "LOGW", "SLOGW", "SLP", "SUMACC", "EPS", "DA_MU", "DA_LEB", "DA_HBAR", "ACCSUM"]
+NUTS_IC = ["DEPTH", "DONE", "DIVERGED", "NLEAF", "RIGHT", "LEAF", "STURN", "SDIV", "GROWING", "NDIV"]
+
+
+class NUTSState(C.Structure):
+    """``pv_nuts_state`` (include/parvar_b200.h)."""
+    POINTERS = ["vec", "ck", "sc", "ic", "theta", "mu_q", "omega", "dtheta", "red", "samples", "samples_lp", "samples_depth"]
+    _fields_ = [("n_chains", C.c_int32), ("n_par", C.c_int32), ("max_depth", C.c_int32), ("reserved", C.c_int32),
+                ("n_ind", C.c_int64), ("n_samples", C.c_int64)] + [(n, C.c_void_p) for n in POINTERS]
+
+
+class NUTSUniforms(C.Structure):
+    """``pv_nuts_uniforms``: one U(0,1) per chain, passed by value inside the kernel parameters."""
+    _fields_ = [("u", C.c_double * NUTS_MAX_CHAINS)]
 
 
 class MT19937State(C.Structure):

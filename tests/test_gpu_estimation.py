@@ -499,3 +499,57 @@ def test_device_resident_hmc_walks_the_numpy_chain(cuda_lib, rt, oracle):
     assert np.all(np.exp(lom_s).mean(axis=0) < 0.8)
     assert np.all(np.isfinite(res.samples))
     pb.close()
+
+
+def test_device_resident_nuts_walks_the_numpy_chain(cuda_lib, rt, oracle):
+    """optimization/nuts.py::nuts_device (pv_nuts_begin / _start / _drift / _leaf / _merge / _finish around the device-resident
+    hierarchical objective) against the numpy loop ``nuts`` around the host objective: same seed -> the same trees (depths,
+    leapfrog counts), step sizes, mass matrix and samples up to round-off over a short run; then a longer run of the device loop
+    alone recovers the population means like the host samplers do."""
+    pytest.importorskip("torch")
+    po = pkg("optimization.petab_optimization")
+    nt = pkg("optimization.nuts")
+    t = np.linspace(0.5, 24, 10)
+    n_ind, C, P = 24, 4, 2
+    rs = np.random.RandomState(0)
+    mu_true, om_true = np.array([0.0, -0.4]), np.array([0.3, 0.25])
+    th_true = np.exp(mu_true + om_true * rs.normal(size=(n_ind, P)))
+    y = np.stack([oracle.simple_pk_exact({"k_abs": a, "CL": c}, t) for a, c in th_true])
+    y = y * (1 + 0.05 * rs.normal(size=y.shape))
+    pb = rt.Problem("simple_pk")
+    pb.set_solver(rtol=1e-8, atol=1e-12)
+    pb.set_columns(["k_abs", "CL"])
+    pb.set_timepoints(t, t0=0.0)
+    pb.set_observables(["y_gut", "y_cent", "y_peri"])
+    pb.set_data(np.stack([po.sufficient_statistics(y[i:i + 1], 0) for i in range(n_ind)], axis=-1), 0.02)
+    priors = dict(mu_prior=[(0.0, 1.0), (0.0, 1.0)], omega_prior=[0.5, 0.5])
+    H = po.HierarchicalObjective(pb, n_ind, **priors)
+    Hd = po.HierarchicalObjectiveDevice(pb, C, n_ind, **priors)
+    dim = n_ind * P + 2 * P
+
+    def lg(X):
+        lth = X[:, :n_ind * P].reshape(-1, n_ind, P)
+        mu, lom = X[:, n_ind * P:n_ind * P + P], X[:, n_ind * P + P:]
+        theta, omega = np.exp(lth), np.exp(lom)
+        lp, dth, dmu, dom = H(theta, mu, omega)
+        return lp + lth.sum(axis=(1, 2)) + lom.sum(axis=1), \
+            np.concatenate([(dth * theta + 1.0).reshape(X.shape[0], -1), dmu, dom * omega + 1.0], axis=1)
+
+    x0 = np.concatenate([np.tile(np.log(th_true).ravel(), (C, 1)) + 0.05 * rs.normal(size=(C, n_ind * P)),
+                         np.zeros((C, P)), np.log(0.3) * np.ones((C, P))], axis=1)
+    kw = dict(n_samples=5, n_warmup=26, step_size=0.02, max_depth=5, seed=6)       # the mass window opens at iteration 13
+    ref = nt.nuts(lg, x0, **kw)
+    got = nt.nuts_device(Hd, x0, **kw)
+    assert got.n_grad_evals == ref.n_grad_evals and np.array_equal(got.tree_depth, ref.tree_depth)
+    assert np.array_equal(got.divergences, ref.divergences)
+    np.testing.assert_allclose(got.step_size, ref.step_size, rtol=1e-5)
+    np.testing.assert_allclose(got.inv_mass, ref.inv_mass, rtol=1e-4)
+    np.testing.assert_allclose(got.accept_rate, ref.accept_rate, rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(got.samples, ref.samples, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(got.logp, ref.logp, rtol=1e-7, atol=1e-5)
+    res = nt.nuts_device(Hd, x0, n_samples=120, n_warmup=150, step_size=0.02, max_depth=6, seed=6)
+    assert np.all(res.accept_rate > 0.55) and res.divergences.sum() <= 6 and res.tree_depth.max() <= 6
+    mu_n = res.samples[:, :, n_ind * P:n_ind * P + P].reshape(-1, P)
+    assert np.all(np.abs(mu_n.mean(axis=0) - np.log(th_true).mean(axis=0)) < 0.25)
+    assert np.all(np.isfinite(res.samples))
+    pb.close()

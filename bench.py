@@ -277,6 +277,18 @@ def logp_grad_leg(rt, torch, dist, rank: int, world: int, local: int) -> dict:
                                    "leapfrog_steps_per_s": res.n_grad_evals / dt_h, "mean_accept": float(np.mean(res.accept_rate)),
                                    "what": "20 HMC iterations x ~10 leapfrog steps of all 8 chains, sampler state device resident, "
                                            "wall clock of the whole call (random-number upload and result download included)"}
+            if label == "weak" and world == 1:
+                # ... and the sampler BASELINE config 3 names: NUTS, tree on the GPU (optimization/nuts.py::nuts_device); the host reads
+                # 8 flags per leapfrog step, so this number includes one stream synchronisation per step
+                nt = importlib.import_module(PKG + ".optimization.nuts")
+                nt.nuts_device(H, x0, n_samples=1, n_warmup=2, step_size=1e-3, max_depth=3, seed=1)
+                t_n = time.perf_counter()
+                rn = nt.nuts_device(H, x0, n_samples=6, n_warmup=6, step_size=1e-3, max_depth=4, seed=1)
+                dt_n = time.perf_counter() - t_n
+                r["nuts_device"] = {"leapfrog_steps": int(rn.n_grad_evals), "ms_per_leapfrog_step": 1e3 * dt_n / rn.n_grad_evals,
+                                    "leapfrog_steps_per_s": rn.n_grad_evals / dt_n, "mean_tree_depth": float(np.mean(rn.tree_depth)),
+                                    "what": "12 NUTS iterations (max depth 4) of all 8 chains, tree state device resident, wall clock of the "
+                                            "whole call"}
             if label == "strong_8x1000" and world > 1:
                 # every rank also evaluates ALL individuals alone: the sharded sums must agree with the unsharded ones
                 pb.set_data(np.stack([po.sufficient_statistics(y[i:i + 1], 0) for i in range(n_ind)], axis=-1), case.sigma)

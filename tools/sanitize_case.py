@@ -78,5 +78,8 @@ Hd = po.HierarchicalObjectiveDevice(pb, C, n_ind, mu_prior=[(0.0, 1.0)] * Pn, om
 x0 = np.concatenate([0.05 * np.random.RandomState(2).normal(size=(C, n_ind * Pn)), np.zeros((C, Pn)), np.log(0.3) * np.ones((C, Pn))], axis=1)
 res = hm.hmc_device(Hd, x0, n_samples=3, n_warmup=14, n_leapfrog=3, step_size=0.02, seed=3)
 assert np.all(np.isfinite(res.samples)) and np.all(np.isfinite(res.logp))
+nt = importlib.import_module("parameter-variability_b200.optimization.nuts")
+rn = nt.nuts_device(Hd, x0, n_samples=2, n_warmup=14, step_size=0.02, max_depth=3, seed=3)
+assert np.all(np.isfinite(rn.samples)) and rn.tree_depth.max() <= 3
 pb.close()
 print("sanitize case ok")

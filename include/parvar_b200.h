@@ -301,6 +301,8 @@ typedef struct pv_nuts_state {
     double *samples;        /* [n_chains][n_samples][dim] */
     double *samples_lp;     /* [n_chains][n_samples] */
     int32_t *samples_depth; /* [n_chains][n_samples] */
+    int32_t *host_flags;    /* [2][n_chains] page-locked HOST memory the kernels write directly (or NULL): ic[PV_NUTS_GROWING] after a
+                             * leaf, ic[PV_NUTS_DONE] after a merge - the host synchronises the stream and reads them, no copy */
 } pv_nuts_state;
 typedef struct pv_nuts_uniforms {
     double u[PV_NUTS_MAX_CHAINS];   /* one U(0,1) per chain */

@@ -257,6 +257,7 @@ __global__ void pv_nuts_leaf_kernel(const pv_nuts_state s, const pv_nuts_uniform
         v.ic(PV_NUTS_LEAF) = leaf + 1;
         v.ic(PV_NUTS_GROWING) = (!sturn && !sdiv && leaf + 1 < (1 << depth)) ? 1 : 0;
     }
+    if (threadIdx.x == 0 && s.host_flags) s.host_flags[c] = v.ic(PV_NUTS_GROWING);
 }
 
 __global__ void pv_nuts_merge_kernel(const pv_nuts_state s, const pv_nuts_uniforms u) {
@@ -294,6 +295,7 @@ __global__ void pv_nuts_merge_kernel(const pv_nuts_state s, const pv_nuts_unifor
         if (sdiv) v.ic(PV_NUTS_DIVERGED) = 1;
         if (sturn || sdiv || whole_turn || depth >= s.max_depth) v.ic(PV_NUTS_DONE) = 1;
     }
+    if (threadIdx.x == 0 && s.host_flags) s.host_flags[s.n_chains + c] = v.ic(PV_NUTS_DONE);
 }
 
 // mode 0: adopt the evaluation of the start point (gn / red of the start -> state); 1: warm-up iteration; 2: sampling iteration

@@ -257,14 +257,18 @@ def nuts_device(H, x0: np.ndarray, n_samples: int = 500, n_warmup: int = 500, st
     samples = torch.zeros((C, n_keep, dim), dtype=torch.float64, device=dev)
     samples_lp = torch.zeros((C, n_keep), dtype=torch.float64, device=dev)
     samples_depth = torch.zeros((C, n_keep), dtype=torch.int32, device=dev)
+    flags = torch.zeros((2, C), dtype=torch.int32).pin_memory()      # written by the leaf / merge kernels, read after a stream sync
+    flags_np = flags.numpy()
     st = runtime.NUTSState()
     st.n_chains, st.n_par, st.max_depth, st.n_ind, st.n_samples = C, P, int(max_depth), L, n_keep
+    st.host_flags = flags.data_ptr()
     for name, t in (("vec", vec), ("ck", ck), ("sc", sc), ("ic", ic), ("theta", theta), ("mu_q", mu_q), ("omega", omega),
                     ("dtheta", H.dtheta), ("red", H.red), ("samples", samples), ("samples_lp", samples_lp),
                     ("samples_depth", samples_depth)):
         setattr(st, name, t.data_ptr())
     sp = ctypes.addressof(st)
-    stream = torch.cuda.current_stream().cuda_stream
+    cur = torch.cuda.current_stream()
+    stream = cur.cuda_stream
     chk = lambda rc: runtime._check(rc, lib)                                               # noqa: E731
     uni = runtime.NUTSUniforms()
     up = ctypes.addressof(uni)
@@ -293,9 +297,11 @@ def nuts_device(H, x0: np.ndarray, n_samples: int = 500, n_warmup: int = 500, st
             while np.any(growing):
                 leapfrog(rs.uniform(size=C))
                 n_evals += 1
-                growing = ic[I["GROWING"]].cpu().numpy() != 0
+                cur.synchronize()
+                growing = flags_np[0] != 0
             chk(lib.pv_nuts_merge(sp, uniforms(rs.uniform(size=C)), stream))
-            done = ic[I["DONE"]].cpu().numpy() != 0
+            cur.synchronize()
+            done = flags_np[1] != 0
         wn = 0
         if warm and adapt_mass and it >= n_warmup // 2:
             w_n += 1

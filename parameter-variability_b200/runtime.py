@@ -431,7 +431,8 @@ NUTS_IC = ["DEPTH", "DONE", "DIVERGED", "NLEAF", "RIGHT", "LEAF", "STURN", "SDIV
 
 class NUTSState(C.Structure):
     """``pv_nuts_state`` (include/parvar_b200.h)."""
-    POINTERS = ["vec", "ck", "sc", "ic", "theta", "mu_q", "omega", "dtheta", "red", "samples", "samples_lp", "samples_depth"]
+    POINTERS = ["vec", "ck", "sc", "ic", "theta", "mu_q", "omega", "dtheta", "red", "samples", "samples_lp", "samples_depth",
+                "host_flags"]
     _fields_ = [("n_chains", C.c_int32), ("n_par", C.c_int32), ("max_depth", C.c_int32), ("reserved", C.c_int32),
                 ("n_ind", C.c_int64), ("n_samples", C.c_int64)] + [(n, C.c_void_p) for n in POINTERS]
 

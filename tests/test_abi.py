@@ -74,3 +74,39 @@ def test_numa_helper_parses_cpulists_and_degrades_without_a_gpu():
     import torch
     if not torch.cuda.is_available():
         assert numa.bind_to_gpu_node(0) is None     # nothing to bind to: the process affinity is left alone
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the header's structs (sampler options, MT19937 state, HMC / NUTS state, NUTS uniforms) have the
+    C compiler's size and field offsets, and the NUTS slot lists follow the header's enums."""
+    import ctypes
+    import shutil
+    import subprocess
+    rt = pkg("runtime")
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    pairs = {"pv_sampler_options": rt.SamplerOptions, "pv_mt19937_state": rt.MT19937State, "pv_hmc_state": rt.HMCState,
+             "pv_nuts_state": rt.NUTSState, "pv_nuts_uniforms": rt.NUTSUniforms}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{ROOT / "include" / "parvar_b200.h"}"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines.append(f'  printf("enums %d %d %d %d\\n", PV_NUTS_NVEC, PV_NUTS_NSC, PV_NUTS_NIC, PV_NUTS_MAX_CHAINS);')
+    lines.append(f'  printf("slots %d %d %d %d %d\\n", PV_NUTS_IM, PV_NUTS_GN, PV_NUTS_EPS, PV_NUTS_GROWING, PV_NUTS_DONE);')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-std=c99", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for line, (cname, cls) in zip(out, pairs.items()):
+        tok = line.split()
+        assert tok[0] == cname
+        assert int(tok[1]) == ctypes.sizeof(cls), cname
+        assert [int(x) for x in tok[2:]] == [getattr(cls, f).offset for f, _ in cls._fields_], cname
+    assert out[-2].split()[1:] == [str(len(rt.NUTS_VEC)), str(len(rt.NUTS_SC)), str(len(rt.NUTS_IC)), str(rt.NUTS_MAX_CHAINS)]
+    assert out[-1].split()[1:] == [str(rt.NUTS_VEC.index("IM")), str(rt.NUTS_VEC.index("GN")), str(rt.NUTS_SC.index("EPS")),
+                                   str(rt.NUTS_IC.index("GROWING")), str(rt.NUTS_IC.index("DONE"))]

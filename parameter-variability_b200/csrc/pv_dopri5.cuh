@@ -303,7 +303,7 @@ struct pv_dopri5_lane {
             const double e = h * fma(pv_dp5[25], k7[i],
                                      fma(pv_dp5[24], k6[i],
                                          fma(pv_dp5[23], k5[i], fma(pv_dp5[22], k4[i], fma(pv_dp5[21], k3[i], pv_dp5[20] * k1[i])))));
-            const double sc = atol + rtol * fmax(fabs(y[i]), fabs(yn[i]));
+            const double sc = atol + rtol * pv_absmax(y[i], yn[i]);
             const double r = e * pv_rcp_approx(sc);
             err2d = fma(r, r, err2d);
         }

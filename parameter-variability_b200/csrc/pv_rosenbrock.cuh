@@ -256,7 +256,7 @@ struct pv_rodas4_lane {
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
                 const double znew = zs[b * NX + i] + K6[b][i];
-                const double sc = fma(rtol, fmax(fabs(z[b * NX + i]), fabs(znew)), atol);
+                const double sc = fma(rtol, pv_absmax(z[b * NX + i], znew), atol);
                 const double r = K6[b][i] * pv_rcp_approx(sc);
                 err2d = fma(r, r, err2d);
                 finite = finite && (fabs(znew) < 1e300);

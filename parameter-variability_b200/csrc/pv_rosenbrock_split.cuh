@@ -383,7 +383,7 @@ pv_rodas4_split_kernel(const __grid_constant__ pv_launch_params_m<M> p) {
 #pragma unroll
                 for (int i = 0; i < NX; ++i) {
                     const double znew = zs[i] + r[i];
-                    const double sc = fma(p.rtol, fmax(fabs(z[i]), fabs(znew)), p.atol);
+                    const double sc = fma(p.rtol, pv_absmax(z[i], znew), p.atol);
                     const double q = r[i] * pv_rcp_approx(sc);
                     e2 = fma(q, q, e2);
                     finite = finite && (fabs(znew) < 1e300);

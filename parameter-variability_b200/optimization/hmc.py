@@ -114,7 +114,8 @@ def hmc_device(H, x0: np.ndarray, n_samples: int = 500, n_warmup: int = 500, n_l
     The unknowns of chain c, in the order of ``x0`` [C, n_individuals * P + 2 P] (all individuals, also when they are sharded
     over ranks): log theta_ci for individual i = 0.., parameter p = 0..P-1 (individual-major), then mu_c [P], then
     log omega_c [P] - the log-scale parameterisation of ``tests/test_gpu_estimation.py``.  Random numbers are drawn here, in
-    the order ``hmc`` draws them, and uploaded once; with the same seed both walk the same chains up to round-off.
+    the order ``hmc`` draws them, and uploaded in blocks of 128 iterations; with the same seed both walk the same chains up to
+    round-off.
     With sharded individuals (``H.world > 1``) every rank passes the same ``x0`` and seed; the returned theta block holds
     this rank's individuals (NaN elsewhere), the hyper-parameters are complete on every rank."""
     import ctypes
@@ -130,14 +131,23 @@ def hmc_device(H, x0: np.ndarray, n_samples: int = 500, n_warmup: int = 500, n_l
     dev = H.red.device
     n_iter = int(n_warmup) + int(n_samples)
     rs = np.random.RandomState(seed)
-    z = np.empty((n_iter, C, dim))
-    u = np.empty((n_iter, C))
-    Ls = []
-    for it in range(n_iter):                 # the draw order of hmc(): momenta, trajectory length, acceptance uniforms
-        z[it] = rs.normal(size=(C, dim))
-        Ls.append(max(1, int(round(n_leapfrog * rs.uniform(0.8, 1.2)))))
-        u[it] = rs.uniform(size=C)
-    z_d, u_d = torch.from_numpy(z).to(dev), torch.from_numpy(u).to(dev)
+    # Random numbers in blocks of 128 iterations (bounded memory: a block of 8 chains x 2004 unknowns is 16 MB).  The next block is
+    # drawn while the GPU works through the kernels queued for the current one; its upload is ordered on the same stream behind
+    # them, so it never overwrites numbers a queued kernel still reads.
+    block = max(1, min(n_iter, 128))
+    z_d = torch.empty((block, C, dim), dtype=torch.float64, device=dev)
+    u_d = torch.empty((block, C), dtype=torch.float64, device=dev)
+    Ls: list[int] = []
+
+    def draw_block(first_it):                # the draw order of hmc(): momenta, trajectory length, acceptance uniforms
+        n = min(block, n_iter - first_it)
+        z, u = np.empty((n, C, dim)), np.empty((n, C))
+        for j in range(n):
+            z[j] = rs.normal(size=(C, dim))
+            Ls.append(max(1, int(round(n_leapfrog * rs.uniform(0.8, 1.2)))))
+            u[j] = rs.uniform(size=C)
+        z_d[:n].copy_(torch.from_numpy(z))
+        u_d[:n].copy_(torch.from_numpy(u))
 
     def t64(*shape, fill=0.0):
         return torch.full(shape, fill, dtype=torch.float64, device=dev)
@@ -182,9 +192,12 @@ def hmc_device(H, x0: np.ndarray, n_samples: int = 500, n_warmup: int = 500, n_l
     reduce_energy()
     chk(lib.pv_hmc_accept(sp, 0, 0, int(n_warmup), None, float(target_accept), float(max_energy_error), int(adapt_mass), 0, stream))
     w_n = 0
+    if n_iter:
+        draw_block(0)
     for it in range(n_iter):
         warm = it < n_warmup
-        chk(lib.pv_hmc_begin(sp, z_d[it].data_ptr(), stream))
+        j = it % block
+        chk(lib.pv_hmc_begin(sp, z_d[j].data_ptr(), stream))
         for k in range(Ls[it]):
             leapfrog(1.0, k == Ls[it] - 1)
         n_evals += Ls[it]
@@ -193,8 +206,10 @@ def hmc_device(H, x0: np.ndarray, n_samples: int = 500, n_warmup: int = 500, n_l
         if warm and adapt_mass and it >= n_warmup // 2:
             w_n += 1
             wn = w_n
-        chk(lib.pv_hmc_accept(sp, 1 if warm else 2, it, int(n_warmup), u_d[it].data_ptr(), float(target_accept),
+        chk(lib.pv_hmc_accept(sp, 1 if warm else 2, it, int(n_warmup), u_d[j].data_ptr(), float(target_accept),
                               float(max_energy_error), int(adapt_mass), wn, stream))
+        if j == block - 1 and it + 1 < n_iter:
+            draw_block(it + 1)
     torch.cuda.current_stream().synchronize()
     samples = np.full((C, n_samples, dim), np.nan)
     if n_samples:
